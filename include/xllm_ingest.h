@@ -1,0 +1,100 @@
+/*
+ * xllm_ingest.h — C-ABI of the B200 request-ingest + prefix-cache routing path.
+ *
+ * One shared library, libxllm_ingest.so (CUDA, sm_100a), replaces the CPU hot path
+ * every request to an xllm-service front door traverses before PD dispatch:
+ *
+ *   Tokenizer::encode            xllm_service/tokenizer/tokenizer.h:32-33
+ *                                (called at xllm_service/scheduler/scheduler.cpp:129)
+ *   xxh3_128bits_hash            xllm_service/common/hash_util.h:56-58, hash_util.cpp:18-45
+ *   GlobalKVCacheMgr::match      xllm_service/scheduler/managers/global_kvcache_mgr.h:39,
+ *                                global_kvcache_mgr.cpp:73-131
+ *   GlobalKVCacheMgr::record_updated_kvcaches / upload_kvcache
+ *                                global_kvcache_mgr.cpp:177-247
+ *   CacheAwareRouting::cost_function / select_instances_pair
+ *                                xllm_service/scheduler/loadbalance_policy/cache_aware_routing.cpp:22-85
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  Every entry point returns
+ * 0 on success or a negative XLLM_ERR_* code and never aborts the process
+ * (the reference's Rust shim panics, lib.rs:32,39,69,77,91; its C++ CHECKs abort).
+ * xllm_last_error() returns a thread-local description of the last failure.
+ *
+ * Threading: a handle may be used from many threads; calls on one handle are
+ * serialised internally (one CUDA stream per handle).  Create one handle per
+ * worker thread / per GPU for concurrency (mirrors the reference's thread_local
+ * tokenizer clone, scheduler.cpp:274-277) — handles created with
+ * xllm_ingest_clone() share the device-resident tables.
+ *
+ * There is no CPU fallback inside this library: without a CUDA device every
+ * compute entry point fails with XLLM_ERR_CUDA.
+ */
+#ifndef XLLM_INGEST_H_
+#define XLLM_INGEST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XLLM_OK 0
+#define XLLM_ERR_INVALID_ARG (-1)
+#define XLLM_ERR_CUDA (-2)
+#define XLLM_ERR_IO (-3)
+#define XLLM_ERR_FORMAT (-4)
+#define XLLM_ERR_UNSUPPORTED (-5)
+#define XLLM_ERR_CAPACITY (-6)
+#define XLLM_ERR_NOMEM (-7)
+
+#define XLLM_KEY_BYTES 16 /* sizeof(XXH128_hash_t), hash_util.h:14 */
+#define XLLM_MAX_INSTANCES 64
+
+typedef struct xllm_ingest* xllm_ingest_t;
+
+/* Mirrors the hot-path gflags (xllm_service/common/global_gflags.cpp:60,114-118). */
+typedef struct {
+  const char* tokenizer_path; /* --tokenizer_path: directory holding tokenizer.model /
+                                 tokenizer.json / a tiktoken vocab; NULL = no tokenizer */
+  int32_t block_size;         /* --block_size, default 128 (0 => 128); must be in [1,251] (hash_util.cpp:29-33) */
+  uint32_t xxh3_seed;         /* --xxh3_128bits_seed, default 1024 */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t max_batch;          /* max requests per batch call (0 => 65536) */
+  int64_t max_batch_bytes;    /* max total prompt bytes per batch call (0 => 64 MiB * ...) */
+  int32_t max_tokens;         /* max token ids per request (0 => 8192) */
+  int64_t index_capacity;     /* max distinct block keys in the prefix index (0 => no index) */
+} xllm_ingest_config;
+
+const char* xllm_last_error(void);
+int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out);
+int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out);
+void xllm_ingest_destroy(xllm_ingest_t h);
+
+/* ---------------------------------------------------------------- block hash
+ * Batch form of the chain in GlobalKVCacheMgr::match (global_kvcache_mgr.cpp:76-94):
+ * request r owns tokens[tok_start[r] .. tok_start[r]+n_tok[r]) and gets
+ * floor(n_tok[r]/block_size) keys of 16 bytes (low64 LE || high64 LE, the memcpy of
+ * XXH128_hash_t at hash_util.cpp:26-27) written at keys + 16*key_start[r].
+ * Trailing tokens past the last full block are ignored (global_kvcache_mgr.cpp:76).
+ *
+ * xllm_hash_blocks        : host pointers; copies in, runs the kernel, copies out.
+ * xllm_hash_blocks_device : device pointers, asynchronous on `cuda_stream`
+ *                           (a cudaStream_t passed as void*; NULL = the handle's stream).
+ */
+int xllm_hash_blocks(xllm_ingest_t h, int32_t n_req, const int32_t* tokens, int64_t n_tokens_total,
+                     const int64_t* tok_start, const int32_t* n_tok, uint8_t* keys, int64_t n_keys_total,
+                     const int64_t* key_start);
+int xllm_hash_blocks_device(xllm_ingest_t h, int32_t n_req, const int32_t* d_tokens, const int64_t* d_tok_start,
+                            const int32_t* d_n_tok, uint8_t* d_keys, const int64_t* d_key_start,
+                            void* cuda_stream);
+
+/* Single-call drop-in for xxh3_128bits_hash(pre_hash_value, token_ids, hash_value)
+ * (hash_util.h:56-58): prev may be NULL (first block) and may alias out.  Fails with
+ * XLLM_ERR_INVALID_ARG where the reference CHECK-fails (16 + 4*n >= 1024). */
+int xllm_xxh3_128bits_hash(xllm_ingest_t h, const uint8_t* prev16, const int32_t* token_ids, size_t n_tokens,
+                           uint8_t* out16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XLLM_INGEST_H_ */

@@ -1,0 +1,88 @@
+"""ctypes bindings of oracle/liboracle.so (the C/C++ restatement of the reference's
+CPU hot path).  TEST INFRASTRUCTURE ONLY — see oracle/__init__.py."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build():
+    """(Re)build liboracle.so with make; a no-op when it is up to date."""
+    subprocess.check_call(["make", "-s", "oracle"], cwd=os.path.dirname(_HERE))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.oracle_xxh3_128_with_seed.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_void_p]
+        L.oracle_xxh3_128_with_seed.restype = None
+        L.oracle_xxh3_128bits_hash.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
+                                               ctypes.c_void_p]
+        L.oracle_xxh3_128bits_hash.restype = ctypes.c_int
+        L.oracle_block_hash_chain.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32,
+                                              ctypes.c_void_p]
+        L.oracle_block_hash_chain.restype = ctypes.c_long
+        L.oracle_block_hash_chain_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                    ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                                    ctypes.c_void_p]
+        L.oracle_block_hash_chain_batch.restype = ctypes.c_long
+        _lib = L
+    return _lib
+
+
+def xxh3_128_with_seed(data: bytes, seed: int) -> bytes:
+    """XXH3_128bits_withSeed; returns the XXH128_hash_t struct bytes (low64 LE || high64 LE)."""
+    out = ctypes.create_string_buffer(16)
+    buf = ctypes.create_string_buffer(bytes(data), len(data)) if len(data) else None
+    lib().oracle_xxh3_128_with_seed(buf, len(data), seed, out)
+    return out.raw
+
+
+def xxh3_128bits_hash(prev, token_ids, seed=1024) -> bytes:
+    """hash_util.cpp:18-45.  prev: 16 bytes or None."""
+    t = np.ascontiguousarray(token_ids, dtype=np.int32)
+    out = ctypes.create_string_buffer(16)
+    pbuf = ctypes.create_string_buffer(bytes(prev), 16) if prev is not None else None
+    rc = lib().oracle_xxh3_128bits_hash(pbuf, t.ctypes.data, t.size, seed, out)
+    if rc != 0:
+        raise ValueError("key size is too small (hash_util.cpp:33)")
+    return out.raw
+
+
+def block_hash_chain(token_ids, block_size=128, seed=1024) -> np.ndarray:
+    """Chain of global_kvcache_mgr.cpp:76-94 -> uint8 [n_blocks, 16]."""
+    t = np.ascontiguousarray(token_ids, dtype=np.int32)
+    nb = t.size // block_size
+    keys = np.zeros((nb, 16), dtype=np.uint8)
+    rc = lib().oracle_block_hash_chain(t.ctypes.data, t.size, block_size, seed, keys.ctypes.data)
+    if rc < 0:
+        raise ValueError("oracle_block_hash_chain failed")
+    return keys
+
+
+def block_hash_chain_batch(tokens, tok_offsets, block_size=128, seed=1024):
+    """CSR batch: tokens int32[total], tok_offsets int64[n+1] -> (keys uint8[total_blocks,16], key_offsets int64[n+1])."""
+    tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+    tok_offsets = np.ascontiguousarray(tok_offsets, dtype=np.int64)
+    n = tok_offsets.size - 1
+    nb = (tok_offsets[1:] - tok_offsets[:-1]) // block_size
+    key_offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(nb, out=key_offsets[1:])
+    keys = np.zeros((int(key_offsets[-1]), 16), dtype=np.uint8)
+    rc = lib().oracle_block_hash_chain_batch(tokens.ctypes.data, tok_offsets.ctypes.data, n, block_size, seed,
+                                             keys.ctypes.data, key_offsets.ctypes.data)
+    if rc < 0:
+        raise ValueError("oracle_block_hash_chain_batch failed")
+    return keys, key_offsets

@@ -1,0 +1,66 @@
+"""ctypes loader for libxllm_ingest.so (built in-tree by `make lib` / __graft_entry__.build())."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libxllm_ingest.so")
+_lib = None
+
+
+class IngestError(RuntimeError):
+    """A C-ABI entry point returned a negative XLLM_ERR_* code."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"xllm_ingest error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+class Config(ctypes.Structure):
+    """xllm_ingest_config (include/xllm_ingest.h)."""
+    _fields_ = [
+        ("tokenizer_path", ctypes.c_char_p),
+        ("block_size", ctypes.c_int32),
+        ("xxh3_seed", ctypes.c_uint32),
+        ("device", ctypes.c_int32),
+        ("max_batch", ctypes.c_int32),
+        ("max_batch_bytes", ctypes.c_int64),
+        ("max_tokens", ctypes.c_int32),
+        ("index_capacity", ctypes.c_int64),
+    ]
+
+
+_VP = ctypes.c_void_p
+
+
+def _declare(L):
+    L.xllm_last_error.restype = ctypes.c_char_p
+    L.xllm_last_error.argtypes = []
+    L.xllm_ingest_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(_VP)]
+    L.xllm_ingest_clone.argtypes = [_VP, ctypes.POINTER(_VP)]
+    L.xllm_ingest_destroy.argtypes = [_VP]
+    L.xllm_ingest_destroy.restype = None
+    L.xllm_hash_blocks.argtypes = [_VP, ctypes.c_int32, _VP, ctypes.c_int64, _VP, _VP, _VP, ctypes.c_int64, _VP]
+    L.xllm_hash_blocks_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]
+    L.xllm_xxh3_128bits_hash.argtypes = [_VP, _VP, _VP, ctypes.c_size_t, _VP]
+
+
+def lib():
+    """Load the CUDA library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise IngestError(-3, f"{_LIB_PATH} not built: run `make lib` or __graft_entry__.build() "
+                                  "(there is no CPU fallback)")
+        L = ctypes.CDLL(_LIB_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise IngestError(rc, lib().xllm_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,230 @@
+// capi.cu — the extern "C" boundary declared in include/xllm_ingest.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/xllm_ingest.h"
+#include "handle.h"
+
+namespace xllm {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return XLLM_OK;
+  release();
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    cap = 0;
+    set_last_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    return XLLM_ERR_NOMEM;
+  }
+  cap = want;
+  return XLLM_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+int PinBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return XLLM_OK;
+  release();
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMallocHost(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    cap = 0;
+    set_last_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    return XLLM_ERR_NOMEM;
+  }
+  cap = want;
+  return XLLM_OK;
+}
+void PinBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
+}  // namespace xllm
+
+using namespace xllm;
+
+#define XLLM_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != XLLM_OK) return _rc; \
+  } while (0)
+
+extern "C" {
+
+const char* xllm_last_error(void) { return g_last_error; }
+
+int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
+  if (!cfg || !out) {
+    set_last_error("xllm_ingest_create: null argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  *out = nullptr;
+  const int bs = cfg->block_size == 0 ? 128 : cfg->block_size;
+  // hash_util.cpp:29-33: CHECK_GT(1024, 4*block_size + 16)
+  if (bs < 1 || 4 * bs + 16 >= 1024) {
+    set_last_error("block_size %d outside [1,251] (hash_util.cpp:29-33 frame limit)", bs);
+    return XLLM_ERR_INVALID_ARG;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    set_last_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    return XLLM_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= n_dev) {
+    set_last_error("device %d out of range [0,%d)", cfg->device, n_dev);
+    return XLLM_ERR_INVALID_ARG;
+  }
+  xllm_ingest* h = new (std::nothrow) xllm_ingest();
+  if (!h) return XLLM_ERR_NOMEM;
+  h->device = cfg->device;
+  h->block_size = bs;
+  h->seed = cfg->xxh3_seed;
+  h->max_batch = cfg->max_batch > 0 ? cfg->max_batch : 65536;
+  h->max_tokens = cfg->max_tokens > 0 ? cfg->max_tokens : 8192;
+  xxh3_make_consts(h->seed, &h->xxh);
+  if (cudaSetDevice(h->device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&h->d_task_counter, 64) != cudaSuccess) {
+    set_last_error("CUDA initialisation failed on device %d: %s", h->device,
+                   cudaGetErrorString(cudaGetLastError()));
+    xllm_ingest_destroy(h);
+    return XLLM_ERR_CUDA;
+  }
+  *out = h;
+  return XLLM_OK;
+}
+
+int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out) {
+  if (!src || !out) {
+    set_last_error("xllm_ingest_clone: null argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  xllm_ingest_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.block_size = src->block_size;
+  cfg.xxh3_seed = src->seed;
+  cfg.device = src->device;
+  cfg.max_batch = src->max_batch;
+  cfg.max_tokens = src->max_tokens;
+  return xllm_ingest_create(&cfg, out);
+}
+
+void xllm_ingest_destroy(xllm_ingest_t h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->d_tokens.release();
+  h->d_tok_start.release();
+  h->d_n_tok.release();
+  h->d_keys.release();
+  h->d_key_start.release();
+  if (h->d_task_counter) cudaFree(h->d_task_counter);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int xllm_hash_blocks_device(xllm_ingest_t h, int32_t n_req, const int32_t* d_tokens, const int64_t* d_tok_start,
+                            const int32_t* d_n_tok, uint8_t* d_keys, const int64_t* d_key_start,
+                            void* cuda_stream) {
+  if (!h || n_req < 0 || (n_req > 0 && (!d_tokens || !d_tok_start || !d_n_tok || !d_keys || !d_key_start))) {
+    set_last_error("xllm_hash_blocks_device: invalid argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  if (n_req == 0) return XLLM_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  XLLM_CUDA_TRY(xxh3_chain_launch(d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start, n_req, h->block_size, h->xxh,
+                                  h->d_task_counter, s));
+  return XLLM_OK;
+}
+
+int xllm_hash_blocks(xllm_ingest_t h, int32_t n_req, const int32_t* tokens, int64_t n_tokens_total,
+                     const int64_t* tok_start, const int32_t* n_tok, uint8_t* keys, int64_t n_keys_total,
+                     const int64_t* key_start) {
+  if (!h || n_req < 0 || n_tokens_total < 0 || n_keys_total < 0 ||
+      (n_req > 0 && (!tok_start || !n_tok || !key_start)) || (n_tokens_total > 0 && !tokens) ||
+      (n_keys_total > 0 && !keys)) {
+    set_last_error("xllm_hash_blocks: invalid argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  if (n_req == 0) return XLLM_OK;
+  // bounds: every row must lie inside the buffers the caller described
+  for (int32_t r = 0; r < n_req; ++r) {
+    const int64_t nb = n_tok[r] < 0 ? -1 : n_tok[r] / h->block_size;
+    if (nb < 0 || tok_start[r] < 0 || tok_start[r] + n_tok[r] > n_tokens_total || key_start[r] < 0 ||
+        key_start[r] + nb > n_keys_total) {
+      set_last_error("xllm_hash_blocks: request %d out of bounds", r);
+      return XLLM_ERR_INVALID_ARG;
+    }
+  }
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  XLLM_TRY(h->d_tokens.reserve((size_t)n_tokens_total * 4 + 16));
+  XLLM_TRY(h->d_tok_start.reserve((size_t)n_req * 8));
+  XLLM_TRY(h->d_n_tok.reserve((size_t)n_req * 4));
+  XLLM_TRY(h->d_keys.reserve((size_t)n_keys_total * 16 + 16));
+  XLLM_TRY(h->d_key_start.reserve((size_t)n_req * 8));
+  cudaStream_t s = h->stream;
+  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_tokens.p, tokens, (size_t)n_tokens_total * 4, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_tok_start.p, tok_start, (size_t)n_req * 8, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_n_tok.p, n_tok, (size_t)n_req * 4, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_key_start.p, key_start, (size_t)n_req * 8, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(xxh3_chain_launch(h->d_tokens.as<int32_t>(), h->d_tok_start.as<int64_t>(), h->d_n_tok.as<int32_t>(),
+                                  h->d_keys.as<uint8_t>(), h->d_key_start.as<int64_t>(), n_req, h->block_size,
+                                  h->xxh, h->d_task_counter, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(keys, h->d_keys.p, (size_t)n_keys_total * 16, cudaMemcpyDeviceToHost, s));
+  XLLM_CUDA_TRY(cudaStreamSynchronize(s));
+  return XLLM_OK;
+}
+
+int xllm_xxh3_128bits_hash(xllm_ingest_t h, const uint8_t* prev16, const int32_t* token_ids, size_t n_tokens,
+                           uint8_t* out16) {
+  if (!h || !out16 || (n_tokens > 0 && !token_ids)) {
+    set_last_error("xllm_xxh3_128bits_hash: invalid argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  // hash_util.cpp:31-33
+  if (prev16 && !(1024 > (int64_t)(4 * n_tokens + 16))) {
+    set_last_error("key size is too small (hash_util.cpp:33): %zu tokens", n_tokens);
+    return XLLM_ERR_INVALID_ARG;
+  }
+  if (n_tokens > 100000000) return XLLM_ERR_INVALID_ARG;
+  // One (possibly chained) hash = the generic kernel over a frame of int32 "tokens".
+  // A chained call hashes prev16 || tokens, i.e. an unchained hash of 4 + n tokens.
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n = n_tokens + (prev16 ? 4 : 0);
+  XLLM_TRY(h->d_tokens.reserve(n * 4 + 16));
+  XLLM_TRY(h->d_keys.reserve(32));
+  cudaStream_t s = h->stream;
+  uint8_t* dt = h->d_tokens.as<uint8_t>();
+  if (prev16) XLLM_CUDA_TRY(cudaMemcpyAsync(dt, prev16, 16, cudaMemcpyHostToDevice, s));
+  if (n_tokens)
+    XLLM_CUDA_TRY(cudaMemcpyAsync(dt + (prev16 ? 16 : 0), token_ids, n_tokens * 4, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(xxh3_single_launch(h->d_tokens.as<uint8_t>(), n * 4, h->d_keys.as<uint8_t>(), h->xxh, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(out16, h->d_keys.p, 16, cudaMemcpyDeviceToHost, s));
+  XLLM_CUDA_TRY(cudaStreamSynchronize(s));
+  return XLLM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// Internal handle behind the C-ABI (include/xllm_ingest.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+#include "xxh3_chain.cuh"
+
+namespace xllm {
+
+// Growable device / pinned-host scratch buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() { return static_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() { return static_cast<T*>(p); }
+};
+
+}  // namespace xllm
+
+struct xllm_ingest {
+  int device = 0;
+  int block_size = 128;
+  uint32_t seed = 1024;
+  int max_batch = 65536;
+  int max_tokens = 8192;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;  // serialises calls on this handle
+  xllm::Xxh3Consts xxh;
+  unsigned int* d_task_counter = nullptr;
+  // scratch for the host-pointer entry points
+  xllm::DevBuf d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start;
+};

@@ -1,0 +1,77 @@
+"""Host-side handle over the C-ABI (include/xllm_ingest.h)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, check
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None and a.size else None
+
+
+class Ingest:
+    """One xllm_ingest_t handle.  Mirrors the hot-path knobs of the reference's Options
+    (block_size, xxh3_128bits_seed, tokenizer_path: global_gflags.cpp:60,114-118)."""
+
+    def __init__(self, tokenizer_path=None, block_size=128, xxh3_seed=1024, device=0, max_batch=0,
+                 max_batch_bytes=0, max_tokens=0, index_capacity=0):
+        self._L = _lib.lib()
+        self._h = ctypes.c_void_p()
+        cfg = Config()
+        cfg.tokenizer_path = tokenizer_path.encode() if tokenizer_path else None
+        cfg.block_size = block_size
+        cfg.xxh3_seed = xxh3_seed
+        cfg.device = device
+        cfg.max_batch = max_batch
+        cfg.max_batch_bytes = max_batch_bytes
+        cfg.max_tokens = max_tokens
+        cfg.index_capacity = index_capacity
+        self.block_size = block_size or 128
+        self.seed = xxh3_seed
+        check(self._L.xllm_ingest_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._L.xllm_ingest_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ hash
+    def xxh3_128bits_hash(self, prev, token_ids) -> bytes:
+        """Drop-in for xxh3_128bits_hash(pre_hash_value, token_ids, hash_value)
+        (xllm_service/common/hash_util.h:56-58)."""
+        t = np.ascontiguousarray(token_ids, dtype=np.int32)
+        out = ctypes.create_string_buffer(16)
+        pbuf = ctypes.create_string_buffer(bytes(prev), 16) if prev is not None else None
+        check(self._L.xllm_xxh3_128bits_hash(self._h, pbuf, _ptr(t), t.size, out))
+        return out.raw
+
+    def hash_blocks(self, tokens, tok_start, n_tok, key_start=None):
+        """Host-buffer batch chain (global_kvcache_mgr.cpp:76-94).  Returns (keys uint8[n_keys,16], key_start)."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        tok_start = np.ascontiguousarray(tok_start, dtype=np.int64)
+        n_tok = np.ascontiguousarray(n_tok, dtype=np.int32)
+        n = n_tok.size
+        nb = n_tok.astype(np.int64) // self.block_size
+        if key_start is None:
+            key_start = np.zeros(n, dtype=np.int64)
+            if n:
+                np.cumsum(nb[:-1], out=key_start[1:])
+        key_start = np.ascontiguousarray(key_start, dtype=np.int64)
+        n_keys = int((key_start + nb).max()) if n else 0
+        keys = np.zeros((n_keys, 16), dtype=np.uint8)
+        check(self._L.xllm_hash_blocks(self._h, n, _ptr(tokens), tokens.size, _ptr(tok_start), _ptr(n_tok),
+                                       _ptr(keys), n_keys, _ptr(key_start)))
+        return keys, key_start
+
+    def hash_blocks_device(self, n_req, d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start, stream=None):
+        """Device-pointer batch chain; arguments are integer device addresses (e.g. torch .data_ptr())."""
+        check(self._L.xllm_hash_blocks_device(self._h, n_req, d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start,
+                                              stream))
