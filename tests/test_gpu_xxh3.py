@@ -129,7 +129,8 @@ def test_full_size_properties_device(ingest, oracle):
     key_start = torch.arange(n, device="cuda", dtype=torch.int64) * (T // 128)
     keys = torch.zeros((n, T // 128, 16), dtype=torch.uint8, device="cuda")
     keys2 = torch.zeros_like(keys)
-    s = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    s = None  # NULL => the handle's own stream
     ingest.hash_blocks_device(n, toks.data_ptr(), tok_start.data_ptr(), n_tok.data_ptr(), keys.data_ptr(),
                               key_start.data_ptr(), s)
     ingest.hash_blocks_device(n, toks.data_ptr(), tok_start.data_ptr(), n_tok.data_ptr(), keys2.data_ptr(),

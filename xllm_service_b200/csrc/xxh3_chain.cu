@@ -92,43 +92,53 @@ __device__ __forceinline__ uint64_t xxh64_avalanche(uint64_t h) {
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
 // ------------------------------------------------------------- fast path kernel
-constexpr int kBlockTokens = 128;               // tokens per KV block on the fast path
-constexpr int kRowU4 = 33;                      // 528-byte row stride (32 x uint4 of data + 1 pad)
-constexpr int kRowsPerWarp = 32;                // lane == request
-constexpr int kKeyRowU4 = 9;                    // 8 keys + 1 pad per row in the output stage
+constexpr int kBlockTokens = 128;   // tokens per KV block on the fast path
+constexpr int kRowsPerWarp = 32;    // lane == request
+constexpr int kQuarterU4 = 8;       // pipeline unit: one 128-byte quarter of a block per row
+constexpr int kQRowU4 = 9;          // padded row stride in the stage: 144 B => conflict-free LDS.128
+constexpr int kKeyRowU4 = 9;        // 8 keys + 1 pad per row in the output stage
 constexpr int kKeysPerFlush = 8;
 
 template <int STAGES>
 struct FastSmem {
-  uint4 stage[STAGES][kRowsPerWarp * kRowU4];   // STAGES x 16.5 KB
+  uint4 stage[STAGES][kRowsPerWarp * kQRowU4];  // STAGES x 4.5 KB
   uint4 keys[kRowsPerWarp * kKeyRowU4];         // 4.5 KB
-  const int32_t* row_tok[kRowsPerWarp];         // token base pointer of each row
   uint8_t* row_key[kRowsPerWarp];               // key base pointer of each row
   int32_t row_nb[kRowsPerWarp];                 // blocks in each row
 };
 
+__device__ __forceinline__ uint4 lds128(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(smem_u32(p)));
+  return v;
+}
+
 // acc[L ^ 1] += dv ; acc[L] += lo32(dv ^ key) * hi32(dv ^ key)
-#define XXH_ROUND(L, DV, KEY)          \
-  do {                                 \
-    acc[(L) ^ 1] += (DV);              \
+#define XXH_ROUND(L, DV, KEY)           \
+  do {                                  \
+    acc[(L) ^ 1] += (DV);               \
     acc[(L)] += mul32x32((DV) ^ (KEY)); \
   } while (0)
 
-// Fold the 64 u64 of one 512-byte token block (shared-memory row) into acc[8].
+// Fold quarter QTR (token u64 16*QTR .. 16*QTR+15) of one 512-byte block into acc[8].
 // CHAINED == false: frame u64 index f = j         (len 512: 7 full stripes + last stripe)
 // CHAINED == true : frame u64 index f = j + 2     (len 528: 8 full stripes + last stripe)
 // Full stripe k = f / 8 (only while f < 8 * nbStripes), lane l = f % 8, key s[k + l].
 // Last stripe = token u64 56..63 (frame bytes len-64 .. len), lane j - 56, key last[j - 56].
-template <bool CHAINED>
-__device__ __forceinline__ void fold_block(const uint4* __restrict__ row, const Xxh3Consts& C, uint64_t (&acc)[8]) {
+template <int QTR, bool CHAINED>
+__device__ __forceinline__ void fold_quarter(const uint4* row, const Xxh3Consts& C, uint64_t (&acc)[8]) {
+  uint4 v[kQuarterU4];
 #pragma unroll
-  for (int q = 0; q < 32; ++q) {
-    const uint4 v = row[q];
-    const uint64_t d0 = u64_of(v.x, v.y);
-    const uint64_t d1 = u64_of(v.z, v.w);
+  for (int q = 0; q < kQuarterU4; ++q) v[q] = lds128(row + q);
+#pragma unroll
+  for (int q = 0; q < kQuarterU4; ++q) {
+    const uint64_t d0 = u64_of(v[q].x, v[q].y);
+    const uint64_t d1 = u64_of(v[q].z, v[q].w);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int j = 2 * q + h;
+      const int j = 16 * QTR + 2 * q + h;
       const uint64_t dv = h ? d1 : d0;
       const int f = CHAINED ? j + 2 : j;
       const int full_limit = CHAINED ? 64 : 56;
@@ -169,6 +179,8 @@ __global__ void __launch_bounds__(32) xxh3_chain128_kernel(const int32_t* __rest
   FastSmem<STAGES>& sm = *reinterpret_cast<FastSmem<STAGES>*>(smem_raw);
   const int lane = threadIdx.x;
   const int n_tasks = (n_req + kRowsPerWarp - 1) / kRowsPerWarp;
+  const int piece = lane & 7;   // which 16 B of a row's 128-byte quarter this lane copies
+  const int rsub = lane >> 3;   // copies cover 4 rows per instruction: row = 4 * it + rsub
 
   for (;;) {
     unsigned int task = 0;
@@ -179,24 +191,39 @@ __global__ void __launch_bounds__(32) xxh3_chain128_kernel(const int32_t* __rest
     const int r = (int)task * kRowsPerWarp + lane;
     const bool valid = r < n_req;
     const int my_nb = valid ? (n_tok[r] / kBlockTokens) : 0;
-    sm.row_tok[lane] = valid ? tokens + tok_start[r] : tokens;
+    const int32_t* my_tok = valid ? tokens + tok_start[r] : tokens;
     sm.row_key[lane] = valid ? keys + 16 * key_start[r] : keys;
     sm.row_nb[lane] = my_nb;
     int max_nb = my_nb;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) max_nb = max(max_nb, __shfl_xor_sync(0xffffffffu, max_nb, o));
+
+    // The 8 rows this lane copies for, kept in registers.
+    const int32_t* cp_src[8];
+    int cp_nb[8];
+    unsigned int aligned_mask = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int q = 4 * it + rsub;
+      const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)my_tok, q);
+      cp_src[it] = reinterpret_cast<const int32_t*>(p) + piece * 4;
+      cp_nb[it] = __shfl_sync(0xffffffffu, my_nb, q);
+      if ((p & 15ull) == 0) aligned_mask |= 1u << it;
+    }
     __syncwarp();
 
-    // Issue the copies of chain step `b` (block b of every row) into stage b % STAGES.
-    auto issue = [&](int b) {
+    // Issue the copies of pipeline unit u = 4 * b + qtr into slot u % STAGES.
+    auto issue = [&](int u, int slot) {
+      const int b = u >> 2;
       if (b < max_nb) {
-        uint4* st = sm.stage[b % STAGES];
-#pragma unroll 8
-        for (int q = 0; q < kRowsPerWarp; ++q) {
-          if (b < sm.row_nb[q]) {
-            const int32_t* src = sm.row_tok[q] + (size_t)b * kBlockTokens + lane * 4;
-            uint4* dst = st + q * kRowU4 + lane;
-            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        uint4* st = sm.stage[slot] + rsub * kQRowU4 + piece;
+        const int tok_off = b * kBlockTokens + (u & 3) * 32;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (b < cp_nb[it]) {
+            const int32_t* src = cp_src[it] + tok_off;
+            uint4* dst = st + it * 4 * kQRowU4;
+            if (aligned_mask & (1u << it)) {
               cp_async_16(dst, src);
             } else {  // row not 16-byte aligned: same bytes, 4-byte copies
               cp_async_4(reinterpret_cast<uint32_t*>(dst) + 0, src + 0);
@@ -210,24 +237,43 @@ __global__ void __launch_bounds__(32) xxh3_chain128_kernel(const int32_t* __rest
       cp_async_commit();  // always commit so group accounting stays uniform
     };
 
+    int issue_slot = 0;
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    for (int s = 0; s < STAGES - 1; ++s) {
+      issue(s, issue_slot);
+      issue_slot = (issue_slot + 1 == STAGES) ? 0 : issue_slot + 1;
+    }
+    int slot = 0;
 
     uint64_t prev_lo = 0, prev_hi = 0;
     for (int b = 0; b < max_nb; ++b) {
-      issue(b + STAGES - 1);
-      cp_async_wait<STAGES - 1>();
-      __syncwarp();
+      uint64_t acc[8] = {P32_3, P64_1, P64_2, P64_3, P64_4, P32_2, P64_5, P32_1};
+      const bool active = b < my_nb;
+#define XXH_STEP(QTR)                                                         \
+  do {                                                                        \
+    issue(4 * b + (QTR) + STAGES - 1, issue_slot);                            \
+    issue_slot = (issue_slot + 1 == STAGES) ? 0 : issue_slot + 1;             \
+    cp_async_wait<STAGES - 1>();                                              \
+    __syncwarp();                                                             \
+    if (active) {                                                             \
+      const uint4* row = sm.stage[slot] + lane * kQRowU4;                     \
+      if (b == 0) fold_quarter<QTR, false>(row, C, acc);                      \
+      else fold_quarter<QTR, true>(row, C, acc);                              \
+    }                                                                         \
+    slot = (slot + 1 == STAGES) ? 0 : slot + 1;                               \
+    __syncwarp(); /* the slot just consumed may be refilled by the next issue */ \
+  } while (0)
+      XXH_STEP(0);
+      XXH_STEP(1);
+      XXH_STEP(2);
+      XXH_STEP(3);
+#undef XXH_STEP
 
-      if (b < my_nb) {
-        const uint4* row = sm.stage[b % STAGES] + lane * kRowU4;
-        uint64_t acc[8] = {P32_3, P64_1, P64_2, P64_3, P64_4, P32_2, P64_5, P32_1};
+      if (active) {
         uint64_t lo, hi;
         if (b == 0) {
-          fold_block<false>(row, C, acc);
           finish_block(acc, C, 512, lo, hi);
         } else {
-          fold_block<true>(row, C, acc);
           XXH_ROUND(0, prev_lo, C.s[0]);  // stripe 0, lane 0 <- previous key low64
           XXH_ROUND(1, prev_hi, C.s[1]);  // stripe 0, lane 1 <- previous key high64
           finish_block(acc, C, 528, lo, hi);
@@ -237,14 +283,13 @@ __global__ void __launch_bounds__(32) xxh3_chain128_kernel(const int32_t* __rest
         sm.keys[lane * kKeyRowU4 + (b % kKeysPerFlush)] =
             make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
       }
-      __syncwarp();  // stage b % STAGES is free again; keys of this step are visible
 
       if ((b % kKeysPerFlush) == kKeysPerFlush - 1 || b == max_nb - 1) {
+        __syncwarp();
         const int b0 = b - (b % kKeysPerFlush);
-        const int piece = lane & 7;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int q = it * 4 + (lane >> 3);
+          const int q = it * 4 + rsub;
           if (b0 + piece < sm.row_nb[q] && b0 + piece <= b) {
             reinterpret_cast<uint4*>(sm.row_key[q])[b0 + piece] = sm.keys[q * kKeyRowU4 + piece];
           }
@@ -504,9 +549,12 @@ cudaError_t xxh3_chain_launch(const int32_t* tokens, const int64_t* tok_start, c
     cudaError_t e = cudaMemsetAsync(task_counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
     const int n_tasks = (n_req + kRowsPerWarp - 1) / kRowsPerWarp;
-    const int warps_per_sm = (int)((227 * 1024) / (smem + 1024));
-    int grid = n_sm * warps_per_sm;
-    if (grid > n_tasks) grid = n_tasks;
+    int warps_per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (warps_per_sm > 16) warps_per_sm = 16;
+    // Balanced persistent grid: every warp runs the same number of 32-request tasks.
+    const int max_warps = n_sm * warps_per_sm;
+    const int rounds = (n_tasks + max_warps - 1) / max_warps;
+    int grid = (n_tasks + rounds - 1) / rounds;
     xxh3_chain128_kernel<kFastStages><<<grid, 32, smem, stream>>>(tokens, tok_start, n_tok, keys, key_start, n_req,
                                                                   consts, task_counter);
     return cudaGetLastError();
