@@ -38,6 +38,19 @@ def lib():
                                                     ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
                                                     ctypes.c_void_p]
         L.oracle_block_hash_chain_batch.restype = ctypes.c_long
+        L.oracle_sp_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.oracle_sp_load.restype = ctypes.c_void_p
+        L.oracle_sp_free.argtypes = [ctypes.c_void_p]
+        L.oracle_sp_free.restype = None
+        L.oracle_sp_piece_count.argtypes = [ctypes.c_void_p]
+        L.oracle_sp_normalize.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p,
+                                          ctypes.c_size_t]
+        L.oracle_sp_normalize.restype = ctypes.c_long
+        L.oracle_sp_encode.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p,
+                                       ctypes.c_size_t]
+        L.oracle_sp_encode.restype = ctypes.c_long
+        L.oracle_sp_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                             ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -86,3 +99,50 @@ def block_hash_chain_batch(tokens, tok_offsets, block_size=128, seed=1024):
     if rc < 0:
         raise ValueError("oracle_block_hash_chain_batch failed")
     return keys, key_offsets
+
+
+class SentencePieceOracle:
+    """SentencePieceTokenizer (xllm_service/tokenizer/sentencepiece_tokenizer.cpp:47-168) over the
+    C++ restatement of libsentencepiece's BPE path (oracle/sp_oracle.cc)."""
+
+    def __init__(self, model_dir_or_file):
+        path = model_dir_or_file
+        if os.path.isdir(path):
+            path = os.path.join(path, "tokenizer.model")  # tokenizer_args.h:37 default vocab_file
+        err = ctypes.create_string_buffer(512)
+        self._h = lib().oracle_sp_load(path.encode(), err, 512)
+        if not self._h:
+            raise ValueError("oracle_sp_load: " + err.value.decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_sp_free(self._h)
+            self._h = None
+
+    def vocab_size(self):
+        return lib().oracle_sp_piece_count(self._h)
+
+    def normalize(self, text: bytes) -> bytes:
+        cap = 3 * len(text) + 16
+        out = ctypes.create_string_buffer(cap)
+        n = lib().oracle_sp_normalize(self._h, text, len(text), out, cap)
+        assert n <= cap
+        return out.raw[:n]
+
+    def encode(self, text: bytes):
+        cap = len(text) * 3 + 16  # every byte can become a byte-fallback id; dummy prefix adds one
+        out = np.zeros(cap, dtype=np.int32)
+        n = lib().oracle_sp_encode(self._h, text, len(text), out.ctypes.data, cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def encode_batch(self, text_u8, offsets, ids_stride, n_threads=1):
+        """CSR batch -> (ids int32[n, ids_stride] zero padded, n_ids int32[n])."""
+        text_u8 = np.ascontiguousarray(text_u8, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        ids = np.zeros((n, ids_stride), dtype=np.int32)
+        n_ids = np.zeros(n, dtype=np.int32)
+        lib().oracle_sp_encode_batch(self._h, text_u8.ctypes.data, offsets.ctypes.data, n, ids.ctypes.data,
+                                     ids_stride, n_ids.ctypes.data, n_threads)
+        return ids, n_ids
