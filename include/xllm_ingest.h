@@ -94,6 +94,42 @@ int xllm_hash_blocks_device(xllm_ingest_t h, int32_t n_req, const int32_t* d_tok
 int xllm_xxh3_128bits_hash(xllm_ingest_t h, const uint8_t* prev16, const int32_t* token_ids, size_t n_tokens,
                            uint8_t* out16);
 
+/* ------------------------------------------------------------------ tokenize
+ * Batch form of Tokenizer::encode (xllm_service/tokenizer/tokenizer.h:32-33; the service calls
+ * it once per request at scheduler.cpp:129).  text holds all prompts back to back;
+ * offsets[n_req + 1] are byte offsets.  Request r's ids are written to ids + r*ids_stride
+ * (at most ids_stride of them); n_ids[r] is the full count; status[r] is 0 (ok),
+ * XLLM_ENC_TRUNCATED (count > ids_stride: call again with a larger stride) or
+ * XLLM_ERR_CAPACITY (a single whitespace-free run longer than the on-chip word buffer).
+ * An empty prompt yields 0 ids (sentencepiece_tokenizer.cpp:117-120).
+ * Backend = SentencePiece BPE `<tokenizer_path>/tokenizer.model`
+ * (sentencepiece_tokenizer.cpp:47-50); returns XLLM_ERR_UNSUPPORTED if the handle has no tokenizer.
+ */
+#define XLLM_ENC_TRUNCATED 1
+int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets, int32_t* ids,
+                      int64_t ids_stride, int32_t* n_ids, int32_t* status);
+int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_text, const int64_t* d_offsets,
+                             int32_t* d_ids, int64_t ids_stride, int32_t* d_n_ids, int32_t* d_status,
+                             void* cuda_stream);
+/* Host-only: parse a tokenizer directory and report the tables the device encoder would use
+ * (no CUDA needed).  split_mode: 1 = words split before every U+2581, 2 = before a U+2581 not
+ * preceded by U+2581, 0 = the vocabulary allows no exact pre-split. */
+typedef struct {
+  int32_t n_pieces;
+  int32_t n_symbols;      /* pieces + single chars that only occur inside pieces */
+  int32_t n_pair_slots;   /* open-addressing slots of the (left,right)->(priority,merged) table */
+  int32_t n_pairs;        /* occupied slots */
+  int32_t split_mode;
+  int32_t max_unit_out;   /* longest normalizer replacement after whitespace escaping (bytes) */
+  int32_t byte_fallback;
+  int32_t unk_id;
+  int32_t trie_units;
+} xllm_tokenizer_info;
+int xllm_tokenizer_probe(const char* tokenizer_path, xllm_tokenizer_info* out);
+
+/* Vocabulary size = GetPieceSize() (sentencepiece_tokenizer.cpp:251). */
+int xllm_vocab_size(xllm_ingest_t h, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

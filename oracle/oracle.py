@@ -126,14 +126,20 @@ class SentencePieceOracle:
         cap = 3 * len(text) + 16
         out = ctypes.create_string_buffer(cap)
         n = lib().oracle_sp_normalize(self._h, text, len(text), out, cap)
-        assert n <= cap
+        if n > cap:  # a charsmap replacement longer than 3x its key (e.g. U+FDFA)
+            cap = n
+            out = ctypes.create_string_buffer(cap)
+            n = lib().oracle_sp_normalize(self._h, text, len(text), out, cap)
         return out.raw[:n]
 
     def encode(self, text: bytes):
         cap = len(text) * 3 + 16  # every byte can become a byte-fallback id; dummy prefix adds one
         out = np.zeros(cap, dtype=np.int32)
         n = lib().oracle_sp_encode(self._h, text, len(text), out.ctypes.data, cap)
-        assert n <= cap
+        if n > cap:  # charsmap expansions (e.g. U+FDFA -> 18 chars)
+            cap = n
+            out = np.zeros(cap, dtype=np.int32)
+            n = lib().oracle_sp_encode(self._h, text, len(text), out.ctypes.data, cap)
         return out[:n].copy()
 
     def encode_batch(self, text_u8, offsets, ids_stride, n_threads=1):

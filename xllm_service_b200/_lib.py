@@ -33,6 +33,12 @@ class Config(ctypes.Structure):
     ]
 
 
+class TokenizerInfo(ctypes.Structure):
+    """xllm_tokenizer_info (include/xllm_ingest.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("n_pieces", "n_symbols", "n_pair_slots", "n_pairs", "split_mode",
+                                              "max_unit_out", "byte_fallback", "unk_id", "trie_units")]
+
+
 _VP = ctypes.c_void_p
 
 
@@ -46,6 +52,10 @@ def _declare(L):
     L.xllm_hash_blocks.argtypes = [_VP, ctypes.c_int32, _VP, ctypes.c_int64, _VP, _VP, _VP, ctypes.c_int64, _VP]
     L.xllm_hash_blocks_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]
     L.xllm_xxh3_128bits_hash.argtypes = [_VP, _VP, _VP, ctypes.c_size_t, _VP]
+    L.xllm_encode_batch.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, ctypes.c_int64, _VP, _VP]
+    L.xllm_encode_batch_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, ctypes.c_int64, _VP, _VP, _VP]
+    L.xllm_tokenizer_probe.argtypes = [ctypes.c_char_p, ctypes.POINTER(TokenizerInfo)]
+    L.xllm_vocab_size.argtypes = [_VP, ctypes.POINTER(ctypes.c_int32)]
 
 
 def lib():
@@ -64,3 +74,10 @@ def lib():
 def check(rc):
     if rc != 0:
         raise IngestError(rc, lib().xllm_last_error().decode("utf-8", "replace"))
+
+
+def tokenizer_probe(path):
+    """Host-only parse of a tokenizer directory -> dict of table statistics (no GPU needed)."""
+    info = TokenizerInfo()
+    check(lib().xllm_tokenizer_probe(path.encode(), ctypes.byref(info)))
+    return {n: getattr(info, n) for n, _ in TokenizerInfo._fields_}

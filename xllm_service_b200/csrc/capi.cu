@@ -109,6 +109,22 @@ int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
     xllm_ingest_destroy(h);
     return XLLM_ERR_CUDA;
   }
+  if (cfg->tokenizer_path && cfg->tokenizer_path[0]) {
+    h->tokenizer_path = cfg->tokenizer_path;
+    h->sp_tables = std::make_shared<SpTables>();
+    int rc = sp_load_model(h->tokenizer_path, h->sp_tables.get());
+    if (rc != XLLM_OK) {
+      set_last_error("tokenizer %s: %s", cfg->tokenizer_path, h->sp_tables->error.c_str());
+      xllm_ingest_destroy(h);
+      return rc;
+    }
+    h->sp_dev = std::make_shared<SpDeviceModel>();
+    rc = h->sp_dev->upload(*h->sp_tables);
+    if (rc != XLLM_OK) {
+      xllm_ingest_destroy(h);
+      return rc;
+    }
+  }
   *out = h;
   return XLLM_OK;
 }
@@ -125,7 +141,14 @@ int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out) {
   cfg.device = src->device;
   cfg.max_batch = src->max_batch;
   cfg.max_tokens = src->max_tokens;
-  return xllm_ingest_create(&cfg, out);
+  int rc = xllm_ingest_create(&cfg, out);
+  if (rc != XLLM_OK) return rc;
+  // clones share the device-resident tokenizer tables (the reference reloads the model per clone:
+  // sentencepiece_tokenizer.cpp:254-256)
+  (*out)->sp_tables = src->sp_tables;
+  (*out)->sp_dev = src->sp_dev;
+  (*out)->tokenizer_path = src->tokenizer_path;
+  return XLLM_OK;
 }
 
 void xllm_ingest_destroy(xllm_ingest_t h) {
@@ -137,6 +160,11 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   h->d_n_tok.release();
   h->d_keys.release();
   h->d_key_start.release();
+  h->d_text.release();
+  h->d_offsets.release();
+  h->d_ids.release();
+  h->d_n_ids.release();
+  h->d_status.release();
   if (h->d_task_counter) cudaFree(h->d_task_counter);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -223,6 +251,104 @@ int xllm_xxh3_128bits_hash(xllm_ingest_t h, const uint8_t* prev16, const int32_t
     XLLM_CUDA_TRY(cudaMemcpyAsync(dt + (prev16 ? 16 : 0), token_ids, n_tokens * 4, cudaMemcpyHostToDevice, s));
   XLLM_CUDA_TRY(xxh3_single_launch(h->d_tokens.as<uint8_t>(), n * 4, h->d_keys.as<uint8_t>(), h->xxh, s));
   XLLM_CUDA_TRY(cudaMemcpyAsync(out16, h->d_keys.p, 16, cudaMemcpyDeviceToHost, s));
+  XLLM_CUDA_TRY(cudaStreamSynchronize(s));
+  return XLLM_OK;
+}
+
+int xllm_tokenizer_probe(const char* tokenizer_path, xllm_tokenizer_info* out) {
+  if (!tokenizer_path || !out) {
+    set_last_error("xllm_tokenizer_probe: null argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  SpTables t;
+  const int rc = sp_load_model(tokenizer_path, &t);
+  if (rc != XLLM_OK) {
+    set_last_error("tokenizer %s: %s", tokenizer_path, t.error.c_str());
+    return rc;
+  }
+  out->n_pieces = (int32_t)t.n_pieces;
+  out->n_symbols = (int32_t)t.n_syms;
+  out->n_pair_slots = (int32_t)t.pair_table.size();
+  int32_t used = 0;
+  for (const auto& e : t.pair_table) used += e.a != kEmptyKey;
+  out->n_pairs = used;
+  out->split_mode = t.split_mode;
+  out->max_unit_out = (int32_t)t.max_unit_out;
+  out->byte_fallback = t.byte_fallback;
+  out->unk_id = t.unk_id;
+  out->trie_units = (int32_t)t.trie.size();
+  return XLLM_OK;
+}
+
+int xllm_vocab_size(xllm_ingest_t h, int32_t* out) {
+  if (!h || !out) return XLLM_ERR_INVALID_ARG;
+  if (!h->sp_tables) {
+    set_last_error("handle has no tokenizer");
+    return XLLM_ERR_UNSUPPORTED;
+  }
+  *out = (int32_t)h->sp_tables->n_pieces;
+  return XLLM_OK;
+}
+
+int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_text, const int64_t* d_offsets,
+                             int32_t* d_ids, int64_t ids_stride, int32_t* d_n_ids, int32_t* d_status,
+                             void* cuda_stream) {
+  if (!h || n_req < 0 || ids_stride < 0 || (n_req > 0 && (!d_offsets || !d_ids || !d_n_ids || !d_status))) {
+    set_last_error("xllm_encode_batch_device: invalid argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  if (!h->sp_dev) {
+    set_last_error("handle has no tokenizer (tokenizer_path was not set)");
+    return XLLM_ERR_UNSUPPORTED;
+  }
+  if (n_req == 0) return XLLM_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), d_text, d_offsets, n_req, d_ids, ids_stride, d_n_ids, d_status,
+                                 h->d_task_counter + 1, s));
+  return XLLM_OK;
+}
+
+int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets, int32_t* ids,
+                      int64_t ids_stride, int32_t* n_ids, int32_t* status) {
+  if (!h || n_req < 0 || ids_stride < 0 || (n_req > 0 && (!offsets || !n_ids || !status)) ||
+      (n_req > 0 && ids_stride > 0 && !ids)) {
+    set_last_error("xllm_encode_batch: invalid argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  if (!h->sp_dev) {
+    set_last_error("handle has no tokenizer (tokenizer_path was not set)");
+    return XLLM_ERR_UNSUPPORTED;
+  }
+  if (n_req == 0) return XLLM_OK;
+  for (int32_t r = 0; r < n_req; ++r) {
+    if (offsets[r + 1] < offsets[r] || offsets[r] < 0 || offsets[r + 1] - offsets[r] > 0x7fffffffLL) {
+      set_last_error("xllm_encode_batch: bad offsets at request %d", r);
+      return XLLM_ERR_INVALID_ARG;
+    }
+  }
+  const size_t text_bytes = (size_t)(offsets[n_req] - offsets[0]);
+  if (text_bytes > 0 && !text) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  XLLM_TRY(h->d_text.reserve(text_bytes + 16));
+  XLLM_TRY(h->d_offsets.reserve((size_t)(n_req + 1) * 8));
+  XLLM_TRY(h->d_ids.reserve((size_t)n_req * (size_t)ids_stride * 4 + 16));
+  XLLM_TRY(h->d_n_ids.reserve((size_t)n_req * 4));
+  XLLM_TRY(h->d_status.reserve((size_t)n_req * 4));
+  cudaStream_t s = h->stream;
+  // offsets are rebased on the device copy of the text: ship them relative to offsets[0]
+  if (text_bytes)
+    XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_text.p, text + offsets[0], text_bytes, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_offsets.p, offsets, (size_t)(n_req + 1) * 8, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), h->d_text.as<uint8_t>() - offsets[0], h->d_offsets.as<int64_t>(),
+                                 n_req, h->d_ids.as<int32_t>(), ids_stride, h->d_n_ids.as<int32_t>(),
+                                 h->d_status.as<int32_t>(), h->d_task_counter + 1, s));
+  if (ids_stride)
+    XLLM_CUDA_TRY(cudaMemcpyAsync(ids, h->d_ids.p, (size_t)n_req * (size_t)ids_stride * 4, cudaMemcpyDeviceToHost, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(n_ids, h->d_n_ids.p, (size_t)n_req * 4, cudaMemcpyDeviceToHost, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(status, h->d_status.p, (size_t)n_req * 4, cudaMemcpyDeviceToHost, s));
   XLLM_CUDA_TRY(cudaStreamSynchronize(s));
   return XLLM_OK;
 }

@@ -8,6 +8,8 @@
 #include <string>
 
 #include "common.cuh"
+#include "sp_encode.cuh"
+#include "sp_model.h"
 #include "xxh3_chain.cuh"
 
 namespace xllm {
@@ -42,6 +44,11 @@ struct xllm_ingest {
   std::mutex mu;  // serialises calls on this handle
   xllm::Xxh3Consts xxh;
   unsigned int* d_task_counter = nullptr;
+  // tokenizer (shared between clones)
+  std::shared_ptr<xllm::SpTables> sp_tables;
+  std::shared_ptr<xllm::SpDeviceModel> sp_dev;
+  std::string tokenizer_path;
   // scratch for the host-pointer entry points
+  xllm::DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status;
   xllm::DevBuf d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start;
 };

@@ -1,0 +1,693 @@
+// sp_encode.cu — batched SentencePiece-BPE encode on sm_100a: one warp per request.
+//
+// Bit-exact target: what SentencePieceTokenizer::encode returns through libsentencepiece
+// (xllm_service/tokenizer/sentencepiece_tokenizer.cpp:115-168 -> sp_processor_.Encode):
+//   normalizer.cc     Normalize(): longest-prefix rewrite through the precompiled charsmap trie,
+//                     invalid UTF-8 -> U+FFFD, whitespace collapse, ' ' -> U+2581, dummy prefix
+//   bpe_model.cc      Encode(): merge the adjacent pair with the best score, leftmost on ties,
+//                     until no adjacent pair concatenates to a NORMAL piece
+//   sentencepiece_processor.cc  byte fallback / consecutive-unknown merging
+//
+// Why this is exact AND parallel: no NORMAL piece of the loaded model holds U+2581 anywhere but
+// at its first char (checked by the host loader: SpTables::split_mode), so no merge can ever
+// span the boundary in front of a U+2581.  The priority-ordered global merge therefore factors
+// into independent per-"word" merges.  The warp streams the request through shared memory:
+//   1. normalise 32 source bytes per step (every lane walks the trie from its own byte; a
+//      ballot resolves which positions start a unit) into a 4 KB normalized-text buffer;
+//   2. when the buffer fills, split it at U+2581 and hand one word per lane: the lane builds its
+//      symbols (chars -> symbol ids), looks up every adjacent pair in the (left,right) ->
+//      (priority, merged) hash table in L2, and runs the serial best-pair merge over a column
+//      of shared memory (alive bitmask in a register);
+//      words with more than 32 chars are merged by the whole warp cooperatively;
+//   3. ids are written straight to the request's output row in order.
+// Algorithmic HBM traffic: text bytes read once + 4 B per id written.
+#include "sp_encode.cuh"
+
+#include <string.h>
+
+#include "common.cuh"
+
+namespace xllm {
+
+namespace {
+
+constexpr int kNBuf = 4096;        // normalized-text staging buffer per warp (bytes)
+constexpr int kMaxSym = 32;        // lane-per-word fast path: chars per word
+constexpr int kCoopMaxSym = 1024;  // warp-cooperative path: chars per word
+constexpr int kMaxWords = 1408;    // >= kNBuf / 3 + 1 word starts
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct WarpSmem {
+  uint32_t S[kCoopMaxSym];   // symbols: lane columns S[j * 32 + lane] (fast path) or flat (cooperative path)
+  uint2 PM[kCoopMaxSym];     // (priority, merged symbol) of the pair starting at j
+  uint8_t nbuf[kNBuf];       // normalized text (always starts at a word start)
+  uint16_t wstart[kMaxWords];
+};
+
+__device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 13;
+  return h;
+}
+__device__ __forceinline__ uint32_t hash_cp(uint32_t cp) {
+  uint32_t h = cp * 0x9E3779B1u;
+  h ^= h >> 16;
+  return h;
+}
+
+// (left, right) -> (priority, merged); priority kNoPrio when A||B is not a piece.
+__device__ __forceinline__ uint2 pair_lookup(const SpDev& T, uint32_t a, uint32_t b) {
+  if ((a | b) & kSymUnknownFlag) return make_uint2(kNoPrio, 0);
+  uint32_t h = hash_pair(a, b) & T.pair_mask;
+  for (;;) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(T.pair_table) + h);
+    if (e.x == a && e.y == b) return make_uint2(e.z, e.w);
+    if (e.x == kEmptyKey) return make_uint2(kNoPrio, 0);
+    h = (h + 1) & T.pair_mask;
+  }
+}
+
+__device__ __forceinline__ uint32_t cp_lookup(const SpDev& T, uint32_t cp) {
+  if (cp == 0x2581u) return T.space_sym;
+  uint32_t h = hash_cp(cp) & T.cp_mask;
+  for (;;) {
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(T.cp_table) + h);
+    if (e.x == cp) return e.y;
+    if (e.x == kEmptyKey) return kSymUnknownFlag | cp;
+    h = (h + 1) & T.cp_mask;
+  }
+}
+
+// util.cc DecodeUTF8 + IsValidDecodeUTF8 on p[0..avail): returns bytes to consume, sets valid.
+__device__ __forceinline__ uint32_t utf8_unit(const uint8_t* p, uint32_t avail, uint8_t b0, bool* valid) {
+  *valid = true;
+  if (b0 < 0x80) return 1;
+  auto trail = [](uint8_t x) { return (x & 0xC0) == 0x80; };
+  if (avail >= 2 && (b0 & 0xE0) == 0xC0) {
+    const uint8_t b1 = p[1];
+    const uint32_t cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu);
+    if (trail(b1) && cp >= 0x80) return 2;
+  } else if (avail >= 3 && (b0 & 0xF0) == 0xE0) {
+    const uint8_t b1 = p[1], b2 = p[2];
+    const uint32_t cp = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
+    if (trail(b1) && trail(b2) && cp >= 0x800 && !(cp >= 0xD800 && cp < 0xE000)) return 3;
+  } else if (avail >= 4 && (b0 & 0xF8) == 0xF0) {
+    const uint8_t b1 = p[1], b2 = p[2], b3 = p[3];
+    const uint32_t cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
+    if (trail(b1) && trail(b2) && trail(b3) && cp >= 0x10000 && cp <= 0x10FFFF) return 4;
+  }
+  *valid = false;  // malformed: consume one byte, emit U+FFFD
+  return 1;
+}
+
+// Char at p (well-formed by construction: normalized text) -> symbol; *adv = its byte length.
+__device__ __forceinline__ uint32_t char_sym(const SpDev& T, const uint8_t* p, uint32_t* adv) {
+  const uint32_t b0 = p[0];
+  if (b0 < 0x80) {
+    *adv = 1;
+    return __ldg(T.ascii_sym + b0);
+  }
+  uint32_t cp, l;
+  if (b0 < 0xE0) { l = 2; cp = ((b0 & 0x1F) << 6) | (p[1] & 0x3F); }
+  else if (b0 < 0xF0) { l = 3; cp = ((b0 & 0x0F) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3F); }
+  else { l = 4; cp = ((b0 & 0x07) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3F); }
+  *adv = l;
+  return cp_lookup(T, cp);
+}
+
+// Token ids of one final symbol.  Returns the count (1..4), ids in out[]; *unk = symbol is unknown.
+__device__ __forceinline__ int sym_ids(const SpDev& T, uint32_t sym, int32_t out[4], bool* unk) {
+  uint32_t cp;
+  *unk = false;
+  if (!(sym & kSymUnknownFlag)) {
+    const int32_t e = __ldg(T.emit + sym);
+    if (e >= 0) { out[0] = e; return 1; }
+    cp = __ldg(T.virt_cp + (sym - T.n_pieces));
+  } else {
+    cp = sym & 0x1FFFFFu;
+  }
+  *unk = true;
+  if (!T.byte_fallback) { out[0] = T.unk_id; return 1; }
+  uint8_t b[4];
+  int n;
+  if (cp < 0x80) { b[0] = (uint8_t)cp; n = 1; }
+  else if (cp < 0x800) { b[0] = 0xC0 | (cp >> 6); b[1] = 0x80 | (cp & 0x3F); n = 2; }
+  else if (cp < 0x10000) { b[0] = 0xE0 | (cp >> 12); b[1] = 0x80 | ((cp >> 6) & 0x3F); b[2] = 0x80 | (cp & 0x3F); n = 3; }
+  else { b[0] = 0xF0 | (cp >> 18); b[1] = 0x80 | ((cp >> 12) & 0x3F); b[2] = 0x80 | ((cp >> 6) & 0x3F); b[3] = 0x80 | (cp & 0x3F); n = 4; }
+  for (int i = 0; i < n; ++i) out[i] = __ldg(T.byte_id + b[i]);
+  return n;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// State of one request while it streams through the warp.
+struct ReqState {
+  const uint8_t* src;
+  uint32_t len;
+  int32_t* out;
+  int64_t cap;          // ids_stride
+  int64_t n_out;        // ids produced so far (may exceed cap)
+  int32_t nlen;         // bytes in nbuf
+  int32_t trailing_bare;  // ids emitted by the current run of trailing bare-U+2581 words
+  bool prev_space;      // normalizer's is_prev_space
+  bool prev_unk;        // last emitted symbol was unknown (byte_fallback off only)
+  bool too_long;
+};
+
+__device__ __forceinline__ void put_id(ReqState& rs, int64_t pos, int32_t id) {
+  if (pos < rs.cap) rs.out[pos] = id;
+}
+
+// ---------------------------------------------------------------------------- normalisation
+// Normalises source bytes [pos, pos + 32) (units that START in that window) and appends the result to nbuf.
+// carry_skip: leading bytes of the window already consumed by the previous window's last unit.
+__device__ __forceinline__ void normalize_window(const SpDev& T, WarpSmem& sm, ReqState& rs, uint32_t pos,
+                                                 uint32_t& carry_skip, int lane) {
+  const uint32_t i = pos + lane;
+  const bool inb = i < rs.len;
+  const uint8_t* p = rs.src + i;
+  const uint8_t b0 = inb ? __ldg(p) : 0;
+  uint32_t consume = 1, kind = 0 /*0 identity, 1 blob, 2 U+FFFD*/, val = 0;
+  if (inb) {
+    uint32_t best_len = 0, best_val = 0;
+    if (T.trie_units) {
+      // Darts-clone commonPrefixSearch; libsentencepiece keeps the first 32 hits and takes the longest
+      uint32_t node = 0;
+      uint32_t unit = __ldg(T.trie);
+      node ^= (unit >> 10) << ((unit & 0x200u) >> 6);
+      uint32_t hits = 0;
+      const uint32_t avail = rs.len - i;
+      for (uint32_t k = 0; k < avail; ++k) {
+        const uint32_t c = k == 0 ? b0 : __ldg(p + k);
+        node ^= c;
+        if (node >= T.trie_units) break;
+        unit = __ldg(T.trie + node);
+        if ((unit & 0x800000FFu) != c) break;
+        node ^= (unit >> 10) << ((unit & 0x200u) >> 6);
+        if (node >= T.trie_units) break;
+        if ((unit >> 8) & 1u) {
+          if (hits < 32) { best_len = k + 1; best_val = __ldg(T.trie + node) & 0x7FFFFFFFu; }
+          ++hits;
+        }
+      }
+    }
+    if (best_len) {
+      consume = best_len; kind = 1; val = best_val;
+    } else {
+      bool valid;
+      consume = utf8_unit(p, rs.len - i, b0, &valid);
+      kind = valid ? 0 : 2;
+    }
+  }
+  // which positions start a unit
+  uint32_t starts;
+  const uint32_t n_in = rs.len - pos < 32 ? rs.len - pos : 32;
+  const uint32_t in_mask = n_in == 32 ? kFull : ((1u << n_in) - 1);
+  const uint32_t multi = __ballot_sync(kFull, inb && consume != 1);
+  uint32_t q_end;
+  if (multi == 0 && carry_skip == 0) {  // every unit is one byte: every position starts one
+    starts = in_mask;
+    q_end = n_in;
+  } else {  // follow the chain of units (uniform across the warp)
+    starts = 0;
+    uint32_t q = carry_skip;
+    while (q < n_in) {
+      starts |= 1u << q;
+      q += __shfl_sync(kFull, consume, q);
+    }
+    q_end = q;
+  }
+  carry_skip = q_end >= 32 ? q_end - 32 : 0;  // only meaningful when another window follows (n_in == 32)
+  const bool is_start = (starts >> lane) & 1u;
+
+  // replacement attributes
+  uint32_t rlen = 0, lead_sp = 0, n_sp = 0;
+  bool ends_sp = false;
+  if (is_start) {
+    if (kind == 0) { rlen = consume; lead_sp = n_sp = (b0 == ' '); ends_sp = (b0 == ' '); }
+    else if (kind == 2) { rlen = 3; }
+    else {
+      const uint8_t* r = T.blob + val;
+      bool leading = true;
+      uint8_t c, last = 0;
+      while ((c = __ldg(r + rlen)) != 0) {
+        if (c == ' ') { ++n_sp; if (leading) ++lead_sp; } else leading = false;
+        last = c;
+        ++rlen;
+      }
+      ends_sp = last == ' ';
+    }
+  }
+  const bool nonempty = is_start && rlen > 0;
+  const bool all_sp = nonempty && lead_sp == rlen;
+  uint32_t strip = 0;
+  if (T.remove_extra_ws) {
+    const uint32_t ne_mask = __ballot_sync(kFull, nonempty);
+    const uint32_t set_mask = __ballot_sync(kFull, nonempty && (all_sp || ends_sp));
+    const uint32_t below = ne_mask & ((1u << lane) - 1);
+    const bool state_before = below ? ((set_mask >> (31 - __clz(below))) & 1u) : rs.prev_space;
+    if (state_before) strip = lead_sp;
+    if (ne_mask) rs.prev_space = (set_mask >> (31 - __clz(ne_mask))) & 1u;
+  }
+  const int out_len = is_start ? (int)((rlen - strip) + 2 * (n_sp - strip)) : 0;
+  const int incl = warp_incl_scan(out_len, lane);
+  const int total = __shfl_sync(kFull, incl, 31);
+  if (out_len) {
+    uint8_t* d = sm.nbuf + rs.nlen + (incl - out_len);
+    const uint8_t* r = kind == 1 ? T.blob + val : p;
+    for (uint32_t k = strip; k < rlen; ++k) {
+      uint8_t c;
+      if (kind == 2) c = k == 0 ? 0xEF : (k == 1 ? 0xBF : 0xBD);
+      else c = __ldg(r + k);
+      if (c == ' ') { d[0] = 0xE2; d[1] = 0x96; d[2] = 0x81; d += 3; }
+      else { *d++ = c; }
+    }
+  }
+  rs.nlen += total;
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------- word merge
+// Fast path: this lane owns word [ws, we) with n <= 32 chars; symbols live in column `lane` of S / PM.
+// Returns the alive mask after all merges.
+__device__ __forceinline__ uint32_t lane_merge(const SpDev& T, WarpSmem& sm, int n, int lane) {
+  uint32_t* S = sm.S + lane;
+  uint2* PM = sm.PM + lane;
+  for (int j = 0; j + 1 < n; ++j) PM[j * 32] = pair_lookup(T, S[j * 32], S[(j + 1) * 32]);
+  PM[(n - 1) * 32] = make_uint2(kNoPrio, 0);
+  uint32_t alive = n == 32 ? kFull : ((1u << n) - 1);
+  for (;;) {
+    uint32_t best = kNoPrio;
+    int bj = 0;
+    for (uint32_t m = alive; m;) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t pr = PM[j * 32].x;
+      if (pr < best) { best = pr; bj = j; }
+    }
+    if (best == kNoPrio) break;
+    const uint32_t hi_mask = ~((2u << bj) - 1u);  // bits above bj (bj == 31 -> 0)
+    const int rj = __ffs(alive & hi_mask) - 1;
+    S[bj * 32] = PM[bj * 32].y;
+    alive &= ~(1u << rj);
+    const uint32_t above = alive & hi_mask;
+    if (above) PM[bj * 32] = pair_lookup(T, S[bj * 32], S[(__ffs(above) - 1) * 32]);
+    else PM[bj * 32].x = kNoPrio;
+    const uint32_t below = alive & ((1u << bj) - 1u);
+    if (below) {
+      const int pj = 31 - __clz(below);
+      PM[pj * 32] = pair_lookup(T, S[pj * 32], S[bj * 32]);
+    }
+  }
+  return alive;
+}
+
+// Cooperative path: the whole warp merges one word of n (33..1024) chars held flat in S[0..n).
+// Returns the final symbol count; S[0..ret) are the final symbols in order.
+__device__ int coop_merge(const SpDev& T, WarpSmem& sm, int n, int lane) {
+  for (int j = lane; j < n; j += 32)
+    sm.PM[j] = j + 1 < n ? pair_lookup(T, sm.S[j], sm.S[j + 1]) : make_uint2(kNoPrio, 0);
+  __syncwarp();
+  for (;;) {
+    unsigned long long best = ~0ull;
+    for (int j = lane; j + 1 < n; j += 32) {
+      const unsigned long long key = ((unsigned long long)sm.PM[j].x << 32) | (unsigned)j;
+      best = key < best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(kFull, best, o);
+      best = t < best ? t : best;
+    }
+    if ((uint32_t)(best >> 32) == kNoPrio) break;
+    const int bj = (int)(uint32_t)best;
+    const uint32_t merged = sm.PM[bj].y;
+    __syncwarp();
+    // remove position bj + 1: shift the tail left by one (tiles in increasing order)
+    for (int base = bj + 1; base < n - 1; base += 32) {
+      const int k = base + lane;
+      uint32_t s = 0;
+      uint2 pm = make_uint2(kNoPrio, 0);
+      const bool act = k < n - 1;
+      if (act) { s = sm.S[k + 1]; pm = sm.PM[k + 1]; }
+      __syncwarp();
+      if (act) { sm.S[k] = s; sm.PM[k] = pm; }
+      __syncwarp();
+    }
+    --n;
+    if (lane == 0) {
+      sm.S[bj] = merged;
+      sm.PM[bj] = bj + 1 < n ? pair_lookup(T, merged, sm.S[bj + 1]) : make_uint2(kNoPrio, 0);
+    }
+    __syncwarp();
+    if (lane == 1 && bj > 0) sm.PM[bj - 1] = pair_lookup(T, sm.S[bj - 1], sm.S[bj]);
+    __syncwarp();
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------- drain
+__device__ __forceinline__ bool is_space_at(const uint8_t* b, int p, int n) {
+  return p + 2 < n && b[p] == 0xE2 && b[p + 1] == 0x96 && b[p + 2] == 0x81;
+}
+
+// Tokenises the complete words held in nbuf (all words when final) and keeps the incomplete tail.
+__device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, int lane) {
+  const uint8_t* nb = sm.nbuf;
+  int nlen = rs.nlen;
+  if (final && T.remove_extra_ws) {
+    // normalizer.cc: "Ignores trailing space" — strip trailing U+2581 from the stream
+    while (nlen >= 3 && nb[nlen - 3] == 0xE2 && nb[nlen - 2] == 0x96 && nb[nlen - 1] == 0x81) nlen -= 3;
+    if (nlen == 0) { rs.n_out -= rs.trailing_bare; rs.trailing_bare = 0; }
+  }
+  if (nlen == 0) { rs.nlen = 0; return; }
+
+  // 1. word starts
+  int nwords = 0;
+  for (int base = 0; base < nlen; base += 32) {
+    const int p = base + lane;
+    bool st = false;
+    if (p < nlen) {
+      if (p == 0) st = true;
+      else if (T.split_mode != 0 && is_space_at(nb, p, nlen)) {
+        st = T.split_mode == 1 || !(p >= 3 && is_space_at(nb, p - 3, nlen));
+      }
+    }
+    const uint32_t m = __ballot_sync(kFull, st);
+    if (st) sm.wstart[nwords + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
+    nwords += __popc(m);
+  }
+  if (lane == 0) sm.wstart[nwords] = (uint16_t)nlen;
+  __syncwarp();
+  const int complete = final ? nwords : nwords - 1;
+
+  // 2. rounds of up to 32 consecutive words
+  int w0 = 0;
+  while (w0 < complete) {
+    const int w = w0 + lane;
+    const bool have = w < complete;
+    int ws = 0, we = 0, nsym = 0;
+    if (have) {
+      ws = sm.wstart[w];
+      we = sm.wstart[w + 1];
+      for (int p = ws; p < we; ++p) nsym += (nb[p] & 0xC0) != 0x80;
+    }
+    const uint32_t long_mask = __ballot_sync(kFull, have && nsym > kMaxSym);
+    const int first_long = long_mask ? __ffs(long_mask) - 1 : 32;
+    const bool active = have && lane < first_long;
+
+    // --- fast path: one word per lane
+    uint32_t alive = 0;
+    int cnt = 0;
+    bool first_unk = false, last_unk = false, bare = false;
+    if (active) {
+      int n = 0;
+      for (int p = ws; p < we;) {
+        uint32_t adv;
+        sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
+        p += adv;
+        ++n;
+      }
+      bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
+      alive = lane_merge(T, sm, n, lane);
+      bool pu = false, first = true;
+      for (uint32_t m = alive; m;) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        int32_t tmp[4];
+        bool unk;
+        const int c = sym_ids(T, sm.S[j * 32 + lane], tmp, &unk);
+        if (first) { first_unk = unk; first = false; }
+        if (!(unk && pu && !T.byte_fallback)) cnt += c;
+        pu = unk;
+      }
+      last_unk = pu;
+    }
+    // cross-word unknown merging (byte_fallback off): drop the first id if the previous symbol was unknown too
+    bool drop_first = false;
+    if (!T.byte_fallback) {
+      const uint32_t act_mask = __ballot_sync(kFull, active);
+      const uint32_t lu_mask = __ballot_sync(kFull, active && last_unk);
+      if (active && first_unk) {
+        const bool prev = lane == 0 ? rs.prev_unk : ((lu_mask >> (lane - 1)) & 1u);
+        if (prev) { drop_first = true; cnt -= 1; }
+      }
+      if (act_mask) rs.prev_unk = (lu_mask >> (31 - __clz(act_mask))) & 1u;
+    }
+    const int incl = warp_incl_scan(cnt, lane);
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (active) {
+      int64_t o = rs.n_out + (incl - cnt);
+      bool pu = false, first = true;
+      for (uint32_t m = alive; m;) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        int32_t tmp[4];
+        bool unk;
+        const int c = sym_ids(T, sm.S[j * 32 + lane], tmp, &unk);
+        const bool skip = (unk && pu && !T.byte_fallback) || (first && drop_first);
+        if (!skip)
+          for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
+        pu = unk;
+        first = false;
+      }
+    }
+    rs.n_out += total;
+    // trailing bare-word bookkeeping: ids of the run of bare words at the end of what was emitted
+    {
+      const uint32_t act_mask = __ballot_sync(kFull, active);
+      const uint32_t nonbare = __ballot_sync(kFull, active && !bare);
+      if (act_mask) {
+        const int last_nb = nonbare ? 31 - __clz(nonbare) : -1;  // last non-bare lane
+        const int tail = __shfl_sync(kFull, incl, 31) - (last_nb >= 0 ? __shfl_sync(kFull, incl, last_nb) : 0);
+        rs.trailing_bare = (last_nb >= 0 ? 0 : rs.trailing_bare) + tail;
+      }
+    }
+    __syncwarp();
+    w0 += first_long < 32 ? first_long : 32;
+    if (w0 >= complete || first_long == 32) continue;
+
+    // --- cooperative path for the long word w0
+    {
+      const int lws = sm.wstart[w0], lwe = sm.wstart[w0 + 1];
+      int n = 0;
+      bool overflow = false;
+      for (int base = lws; base < lwe; base += 32) {
+        const int p = base + lane;
+        const bool lead = p < lwe && (nb[p] & 0xC0) != 0x80;
+        const uint32_t m = __ballot_sync(kFull, lead);
+        const int idx = n + __popc(m & ((1u << lane) - 1));
+        if (lead) {
+          if (idx < kCoopMaxSym) { uint32_t adv; sm.S[idx] = char_sym(T, nb + p, &adv); }
+          else overflow = true;
+        }
+        n += __popc(m);
+      }
+      overflow = __any_sync(kFull, overflow);
+      __syncwarp();
+      if (overflow) {
+        rs.too_long = true;
+      } else {
+        n = coop_merge(T, sm, n, lane);
+        for (int base = 0; base < n; base += 32) {
+          const int j = base + lane;
+          int32_t tmp[4];
+          bool unk = false;
+          int c = 0;
+          if (j < n) c = sym_ids(T, sm.S[j], tmp, &unk);
+          bool skip = false;
+          if (!T.byte_fallback) {
+            const uint32_t um = __ballot_sync(kFull, j < n && unk);
+            const bool prev = lane == 0 ? rs.prev_unk : ((um >> (lane - 1)) & 1u);
+            skip = unk && prev;
+            const int lastl = (n - base) >= 32 ? 31 : (n - base - 1);
+            rs.prev_unk = (um >> lastl) & 1u;
+          }
+          if (skip) c = 0;
+          const int inc2 = warp_incl_scan(c, lane);
+          int64_t o = rs.n_out + (inc2 - c);
+          for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
+          rs.n_out += __shfl_sync(kFull, inc2, 31);
+        }
+        rs.trailing_bare = 0;
+      }
+      __syncwarp();
+      w0 += 1;
+    }
+  }
+
+  // 3. keep the incomplete tail at the front of nbuf
+  if (!final) {
+    const int ts = sm.wstart[nwords - 1];
+    const int tl = nlen - ts;
+    if (ts > 0) {
+      for (int base = 0; base < tl; base += 32) {
+        const int k = base + lane;
+        uint8_t c = 0;
+        if (k < tl) c = sm.nbuf[ts + k];
+        __syncwarp();
+        if (k < tl) sm.nbuf[k] = c;
+        __syncwarp();
+      }
+    }
+    rs.nlen = tl;
+  } else {
+    rs.nlen = 0;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) sp_encode_kernel(const uint8_t* __restrict__ text,
+                                                       const int64_t* __restrict__ offsets, int n_req,
+                                                       int32_t* __restrict__ ids, int64_t ids_stride,
+                                                       int32_t* __restrict__ n_ids, int32_t* __restrict__ status,
+                                                       const __grid_constant__ SpDev T,
+                                                       unsigned int* __restrict__ task_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpSmem& sm = *reinterpret_cast<WarpSmem*>(smem_raw);
+  const int lane = threadIdx.x;
+  const int drain_at = kNBuf - 32 * (int)T.max_unit_out - 8;
+
+  for (;;) {
+    unsigned int r = 0;
+    if (lane == 0) r = atomicAdd(task_counter, 1u);
+    r = __shfl_sync(kFull, r, 0);
+    if (r >= (unsigned)n_req) break;
+
+    ReqState rs;
+    const int64_t beg = offsets[r];
+    rs.src = text + beg;
+    rs.len = (uint32_t)(offsets[r + 1] - beg);
+    rs.out = ids + (int64_t)r * ids_stride;
+    rs.cap = ids_stride;
+    rs.n_out = 0;
+    rs.nlen = 0;
+    rs.trailing_bare = 0;
+    rs.prev_space = T.remove_extra_ws;
+    rs.prev_unk = false;
+    rs.too_long = false;
+
+    if (rs.len > 0) {
+      if (T.add_dummy_prefix) {
+        if (lane == 0) { sm.nbuf[0] = 0xE2; sm.nbuf[1] = 0x96; sm.nbuf[2] = 0x81; }
+        rs.nlen = 3;
+      }
+      __syncwarp();
+      uint32_t carry_skip = 0;
+      for (uint32_t pos = 0; pos < rs.len; pos += 32) {
+        normalize_window(T, sm, rs, pos, carry_skip, lane);
+        if (rs.nlen > drain_at) {
+          drain(T, sm, rs, false, lane);
+          if (rs.nlen > drain_at) {  // one pre-token longer than the staging buffer
+            rs.too_long = true;
+            break;
+          }
+        }
+      }
+      if (!rs.too_long) drain(T, sm, rs, true, lane);
+    }
+    if (lane == 0) {
+      n_ids[r] = rs.too_long ? 0 : (int32_t)rs.n_out;
+      status[r] = rs.too_long ? kEncWordTooLong : (rs.n_out > rs.cap ? kEncTruncated : kEncOk);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ host side
+SpDeviceModel::~SpDeviceModel() {
+  for (int i = 0; i < n_allocs_; ++i) cudaFree(allocs_[i]);
+}
+
+int SpDeviceModel::upload(const SpTables& t) {
+  if (32 * t.max_unit_out + 64 > (uint32_t)kNBuf / 2) {
+    set_last_error("normalizer replacement of %u bytes exceeds the device staging budget", t.max_unit_out);
+    return XLLM_ERR_UNSUPPORTED;
+  }
+  auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+    void* d = nullptr;
+    const size_t alloc = bytes ? bytes : 16;
+    cudaError_t e = cudaMalloc(&d, alloc);
+    if (e != cudaSuccess) {
+      set_last_error("cudaMalloc(%zu) for tokenizer tables failed: %s", alloc, cudaGetErrorString(e));
+      return XLLM_ERR_NOMEM;
+    }
+    allocs_[n_allocs_++] = d;
+    if (bytes) {
+      e = cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) {
+        set_last_error("cudaMemcpy of tokenizer tables failed: %s", cudaGetErrorString(e));
+        return XLLM_ERR_CUDA;
+      }
+    }
+    *dst = d;
+    return XLLM_OK;
+  };
+  int rc;
+#define UP(vec, field)                                                                                      \
+  if ((rc = up((vec).data(), (vec).size() * sizeof((vec)[0]), reinterpret_cast<const void**>(&dev_.field))) != \
+      XLLM_OK)                                                                                              \
+    return rc;
+  UP(t.trie, trie);
+  UP(t.blob, blob);
+  UP(t.ascii_sym, ascii_sym);
+  UP(t.cp_table, cp_table);
+  UP(t.pair_table, pair_table);
+  UP(t.emit, emit);
+  UP(t.virt_cp, virt_cp);
+  UP(t.byte_id, byte_id);
+#undef UP
+  dev_.trie_units = (uint32_t)t.trie.size();
+  dev_.cp_mask = (uint32_t)t.cp_table.size() - 1;
+  dev_.pair_mask = (uint32_t)t.pair_table.size() - 1;
+  dev_.n_pieces = t.n_pieces;
+  dev_.space_sym = t.space_sym;
+  dev_.unk_id = t.unk_id;
+  dev_.max_unit_out = t.max_unit_out;
+  dev_.byte_fallback = t.byte_fallback;
+  dev_.add_dummy_prefix = t.add_dummy_prefix;
+  dev_.remove_extra_ws = t.remove_extra_whitespaces;
+  dev_.split_mode = (uint8_t)t.split_mode;
+  return XLLM_OK;
+}
+
+cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
+                             int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* task_counter,
+                             cudaStream_t stream) {
+  if (n_req <= 0) return cudaSuccess;
+  static int n_sm = 0;
+  static bool attr_set = false;
+  const size_t smem = sizeof(WarpSmem);
+  if (!attr_set) {
+    int d = 0;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sp_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaError_t e = cudaMemsetAsync(task_counter, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  int warps_per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (warps_per_sm > 32) warps_per_sm = 32;
+  int grid = n_sm * warps_per_sm;
+  if (grid > n_req) grid = n_req;
+  sp_encode_kernel<<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status, dev,
+                                               task_counter);
+  return cudaGetLastError();
+}
+
+}  // namespace xllm

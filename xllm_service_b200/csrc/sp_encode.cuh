@@ -1,0 +1,57 @@
+// sp_encode.cuh — device-resident SentencePiece-BPE tables + the batched encode kernel launcher.
+//
+// Device replacement for Tokenizer::encode on the SentencePiece backend
+// (xllm_service/tokenizer/tokenizer.h:32-33, sentencepiece_tokenizer.cpp:115-168; called per
+// request at xllm_service/scheduler/scheduler.cpp:129).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sp_model.h"
+
+namespace xllm {
+
+// Pointers into device memory, passed to the kernel by value (__grid_constant__).
+struct SpDev {
+  const uint32_t* trie;
+  const uint8_t* blob;
+  const uint32_t* ascii_sym;
+  const CpEntry* cp_table;
+  const PairEntry* pair_table;
+  const int32_t* emit;
+  const uint32_t* virt_cp;
+  const int32_t* byte_id;
+  uint32_t trie_units;
+  uint32_t cp_mask;
+  uint32_t pair_mask;
+  uint32_t n_pieces;
+  uint32_t space_sym;
+  int32_t unk_id;
+  uint32_t max_unit_out;
+  uint8_t byte_fallback, add_dummy_prefix, remove_extra_ws, split_mode;
+};
+
+// Per-request status written by the kernel.
+constexpr int32_t kEncOk = 0;
+constexpr int32_t kEncTruncated = 1;     // more ids than ids_stride: n_ids holds the full count, the row its prefix
+constexpr int32_t kEncWordTooLong = -6;  // a single pre-token exceeds the on-chip word capacity (XLLM_ERR_CAPACITY)
+
+class SpDeviceModel {
+ public:
+  ~SpDeviceModel();
+  int upload(const SpTables& t);  // XLLM_OK or error (set_last_error)
+  const SpDev& dev() const { return dev_; }
+
+ private:
+  SpDev dev_{};
+  void* allocs_[8] = {nullptr};
+  int n_allocs_ = 0;
+};
+
+// text: all prompts back to back; offsets[n_req + 1] (bytes).  Request r's ids go to
+// ids + r * ids_stride (at most ids_stride of them), n_ids[r] = full count, status[r] = kEnc*.
+cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
+                             int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* task_counter,
+                             cudaStream_t stream);
+
+}  // namespace xllm

@@ -1,0 +1,61 @@
+// sp_model.h — host-side loader that turns a SentencePiece `.model` (BPE) into the flat
+// device tables the encode kernel walks.
+//
+// Replaces what SentencePieceTokenizer's constructor does through libsentencepiece
+// (xllm_service/tokenizer/sentencepiece_tokenizer.cpp:43-54: sp_processor_.Load(<dir>/tokenizer.model)).
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace xllm {
+
+constexpr uint32_t kSymUnknownFlag = 0x80000000u;  // sym = flag | codepoint : a char no piece contains
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+constexpr uint32_t kNoPrio = 0xFFFFFFFFu;
+
+struct PairEntry {  // 16 bytes: one LDG.128 per probe
+  uint32_t a, b;    // left / right symbol; a == kEmptyKey marks an empty slot
+  uint32_t prio;    // merge priority: rank of the merged piece's score, 0 = highest score (merges first)
+  uint32_t merged;  // symbol of the concatenation
+};
+struct CpEntry {
+  uint32_t cp;   // Unicode code point, kEmptyKey = empty
+  uint32_t sym;  // its symbol
+};
+
+// Everything the kernel needs, as host vectors (uploaded verbatim).
+struct SpTables {
+  // normalizer (NormalizerSpec.precompiled_charsmap = Darts double array + NUL-separated replacements)
+  std::vector<uint32_t> trie;
+  std::vector<uint8_t> blob;
+  uint32_t max_unit_out = 3;  // max bytes one normalisation unit can append to the normalized stream
+  bool add_dummy_prefix = true;
+  bool remove_extra_whitespaces = true;
+  // symbols: [0, n_pieces) = piece ids; [n_pieces, n_syms) = single chars that occur inside
+  // pieces (or are reserved single-char pieces) without being NORMAL pieces themselves
+  uint32_t n_pieces = 0, n_syms = 0;
+  std::vector<uint32_t> ascii_sym;  // [128]
+  std::vector<CpEntry> cp_table;    // open addressing, power-of-two size
+  std::vector<PairEntry> pair_table;
+  std::vector<int32_t> emit;        // [n_syms]: token id, or -1 = unknown (byte fallback / unk)
+  std::vector<uint32_t> virt_cp;    // [n_syms - n_pieces] code point of each virtual symbol
+  std::vector<int32_t> byte_id;     // [256] ids of <0x00>..<0xFF> (all -1 without byte_fallback)
+  int32_t unk_id = 0;
+  bool byte_fallback = false;
+  uint32_t space_sym = 0;  // symbol of U+2581
+  // 0: no exact pre-split exists (whole text is one word); 1: split before every U+2581;
+  // 2: split before a U+2581 unless the previous char is U+2581 too
+  int split_mode = 1;
+  // vocabulary strings for decode / id_to_token / token_to_id
+  std::vector<std::string> piece_str;
+  std::vector<uint8_t> piece_type;
+  std::string error;
+};
+
+// Loads <path> (file, or directory containing tokenizer.model).  Returns XLLM_OK or an error code
+// (message in out->error).
+int sp_load_model(const std::string& path, SpTables* out);
+
+}  // namespace xllm

@@ -75,3 +75,41 @@ class Ingest:
         """Device-pointer batch chain; arguments are integer device addresses (e.g. torch .data_ptr())."""
         check(self._L.xllm_hash_blocks_device(self._h, n_req, d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start,
                                               stream))
+
+    # -------------------------------------------------------------- tokenize
+    def vocab_size(self):
+        out = ctypes.c_int32()
+        check(self._L.xllm_vocab_size(self._h, ctypes.byref(out)))
+        return out.value
+
+    def encode_batch(self, text, offsets, ids_stride):
+        """Batch Tokenizer::encode over host buffers.  text: uint8 array, offsets int64[n+1].
+        Returns (ids int32[n, ids_stride], n_ids int32[n], status int32[n])."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        ids = np.zeros((n, ids_stride), dtype=np.int32)
+        n_ids = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        check(self._L.xllm_encode_batch(self._h, n, _ptr(text), _ptr(offsets), _ptr(ids), ids_stride, _ptr(n_ids),
+                                        _ptr(status)))
+        return ids, n_ids, status
+
+    def encode(self, text: bytes):
+        """Single-request Tokenizer::encode (tokenizer.h:32-33): returns the id list; raises on failure
+        (the reference returns false, scheduler.cpp:129-132)."""
+        if isinstance(text, str):
+            text = text.encode("utf-8")
+        t = np.frombuffer(text, dtype=np.uint8)
+        off = np.array([0, t.size], dtype=np.int64)
+        stride = max(16, 3 * t.size + 8)
+        ids, n_ids, status = self.encode_batch(t, off, stride)
+        if status[0] == 1:  # XLLM_ENC_TRUNCATED: n_ids holds the needed size
+            ids, n_ids, status = self.encode_batch(t, off, int(n_ids[0]))
+        if status[0] < 0:
+            raise _lib.IngestError(int(status[0]), "encode failed")
+        return ids[0, :n_ids[0]].tolist()
+
+    def encode_batch_device(self, n_req, d_text, d_offsets, d_ids, ids_stride, d_n_ids, d_status, stream=None):
+        check(self._L.xllm_encode_batch_device(self._h, n_req, d_text, d_offsets, d_ids, ids_stride, d_n_ids,
+                                               d_status, stream))
