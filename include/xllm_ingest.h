@@ -94,6 +94,69 @@ int xllm_hash_blocks_device(xllm_ingest_t h, int32_t n_req, const int32_t* d_tok
 int xllm_xxh3_128bits_hash(xllm_ingest_t h, const uint8_t* prev16, const int32_t* token_ids, size_t n_tokens,
                            uint8_t* out16);
 
+/* ----------------------------------------------------------- prefix index (write side)
+ * Instances are addressed by id 0..63 (bit positions of the per-tier instance masks that replace
+ * CacheLocations' three unordered_set<string>, types.h:320-365); the host adaptor keeps name<->id.
+ *
+ * xllm_index_apply   = GlobalKVCacheMgr::record_updated_kvcaches(instance, KvCacheEvent)
+ *                      (global_kvcache_mgr.cpp:177-225): keys are 16-byte XXH3Key values; stored,
+ *                      then offload (HBM->DRAM, else DRAM->SSD), then removed; staged, NOT yet visible.
+ * xllm_index_put / _erase = the replica path update_kvcache PUT / DELETE (:133-175); staged.
+ * xllm_index_publish = upload_kvcache's local effect (:227-247): replays the staged events on the
+ *                      device table (entries left empty are erased) and makes them visible to match.
+ */
+int xllm_index_apply(xllm_ingest_t h, int32_t instance_id, const uint8_t* stored, size_t n_stored,
+                     const uint8_t* offload, size_t n_offload, const uint8_t* removed, size_t n_removed);
+int xllm_index_put(xllm_ingest_t h, const uint8_t* key16, uint64_t hbm_mask, uint64_t dram_mask, uint64_t ssd_mask);
+int xllm_index_erase(xllm_ingest_t h, const uint8_t* key16);
+int xllm_index_publish(xllm_ingest_t h);
+int xllm_index_size(xllm_ingest_t h, int64_t* n_keys);
+int xllm_index_get(xllm_ingest_t h, const uint8_t* key16, uint64_t masks3[3], int32_t* found);
+
+/* Instance view read by the routing step: InstanceMgr's instances_ / load_metrics_ as consumed by
+ * get_load_metrics (instance_mgr.cpp:287-359).  type: 0 DEFAULT, 1 PREFILL, 2 DECODE, 3 MIX. */
+int xllm_set_instance(xllm_ingest_t h, int32_t instance_id, int32_t type, int32_t schedulable);
+int xllm_set_load_metrics(xllm_ingest_t h, int32_t instance_id, int32_t has_metrics, uint64_t waiting_requests_num,
+                          float gpu_cache_usage_perc);
+
+/* ------------------------------------------------------------- match + cache-aware routing
+ * xllm_match_out = OverlapScores (types.h:376-403) with instance ids for names; a score of 0 means the
+ * instance is absent from that score map.  xllm_routing_out = Routing (types.h:43-55) + the return
+ * value of CacheAwareRouting::select_instances_pair (ok == 0 <=> false, "No node available").
+ * Ties in cost_function are broken by the lowest instance id (the reference: unordered_map order).
+ */
+typedef struct {
+  uint32_t max_block_num;
+  uint32_t max_matched_block_num;
+  uint64_t instances;
+  uint16_t hbm_instance_score[XLLM_MAX_INSTANCES];
+  uint16_t dram_instance_score[XLLM_MAX_INSTANCES];
+  uint16_t ssd_instance_score[XLLM_MAX_INSTANCES];
+} xllm_match_out;
+typedef struct {
+  int32_t prefill_id; /* -1: prefill_name left empty */
+  int32_t decode_id;
+  int32_t ok;
+  float prefill_score;
+  float decode_score;
+} xllm_routing_out;
+
+/* keys: the block keys of all requests; request r owns n_blocks[r] keys starting at key_start[r].
+ * match / routing may be NULL.  Host-pointer and device-pointer forms. */
+int xllm_match_route(xllm_ingest_t h, int32_t n_req, const uint8_t* keys, int64_t n_keys_total,
+                     const int64_t* key_start, const int32_t* n_blocks, xllm_match_out* match,
+                     xllm_routing_out* routing);
+int xllm_match_route_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_keys, int64_t n_keys_total,
+                            const int64_t* d_key_start, const int32_t* d_n_blocks, xllm_match_out* d_match,
+                            xllm_routing_out* d_routing, void* cuda_stream);
+/* The two halves, for a hash-range-sharded index (keys exchanged between GPUs in between):
+ * probe: masks3[k] = {hbm, dram, ssd} of keys[k] (zeros when absent); score: first-miss scan + routing. */
+int xllm_index_probe_device(xllm_ingest_t h, const uint8_t* d_keys, int64_t n_keys, uint64_t* d_masks3,
+                            void* cuda_stream);
+int xllm_score_route_device(xllm_ingest_t h, int32_t n_req, const uint64_t* d_masks3, const int64_t* d_key_start,
+                            const int32_t* d_n_blocks, xllm_match_out* d_match, xllm_routing_out* d_routing,
+                            void* cuda_stream);
+
 /* ------------------------------------------------------------------ tokenize
  * Batch form of Tokenizer::encode (xllm_service/tokenizer/tokenizer.h:32-33; the service calls
  * it once per request at scheduler.cpp:129).  text holds all prompts back to back;

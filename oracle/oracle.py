@@ -51,6 +51,36 @@ def lib():
         L.oracle_sp_encode.restype = ctypes.c_long
         L.oracle_sp_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                              ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]
+        VP = ctypes.c_void_p
+        L.oracle_index_new.restype = VP
+        L.oracle_index_free.argtypes = [VP]
+        L.oracle_index_free.restype = None
+        L.oracle_index_size.argtypes = [VP]
+        L.oracle_index_size.restype = ctypes.c_long
+        L.oracle_index_record.argtypes = [VP, ctypes.c_char_p, VP, ctypes.c_size_t, VP, ctypes.c_size_t, VP,
+                                          ctypes.c_size_t]
+        L.oracle_index_record.restype = None
+        L.oracle_index_upload.argtypes = [VP]
+        L.oracle_index_upload.restype = None
+        L.oracle_index_put.argtypes = [VP, VP, VP, ctypes.c_int, VP, ctypes.c_int, VP, ctypes.c_int]
+        L.oracle_index_put.restype = None
+        L.oracle_index_delete.argtypes = [VP, VP]
+        L.oracle_index_delete.restype = None
+        L.oracle_index_get.argtypes = [VP, VP, VP, ctypes.c_int, VP]
+        L.oracle_index_match.argtypes = [VP, VP, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, VP, ctypes.c_int,
+                                         VP, VP, VP, VP]
+        L.oracle_index_match.restype = None
+        L.oracle_registry_new.restype = VP
+        L.oracle_registry_free.argtypes = [VP]
+        L.oracle_registry_free.restype = None
+        L.oracle_registry_set_instance.argtypes = [VP, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+        L.oracle_registry_set_instance.restype = None
+        L.oracle_registry_set_load.argtypes = [VP, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_float]
+        L.oracle_registry_set_load.restype = None
+        L.oracle_registry_clear_load.argtypes = [VP, ctypes.c_char_p]
+        L.oracle_registry_clear_load.restype = None
+        L.oracle_route_car.argtypes = [VP, VP, VP, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, VP, ctypes.c_int,
+                                       VP, VP, VP, VP, VP, VP]
         _lib = L
     return _lib
 
@@ -115,9 +145,12 @@ class SentencePieceOracle:
             raise ValueError("oracle_sp_load: " + err.value.decode())
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().oracle_sp_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().oracle_sp_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def vocab_size(self):
         return lib().oracle_sp_piece_count(self._h)
@@ -152,3 +185,97 @@ class SentencePieceOracle:
         lib().oracle_sp_encode_batch(self._h, text_u8.ctypes.data, offsets.ctypes.data, n, ids.ctypes.data,
                                      ids_stride, n_ids.ctypes.data, n_threads)
         return ids, n_ids
+
+
+def _name_array(names):
+    arr = (ctypes.c_char_p * len(names))(*[n.encode() for n in names])
+    return arr
+
+
+def _keys_buf(keys):
+    """list of 16-byte keys / uint8 [n,16] -> (contiguous uint8 array, n)."""
+    a = np.ascontiguousarray(np.asarray(keys, dtype=np.uint8).reshape(-1, 16)) if len(keys) else np.zeros((0, 16),
+                                                                                                         np.uint8)
+    return a, a.shape[0]
+
+
+class PrefixOracle:
+    """GlobalKVCacheMgr + InstanceMgr::get_load_metrics + CacheAwareRouting with the reference's own
+    containers (oracle/prefix_oracle.cc).  Instances are NAMES here, exactly as in the reference;
+    `names` (id -> name) only translates results to the id space the device path uses."""
+    DEFAULT, PREFILL, DECODE, MIX = 0, 1, 2, 3
+
+    def __init__(self, names, block_size=128, seed=1024):
+        self.names = list(names)
+        self._names = _name_array(self.names)
+        self.block_size, self.seed = block_size, seed
+        self._ix = lib().oracle_index_new()
+        self._reg = lib().oracle_registry_new()
+
+    def __del__(self):
+        try:
+            lib().oracle_index_free(self._ix)
+            lib().oracle_registry_free(self._reg)
+        except Exception:
+            pass
+
+    # write side
+    def record(self, name, stored=(), offload=(), removed=()):
+        s, ns = _keys_buf(stored)
+        o, no = _keys_buf(offload)
+        r, nr = _keys_buf(removed)
+        lib().oracle_index_record(self._ix, name.encode(), s.ctypes.data, ns, o.ctypes.data, no, r.ctypes.data, nr)
+
+    def upload(self):
+        lib().oracle_index_upload(self._ix)
+
+    def put(self, key, hbm=(), dram=(), ssd=()):
+        k = np.ascontiguousarray(np.frombuffer(bytes(key), dtype=np.uint8))
+        lib().oracle_index_put(self._ix, k.ctypes.data, _name_array(list(hbm)), len(hbm), _name_array(list(dram)),
+                               len(dram), _name_array(list(ssd)), len(ssd))
+
+    def delete(self, key):
+        k = np.ascontiguousarray(np.frombuffer(bytes(key), dtype=np.uint8))
+        lib().oracle_index_delete(self._ix, k.ctypes.data)
+
+    def size(self):
+        return lib().oracle_index_size(self._ix)
+
+    def get(self, key):
+        k = np.ascontiguousarray(np.frombuffer(bytes(key), dtype=np.uint8))
+        m = np.zeros(3, dtype=np.uint64)
+        found = lib().oracle_index_get(self._ix, k.ctypes.data, self._names, len(self.names), m.ctypes.data)
+        return bool(found), [int(x) for x in m]
+
+    # registry
+    def set_instance(self, name, type_, schedulable=True):
+        lib().oracle_registry_set_instance(self._reg, name.encode(), type_, int(schedulable))
+
+    def set_load(self, name, waiting, usage):
+        lib().oracle_registry_set_load(self._reg, name.encode(), int(waiting), float(usage))
+
+    def clear_load(self, name):
+        lib().oracle_registry_clear_load(self._reg, name.encode())
+
+    # read side
+    def match(self, tokens):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        n = len(self.names)
+        scores = np.zeros((3, n), dtype=np.uint32)
+        inst = ctypes.c_uint64()
+        mb, mm = ctypes.c_uint32(), ctypes.c_uint32()
+        lib().oracle_index_match(self._ix, t.ctypes.data, t.size, self.block_size, self.seed, self._names, n,
+                                 scores.ctypes.data, ctypes.byref(inst), ctypes.byref(mb), ctypes.byref(mm))
+        return {"hbm": scores[0], "dram": scores[1], "ssd": scores[2], "instances": inst.value,
+                "max_block_num": mb.value, "max_matched_block_num": mm.value}
+
+    def route(self, tokens):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        pid, did = ctypes.c_int(), ctypes.c_int()
+        pb, db = ctypes.c_float(), ctypes.c_float()
+        pa, da = ctypes.c_uint64(), ctypes.c_uint64()
+        ok = lib().oracle_route_car(self._ix, self._reg, t.ctypes.data, t.size, self.block_size, self.seed,
+                                    self._names, len(self.names), ctypes.byref(pid), ctypes.byref(did),
+                                    ctypes.byref(pb), ctypes.byref(db), ctypes.byref(pa), ctypes.byref(da))
+        return {"ok": bool(ok), "prefill_id": pid.value, "decode_id": did.value, "prefill_score": pb.value,
+                "decode_score": db.value, "prefill_argmax": pa.value, "decode_argmax": da.value}

@@ -39,6 +39,24 @@ class TokenizerInfo(ctypes.Structure):
                                               "max_unit_out", "byte_fallback", "unk_id", "trie_units")]
 
 
+class MatchOut(ctypes.Structure):
+    """xllm_match_out (include/xllm_ingest.h)."""
+    _fields_ = [("max_block_num", ctypes.c_uint32), ("max_matched_block_num", ctypes.c_uint32),
+                ("instances", ctypes.c_uint64), ("hbm_instance_score", ctypes.c_uint16 * 64),
+                ("dram_instance_score", ctypes.c_uint16 * 64), ("ssd_instance_score", ctypes.c_uint16 * 64)]
+
+
+class RoutingOut(ctypes.Structure):
+    """xllm_routing_out (include/xllm_ingest.h)."""
+    _fields_ = [("prefill_id", ctypes.c_int32), ("decode_id", ctypes.c_int32), ("ok", ctypes.c_int32),
+                ("prefill_score", ctypes.c_float), ("decode_score", ctypes.c_float)]
+
+
+MATCH_DTYPE = [("max_block_num", "<u4"), ("max_matched_block_num", "<u4"), ("instances", "<u8"),
+               ("hbm", "<u2", (64,)), ("dram", "<u2", (64,)), ("ssd", "<u2", (64,))]
+ROUTING_DTYPE = [("prefill_id", "<i4"), ("decode_id", "<i4"), ("ok", "<i4"), ("prefill_score", "<f4"),
+                 ("decode_score", "<f4")]
+
 _VP = ctypes.c_void_p
 
 
@@ -54,6 +72,19 @@ def _declare(L):
     L.xllm_xxh3_128bits_hash.argtypes = [_VP, _VP, _VP, ctypes.c_size_t, _VP]
     L.xllm_encode_batch.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, ctypes.c_int64, _VP, _VP]
     L.xllm_encode_batch_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, ctypes.c_int64, _VP, _VP, _VP]
+    SZ = ctypes.c_size_t
+    L.xllm_index_apply.argtypes = [_VP, ctypes.c_int32, _VP, SZ, _VP, SZ, _VP, SZ]
+    L.xllm_index_put.argtypes = [_VP, _VP, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]
+    L.xllm_index_erase.argtypes = [_VP, _VP]
+    L.xllm_index_publish.argtypes = [_VP]
+    L.xllm_index_size.argtypes = [_VP, ctypes.POINTER(ctypes.c_int64)]
+    L.xllm_index_get.argtypes = [_VP, _VP, _VP, ctypes.POINTER(ctypes.c_int32)]
+    L.xllm_set_instance.argtypes = [_VP, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+    L.xllm_set_load_metrics.argtypes = [_VP, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_float]
+    L.xllm_match_route.argtypes = [_VP, ctypes.c_int32, _VP, ctypes.c_int64, _VP, _VP, _VP, _VP]
+    L.xllm_match_route_device.argtypes = [_VP, ctypes.c_int32, _VP, ctypes.c_int64, _VP, _VP, _VP, _VP, _VP]
+    L.xllm_index_probe_device.argtypes = [_VP, _VP, ctypes.c_int64, _VP, _VP]
+    L.xllm_score_route_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]
     L.xllm_tokenizer_probe.argtypes = [ctypes.c_char_p, ctypes.POINTER(TokenizerInfo)]
     L.xllm_vocab_size.argtypes = [_VP, ctypes.POINTER(ctypes.c_int32)]
 

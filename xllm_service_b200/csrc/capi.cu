@@ -125,6 +125,22 @@ int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
       return rc;
     }
   }
+  h->inst_host = std::make_shared<InstanceTable>();
+  memset(h->inst_host.get(), 0, sizeof(InstanceTable));
+  h->index_mu = std::make_shared<std::mutex>();
+  if (cudaMalloc(&h->d_inst, sizeof(InstanceTable)) != cudaSuccess) {
+    set_last_error("cudaMalloc(InstanceTable) failed");
+    xllm_ingest_destroy(h);
+    return XLLM_ERR_NOMEM;
+  }
+  if (cfg->index_capacity > 0) {
+    h->index = std::make_shared<PrefixIndex>();
+    int rc = h->index->init(cfg->index_capacity);
+    if (rc != XLLM_OK) {
+      xllm_ingest_destroy(h);
+      return rc;
+    }
+  }
   *out = h;
   return XLLM_OK;
 }
@@ -148,6 +164,9 @@ int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out) {
   (*out)->sp_tables = src->sp_tables;
   (*out)->sp_dev = src->sp_dev;
   (*out)->tokenizer_path = src->tokenizer_path;
+  (*out)->index = src->index;
+  (*out)->index_mu = src->index_mu;
+  (*out)->inst_host = src->inst_host;
   return XLLM_OK;
 }
 
@@ -165,6 +184,11 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   h->d_ids.release();
   h->d_n_ids.release();
   h->d_status.release();
+  h->d_masks.release();
+  h->d_match.release();
+  h->d_routing.release();
+  h->d_nblk.release();
+  if (h->d_inst) cudaFree(h->d_inst);
   if (h->d_task_counter) cudaFree(h->d_task_counter);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -251,6 +275,187 @@ int xllm_xxh3_128bits_hash(xllm_ingest_t h, const uint8_t* prev16, const int32_t
     XLLM_CUDA_TRY(cudaMemcpyAsync(dt + (prev16 ? 16 : 0), token_ids, n_tokens * 4, cudaMemcpyHostToDevice, s));
   XLLM_CUDA_TRY(xxh3_single_launch(h->d_tokens.as<uint8_t>(), n * 4, h->d_keys.as<uint8_t>(), h->xxh, s));
   XLLM_CUDA_TRY(cudaMemcpyAsync(out16, h->d_keys.p, 16, cudaMemcpyDeviceToHost, s));
+  XLLM_CUDA_TRY(cudaStreamSynchronize(s));
+  return XLLM_OK;
+}
+
+// ------------------------------------------------------------------ prefix index
+static int need_index(xllm_ingest_t h) {
+  if (!h) {
+    set_last_error("null handle");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  if (!h->index || !h->index->ready()) {
+    set_last_error("prefix index not configured (index_capacity == 0)");
+    return XLLM_ERR_UNSUPPORTED;
+  }
+  return XLLM_OK;
+}
+
+int xllm_index_apply(xllm_ingest_t h, int32_t instance_id, const uint8_t* stored, size_t n_stored,
+                     const uint8_t* offload, size_t n_offload, const uint8_t* removed, size_t n_removed) {
+  XLLM_TRY(need_index(h));
+  if (instance_id < 0 || instance_id >= kMaxInstances || (n_stored && !stored) || (n_offload && !offload) ||
+      (n_removed && !removed)) {
+    set_last_error("xllm_index_apply: invalid argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  std::lock_guard<std::mutex> lock(*h->index_mu);
+  h->index->record(instance_id, stored, n_stored, offload, n_offload, removed, n_removed);
+  return XLLM_OK;
+}
+int xllm_index_put(xllm_ingest_t h, const uint8_t* key16, uint64_t hbm, uint64_t dram, uint64_t ssd) {
+  XLLM_TRY(need_index(h));
+  if (!key16) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(*h->index_mu);
+  h->index->put(key16, hbm, dram, ssd);
+  return XLLM_OK;
+}
+int xllm_index_erase(xllm_ingest_t h, const uint8_t* key16) {
+  XLLM_TRY(need_index(h));
+  if (!key16) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(*h->index_mu);
+  h->index->erase(key16);
+  return XLLM_OK;
+}
+int xllm_index_publish(xllm_ingest_t h) {
+  XLLM_TRY(need_index(h));
+  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::mutex> lock2(*h->index_mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  return h->index->publish(h->stream);
+}
+int xllm_index_size(xllm_ingest_t h, int64_t* n_keys) {
+  XLLM_TRY(need_index(h));
+  if (!n_keys) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  return h->index->size(h->stream, n_keys);
+}
+int xllm_index_get(xllm_ingest_t h, const uint8_t* key16, uint64_t masks3[3], int32_t* found) {
+  XLLM_TRY(need_index(h));
+  if (!key16 || !masks3 || !found) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::mutex> lock2(*h->index_mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  int f = 0;
+  int rc = h->index->get(h->stream, key16, masks3, &f);
+  *found = f;
+  return rc;
+}
+
+int xllm_set_instance(xllm_ingest_t h, int32_t id, int32_t type, int32_t schedulable) {
+  if (!h || id < 0 || id >= kMaxInstances || type < 0 || type > 3) {
+    set_last_error("xllm_set_instance: invalid argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  std::lock_guard<std::mutex> lock(*h->index_mu);
+  InstanceTable& t = *h->inst_host;
+  const uint64_t bit = 1ull << id;
+  t.schedulable = schedulable ? (t.schedulable | bit) : (t.schedulable & ~bit);
+  t.decode_type = type == 2 ? (t.decode_type | bit) : (t.decode_type & ~bit);
+  h->inst_dirty = true;
+  return XLLM_OK;
+}
+int xllm_set_load_metrics(xllm_ingest_t h, int32_t id, int32_t has_metrics, uint64_t waiting, float usage) {
+  if (!h || id < 0 || id >= kMaxInstances) {
+    set_last_error("xllm_set_load_metrics: invalid argument");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  std::lock_guard<std::mutex> lock(*h->index_mu);
+  InstanceTable& t = *h->inst_host;
+  const uint64_t bit = 1ull << id;
+  t.has_metrics = has_metrics ? (t.has_metrics | bit) : (t.has_metrics & ~bit);
+  t.waiting[id] = waiting;
+  t.usage[id] = usage;
+  h->inst_dirty = true;
+  return XLLM_OK;
+}
+
+// uploads the instance view if it changed (always: clones share the host copy, so it is cheap to resend)
+static int sync_instances(xllm_ingest_t h, cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(*h->index_mu);
+  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_inst, h->inst_host.get(), sizeof(InstanceTable), cudaMemcpyHostToDevice, s));
+  h->inst_dirty = false;
+  return XLLM_OK;
+}
+
+int xllm_index_probe_device(xllm_ingest_t h, const uint8_t* d_keys, int64_t n_keys, uint64_t* d_masks3,
+                            void* cuda_stream) {
+  XLLM_TRY(need_index(h));
+  if (n_keys < 0 || (n_keys > 0 && (!d_keys || !d_masks3))) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  XLLM_CUDA_TRY(h->index->probe(d_keys, n_keys, d_masks3, s));
+  return XLLM_OK;
+}
+
+int xllm_score_route_device(xllm_ingest_t h, int32_t n_req, const uint64_t* d_masks3, const int64_t* d_key_start,
+                            const int32_t* d_n_blocks, xllm_match_out* d_match, xllm_routing_out* d_routing,
+                            void* cuda_stream) {
+  if (!h || n_req < 0 || (n_req > 0 && (!d_masks3 || !d_key_start || !d_n_blocks))) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  XLLM_TRY(sync_instances(h, s));
+  XLLM_CUDA_TRY(score_route_launch(d_masks3, d_key_start, d_n_blocks, n_req, h->d_inst,
+                                   reinterpret_cast<MatchOut*>(d_match), reinterpret_cast<RoutingOut*>(d_routing), s));
+  return XLLM_OK;
+}
+
+int xllm_match_route_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_keys, int64_t n_keys_total,
+                            const int64_t* d_key_start, const int32_t* d_n_blocks, xllm_match_out* d_match,
+                            xllm_routing_out* d_routing, void* cuda_stream) {
+  XLLM_TRY(need_index(h));
+  if (n_req < 0 || n_keys_total < 0 || (n_req > 0 && (!d_key_start || !d_n_blocks)) || (n_keys_total > 0 && !d_keys))
+    return XLLM_ERR_INVALID_ARG;
+  if (n_req == 0) return XLLM_OK;
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  XLLM_TRY(h->d_masks.reserve((size_t)n_keys_total * 24 + 64));
+  XLLM_TRY(sync_instances(h, s));
+  XLLM_CUDA_TRY(h->index->probe(d_keys, n_keys_total, h->d_masks.as<uint64_t>(), s));
+  XLLM_CUDA_TRY(score_route_launch(h->d_masks.as<uint64_t>(), d_key_start, d_n_blocks, n_req, h->d_inst,
+                                   reinterpret_cast<MatchOut*>(d_match), reinterpret_cast<RoutingOut*>(d_routing), s));
+  return XLLM_OK;
+}
+
+int xllm_match_route(xllm_ingest_t h, int32_t n_req, const uint8_t* keys, int64_t n_keys_total,
+                     const int64_t* key_start, const int32_t* n_blocks, xllm_match_out* match,
+                     xllm_routing_out* routing) {
+  XLLM_TRY(need_index(h));
+  if (n_req < 0 || n_keys_total < 0 || (n_req > 0 && (!key_start || !n_blocks)) || (n_keys_total > 0 && !keys))
+    return XLLM_ERR_INVALID_ARG;
+  if (n_req == 0) return XLLM_OK;
+  for (int32_t r = 0; r < n_req; ++r)
+    if (n_blocks[r] < 0 || n_blocks[r] > 65535 || key_start[r] < 0 || key_start[r] + n_blocks[r] > n_keys_total) {
+      set_last_error("xllm_match_route: request %d out of bounds", r);
+      return XLLM_ERR_INVALID_ARG;
+    }
+  std::lock_guard<std::mutex> lock(h->mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  XLLM_TRY(h->d_keys.reserve((size_t)n_keys_total * 16 + 64));
+  XLLM_TRY(h->d_key_start.reserve((size_t)n_req * 8));
+  XLLM_TRY(h->d_nblk.reserve((size_t)n_req * 4));
+  XLLM_TRY(h->d_masks.reserve((size_t)n_keys_total * 24 + 64));
+  XLLM_TRY(h->d_match.reserve((size_t)n_req * sizeof(MatchOut)));
+  XLLM_TRY(h->d_routing.reserve((size_t)n_req * sizeof(RoutingOut)));
+  if (n_keys_total)
+    XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_keys.p, keys, (size_t)n_keys_total * 16, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_key_start.p, key_start, (size_t)n_req * 8, cudaMemcpyHostToDevice, s));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_nblk.p, n_blocks, (size_t)n_req * 4, cudaMemcpyHostToDevice, s));
+  XLLM_TRY(sync_instances(h, s));
+  XLLM_CUDA_TRY(h->index->probe(h->d_keys.as<uint8_t>(), n_keys_total, h->d_masks.as<uint64_t>(), s));
+  XLLM_CUDA_TRY(score_route_launch(h->d_masks.as<uint64_t>(), h->d_key_start.as<int64_t>(), h->d_nblk.as<int32_t>(),
+                                   n_req, h->d_inst, h->d_match.as<MatchOut>(), h->d_routing.as<RoutingOut>(), s));
+  if (match)
+    XLLM_CUDA_TRY(cudaMemcpyAsync(match, h->d_match.p, (size_t)n_req * sizeof(MatchOut), cudaMemcpyDeviceToHost, s));
+  if (routing)
+    XLLM_CUDA_TRY(
+        cudaMemcpyAsync(routing, h->d_routing.p, (size_t)n_req * sizeof(RoutingOut), cudaMemcpyDeviceToHost, s));
   XLLM_CUDA_TRY(cudaStreamSynchronize(s));
   return XLLM_OK;
 }

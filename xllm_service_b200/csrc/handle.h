@@ -8,6 +8,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "prefix_index.cuh"
 #include "sp_encode.cuh"
 #include "sp_model.h"
 #include "xxh3_chain.cuh"
@@ -48,6 +49,13 @@ struct xllm_ingest {
   std::shared_ptr<xllm::SpTables> sp_tables;
   std::shared_ptr<xllm::SpDeviceModel> sp_dev;
   std::string tokenizer_path;
+  // prefix index + instance view (shared between clones)
+  std::shared_ptr<xllm::PrefixIndex> index;
+  std::shared_ptr<std::mutex> index_mu;
+  std::shared_ptr<xllm::InstanceTable> inst_host;  // host copy
+  xllm::InstanceTable* d_inst = nullptr;           // this handle's device copy
+  bool inst_dirty = true;
+  xllm::DevBuf d_masks, d_match, d_routing, d_nblk;
   // scratch for the host-pointer entry points
   xllm::DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status;
   xllm::DevBuf d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start;

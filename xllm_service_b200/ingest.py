@@ -113,3 +113,71 @@ class Ingest:
     def encode_batch_device(self, n_req, d_text, d_offsets, d_ids, ids_stride, d_n_ids, d_status, stream=None):
         check(self._L.xllm_encode_batch_device(self._h, n_req, d_text, d_offsets, d_ids, ids_stride, d_n_ids,
                                                d_status, stream))
+
+    # ---------------------------------------------------------- prefix index
+    @staticmethod
+    def _keys(keys):
+        if keys is None:
+            return np.zeros((0, 16), np.uint8)
+        return np.ascontiguousarray(np.asarray(keys, dtype=np.uint8).reshape(-1, 16))
+
+    def index_apply(self, instance_id, stored=None, offload=None, removed=None):
+        """GlobalKVCacheMgr::record_updated_kvcaches (global_kvcache_mgr.cpp:177-225); staged."""
+        s, o, r = self._keys(stored), self._keys(offload), self._keys(removed)
+        check(self._L.xllm_index_apply(self._h, instance_id, _ptr(s), s.shape[0], _ptr(o), o.shape[0], _ptr(r),
+                                       r.shape[0]))
+
+    def index_put(self, key, hbm_mask=0, dram_mask=0, ssd_mask=0):
+        k = self._keys(key)
+        check(self._L.xllm_index_put(self._h, _ptr(k), hbm_mask, dram_mask, ssd_mask))
+
+    def index_erase(self, key):
+        k = self._keys(key)
+        check(self._L.xllm_index_erase(self._h, _ptr(k)))
+
+    def index_publish(self):
+        """upload_kvcache (global_kvcache_mgr.cpp:227-247): staged events become visible to match."""
+        check(self._L.xllm_index_publish(self._h))
+
+    def index_size(self):
+        n = ctypes.c_int64()
+        check(self._L.xllm_index_size(self._h, ctypes.byref(n)))
+        return n.value
+
+    def index_get(self, key):
+        k = self._keys(key)
+        m = np.zeros(3, dtype=np.uint64)
+        f = ctypes.c_int32()
+        check(self._L.xllm_index_get(self._h, _ptr(k), _ptr(m), ctypes.byref(f)))
+        return bool(f.value), [int(x) for x in m]
+
+    def set_instance(self, instance_id, type_, schedulable=True):
+        check(self._L.xllm_set_instance(self._h, instance_id, type_, int(schedulable)))
+
+    def set_load_metrics(self, instance_id, waiting, usage, has_metrics=True):
+        check(self._L.xllm_set_load_metrics(self._h, instance_id, int(has_metrics), int(waiting), float(usage)))
+
+    def match_route(self, keys, key_start, n_blocks):
+        """GlobalKVCacheMgr::match + CacheAwareRouting::select_instances_pair over host buffers.
+        Returns (match structured array, routing structured array)."""
+        keys = self._keys(keys)
+        key_start = np.ascontiguousarray(key_start, dtype=np.int64)
+        n_blocks = np.ascontiguousarray(n_blocks, dtype=np.int32)
+        n = n_blocks.size
+        match = np.zeros(n, dtype=_lib.MATCH_DTYPE)
+        routing = np.zeros(n, dtype=_lib.ROUTING_DTYPE)
+        assert match.itemsize == 400 and routing.itemsize == 20
+        check(self._L.xllm_match_route(self._h, n, _ptr(keys), keys.shape[0], _ptr(key_start), _ptr(n_blocks),
+                                       _ptr(match), _ptr(routing)))
+        return match, routing
+
+    def match_route_device(self, n_req, d_keys, n_keys, d_key_start, d_n_blocks, d_match, d_routing, stream=None):
+        check(self._L.xllm_match_route_device(self._h, n_req, d_keys, n_keys, d_key_start, d_n_blocks, d_match,
+                                              d_routing, stream))
+
+    def index_probe_device(self, d_keys, n_keys, d_masks3, stream=None):
+        check(self._L.xllm_index_probe_device(self._h, d_keys, n_keys, d_masks3, stream))
+
+    def score_route_device(self, n_req, d_masks3, d_key_start, d_n_blocks, d_match, d_routing, stream=None):
+        check(self._L.xllm_score_route_device(self._h, n_req, d_masks3, d_key_start, d_n_blocks, d_match, d_routing,
+                                              stream))
