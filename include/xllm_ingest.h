@@ -174,6 +174,36 @@ int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const
 int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_text, const int64_t* d_offsets,
                              int32_t* d_ids, int64_t ids_stride, int32_t* d_n_ids, int32_t* d_status,
                              void* cuda_stream);
+/* ------------------------------------------------------------ the whole path, one call
+ * What Scheduler::schedule does per request between scheduler.cpp:128 and :135 — Tokenizer::encode,
+ * then CacheAwareRouting::select_instances_pair (GlobalKVCacheMgr::match + cost_function) — for a
+ * whole batch: host text in, token ids / block keys / OverlapScores / Routing out.  The batch is
+ * pipelined in chunks over several CUDA streams; pass page-locked buffers (xllm_host_alloc) so
+ * the PCIe copies overlap the kernels.  keys / match / routing may be NULL to skip those outputs
+ * (match or routing != NULL requires an index).  keys_stride = 16-byte keys per request row
+ * (0 => ids_stride / block_size); rows are zero-padded past floor(n_ids/block_size).
+ */
+typedef struct {
+  int32_t n_req;
+  const uint8_t* text;    /* all prompts back to back */
+  const int64_t* offsets; /* [n_req + 1] byte offsets into text */
+  int32_t* ids;           /* [n_req][ids_stride] */
+  int64_t ids_stride;
+  int32_t* n_ids;         /* [n_req] full token counts */
+  int32_t* status;        /* [n_req] 0 / XLLM_ENC_TRUNCATED / XLLM_ERR_CAPACITY */
+  uint8_t* keys;          /* [n_req][keys_stride][16] or NULL */
+  int64_t keys_stride;
+  xllm_match_out* match;     /* [n_req] or NULL */
+  xllm_routing_out* routing; /* [n_req] or NULL */
+} xllm_ingest_io;
+int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io);
+/* Pipeline chunking of xllm_ingest_batch: at most chunk_requests requests and chunk_bytes text bytes
+ * per chunk (defaults 4096 / 96 MiB). */
+int xllm_set_pipeline(xllm_ingest_t h, int32_t chunk_requests, int64_t chunk_bytes);
+/* Page-locked host memory for the batch buffers. */
+int xllm_host_alloc(void** out, size_t bytes);
+void xllm_host_free(void* p);
+
 /* Host-only: parse a tokenizer directory and report the tables the device encoder would use
  * (no CUDA needed).  split_mode: 1 = words split before every U+2581, 2 = before a U+2581 not
  * preceded by U+2581, 0 = the vocabulary allows no exact pre-split. */

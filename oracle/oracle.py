@@ -81,6 +81,8 @@ def lib():
         L.oracle_registry_clear_load.restype = None
         L.oracle_route_car.argtypes = [VP, VP, VP, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, VP, ctypes.c_int,
                                        VP, VP, VP, VP, VP, VP]
+        L.oracle_ingest_batch.argtypes = [VP, VP, VP, VP, VP, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, VP,
+                                          ctypes.c_int, ctypes.c_int, VP, ctypes.c_int64, VP, VP, VP, VP]
         _lib = L
     return _lib
 
@@ -279,3 +281,24 @@ class PrefixOracle:
                                     ctypes.byref(pb), ctypes.byref(db), ctypes.byref(pa), ctypes.byref(da))
         return {"ok": bool(ok), "prefill_id": pid.value, "decode_id": did.value, "prefill_score": pb.value,
                 "decode_score": db.value, "prefill_argmax": pa.value, "decode_argmax": da.value}
+
+
+def ingest_batch(sp, prefix, text_u8, offsets, ids_stride, n_threads=1, want_ids=True):
+    """Scheduler::schedule's encode + select_instances_pair for every request of a CSR batch, one request
+    at a time per worker thread.  sp: SentencePieceOracle; prefix: PrefixOracle or None.
+    Returns dict(ids, n_ids, prefill_id, decode_id, ok)."""
+    text_u8 = np.ascontiguousarray(text_u8, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    ids = np.zeros((n, ids_stride), dtype=np.int32) if want_ids else None
+    n_ids = np.zeros(n, np.int32)
+    pid = np.full(n, -1, np.int32)
+    did = np.full(n, -1, np.int32)
+    ok = np.zeros(n, np.int32)
+    lib().oracle_ingest_batch(sp._h, prefix._ix if prefix else None, prefix._reg if prefix else None,
+                              text_u8.ctypes.data, offsets.ctypes.data, n,
+                              prefix.block_size if prefix else 128, prefix.seed if prefix else 1024,
+                              prefix._names if prefix else None, len(prefix.names) if prefix else 0, n_threads,
+                              ids.ctypes.data if want_ids else None, ids_stride, n_ids.ctypes.data, pid.ctypes.data,
+                              did.ctypes.data, ok.ctypes.data)
+    return {"ids": ids, "n_ids": n_ids, "prefill_id": pid, "decode_id": did, "ok": ok}

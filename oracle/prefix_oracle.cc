@@ -378,3 +378,50 @@ int oracle_route_car(void* index, void* registry, const int32_t* tokens, size_t 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// The reference's whole per-request ingest step, Scheduler::schedule (scheduler.cpp:107-153) minus
+// the chat template and the bookkeeping after routing: Tokenizer::encode on the worker thread, then
+// CacheAwareRouting::select_instances_pair (match -> get_load_metrics -> cost_function x2).
+// n_threads workers each take one request at a time (brpc worker model, scheduler.cpp:274-277).
+// Used by bench.py's cpu_baseline / --impl reference legs and by the pipeline parity test.
+extern "C" long oracle_sp_encode(void* h, const char* text, size_t len, int32_t* ids_out, size_t cap);
+
+#include <atomic>
+#include <thread>
+
+extern "C" int oracle_ingest_batch(void* sp, void* index, void* registry, const char* text, const int64_t* offsets,
+                                   size_t n_req, uint32_t block_size, uint32_t seed, const char* const* names,
+                                   int n_names, int n_threads, int32_t* ids_out, int64_t ids_stride, int32_t* n_ids,
+                                   int32_t* prefill_id, int32_t* decode_id, int32_t* ok) {
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    std::vector<int32_t> ids((size_t)ids_stride);
+    for (;;) {
+      const size_t r = next.fetch_add(1);
+      if (r >= n_req) break;
+      long n = oracle_sp_encode(sp, text + offsets[r], (size_t)(offsets[r + 1] - offsets[r]), ids.data(),
+                                (size_t)ids_stride);
+      const size_t kept = (size_t)std::min<long>(n, (long)ids_stride);
+      n_ids[r] = (int32_t)n;
+      if (ids_out) memcpy(ids_out + r * ids_stride, ids.data(), kept * sizeof(int32_t));
+      if (index && registry) {
+        int p, d;
+        float pb, db;
+        uint64_t pa, da;
+        ok[r] = oracle_route_car(index, registry, ids.data(), kept, block_size, seed, names, n_names, &p, &d, &pb, &db,
+                                 &pa, &da);
+        prefill_id[r] = p;
+        decode_id[r] = d;
+      }
+    }
+  };
+  if (n_threads <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  return 0;
+}

@@ -1,0 +1,70 @@
+"""End-to-end parity of xllm_ingest_batch (tokenize -> block hash -> match -> route, chunk-pipelined over
+several streams) against the CPU oracle's per-request Scheduler::schedule path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+import os  # noqa: E402
+
+HERE = os.path.dirname(__file__)
+MODEL_DIR = os.path.join(HERE, "golden", "sp_bpe_8k")
+NAMES = ["inst%02d" % i for i in range(16)]
+
+
+def test_pipeline_matches_oracle(oracle):
+    import xllm_service_b200 as x
+    from xllm_service_b200 import workload
+    rng = np.random.default_rng(11)
+    h = x.Ingest(tokenizer_path=MODEL_DIR, index_capacity=1 << 15)
+    h.set_pipeline(37, 1 << 20)  # small chunks: many chunks in flight, odd boundaries
+    sp = oracle.SentencePieceOracle(MODEL_DIR)
+    P = oracle.PrefixOracle(NAMES)
+    vocab = workload.make_vocabulary()
+    wb = workload.pack_prompts(vocab)
+    _, wcnt = sp.encode_batch(wb.text, wb.offsets, 32)
+    T = 1024
+    batch, meta = workload.make_prompts_exact_tokens(
+        300, T, wcnt, seed=5, shared_prefix=dict(n_prefixes=8, frac=0.8, min_blocks=2, max_blocks=6, block_tokens=128))
+    # ragged extras: empty, short, invalid utf-8
+    extra = [b"", b"hi", b"\xff\xfe broken \xe6\x97", "日本 語".encode(), b" ".join(vocab[:50])]
+    texts = [batch.prompt(i) for i in range(batch.n)] + extra
+    b = workload.pack_prompts(texts)
+    for i, n in enumerate(NAMES):
+        t = 2 if i % 2 else 1
+        w, u = int(rng.integers(0, 9)), float(np.float32(rng.random()))
+        P.set_instance(n, t)
+        P.set_load(n, w, u)
+        h.set_instance(i, t)
+        h.set_load_metrics(i, w, u)
+    # index content: prefixes of the first requests
+    ref = oracle.ingest_batch(sp, None, b.text, b.offsets, T)
+    for r in range(0, 60):
+        keys = oracle.block_hash_chain(ref["ids"][r, :ref["n_ids"][r]])
+        i = int(rng.integers(0, len(NAMES)))
+        k = keys[:int(rng.integers(0, keys.shape[0] + 1))]
+        P.record(NAMES[i], k)
+        h.index_apply(i, k)
+    P.upload()
+    h.index_publish()
+    out = h.ingest_batch(b.text, b.offsets, T)
+    ref = oracle.ingest_batch(sp, P, b.text, b.offsets, T)
+    assert (out["status"] == 0).all()
+    assert (out["n_ids"] == ref["n_ids"]).all()
+    for r in range(b.n):
+        n = ref["n_ids"][r]
+        assert (out["ids"][r, :n] == ref["ids"][r, :n]).all(), r
+        want = oracle.block_hash_chain(ref["ids"][r, :n])
+        assert (out["keys"][r, :want.shape[0]] == want).all(), r
+        assert not out["keys"][r, want.shape[0]:].any(), r  # zero padding past the last full block
+        m = P.match(ref["ids"][r, :n])
+        assert out["match"]["max_matched_block_num"][r] == m["max_matched_block_num"], r
+        assert out["match"]["hbm"][r][:len(NAMES)].tolist() == m["hbm"].tolist(), r
+        ro = P.route(ref["ids"][r, :n])
+        assert bool(out["routing"]["ok"][r]) == ro["ok"]
+        assert out["routing"]["prefill_score"][r] == np.float32(ro["prefill_score"]), r
+        assert (ro["prefill_argmax"] >> int(out["routing"]["prefill_id"][r])) & 1, r
+        assert (ro["decode_argmax"] >> int(out["routing"]["decode_id"][r])) & 1, r
+    # tokenizer-only call (no index outputs) and keys-only call
+    o2 = h.ingest_batch(b.text, b.offsets, T, want_keys=True, want_match=False)
+    assert (o2["ids"] == out["ids"]).all() and (o2["keys"] == out["keys"]).all()
+    h.close()

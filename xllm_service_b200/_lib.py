@@ -57,6 +57,14 @@ MATCH_DTYPE = [("max_block_num", "<u4"), ("max_matched_block_num", "<u4"), ("ins
 ROUTING_DTYPE = [("prefill_id", "<i4"), ("decode_id", "<i4"), ("ok", "<i4"), ("prefill_score", "<f4"),
                  ("decode_score", "<f4")]
 
+class IngestIO(ctypes.Structure):
+    """xllm_ingest_io (include/xllm_ingest.h)."""
+    _fields_ = [("n_req", ctypes.c_int32), ("text", ctypes.c_void_p), ("offsets", ctypes.c_void_p),
+                ("ids", ctypes.c_void_p), ("ids_stride", ctypes.c_int64), ("n_ids", ctypes.c_void_p),
+                ("status", ctypes.c_void_p), ("keys", ctypes.c_void_p), ("keys_stride", ctypes.c_int64),
+                ("match", ctypes.c_void_p), ("routing", ctypes.c_void_p)]
+
+
 _VP = ctypes.c_void_p
 
 
@@ -85,6 +93,11 @@ def _declare(L):
     L.xllm_match_route_device.argtypes = [_VP, ctypes.c_int32, _VP, ctypes.c_int64, _VP, _VP, _VP, _VP, _VP]
     L.xllm_index_probe_device.argtypes = [_VP, _VP, ctypes.c_int64, _VP, _VP]
     L.xllm_score_route_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]
+    L.xllm_ingest_batch.argtypes = [_VP, ctypes.POINTER(IngestIO)]
+    L.xllm_set_pipeline.argtypes = [_VP, ctypes.c_int32, ctypes.c_int64]
+    L.xllm_host_alloc.argtypes = [ctypes.POINTER(_VP), ctypes.c_size_t]
+    L.xllm_host_free.argtypes = [_VP]
+    L.xllm_host_free.restype = None
     L.xllm_tokenizer_probe.argtypes = [ctypes.c_char_p, ctypes.POINTER(TokenizerInfo)]
     L.xllm_vocab_size.argtypes = [_VP, ctypes.POINTER(ctypes.c_int32)]
 

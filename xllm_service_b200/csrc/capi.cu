@@ -189,6 +189,7 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   h->d_routing.release();
   h->d_nblk.release();
   if (h->d_inst) cudaFree(h->d_inst);
+  for (int i = 0; i < kPipeSlots; ++i) h->pipe[i].release();
   if (h->d_task_counter) cudaFree(h->d_task_counter);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

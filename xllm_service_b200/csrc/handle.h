@@ -33,6 +33,17 @@ struct PinBuf {
   T* as() { return static_cast<T*>(p); }
 };
 
+// One in-flight chunk of xllm_ingest_batch: its own stream + device buffers.
+constexpr int kPipeSlots = 3;
+struct PipeSlot {
+  cudaStream_t stream = nullptr;
+  unsigned int* counters = nullptr;
+  DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status, d_tok_start, d_n_tok, d_key_start, d_n_blocks, d_keys, d_masks,
+      d_match, d_routing;
+  int ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_stride);
+  void release();
+};
+
 }  // namespace xllm
 
 struct xllm_ingest {
@@ -56,6 +67,10 @@ struct xllm_ingest {
   xllm::InstanceTable* d_inst = nullptr;           // this handle's device copy
   bool inst_dirty = true;
   xllm::DevBuf d_masks, d_match, d_routing, d_nblk;
+  // xllm_ingest_batch pipeline
+  xllm::PipeSlot pipe[xllm::kPipeSlots];
+  int pipe_chunk_req = 4096;
+  int64_t pipe_chunk_bytes = 96ll << 20;
   // scratch for the host-pointer entry points
   xllm::DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status;
   xllm::DevBuf d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start;

@@ -181,3 +181,33 @@ class Ingest:
     def score_route_device(self, n_req, d_masks3, d_key_start, d_n_blocks, d_match, d_routing, stream=None):
         check(self._L.xllm_score_route_device(self._h, n_req, d_masks3, d_key_start, d_n_blocks, d_match, d_routing,
                                               stream))
+
+    # ------------------------------------------------------- the whole path
+    def set_pipeline(self, chunk_requests, chunk_bytes):
+        check(self._L.xllm_set_pipeline(self._h, chunk_requests, chunk_bytes))
+
+    def ingest_batch_ptrs(self, n_req, text, offsets, ids, ids_stride, n_ids, status, keys=0, keys_stride=0,
+                          match=0, routing=0):
+        """xllm_ingest_batch over raw host addresses (ints), e.g. pinned torch tensors' data_ptr()."""
+        io = _lib.IngestIO(n_req, text, offsets, ids, ids_stride, n_ids, status, keys or None, keys_stride,
+                           match or None, routing or None)
+        check(self._L.xllm_ingest_batch(self._h, ctypes.byref(io)))
+
+    def ingest_batch(self, text, offsets, ids_stride, want_keys=True, want_match=True):
+        """tokenize + block-hash + match + route for a batch of prompts (numpy host buffers).
+        Returns dict(ids, n_ids, status, keys, match, routing)."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        ks = ids_stride // self.block_size
+        out = {"ids": np.zeros((n, ids_stride), np.int32), "n_ids": np.zeros(n, np.int32),
+               "status": np.zeros(n, np.int32), "keys": None, "match": None, "routing": None}
+        if want_keys:
+            out["keys"] = np.zeros((n, ks, 16), np.uint8)
+        if want_match:
+            out["match"] = np.zeros(n, dtype=_lib.MATCH_DTYPE)
+            out["routing"] = np.zeros(n, dtype=_lib.ROUTING_DTYPE)
+        a = lambda x: x.ctypes.data if x is not None and x.size else 0  # noqa: E731
+        self.ingest_batch_ptrs(n, a(text), a(offsets), a(out["ids"]), ids_stride, a(out["n_ids"]), a(out["status"]),
+                               a(out["keys"]), ks if want_keys else 0, a(out["match"]), a(out["routing"]))
+        return out

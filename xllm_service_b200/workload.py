@@ -94,84 +94,138 @@ def _exact_row(rng, n_tokens, wtc, by_count, max_cnt, V, est_words):
         np.int32)
 
 
+def _materialise(words, row_nwords, word_len, word_off, flat):
+    """torch: flat word ids of consecutive rows + words per row -> (text uint8, row byte lengths);
+    words joined by single spaces."""
+    import torch
+    dev = words.device
+    wl = word_len[words]
+    n_rows = row_nwords.numel()
+    row_first = torch.cumsum(row_nwords, 0) - row_nwords
+    row_of = torch.repeat_interleave(torch.arange(n_rows, device=dev), row_nwords)
+    step = wl + 1                                            # word + one separator
+    excl = torch.cumsum(step, 0) - step                      # byte offset if every word kept its separator
+    lens = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+    lens.index_add_(0, row_of, step)
+    lens = torch.where(row_nwords > 0, lens - 1, lens)       # each row drops its last separator
+    row_base = torch.cumsum(lens, 0) - lens
+    first_excl = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+    nz = row_nwords > 0
+    first_excl[nz] = excl[row_first[nz]]
+    start = row_base[row_of] + (excl - first_excl[row_of])
+    lexcl = torch.cumsum(wl, 0) - wl
+    within = torch.arange(int(wl.sum()), device=dev) - torch.repeat_interleave(lexcl, wl)
+    text = torch.full((int(lens.sum()),), 32, dtype=torch.uint8, device=dev)
+    text[torch.repeat_interleave(start, wl) + within] = flat[torch.repeat_interleave(word_off[words], wl) + within]
+    return text, lens
+
+
 def make_prompts_exact_tokens(n_prompts, n_tokens, word_token_counts, seed=0, vocabulary=None,
-                              shared_prefix=None):
+                              shared_prefix=None, chunk=2048, device="cpu"):
     """Build n_prompts prompts that each encode to EXACTLY n_tokens tokens under a tokenizer for
     which words tokenize independently (SentencePiece-BPE with a whitespace-split vocabulary):
     word_token_counts[i] = number of tokens of the word "▁" + vocabulary[i].  Words are drawn
-    Zipf(0.9); the tail of a prompt is re-drawn from the words with exactly the remaining count.
+    Zipf(0.9); the last word of a prompt is re-drawn from the words with exactly the remaining count.
+    Array work runs in torch on `device` ("cuda" for the 1 GB batches of bench.py); the result is
+    deterministic in (seed, device type).
 
     shared_prefix: optional dict(n_prefixes, frac, min_blocks, max_blocks, block_tokens) — the
     BASELINE config-3 workload: `frac` of the prompts start with one of n_prefixes shared
     prefixes (popularity Zipf(0.9)) whose length is uniform in [min_blocks, max_blocks] KV blocks.
 
-    Returns (PromptBatch, list of per-prompt int32 word-id arrays).
+    Returns (PromptBatch, meta) with meta = dict(prefix_id int32[n] (-1 = none),
+    prefix_blocks int32[n], n_prefixes).
     """
+    import torch
     vocab = vocabulary or make_vocabulary()
     V = len(vocab)
-    wtc = np.asarray(word_token_counts, dtype=np.int64)
-    assert wtc.size == V and wtc.min() >= 1
+    wtc_np = np.asarray(word_token_counts, dtype=np.int64)
+    assert wtc_np.size == V and wtc_np.min() >= 1
     rng = np.random.default_rng(seed)
-    max_cnt = int(wtc.max())
-    by_count = {c: np.nonzero(wtc == c)[0] for c in range(1, max_cnt + 1)}
-    assert by_count[1].size > 0, "need at least one single-token word to fill exactly"
-    word_len = np.array([len(w) for w in vocab], dtype=np.int64)
-    flat = np.frombuffer(b"".join(vocab), dtype=np.uint8)
-    word_off = np.zeros(V + 1, dtype=np.int64)
-    np.cumsum(word_len, out=word_off[1:])
+    max_cnt = int(wtc_np.max())
+    by_count = {c: np.nonzero(wtc_np == c)[0] for c in range(1, max_cnt + 1)}
+    assert all(by_count[c].size > 0 for c in range(1, max_cnt)), "need a word for every remainder"
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed) * 7919 + 17)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    wtc = T(wtc_np)
+    word_len = T(np.array([len(w) for w in vocab], dtype=np.int64))
+    flat = T(np.frombuffer(b"".join(vocab), dtype=np.uint8).copy())
+    word_off = torch.cumsum(word_len, 0) - word_len
+    zipf_cdf = T(np.cumsum(zipf_probs(V)))
+    by_count_t = {c: T(v) for c, v in by_count.items()}
 
-    est_words = int(n_tokens / wtc[sample_word_ids(rng, 1, 4096, V)[0]].mean() * 1.15) + 8
-    prefixes = None
+    est_words = int(n_tokens / wtc_np[sample_word_ids(rng, 1, 4096, V)[0]].mean() * 1.1) + 64
+    n_pref = 0
+    pref_blk_np = np.zeros(0, np.int64)
     if shared_prefix:
         sp = shared_prefix
-        prefixes = [_exact_row(rng, int(rng.integers(sp["min_blocks"], sp["max_blocks"] + 1)) * sp["block_tokens"],
-                               wtc, by_count, max_cnt, V, est_words) for _ in range(sp["n_prefixes"])]
-        pref_tok = [int(wtc[p].sum()) for p in prefixes]
-        pref_p = zipf_probs(sp["n_prefixes"])
-    rows = []
-    chunk = 2048
+        n_pref = sp["n_prefixes"]
+        pref_blk_np = rng.integers(sp["min_blocks"], sp["max_blocks"] + 1, size=n_pref)
+        pref_rows = [_exact_row(rng, int(b) * sp["block_tokens"], wtc_np, by_count, max_cnt, V, est_words)
+                     for b in pref_blk_np]
+        pref_tok = T(pref_blk_np * sp["block_tokens"])
+        pref_cdf = T(np.cumsum(zipf_probs(n_pref)))
+        pref_len = T(np.array([len(p) for p in pref_rows], dtype=np.int64))
+        pref_flat = T(np.concatenate(pref_rows).astype(np.int64))
+        pref_off = torch.cumsum(pref_len, 0) - pref_len
+    prefix_id = np.full(n_prompts, -1, dtype=np.int32)
+    texts, lens_all = [], []
     for c0 in range(0, n_prompts, chunk):
         m = min(chunk, n_prompts - c0)
-        ids = sample_word_ids(rng, m, est_words, V)
-        csum = np.cumsum(wtc[ids], axis=1)
-        for i in range(m):
-            budget = n_tokens
-            head = None
-            if prefixes is not None and rng.random() < shared_prefix["frac"]:
-                j = int(rng.choice(len(prefixes), p=pref_p))
-                if pref_tok[j] <= n_tokens:
-                    head = prefixes[j]
-                    budget = n_tokens - pref_tok[j]
-            k = int(np.searchsorted(csum[i], budget, side="right"))  # words that fit entirely
-            rem = budget - (int(csum[i, k - 1]) if k else 0)
-            parts = [ids[i, :k]]
-            if rem:
-                parts.append(np.asarray(_fill_exact(rng, rem, by_count, max_cnt), dtype=np.int32))
-            if head is not None:
-                parts.insert(0, head)
-            rows.append(np.concatenate(parts).astype(np.int32))
-    return rows_to_batch(rows, vocab, word_len, word_off, flat), rows
-
-
-def rows_to_batch(rows, vocab, word_len=None, word_off=None, flat=None):
-    """Materialise word-id rows as text: words joined by single spaces."""
-    if word_len is None:
-        word_len = np.array([len(w) for w in vocab], dtype=np.int64)
-        flat = np.frombuffer(b"".join(vocab), dtype=np.uint8)
-        word_off = np.zeros(len(vocab) + 1, dtype=np.int64)
-        np.cumsum(word_len, out=word_off[1:])
-    n = len(rows)
-    lens = np.array([int(word_len[r].sum()) + max(len(r) - 1, 0) for r in rows], dtype=np.int64)
-    offsets = np.zeros(n + 1, dtype=np.int64)
+        pid = torch.full((m,), -1, dtype=torch.int64, device=dev)
+        if shared_prefix:
+            use = torch.rand(m, generator=gen, device=dev) < shared_prefix["frac"]
+            pick = torch.clamp(torch.searchsorted(pref_cdf, torch.rand(m, generator=gen, device=dev,
+                                                                       dtype=torch.float64)), max=n_pref - 1)
+            pid = torch.where(use & (pref_tok[pick] <= n_tokens), pick, pid)
+        has = pid >= 0
+        budget = torch.full((m,), n_tokens, dtype=torch.int64, device=dev)
+        plen = torch.zeros(m, dtype=torch.int64, device=dev)
+        if shared_prefix:
+            safe = torch.clamp(pid, min=0)
+            budget = torch.where(has, budget - pref_tok[safe], budget)
+            plen = torch.where(has, pref_len[safe], plen)
+        u = torch.rand((m, est_words), generator=gen, device=dev, dtype=torch.float64)
+        ids = torch.clamp(torch.searchsorted(zipf_cdf, u), max=V - 1)
+        csum = torch.cumsum(wtc[ids], 1)
+        k = (csum <= budget[:, None]).sum(1)                                # body words that fit entirely
+        assert bool((k < est_words).all())
+        used = torch.where(k > 0, csum.gather(1, torch.clamp(k - 1, min=0)[:, None])[:, 0], torch.zeros_like(k))
+        rem = budget - used                                                  # 0 .. max_cnt - 1
+        tail = torch.full((m,), -1, dtype=torch.int64, device=dev)
+        for c in range(1, max_cnt):
+            sel = rem == c
+            cnt = int(sel.sum())
+            if cnt:
+                tail[sel] = by_count_t[c][torch.randint(0, by_count_t[c].numel(), (cnt,), generator=gen, device=dev)]
+        assert bool(((rem == 0) | (tail >= 0)).all())
+        has_tail = tail >= 0
+        nw = plen + k + has_tail.to(torch.int64)
+        width = int(nw.max())
+        M = torch.full((m, width), -1, dtype=torch.int64, device=dev)
+        if shared_prefix and bool(has.any()):                                # prefix words
+            hp = plen[has]
+            rr = torch.repeat_interleave(torch.nonzero(has)[:, 0], hp)
+            cc = torch.arange(int(hp.sum()), device=dev) - torch.repeat_interleave(torch.cumsum(hp, 0) - hp, hp)
+            M[rr, cc] = pref_flat[torch.repeat_interleave(pref_off[pid[has]], hp) + cc]
+        body = torch.arange(est_words, device=dev)[None, :] < k[:, None]
+        rc = torch.nonzero(body)
+        M[rc[:, 0], plen[rc[:, 0]] + rc[:, 1]] = ids[rc[:, 0], rc[:, 1]]
+        tr = torch.nonzero(has_tail)[:, 0]
+        M[tr, (plen + k)[tr]] = tail[tr]
+        words = M[M >= 0]
+        text, lens = _materialise(words, nw, word_len, word_off, flat)
+        texts.append(text.cpu().numpy())
+        lens_all.append(lens.cpu().numpy())
+        prefix_id[c0:c0 + m] = pid.cpu().numpy()
+    lens = np.concatenate(lens_all) if lens_all else np.zeros(0, np.int64)
+    offsets = np.zeros(n_prompts + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
-    text = np.full(int(offsets[-1]), 32, dtype=np.uint8)
-    for i, r in enumerate(rows):
-        if len(r) == 0:
-            continue
-        wl = word_len[r]
-        tot = int(wl.sum())
-        excl = np.concatenate([[0], np.cumsum(wl[:-1])])          # exclusive prefix of word lengths
-        dst0 = offsets[i] + excl + np.arange(len(r))               # +1 space per preceding word
-        ar = np.arange(tot) - np.repeat(excl, wl)                  # byte index inside its word
-        text[np.repeat(dst0, wl) + ar] = flat[np.repeat(word_off[r], wl) + ar]
-    return PromptBatch(text, offsets)
+    text = np.concatenate(texts) if texts else np.zeros(0, np.uint8)
+    pb = np.zeros(n_prompts, dtype=np.int32)
+    if shared_prefix:
+        pb[prefix_id >= 0] = pref_blk_np[prefix_id[prefix_id >= 0]]
+    meta = {"prefix_id": prefix_id, "prefix_blocks": pb, "n_prefixes": n_pref}
+    return PromptBatch(text, offsets), meta
