@@ -32,10 +32,12 @@ namespace xllm {
 namespace {
 
 constexpr int kNBuf = 4096;        // normalized-text staging buffer per warp (bytes)
+constexpr int kFastWin = 128;      // source bytes per fast-path step (4 per lane)
 constexpr int kMaxSym = 32;        // lane-per-word fast path: chars per word
 constexpr int kCoopMaxSym = 1024;  // warp-cooperative path: chars per word
 constexpr int kMaxWords = 1408;    // >= kNBuf / 3 + 1 word starts
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kResolvedFlag = 0x40000000u;  // S[] entry holds a token id, not a symbol (bit 31 clear)
 
 struct WarpSmem {
   uint32_t S[kCoopMaxSym];   // symbols: lane columns S[j * 32 + lane] (fast path) or flat (cooperative path)
@@ -158,6 +160,9 @@ struct ReqState {
   int64_t n_out;        // ids produced so far (may exceed cap)
   int32_t nlen;         // bytes in nbuf
   int32_t trailing_bare;  // ids emitted by the current run of trailing bare-U+2581 words
+  int32_t nw;           // word starts recorded so far in wstart[] (valid when !rescan)
+  bool rescan;          // a general-path window ran since the last drain: word starts must be re-derived
+  bool ascii;           // nbuf holds only ASCII and U+2581 (written by the fast path)
   bool prev_space;      // normalizer's is_prev_space
   bool prev_unk;        // last emitted symbol was unknown (byte_fallback off only)
   bool too_long;
@@ -273,7 +278,92 @@ __device__ __forceinline__ void normalize_window(const SpDev& T, WarpSmem& sm, R
     }
   }
   rs.nlen += total;
+  rs.rescan = true;   // word starts of this window are not tracked incrementally
+  rs.ascii = false;
   __syncwarp();
+}
+
+// Fast path: 128 source bytes per step, 4 per lane, valid when every byte is a "simple" ASCII byte
+// (SpTables::simple_ascii) and is followed by another ASCII byte: then every byte is its own unit and
+// normalises to itself, so only the whitespace rules remain:  a space is dropped iff the byte before it
+// is a space (is_prev_space), kept spaces become U+2581 and start a word.  Returns false (nothing done)
+// when the window does not qualify.
+__device__ __forceinline__ bool normalize_fast(const SpDev& T, WarpSmem& sm, ReqState& rs, uint32_t pos, int lane) {
+  const uint32_t base = pos + 4u * lane;
+  const uint32_t nvalid = base >= rs.len ? 0u : (rs.len - base < 4u ? rs.len - base : 4u);
+  const uint8_t* p = rs.src + base;
+  uint32_t b[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) b[k] = (uint32_t)k < nvalid ? __ldg(p + k) : 0x61u;
+  uint32_t nextb = __shfl_down_sync(kFull, b[0], 1);
+  if (lane == 31) nextb = base + 4 < rs.len ? __ldg(p + 4) : 0x61u;
+  bool ok = nextb < 0x80 || nvalid < 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    ok = ok && ((uint32_t)k >= nvalid || (b[k] < 0x80 && ((T.simple_ascii[(b[k] >> 5) & 3] >> (b[k] & 31)) & 1u)));
+  if (!__all_sync(kFull, ok)) return false;
+
+  bool sp[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sp[k] = (uint32_t)k < nvalid && b[k] == ' ';
+  // is the byte before this lane's first byte a space?  (lanes before a valid lane are full)
+  const bool last_sp = sp[3];
+  bool prev = __shfl_up_sync(kFull, last_sp, 1);
+  if (lane == 0) {
+    // remove_extra_whitespaces: the normalizer's is_prev_space; otherwise "the last emitted char is U+2581"
+    const int nl = rs.nlen;
+    prev = T.remove_extra_ws ? rs.prev_space
+                             : (nl >= 3 && sm.nbuf[nl - 3] == 0xE2 && sm.nbuf[nl - 2] == 0x96 && sm.nbuf[nl - 1] == 0x81);
+  }
+  const bool buffer_empty = rs.nlen == 0;  // offset 0 is a word start by definition: do not record it twice
+  uint32_t out_len = 0, n_start = 0;
+  uint32_t keep = 0, start = 0;  // bit k: byte k is emitted / starts a word
+  bool pv = prev;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if ((uint32_t)k < nvalid) {
+      const bool drop = T.remove_extra_ws && sp[k] && pv;
+      if (!drop) {
+        keep |= 1u << k;
+        out_len += sp[k] ? 3u : 1u;
+        const bool at_zero = buffer_empty && lane == 0 && out_len == (sp[k] ? 3u : 1u);
+        if (sp[k] && !at_zero && (T.split_mode == 1 || (T.split_mode == 2 && !pv))) { start |= 1u << k; ++n_start; }
+      }
+      pv = sp[k];
+    }
+  }
+  const int packed = (int)(out_len | (n_start << 16));
+  const int incl = warp_incl_scan(packed, lane);
+  const int total = __shfl_sync(kFull, incl, 31);
+  if (buffer_empty) {
+    if (lane == 0) sm.wstart[0] = 0;
+    rs.nw = 1;
+  }
+  uint32_t o = (uint32_t)rs.nlen + ((uint32_t)(incl - packed) & 0xFFFFu);
+  uint32_t wi = (uint32_t)rs.nw + ((uint32_t)(incl - packed) >> 16);
+  uint8_t* d = sm.nbuf;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if ((keep >> k) & 1u) {
+      if (sp[k]) {
+        if ((start >> k) & 1u) sm.wstart[wi++] = (uint16_t)o;
+        d[o] = 0xE2; d[o + 1] = 0x96; d[o + 2] = 0x81;
+        o += 3;
+      } else {
+        d[o++] = (uint8_t)b[k];
+      }
+    }
+  }
+  // is_prev_space after the window = the last source byte is a space (every unit here is non-empty)
+  const uint32_t n_in = rs.len - pos < (uint32_t)kFastWin ? rs.len - pos : (uint32_t)kFastWin;
+  const uint32_t last_lane = (n_in - 1) >> 2, last_k = (n_in - 1) & 3;
+  const bool mine = last_k == 0 ? sp[0] : (last_k == 1 ? sp[1] : (last_k == 2 ? sp[2] : sp[3]));
+  const bool ws = __shfl_sync(kFull, mine, last_lane);
+  if (T.remove_extra_ws) rs.prev_space = ws;
+  rs.nlen += total & 0xFFFF;
+  rs.nw += total >> 16;
+  __syncwarp();
+  return true;
 }
 
 // ---------------------------------------------------------------------------- word merge
@@ -371,21 +461,30 @@ __device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, in
   }
   if (nlen == 0) { rs.nlen = 0; return; }
 
-  // 1. word starts
+  // 1. word starts: recorded by the fast path, or re-derived after any general-path window
   int nwords = 0;
-  for (int base = 0; base < nlen; base += 32) {
-    const int p = base + lane;
-    bool st = false;
-    if (p < nlen) {
-      if (p == 0) st = true;
-      else if (T.split_mode != 0 && is_space_at(nb, p, nlen)) {
-        st = T.split_mode == 1 || !(p >= 3 && is_space_at(nb, p - 3, nlen));
+  if (!rs.rescan && !(final && nlen != rs.nlen)) {
+    nwords = rs.nw;
+  } else if (!rs.rescan) {
+    // trailing U+2581 were stripped: drop the starts that now lie at or past the end
+    nwords = rs.nw;
+    while (nwords > 1 && sm.wstart[nwords - 1] >= nlen) --nwords;
+  } else {
+    for (int base = 0; base < nlen; base += 32) {
+      const int p = base + lane;
+      bool st = false;
+      if (p < nlen) {
+        if (p == 0) st = true;
+        else if (T.split_mode != 0 && is_space_at(nb, p, nlen)) {
+          st = T.split_mode == 1 || !(p >= 3 && is_space_at(nb, p - 3, nlen));
+        }
       }
+      const uint32_t m = __ballot_sync(kFull, st);
+      if (st) sm.wstart[nwords + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
+      nwords += __popc(m);
     }
-    const uint32_t m = __ballot_sync(kFull, st);
-    if (st) sm.wstart[nwords + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
-    nwords += __popc(m);
   }
+  __syncwarp();
   if (lane == 0) sm.wstart[nwords] = (uint16_t)nlen;
   __syncwarp();
   const int complete = final ? nwords : nwords - 1;
@@ -399,7 +498,9 @@ __device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, in
     if (have) {
       ws = sm.wstart[w];
       we = sm.wstart[w + 1];
-      for (int p = ws; p < we; ++p) nsym += (nb[p] & 0xC0) != 0x80;
+      if (rs.ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
+      else
+        for (int p = ws; p < we; ++p) nsym += (nb[p] & 0xC0) != 0x80;
     }
     const uint32_t long_mask = __ballot_sync(kFull, have && nsym > kMaxSym);
     const int first_long = long_mask ? __ffs(long_mask) - 1 : 32;
@@ -419,14 +520,18 @@ __device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, in
       }
       bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
       alive = lane_merge(T, sm, n, lane);
+      // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
+      // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
       bool pu = false, first = true;
       for (uint32_t m = alive; m;) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
         int32_t tmp[4];
         bool unk;
-        const int c = sym_ids(T, sm.S[j * 32 + lane], tmp, &unk);
+        const uint32_t sym = sm.S[j * 32 + lane];
+        const int c = sym_ids(T, sym, tmp, &unk);
         if (first) { first_unk = unk; first = false; }
+        if (!unk) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
         if (!(unk && pu && !T.byte_fallback)) cnt += c;
         pu = unk;
       }
@@ -451,13 +556,19 @@ __device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, in
       for (uint32_t m = alive; m;) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        int32_t tmp[4];
-        bool unk;
-        const int c = sym_ids(T, sm.S[j * 32 + lane], tmp, &unk);
-        const bool skip = (unk && pu && !T.byte_fallback) || (first && drop_first);
-        if (!skip)
-          for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
-        pu = unk;
+        const uint32_t sym = sm.S[j * 32 + lane];
+        if ((sym & 0xC0000000u) == kResolvedFlag) {  // known symbol: one id
+          put_id(rs, o++, (int32_t)(sym & 0x3FFFFFFFu));
+          pu = false;
+        } else {
+          int32_t tmp[4];
+          bool unk;
+          const int c = sym_ids(T, sym, tmp, &unk);
+          const bool skip = (unk && pu && !T.byte_fallback) || (first && drop_first);
+          if (!skip)
+            for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
+          pu = unk;
+        }
         first = false;
       }
     }
@@ -540,9 +651,20 @@ __device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, in
       }
     }
     rs.nlen = tl;
+    if (lane == 0) sm.wstart[0] = 0;
+    rs.nw = 1;
+    if (!rs.ascii) {  // the kept tail decides whether the buffer is ASCII-only again
+      bool non_ascii = false;
+      const bool lead = tl >= 3 && sm.nbuf[0] == 0xE2 && sm.nbuf[1] == 0x96 && sm.nbuf[2] == 0x81;
+      for (int k = lane; k < tl; k += 32) non_ascii |= sm.nbuf[k] >= 0x80 && !(lead && k < 3);
+      rs.ascii = !__any_sync(kFull, non_ascii);
+    }
   } else {
     rs.nlen = 0;
+    rs.nw = 0;
+    rs.ascii = true;
   }
+  rs.rescan = false;
   __syncwarp();
 }
 
@@ -572,19 +694,28 @@ __global__ void __launch_bounds__(32) sp_encode_kernel(const uint8_t* __restrict
     rs.n_out = 0;
     rs.nlen = 0;
     rs.trailing_bare = 0;
+    rs.nw = 0;
+    rs.rescan = false;
+    rs.ascii = true;
     rs.prev_space = T.remove_extra_ws;
     rs.prev_unk = false;
     rs.too_long = false;
 
     if (rs.len > 0) {
       if (T.add_dummy_prefix) {
-        if (lane == 0) { sm.nbuf[0] = 0xE2; sm.nbuf[1] = 0x96; sm.nbuf[2] = 0x81; }
+        if (lane == 0) { sm.nbuf[0] = 0xE2; sm.nbuf[1] = 0x96; sm.nbuf[2] = 0x81; sm.wstart[0] = 0; }
         rs.nlen = 3;
+        rs.nw = 1;
       }
       __syncwarp();
       uint32_t carry_skip = 0;
-      for (uint32_t pos = 0; pos < rs.len; pos += 32) {
-        normalize_window(T, sm, rs, pos, carry_skip, lane);
+      for (uint32_t pos = 0; pos < rs.len;) {
+        if (carry_skip == 0 && normalize_fast(T, sm, rs, pos, lane)) {
+          pos += kFastWin;
+        } else {
+          normalize_window(T, sm, rs, pos, carry_skip, lane);
+          pos += 32;
+        }
         if (rs.nlen > drain_at) {
           drain(T, sm, rs, false, lane);
           if (rs.nlen > drain_at) {  // one pre-token longer than the staging buffer
@@ -655,6 +786,7 @@ int SpDeviceModel::upload(const SpTables& t) {
   dev_.space_sym = t.space_sym;
   dev_.unk_id = t.unk_id;
   dev_.max_unit_out = t.max_unit_out;
+  for (int i = 0; i < 4; ++i) dev_.simple_ascii[i] = t.simple_ascii[i];
   dev_.byte_fallback = t.byte_fallback;
   dev_.add_dummy_prefix = t.add_dummy_prefix;
   dev_.remove_extra_ws = t.remove_extra_whitespaces;

@@ -28,6 +28,7 @@ struct SpDev {
   uint32_t space_sym;
   int32_t unk_id;
   uint32_t max_unit_out;
+  uint32_t simple_ascii[4];
   uint8_t byte_fallback, add_dummy_prefix, remove_extra_ws, split_mode;
 };
 

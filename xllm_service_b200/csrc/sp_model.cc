@@ -264,6 +264,27 @@ int sp_load_model(const std::string& path_in, SpTables* t) {
     t->blob.assign(m.charsmap.begin() + 4 + trie_bytes, m.charsmap.end());
     t->blob.push_back(0);  // make every replacement NUL-terminated even if the blob is not
   }
+  if (!t->trie.empty()) {
+    // classify ASCII first bytes against the Darts trie (see SpTables::simple_ascii)
+    const std::vector<uint32_t>& tr = t->trie;
+    auto off = [](uint32_t u) { return (u >> 10) << ((u & 0x200u) >> 6); };
+    const uint32_t root = off(tr[0]);
+    for (uint32_t b = 0; b < 128; ++b) {
+      bool simple = true;
+      const uint32_t node = root ^ b;
+      if (node < tr.size() && (tr[node] & 0x800000FFu) == b) {
+        const uint32_t u = tr[node];
+        if ((u >> 8) & 1u) simple = false;  // b alone is a key
+        const uint32_t next = node ^ off(u);
+        for (uint32_t c = 0; c < 128 && simple; ++c) {
+          const uint32_t ch = next ^ c;
+          if (ch < tr.size() && (tr[ch] & 0x800000FFu) == c && c != 0) simple = false;  // continues with ASCII
+        }
+      }
+      if (b == 0) simple = false;  // NUL always takes the general path
+      if (!simple) t->simple_ascii[b >> 5] &= ~(1u << (b & 31));
+    }
+  }
   {
     // the longest escaped replacement bounds what one unit can append (U+FFFD / identity: <= 4; ' ' -> 3)
     uint32_t cur = 0, mx = 4;

@@ -31,6 +31,9 @@ struct SpTables {
   std::vector<uint32_t> trie;
   std::vector<uint8_t> blob;
   uint32_t max_unit_out = 3;  // max bytes one normalisation unit can append to the normalized stream
+  // bit b set <=> ASCII byte b is "simple": the charsmap has no key that is exactly b and every longer key
+  // starting with b continues with a byte >= 0x80, so b followed by an ASCII byte normalises to itself
+  uint32_t simple_ascii[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
   bool add_dummy_prefix = true;
   bool remove_extra_whitespaces = true;
   // symbols: [0, n_pieces) = piece ids; [n_pieces, n_syms) = single chars that occur inside
