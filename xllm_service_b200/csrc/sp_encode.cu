@@ -23,6 +23,7 @@
 // Algorithmic HBM traffic: text bytes read once + 4 B per id written.
 #include "sp_encode.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -31,18 +32,42 @@ namespace xllm {
 
 namespace {
 
-constexpr int kNBuf = 4096;        // normalized-text staging buffer per warp (bytes)
+constexpr int kNBuf = 2048;        // normalized-text staging buffer per warp (bytes)
 constexpr int kFastWin = 128;      // source bytes per fast-path step (4 per lane)
 constexpr int kMaxSym = 32;        // lane-per-word fast path: chars per word
 constexpr int kCoopMaxSym = 1024;  // warp-cooperative path: chars per word
-constexpr int kMaxWords = 1408;    // >= kNBuf / 3 + 1 word starts
+constexpr int kMaxWords = 704;     // >= kNBuf / 3 + 2 word starts
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kResolvedFlag = 0x40000000u;  // S[] entry holds a token id, not a symbol (bit 31 clear)
 
-struct WarpSmem {
-  uint32_t S[kCoopMaxSym];   // symbols: lane columns S[j * 32 + lane] (fast path) or flat (cooperative path)
-  uint2 PM[kCoopMaxSym];     // (priority, merged symbol) of the pair starting at j
-  uint8_t nbuf[kNBuf];       // normalized text (always starts at a word start)
+// (priority, merged symbol) of the pair starting at a position.  SMALL (ranks and piece ids < 65535):
+// packed into one u32 so a warp's merge scratch is 8 KB instead of 12 KB (more resident warps per SM).
+template <bool SMALL>
+struct PMOps;
+template <>
+struct PMOps<false> {
+  using T = uint2;
+  static constexpr uint32_t kNone = kNoPrio;
+  static __device__ __forceinline__ T pack(uint2 v) { return v; }
+  static __device__ __forceinline__ T none() { return make_uint2(kNoPrio, 0); }
+  static __device__ __forceinline__ uint32_t prio(T v) { return v.x; }
+  static __device__ __forceinline__ uint32_t merged(T v) { return v.y; }
+};
+template <>
+struct PMOps<true> {
+  using T = uint32_t;
+  static constexpr uint32_t kNone = 0xFFFFu;
+  static __device__ __forceinline__ T pack(uint2 v) { return v.x == kNoPrio ? 0xFFFF0000u : ((v.x << 16) | v.y); }
+  static __device__ __forceinline__ T none() { return 0xFFFF0000u; }
+  static __device__ __forceinline__ uint32_t prio(T v) { return v >> 16; }
+  static __device__ __forceinline__ uint32_t merged(T v) { return v & 0xFFFFu; }
+};
+
+template <bool SMALL>
+struct WarpSmemT {
+  uint32_t S[kCoopMaxSym];                   // symbols: lane columns S[j * 32 + lane] (lane path) or flat (cooperative)
+  typename PMOps<SMALL>::T PM[kCoopMaxSym];  // pair state at position j
+  uint8_t nbuf[kNBuf];                       // normalized text (always starts at a word start)
   uint16_t wstart[kMaxWords];
 };
 
@@ -175,7 +200,8 @@ __device__ __forceinline__ void put_id(ReqState& rs, int64_t pos, int32_t id) {
 // ---------------------------------------------------------------------------- normalisation
 // Normalises source bytes [pos, pos + 32) (units that START in that window) and appends the result to nbuf.
 // carry_skip: leading bytes of the window already consumed by the previous window's last unit.
-__device__ __forceinline__ void normalize_window(const SpDev& T, WarpSmem& sm, ReqState& rs, uint32_t pos,
+template <typename SM>
+__device__ __forceinline__ bool normalize_window(const SpDev& T, SM& sm, ReqState& rs, uint32_t pos,
                                                  uint32_t& carry_skip, int lane) {
   const uint32_t i = pos + lane;
   const bool inb = i < rs.len;
@@ -231,7 +257,7 @@ __device__ __forceinline__ void normalize_window(const SpDev& T, WarpSmem& sm, R
     }
     q_end = q;
   }
-  carry_skip = q_end >= 32 ? q_end - 32 : 0;  // only meaningful when another window follows (n_in == 32)
+  const uint32_t new_carry = q_end >= 32 ? q_end - 32 : 0;  // only meaningful when another window follows
   const bool is_start = (starts >> lane) & 1u;
 
   // replacement attributes
@@ -255,17 +281,21 @@ __device__ __forceinline__ void normalize_window(const SpDev& T, WarpSmem& sm, R
   const bool nonempty = is_start && rlen > 0;
   const bool all_sp = nonempty && lead_sp == rlen;
   uint32_t strip = 0;
+  bool new_prev_space = rs.prev_space;
   if (T.remove_extra_ws) {
     const uint32_t ne_mask = __ballot_sync(kFull, nonempty);
     const uint32_t set_mask = __ballot_sync(kFull, nonempty && (all_sp || ends_sp));
     const uint32_t below = ne_mask & ((1u << lane) - 1);
     const bool state_before = below ? ((set_mask >> (31 - __clz(below))) & 1u) : rs.prev_space;
     if (state_before) strip = lead_sp;
-    if (ne_mask) rs.prev_space = (set_mask >> (31 - __clz(ne_mask))) & 1u;
+    if (ne_mask) new_prev_space = (set_mask >> (31 - __clz(ne_mask))) & 1u;
   }
   const int out_len = is_start ? (int)((rlen - strip) + 2 * (n_sp - strip)) : 0;
   const int incl = warp_incl_scan(out_len, lane);
   const int total = __shfl_sync(kFull, incl, 31);
+  if (rs.nlen + total > kNBuf) return false;  // does not fit: the caller drains and retries this window
+  carry_skip = new_carry;
+  rs.prev_space = new_prev_space;
   if (out_len) {
     uint8_t* d = sm.nbuf + rs.nlen + (incl - out_len);
     const uint8_t* r = kind == 1 ? T.blob + val : p;
@@ -281,6 +311,7 @@ __device__ __forceinline__ void normalize_window(const SpDev& T, WarpSmem& sm, R
   rs.rescan = true;   // word starts of this window are not tracked incrementally
   rs.ascii = false;
   __syncwarp();
+  return true;
 }
 
 // Fast path: 128 source bytes per step, 4 per lane, valid when every byte is a "simple" ASCII byte
@@ -288,7 +319,8 @@ __device__ __forceinline__ void normalize_window(const SpDev& T, WarpSmem& sm, R
 // normalises to itself, so only the whitespace rules remain:  a space is dropped iff the byte before it
 // is a space (is_prev_space), kept spaces become U+2581 and start a word.  Returns false (nothing done)
 // when the window does not qualify.
-__device__ __forceinline__ bool normalize_fast(const SpDev& T, WarpSmem& sm, ReqState& rs, uint32_t pos, int lane) {
+template <typename SM>
+__device__ __forceinline__ bool normalize_fast(const SpDev& T, SM& sm, ReqState& rs, uint32_t pos, int lane) {
   const uint32_t base = pos + 4u * lane;
   const uint32_t nvalid = base >= rs.len ? 0u : (rs.len - base < 4u ? rs.len - base : 4u);
   const uint8_t* p = rs.src + base;
@@ -369,33 +401,35 @@ __device__ __forceinline__ bool normalize_fast(const SpDev& T, WarpSmem& sm, Req
 // ---------------------------------------------------------------------------- word merge
 // Fast path: this lane owns word [ws, we) with n <= 32 chars; symbols live in column `lane` of S / PM.
 // Returns the alive mask after all merges.
-__device__ __forceinline__ uint32_t lane_merge(const SpDev& T, WarpSmem& sm, int n, int lane) {
+template <bool SMALL, typename SM>
+__device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, int lane) {
+  using P = PMOps<SMALL>;
   uint32_t* S = sm.S + lane;
-  uint2* PM = sm.PM + lane;
-  for (int j = 0; j + 1 < n; ++j) PM[j * 32] = pair_lookup(T, S[j * 32], S[(j + 1) * 32]);
-  PM[(n - 1) * 32] = make_uint2(kNoPrio, 0);
+  typename P::T* PM = sm.PM + lane;
+  for (int j = 0; j + 1 < n; ++j) PM[j * 32] = P::pack(pair_lookup(T, S[j * 32], S[(j + 1) * 32]));
+  PM[(n - 1) * 32] = P::none();
   uint32_t alive = n == 32 ? kFull : ((1u << n) - 1);
   for (;;) {
-    uint32_t best = kNoPrio;
+    uint32_t best = P::kNone;
     int bj = 0;
     for (uint32_t m = alive; m;) {
       const int j = __ffs(m) - 1;
       m &= m - 1;
-      const uint32_t pr = PM[j * 32].x;
+      const uint32_t pr = P::prio(PM[j * 32]);
       if (pr < best) { best = pr; bj = j; }
     }
-    if (best == kNoPrio) break;
+    if (best == P::kNone) break;
     const uint32_t hi_mask = ~((2u << bj) - 1u);  // bits above bj (bj == 31 -> 0)
     const int rj = __ffs(alive & hi_mask) - 1;
-    S[bj * 32] = PM[bj * 32].y;
+    S[bj * 32] = P::merged(PM[bj * 32]);
     alive &= ~(1u << rj);
     const uint32_t above = alive & hi_mask;
-    if (above) PM[bj * 32] = pair_lookup(T, S[bj * 32], S[(__ffs(above) - 1) * 32]);
-    else PM[bj * 32].x = kNoPrio;
+    if (above) PM[bj * 32] = P::pack(pair_lookup(T, S[bj * 32], S[(__ffs(above) - 1) * 32]));
+    else PM[bj * 32] = P::none();
     const uint32_t below = alive & ((1u << bj) - 1u);
     if (below) {
       const int pj = 31 - __clz(below);
-      PM[pj * 32] = pair_lookup(T, S[pj * 32], S[bj * 32]);
+      PM[pj * 32] = P::pack(pair_lookup(T, S[pj * 32], S[bj * 32]));
     }
   }
   return alive;
@@ -403,14 +437,16 @@ __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, WarpSmem& sm, int
 
 // Cooperative path: the whole warp merges one word of n (33..1024) chars held flat in S[0..n).
 // Returns the final symbol count; S[0..ret) are the final symbols in order.
-__device__ int coop_merge(const SpDev& T, WarpSmem& sm, int n, int lane) {
+template <bool SMALL, typename SM>
+__device__ int coop_merge(const SpDev& T, SM& sm, int n, int lane) {
+  using P = PMOps<SMALL>;
   for (int j = lane; j < n; j += 32)
-    sm.PM[j] = j + 1 < n ? pair_lookup(T, sm.S[j], sm.S[j + 1]) : make_uint2(kNoPrio, 0);
+    sm.PM[j] = j + 1 < n ? P::pack(pair_lookup(T, sm.S[j], sm.S[j + 1])) : P::none();
   __syncwarp();
   for (;;) {
     unsigned long long best = ~0ull;
     for (int j = lane; j + 1 < n; j += 32) {
-      const unsigned long long key = ((unsigned long long)sm.PM[j].x << 32) | (unsigned)j;
+      const unsigned long long key = ((unsigned long long)P::prio(sm.PM[j]) << 32) | (unsigned)j;
       best = key < best ? key : best;
     }
 #pragma unroll
@@ -418,28 +454,28 @@ __device__ int coop_merge(const SpDev& T, WarpSmem& sm, int n, int lane) {
       const unsigned long long t = __shfl_xor_sync(kFull, best, o);
       best = t < best ? t : best;
     }
-    if ((uint32_t)(best >> 32) == kNoPrio) break;
+    if ((uint32_t)(best >> 32) >= P::kNone) break;
     const int bj = (int)(uint32_t)best;
-    const uint32_t merged = sm.PM[bj].y;
+    const uint32_t merged = P::merged(sm.PM[bj]);
     __syncwarp();
     // remove position bj + 1: shift the tail left by one (tiles in increasing order)
     for (int base = bj + 1; base < n - 1; base += 32) {
       const int k = base + lane;
-      uint32_t s = 0;
-      uint2 pm = make_uint2(kNoPrio, 0);
+      uint32_t sv = 0;
+      typename P::T pm = P::none();
       const bool act = k < n - 1;
-      if (act) { s = sm.S[k + 1]; pm = sm.PM[k + 1]; }
+      if (act) { sv = sm.S[k + 1]; pm = sm.PM[k + 1]; }
       __syncwarp();
-      if (act) { sm.S[k] = s; sm.PM[k] = pm; }
+      if (act) { sm.S[k] = sv; sm.PM[k] = pm; }
       __syncwarp();
     }
     --n;
     if (lane == 0) {
       sm.S[bj] = merged;
-      sm.PM[bj] = bj + 1 < n ? pair_lookup(T, merged, sm.S[bj + 1]) : make_uint2(kNoPrio, 0);
+      sm.PM[bj] = bj + 1 < n ? P::pack(pair_lookup(T, merged, sm.S[bj + 1])) : P::none();
     }
     __syncwarp();
-    if (lane == 1 && bj > 0) sm.PM[bj - 1] = pair_lookup(T, sm.S[bj - 1], sm.S[bj]);
+    if (lane == 1 && bj > 0) sm.PM[bj - 1] = P::pack(pair_lookup(T, sm.S[bj - 1], sm.S[bj]));
     __syncwarp();
   }
   return n;
@@ -451,7 +487,8 @@ __device__ __forceinline__ bool is_space_at(const uint8_t* b, int p, int n) {
 }
 
 // Tokenises the complete words held in nbuf (all words when final) and keeps the incomplete tail.
-__device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, int lane) {
+template <bool SMALL, typename SM>
+__device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane) {
   const uint8_t* nb = sm.nbuf;
   int nlen = rs.nlen;
   if (final && T.remove_extra_ws) {
@@ -519,7 +556,7 @@ __device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, in
         ++n;
       }
       bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
-      alive = lane_merge(T, sm, n, lane);
+      alive = lane_merge<SMALL>(T, sm, n, lane);
       // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
       // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
       bool pu = false, first = true;
@@ -608,7 +645,7 @@ __device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, in
       if (overflow) {
         rs.too_long = true;
       } else {
-        n = coop_merge(T, sm, n, lane);
+        n = coop_merge<SMALL>(T, sm, n, lane);
         for (int base = 0; base < n; base += 32) {
           const int j = base + lane;
           int32_t tmp[4];
@@ -668,6 +705,7 @@ __device__ void drain(const SpDev& T, WarpSmem& sm, ReqState& rs, bool final, in
   __syncwarp();
 }
 
+template <bool SMALL>
 __global__ void __launch_bounds__(32) sp_encode_kernel(const uint8_t* __restrict__ text,
                                                        const int64_t* __restrict__ offsets, int n_req,
                                                        int32_t* __restrict__ ids, int64_t ids_stride,
@@ -675,9 +713,10 @@ __global__ void __launch_bounds__(32) sp_encode_kernel(const uint8_t* __restrict
                                                        const __grid_constant__ SpDev T,
                                                        unsigned int* __restrict__ task_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpSmem& sm = *reinterpret_cast<WarpSmem*>(smem_raw);
+  using SM = WarpSmemT<SMALL>;
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int lane = threadIdx.x;
-  const int drain_at = kNBuf - 32 * (int)T.max_unit_out - 8;
+  const int drain_at = kNBuf - 3 * kFastWin - 8;  // room for one more fast-path step
 
   for (;;) {
     unsigned int r = 0;
@@ -713,18 +752,24 @@ __global__ void __launch_bounds__(32) sp_encode_kernel(const uint8_t* __restrict
         if (carry_skip == 0 && normalize_fast(T, sm, rs, pos, lane)) {
           pos += kFastWin;
         } else {
-          normalize_window(T, sm, rs, pos, carry_skip, lane);
+          if (!normalize_window(T, sm, rs, pos, carry_skip, lane)) {
+            drain<SMALL>(T, sm, rs, false, lane);  // make room, then this window must fit
+            if (!normalize_window(T, sm, rs, pos, carry_skip, lane)) {
+              rs.too_long = true;
+              break;
+            }
+          }
           pos += 32;
         }
         if (rs.nlen > drain_at) {
-          drain(T, sm, rs, false, lane);
+          drain<SMALL>(T, sm, rs, false, lane);
           if (rs.nlen > drain_at) {  // one pre-token longer than the staging buffer
             rs.too_long = true;
             break;
           }
         }
       }
-      if (!rs.too_long) drain(T, sm, rs, true, lane);
+      if (!rs.too_long) drain<SMALL>(T, sm, rs, true, lane);
     }
     if (lane == 0) {
       n_ids[r] = rs.too_long ? 0 : (int32_t)rs.n_out;
@@ -737,12 +782,14 @@ __global__ void __launch_bounds__(32) sp_encode_kernel(const uint8_t* __restrict
 }  // namespace
 
 // ------------------------------------------------------------------------------ host side
+int g_warps_per_sm_override = 0;  // tuning knob (XLLM_SP_WARPS_PER_SM), 0 = fill shared memory
+
 SpDeviceModel::~SpDeviceModel() {
   for (int i = 0; i < n_allocs_; ++i) cudaFree(allocs_[i]);
 }
 
 int SpDeviceModel::upload(const SpTables& t) {
-  if (32 * t.max_unit_out + 64 > (uint32_t)kNBuf / 2) {
+  if (32 * t.max_unit_out + 64 > (uint32_t)kNBuf) {
     set_last_error("normalizer replacement of %u bytes exceeds the device staging budget", t.max_unit_out);
     return XLLM_ERR_UNSUPPORTED;
   }
@@ -786,6 +833,11 @@ int SpDeviceModel::upload(const SpTables& t) {
   dev_.space_sym = t.space_sym;
   dev_.unk_id = t.unk_id;
   dev_.max_unit_out = t.max_unit_out;
+  uint32_t max_rank = 0;
+  for (const auto& e : t.pair_table)
+    if (e.a != kEmptyKey && e.prio > max_rank) max_rank = e.prio;
+  dev_.small_vocab = (t.n_pieces < 65535 && max_rank < 65535) ? 1 : 0;
+  if (const char* w = getenv("XLLM_SP_WARPS_PER_SM")) g_warps_per_sm_override = atoi(w);
   for (int i = 0; i < 4; ++i) dev_.simple_ascii[i] = t.simple_ascii[i];
   dev_.byte_fallback = t.byte_fallback;
   dev_.add_dummy_prefix = t.add_dummy_prefix;
@@ -800,14 +852,19 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
   if (n_req <= 0) return cudaSuccess;
   static int n_sm = 0;
   static bool attr_set = false;
-  const size_t smem = sizeof(WarpSmem);
+  const bool small = dev.small_vocab != 0;
+  const size_t smem = small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>);
   if (!attr_set) {
     int d = 0;
     cudaError_t e = cudaGetDevice(&d);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sp_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(sp_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(WarpSmemT<true>));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sp_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(WarpSmemT<false>));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -815,10 +872,15 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
   if (e != cudaSuccess) return e;
   int warps_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (warps_per_sm > 32) warps_per_sm = 32;
+  if (g_warps_per_sm_override > 0 && g_warps_per_sm_override < warps_per_sm) warps_per_sm = g_warps_per_sm_override;
   int grid = n_sm * warps_per_sm;
   if (grid > n_req) grid = n_req;
-  sp_encode_kernel<<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status, dev,
-                                               task_counter);
+  if (small)
+    sp_encode_kernel<true><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status, dev,
+                                                       task_counter);
+  else
+    sp_encode_kernel<false><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status, dev,
+                                                        task_counter);
   return cudaGetLastError();
 }
 

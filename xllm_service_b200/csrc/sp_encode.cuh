@@ -30,6 +30,7 @@ struct SpDev {
   uint32_t max_unit_out;
   uint32_t simple_ascii[4];
   uint8_t byte_fallback, add_dummy_prefix, remove_extra_ws, split_mode;
+  uint8_t small_vocab;  // ranks and piece ids fit 16 bits: packed merge scratch
 };
 
 // Per-request status written by the kernel.
