@@ -73,9 +73,9 @@ def test_long_prompts_and_windows(tok, sp_oracle):
     from xllm_service_b200 import workload
     vocab = workload.make_vocabulary()
     texts = [s.encode() for s in workload.sentences(24, (700, 1100), seed=11, vocabulary=vocab)]
-    # medium-long words (33..900 chars) take the cooperative path
+    # medium-long words (17..512 chars) take the cooperative path
     rnd = random.Random(3)
-    for n in (33, 34, 64, 100, 257, 900):
+    for n in (15, 16, 17, 33, 34, 64, 100, 257, 500):
         texts.append(("".join(rnd.choice("abcdefgh") for _ in range(n)) + " tail " +
                       "".join(rnd.choice("xyz") for _ in range(n))).encode())
     texts.append((" ".join("w%d" % i for i in range(3000))).encode())

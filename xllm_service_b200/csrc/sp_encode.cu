@@ -34,8 +34,8 @@ namespace {
 
 constexpr int kNBuf = 2048;        // normalized-text staging buffer per warp (bytes)
 constexpr int kFastWin = 128;      // source bytes per fast-path step (4 per lane)
-constexpr int kMaxSym = 32;        // lane-per-word fast path: chars per word
-constexpr int kCoopMaxSym = 1024;  // warp-cooperative path: chars per word
+constexpr int kMaxSym = 16;        // lane-per-word path: chars per word (alive set = 16 bits of a register)
+constexpr int kCoopMaxSym = 512;   // warp-cooperative path: chars per word (= 32 * kMaxSym scratch entries)
 constexpr int kMaxWords = 704;     // >= kNBuf / 3 + 2 word starts
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kResolvedFlag = 0x40000000u;  // S[] entry holds a token id, not a symbol (bit 31 clear)
@@ -85,15 +85,28 @@ __device__ __forceinline__ uint32_t hash_cp(uint32_t cp) {
 }
 
 // (left, right) -> (priority, merged); priority kNoPrio when A||B is not a piece.
-__device__ __forceinline__ uint2 pair_lookup(const SpDev& T, uint32_t a, uint32_t b) {
-  if ((a | b) & kSymUnknownFlag) return make_uint2(kNoPrio, 0);
-  uint32_t h = hash_pair(a, b) & T.pair_mask;
+// Split in two so callers can put several first probes in flight before consuming any of them.
+struct PairProbe {
+  uint32_t h;
+  uint4 e;
+};
+__device__ __forceinline__ PairProbe pair_probe_begin(const SpDev& T, uint32_t a, uint32_t b) {
+  PairProbe p;
+  p.h = hash_pair(a, b) & T.pair_mask;
+  p.e = ((a | b) & kSymUnknownFlag) ? make_uint4(kEmptyKey, 0, 0, 0)
+                                    : __ldg(reinterpret_cast<const uint4*>(T.pair_table) + p.h);
+  return p;
+}
+__device__ __forceinline__ uint2 pair_probe_finish(const SpDev& T, uint32_t a, uint32_t b, PairProbe p) {
   for (;;) {
-    const uint4 e = __ldg(reinterpret_cast<const uint4*>(T.pair_table) + h);
-    if (e.x == a && e.y == b) return make_uint2(e.z, e.w);
-    if (e.x == kEmptyKey) return make_uint2(kNoPrio, 0);
-    h = (h + 1) & T.pair_mask;
+    if (p.e.x == a && p.e.y == b) return make_uint2(p.e.z, p.e.w);
+    if (p.e.x == kEmptyKey) return make_uint2(kNoPrio, 0);
+    p.h = (p.h + 1) & T.pair_mask;
+    p.e = __ldg(reinterpret_cast<const uint4*>(T.pair_table) + p.h);
   }
+}
+__device__ __forceinline__ uint2 pair_lookup(const SpDev& T, uint32_t a, uint32_t b) {
+  return pair_probe_finish(T, a, b, pair_probe_begin(T, a, b));
 }
 
 __device__ __forceinline__ uint32_t cp_lookup(const SpDev& T, uint32_t cp) {
@@ -406,9 +419,27 @@ __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, in
   using P = PMOps<SMALL>;
   uint32_t* S = sm.S + lane;
   typename P::T* PM = sm.PM + lane;
-  for (int j = 0; j + 1 < n; ++j) PM[j * 32] = P::pack(pair_lookup(T, S[j * 32], S[(j + 1) * 32]));
+  {
+    // initial adjacent pairs, four first probes in flight at a time
+    uint32_t left = S[0];
+    for (int j0 = 0; j0 + 1 < n; j0 += 4) {
+      uint32_t sy[5];
+      PairProbe pr[4];
+      sy[0] = left;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool have = j0 + u + 1 < n;
+        sy[u + 1] = have ? S[(j0 + u + 1) * 32] : kSymUnknownFlag;
+        pr[u] = pair_probe_begin(T, sy[u], sy[u + 1]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u + 1 < n) PM[(j0 + u) * 32] = P::pack(pair_probe_finish(T, sy[u], sy[u + 1], pr[u]));
+      left = sy[4];
+    }
+  }
   PM[(n - 1) * 32] = P::none();
-  uint32_t alive = n == 32 ? kFull : ((1u << n) - 1);
+  uint32_t alive = (1u << n) - 1;
   for (;;) {
     uint32_t best = P::kNone;
     int bj = 0;
@@ -419,18 +450,21 @@ __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, in
       if (pr < best) { best = pr; bj = j; }
     }
     if (best == P::kNone) break;
-    const uint32_t hi_mask = ~((2u << bj) - 1u);  // bits above bj (bj == 31 -> 0)
+    const uint32_t hi_mask = ~((2u << bj) - 1u);  // bits above bj
     const int rj = __ffs(alive & hi_mask) - 1;
     S[bj * 32] = P::merged(PM[bj * 32]);
     alive &= ~(1u << rj);
+    // the two pairs the merge created: both first probes in flight before either is consumed
     const uint32_t above = alive & hi_mask;
-    if (above) PM[bj * 32] = P::pack(pair_lookup(T, S[bj * 32], S[(__ffs(above) - 1) * 32]));
-    else PM[bj * 32] = P::none();
     const uint32_t below = alive & ((1u << bj) - 1u);
-    if (below) {
-      const int pj = 31 - __clz(below);
-      PM[pj * 32] = P::pack(pair_lookup(T, S[pj * 32], S[bj * 32]));
-    }
+    const int pj = below ? 31 - __clz(below) : 0;
+    const uint32_t sm_ = S[bj * 32];
+    const uint32_t sr = above ? S[(__ffs(above) - 1) * 32] : kSymUnknownFlag;
+    const uint32_t sl = below ? S[pj * 32] : kSymUnknownFlag;
+    const PairProbe pa = pair_probe_begin(T, sm_, sr);
+    const PairProbe pb = pair_probe_begin(T, sl, sm_);
+    PM[bj * 32] = P::pack(pair_probe_finish(T, sm_, sr, pa));
+    if (below) PM[pj * 32] = P::pack(pair_probe_finish(T, sl, sm_, pb));
   }
   return alive;
 }
