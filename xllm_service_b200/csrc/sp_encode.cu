@@ -740,7 +740,7 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
 }
 
 template <bool SMALL>
-__global__ void __launch_bounds__(32) sp_encode_kernel(const uint8_t* __restrict__ text,
+__global__ void __launch_bounds__(32, 27) sp_encode_kernel(const uint8_t* __restrict__ text,
                                                        const int64_t* __restrict__ offsets, int n_req,
                                                        int32_t* __restrict__ ids, int64_t ids_stride,
                                                        int32_t* __restrict__ n_ids, int32_t* __restrict__ status,
