@@ -474,7 +474,7 @@ def main():
                 "d2h_bytes_per_step": 4 * n * T + 8 * n + 16 * n * nb + 420 * n,
                 "api": "xllm_ingest_batch (C-ABI, page-locked host buffers)"},
         # value region: encode + hash + probe + score per step; e2e region: 5 kernels (+ row prep) per chunk
-        "gpu_launches": args.steps * (4 + 5 * (-(-n // (args.chunk_requests or 4096)))),
+        "gpu_launches": args.steps * (4 + 5 * (-(-n // (args.chunk_requests or 1024)))),
         "roofline": roofline,
         "kernels": kernels,
     }

@@ -198,7 +198,7 @@ typedef struct {
 } xllm_ingest_io;
 int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io);
 /* Pipeline chunking of xllm_ingest_batch: at most chunk_requests requests and chunk_bytes text bytes
- * per chunk (defaults 4096 / 96 MiB). */
+ * per chunk (defaults 1024 / 96 MiB; 8 chunks in flight). */
 int xllm_set_pipeline(xllm_ingest_t h, int32_t chunk_requests, int64_t chunk_bytes);
 /* Page-locked host memory for the batch buffers. */
 int xllm_host_alloc(void** out, size_t bytes);

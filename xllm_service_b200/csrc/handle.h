@@ -34,7 +34,7 @@ struct PinBuf {
 };
 
 // One in-flight chunk of xllm_ingest_batch: its own stream + device buffers.
-constexpr int kPipeSlots = 3;
+constexpr int kPipeSlots = 8;
 struct PipeSlot {
   cudaStream_t stream = nullptr;
   unsigned int* counters = nullptr;
@@ -69,7 +69,7 @@ struct xllm_ingest {
   xllm::DevBuf d_masks, d_match, d_routing, d_nblk;
   // xllm_ingest_batch pipeline
   xllm::PipeSlot pipe[xllm::kPipeSlots];
-  int pipe_chunk_req = 4096;
+  int pipe_chunk_req = 1024;
   int64_t pipe_chunk_bytes = 96ll << 20;
   // scratch for the host-pointer entry points
   xllm::DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status;
