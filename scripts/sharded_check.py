@@ -44,9 +44,10 @@ for i in range(64):
     off = k[rng.random(k.shape[0]) < 0.15]
     full.index_apply(i, None, off)
     sh.apply(i, None, off)
+    w, u = int(rng.integers(0, 16)), float(np.float32(rng.random()))
     for h in (full, part):
         h.set_instance(i, 2 if i % 2 else 1, True)
-        h.set_load_metrics(i, int(rng.integers(0, 16)), float(np.float32(rng.random())))
+        h.set_load_metrics(i, w, u)
 full.index_publish()
 sh.publish()
 sizes = torch.tensor([part.index_size()], device=dev)

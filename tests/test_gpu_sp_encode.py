@@ -85,17 +85,53 @@ def test_long_prompts_and_windows(tok, sp_oracle):
         assert g == sp_oracle.encode(t).tolist(), t[:60]
 
 
-def test_truncation_and_too_long(tok, sp_oracle):
+def test_truncation(tok, sp_oracle):
     t = b"hello world this is a test of truncation"
     full = sp_oracle.encode(t).tolist()
     got, status = _encode_all(tok, [t], stride=4)
     assert status[0] == 1  # XLLM_ENC_TRUNCATED
     ids, n_ids, _ = tok.encode_batch(np.frombuffer(t, np.uint8), np.array([0, len(t)], np.int64), 4)
     assert n_ids[0] == len(full) and ids[0].tolist() == full[:4]
-    # one whitespace-free run longer than the on-chip word capacity fails loudly, never silently
-    big = b"a" * 5000
-    _, status = _encode_all(tok, [big, b"ok fine"])
-    assert status[0] == -6 and status[1] == 0
+
+
+def test_very_long_words_take_the_scratch_path(tok, sp_oracle):
+    """Whitespace-free runs longer than the shared-memory paths hold (> 512 chars / > 2 KB) are streamed
+    through the global scratch slots and must still be bit-exact."""
+    rnd = random.Random(17)
+    letters = "abcdefghijklmnopqrstuvwxyz"
+    texts = [
+        b"a" * 5000,
+        ("".join(rnd.choice(letters) for _ in range(20000))).encode(),
+        ("short words then " + "".join(rnd.choice(letters) for _ in range(3000)) + " and after it more words").encode(),
+        ("".join(rnd.choice(letters) for _ in range(1500)) + " " +
+         "".join(rnd.choice(letters) for _ in range(2500))).encode(),
+        ("日本語のテキスト" * 400).encode(),                      # 3200 unknown chars, byte fallback, no spaces
+        ("x" * 700 + "▁" + "y" * 900 + "▁▁" + "z" * 600).encode(),  # literal U+2581 splits long runs
+        ("ab" * 1000 + "   ").encode(),                              # long word, then trailing spaces
+        ("   " + "q" * 513).encode(),                                # just past the cooperative limit
+        (" ".join("w" * n for n in (511, 512, 513, 600, 16, 17, 1)) ).encode(),
+        bytes(rnd.choice(b"abcdefgh\xc3\xa9") for _ in range(4000)),
+    ]
+    got, status = _encode_all(tok, texts)
+    assert (status == 0).all(), status
+    for t, g in zip(texts, got):
+        assert g == sp_oracle.encode(t).tolist(), t[:50]
+
+
+def test_scratch_capacity_failure_is_loud(sp_oracle):
+    import xllm_service_b200 as x
+    os.environ["XLLM_SP_LONG_CAP"] = "4096"
+    try:
+        h = x.Ingest(tokenizer_path=MODEL_DIR)
+    finally:
+        del os.environ["XLLM_SP_LONG_CAP"]
+    big = b"z" * 6000
+    ok = b"z" * 3000
+    got, status = _encode_all(h, [big, ok, b"fine words"])
+    assert status[0] == -6          # XLLM_ERR_CAPACITY: never a silent wrong answer
+    assert status[1] == 0 and got[1] == sp_oracle.encode(ok).tolist()
+    assert status[2] == 0
+    h.close()
 
 
 def test_empty_batch_and_empty_prompts(tok):

@@ -184,6 +184,7 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   h->d_ids.release();
   h->d_n_ids.release();
   h->d_status.release();
+  h->d_defer.release();
   h->d_masks.release();
   h->d_match.release();
   h->d_routing.release();
@@ -511,8 +512,9 @@ int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_te
   std::lock_guard<std::mutex> lock(h->mu);
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  XLLM_TRY(h->d_defer.reserve((size_t)n_req * 4));
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), d_text, d_offsets, n_req, d_ids, ids_stride, d_n_ids, d_status,
-                                 h->d_task_counter + 1, s));
+                                 h->d_task_counter + 4, h->d_defer.as<int32_t>(), s));
   return XLLM_OK;
 }
 
@@ -543,6 +545,7 @@ int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const
   XLLM_TRY(h->d_ids.reserve((size_t)n_req * (size_t)ids_stride * 4 + 16));
   XLLM_TRY(h->d_n_ids.reserve((size_t)n_req * 4));
   XLLM_TRY(h->d_status.reserve((size_t)n_req * 4));
+  XLLM_TRY(h->d_defer.reserve((size_t)n_req * 4));
   cudaStream_t s = h->stream;
   // offsets are rebased on the device copy of the text: ship them relative to offsets[0]
   if (text_bytes)
@@ -550,7 +553,7 @@ int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const
   XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_offsets.p, offsets, (size_t)(n_req + 1) * 8, cudaMemcpyHostToDevice, s));
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), h->d_text.as<uint8_t>() - offsets[0], h->d_offsets.as<int64_t>(),
                                  n_req, h->d_ids.as<int32_t>(), ids_stride, h->d_n_ids.as<int32_t>(),
-                                 h->d_status.as<int32_t>(), h->d_task_counter + 1, s));
+                                 h->d_status.as<int32_t>(), h->d_task_counter + 4, h->d_defer.as<int32_t>(), s));
   if (ids_stride)
     XLLM_CUDA_TRY(cudaMemcpyAsync(ids, h->d_ids.p, (size_t)n_req * (size_t)ids_stride * 4, cudaMemcpyDeviceToHost, s));
   XLLM_CUDA_TRY(cudaMemcpyAsync(n_ids, h->d_n_ids.p, (size_t)n_req * 4, cudaMemcpyDeviceToHost, s));

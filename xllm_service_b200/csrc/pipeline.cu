@@ -41,6 +41,7 @@ int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_
   if ((rc = d_ids.reserve((size_t)n * (size_t)ids_stride * 4 + 64)) != XLLM_OK) return rc;
   if ((rc = d_n_ids.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_status.reserve((size_t)n * 4)) != XLLM_OK) return rc;
+  if ((rc = d_defer.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_tok_start.reserve((size_t)n * 8)) != XLLM_OK) return rc;
   if ((rc = d_n_tok.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_key_start.reserve((size_t)n * 8)) != XLLM_OK) return rc;
@@ -53,6 +54,7 @@ int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_
 }
 
 void PipeSlot::release() {
+  d_defer.release();
   d_text.release(); d_offsets.release(); d_ids.release(); d_n_ids.release(); d_status.release();
   d_tok_start.release(); d_n_tok.release(); d_key_start.release(); d_n_blocks.release();
   d_keys.release(); d_masks.release(); d_match.release(); d_routing.release();
@@ -152,7 +154,7 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
     XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_offsets.p, io->offsets + c0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, s));
     XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), m,
                                    sl.d_ids.as<int32_t>(), io->ids_stride, sl.d_n_ids.as<int32_t>(),
-                                   sl.d_status.as<int32_t>(), sl.counters, s));
+                                   sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s));
     XLLM_CUDA_TRY(cudaMemcpyAsync(io->ids + (size_t)c0 * io->ids_stride, sl.d_ids.p,
                                   (size_t)m * (size_t)io->ids_stride * 4, cudaMemcpyDeviceToHost, s));
     XLLM_CUDA_TRY(cudaMemcpyAsync(io->n_ids + c0, sl.d_n_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
@@ -166,7 +168,7 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
       if (io->keys) XLLM_CUDA_TRY(cudaMemsetAsync(sl.d_keys.p, 0, (size_t)m * (size_t)keys_stride * 16, s));
       XLLM_CUDA_TRY(xxh3_chain_launch(sl.d_ids.as<int32_t>(), sl.d_tok_start.as<int64_t>(), sl.d_n_tok.as<int32_t>(),
                                       sl.d_keys.as<uint8_t>(), sl.d_key_start.as<int64_t>(), m, h->block_size, h->xxh,
-                                      sl.counters + 1, s));
+                                      sl.counters + 8, s));
       if (io->keys)
         XLLM_CUDA_TRY(cudaMemcpyAsync(io->keys + (size_t)c0 * (size_t)keys_stride * 16, sl.d_keys.p,
                                       (size_t)m * (size_t)keys_stride * 16, cudaMemcpyDeviceToHost, s));

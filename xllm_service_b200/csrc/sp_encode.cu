@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "sp_long_word.cuh"
 
 namespace xllm {
 
@@ -34,6 +35,8 @@ namespace {
 
 constexpr int kNBuf = 2048;        // normalized-text staging buffer per warp (bytes)
 constexpr int kFastWin = 128;      // source bytes per fast-path step (4 per lane)
+constexpr int kLongEnterAt = 1024;   // a kept tail (one incomplete word) longer than this switches to long mode
+constexpr int kLongFlushAt = 1024;   // long mode: move nbuf into the scratch slot once it holds this much
 constexpr int kMaxSym = 16;        // lane-per-word path: chars per word (alive set = 16 bits of a register)
 constexpr int kCoopMaxSym = 512;   // warp-cooperative path: chars per word (= 32 * kMaxSym scratch entries)
 constexpr int kMaxWords = 704;     // >= kNBuf / 3 + 2 word starts
@@ -204,6 +207,12 @@ struct ReqState {
   bool prev_space;      // normalizer's is_prev_space
   bool prev_unk;        // last emitted symbol was unknown (byte_fallback off only)
   bool too_long;
+  bool deferred;       // needs the long-word kernel (this one was built without it)
+  // long-word mode: the current pre-token is being streamed into a global scratch slot
+  bool long_mode;
+  bool long_last_sp;   // the last char appended to the slot is U+2581
+  int long_slot;
+  uint32_t long_n;     // symbols appended so far
 };
 
 __device__ __forceinline__ void put_id(ReqState& rs, int64_t pos, int32_t id) {
@@ -520,8 +529,185 @@ __device__ __forceinline__ bool is_space_at(const uint8_t* b, int p, int n) {
   return p + 2 < n && b[p] == 0xE2 && b[p + 1] == 0x96 && b[p + 2] == 0x81;
 }
 
+// ---------------------------------------------------------------------------- long words
+constexpr uint32_t kDeadSym = 0xFFFFFFFFu;
+constexpr uint32_t kNoLink = 0xFFFFFFFFu;
+
+// Appends the chars of nbuf[from, to) as symbols to the request's scratch slot.  Returns false when the
+// slot's capacity is exceeded.
+template <typename SM>
+__device__ __noinline__ bool long_append(const SpDev& T, SM& sm, ReqState& rs, int from, int to, int lane) {
+  const LongSlot L = long_slot_view(T.long_pool, T.long_cap, rs.long_slot);
+  const uint8_t* nb = sm.nbuf;
+  bool ok = true;
+  for (int base = from; base < to; base += 32) {
+    const int p = base + lane;
+    const bool lead = p < to && (nb[p] & 0xC0) != 0x80;
+    const uint32_t m = __ballot_sync(kFull, lead);
+    const uint32_t idx = rs.long_n + __popc(m & ((1u << lane) - 1));
+    if (lead) {
+      if (idx < T.long_cap) { uint32_t adv; L.sym[idx] = char_sym(T, nb + p, &adv); }
+      else ok = false;
+    }
+    rs.long_n += __popc(m);
+  }
+  if (to - from >= 3) rs.long_last_sp = nb[to - 3] == 0xE2 && nb[to - 2] == 0x96 && nb[to - 1] == 0x81;
+  else if (to > from) rs.long_last_sp = false;
+  __syncwarp();
+  return !__any_sync(kFull, !ok);
+}
+
+// Merges the slot's symbols (bpe_model.cc order: best priority, leftmost on ties) and emits their ids.
+__device__ __noinline__ void long_finish(const SpDev& T, ReqState& rs, bool strip_trailing_space, int lane) {
+  const LongSlot L = long_slot_view(T.long_pool, T.long_cap, rs.long_slot);
+  uint32_t n = rs.long_n;
+  if (strip_trailing_space)
+    while (n > 0 && L.sym[n - 1] == T.space_sym) --n;
+  if (n == 0) return;
+  for (uint32_t j = lane; j < n; j += 32) {
+    L.next[j] = j + 1 < n ? j + 1 : kNoLink;
+    L.prev[j] = j ? j - 1 : kNoLink;
+    const uint2 pm = j + 1 < n ? pair_lookup(T, L.sym[j], L.sym[j + 1]) : make_uint2(kNoPrio, 0);
+    L.prio[j] = pm.x;
+    L.merged[j] = pm.y;
+  }
+  __syncwarp();
+  const uint32_t nb = (n + 31) / 32;
+  for (uint32_t b = 0; b < nb; ++b) long_block_min(L, n, b, lane);
+  for (;;) {
+    unsigned long long best = ~0ull;
+    for (uint32_t b = lane; b < nb; b += 32) {
+      const unsigned long long k = L.bmin[b];
+      best = k < best ? k : best;
+    }
+    best = warp_min_u64(best);
+    if ((uint32_t)(best >> 32) == kNoPrio) break;
+    const uint32_t j = (uint32_t)best;
+    uint32_t r = 0, p = kNoLink;
+    if (lane == 0) {
+      r = L.next[j];
+      const uint32_t m = L.merged[j];
+      const uint32_t nr = L.next[r];
+      p = L.prev[j];
+      L.sym[j] = m;
+      L.next[j] = nr;
+      if (nr != kNoLink) L.prev[nr] = j;
+      L.prio[r] = kNoPrio;
+      L.sym[r] = kDeadSym;
+      const uint2 a = nr != kNoLink ? pair_lookup(T, m, L.sym[nr]) : make_uint2(kNoPrio, 0);
+      L.prio[j] = a.x;
+      L.merged[j] = a.y;
+      if (p != kNoLink) {
+        const uint2 c = pair_lookup(T, L.sym[p], m);
+        L.prio[p] = c.x;
+        L.merged[p] = c.y;
+      }
+    }
+    __syncwarp();
+    r = __shfl_sync(kFull, r, 0);
+    p = __shfl_sync(kFull, p, 0);
+    const uint32_t bj = j >> 5, br = r >> 5;
+    long_block_min(L, n, bj, lane);
+    if (br != bj) long_block_min(L, n, br, lane);
+    if (p != kNoLink && (p >> 5) != bj && (p >> 5) != br) long_block_min(L, n, p >> 5, lane);
+  }
+  // emit the surviving symbols in order
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t j = base + lane;
+    const uint32_t sym = j < n ? L.sym[j] : kDeadSym;
+    const bool alive = sym != kDeadSym;
+    int32_t tmp[4];
+    bool unk = false;
+    int c = alive ? sym_ids(T, sym, tmp, &unk) : 0;
+    if (!T.byte_fallback) {
+      const uint32_t am = __ballot_sync(kFull, alive);
+      const uint32_t um = __ballot_sync(kFull, alive && unk);
+      const uint32_t below = am & ((1u << lane) - 1);
+      const bool prev = below ? ((um >> (31 - __clz(below))) & 1u) : rs.prev_unk;
+      if (alive && unk && prev) c = 0;
+      if (am) rs.prev_unk = (um >> (31 - __clz(am))) & 1u;
+    }
+    const int inc = warp_incl_scan(c, lane);
+    int64_t o = rs.n_out + (inc - c);
+    for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
+    rs.n_out += __shfl_sync(kFull, inc, 31);
+  }
+  rs.trailing_bare = 0;
+  __syncwarp();
+}
+
+// Long mode: nbuf continues the slot's word.  Appends up to the first word boundary (or everything),
+// finishes the word when its end is known, and returns to the normal mode with the rest of nbuf.
+template <typename SM>
+__device__ __noinline__ void long_consume(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane) {
+  const uint8_t* nb = sm.nbuf;
+  const int nlen = rs.nlen;
+  int cut = nlen;
+  if (T.split_mode != 0) {
+    for (int base = 0; base < nlen && cut == nlen; base += 32) {
+      const int p = base + lane;
+      bool st = false;
+      if (p < nlen && is_space_at(nb, p, nlen)) {
+        const bool prev_sp = p >= 3 ? is_space_at(nb, p - 3, nlen) : (p == 0 && rs.long_last_sp);
+        st = T.split_mode == 1 || !prev_sp;
+      }
+      const uint32_t m = __ballot_sync(kFull, st);
+      if (m) cut = base + __ffs(m) - 1;
+    }
+  }
+  if (!long_append(T, sm, rs, 0, cut, lane)) {
+    rs.too_long = true;
+    long_slot_release(T.long_locks, rs.long_slot, lane);
+    rs.long_mode = false;
+    return;
+  }
+  if (cut < nlen || final) {
+    long_finish(T, rs, final && cut == nlen && T.remove_extra_ws, lane);
+    long_slot_release(T.long_locks, rs.long_slot, lane);
+    rs.long_mode = false;
+    const int tl = nlen - cut;
+    if (cut > 0) {
+      for (int base = 0; base < tl; base += 32) {
+        const int k = base + lane;
+        uint8_t c = 0;
+        if (k < tl) c = sm.nbuf[cut + k];
+        __syncwarp();
+        if (k < tl) sm.nbuf[k] = c;
+        __syncwarp();
+      }
+    }
+    rs.nlen = tl;
+  } else {
+    rs.nlen = 0;
+  }
+  rs.rescan = true;
+  rs.ascii = false;
+  rs.nw = 0;
+  __syncwarp();
+}
+
+// Switches to long mode: nbuf holds exactly one incomplete word (the tail a drain kept).
+template <typename SM>
+__device__ __noinline__ bool long_enter(const SpDev& T, SM& sm, ReqState& rs, int lane) {
+  if (T.long_slots <= 0) return false;
+  rs.long_slot = long_slot_acquire(T.long_locks, T.long_slots, lane);
+  rs.long_n = 0;
+  rs.long_last_sp = false;
+  rs.long_mode = true;
+  if (!long_append(T, sm, rs, 0, rs.nlen, lane)) {
+    long_slot_release(T.long_locks, rs.long_slot, lane);
+    rs.long_mode = false;
+    return false;
+  }
+  rs.nlen = 0;
+  rs.rescan = true;
+  rs.ascii = false;
+  rs.nw = 0;
+  return true;
+}
+
 // Tokenises the complete words held in nbuf (all words when final) and keeps the incomplete tail.
-template <bool SMALL, typename SM>
+template <bool SMALL, bool LONG, typename SM>
 __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane) {
   const uint8_t* nb = sm.nbuf;
   int nlen = rs.nlen;
@@ -562,7 +748,7 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
 
   // 2. rounds of up to 32 consecutive words
   int w0 = 0;
-  while (w0 < complete) {
+  while (w0 < complete && !rs.deferred) {
     const int w = w0 + lane;
     const bool have = w < complete;
     int ws = 0, we = 0, nsym = 0;
@@ -677,7 +863,18 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
       overflow = __any_sync(kFull, overflow);
       __syncwarp();
       if (overflow) {
-        rs.too_long = true;
+        // more chars than the shared-memory scratch holds: merge it in a global scratch slot
+        if constexpr (!LONG) {
+          rs.deferred = true;
+        } else if (T.long_slots <= 0) {
+          rs.too_long = true;
+        } else {
+          rs.long_slot = long_slot_acquire(T.long_locks, T.long_slots, lane);
+          rs.long_n = 0;
+          if (long_append(T, sm, rs, lws, lwe, lane)) long_finish(T, rs, false, lane);
+          else rs.too_long = true;
+          long_slot_release(T.long_locks, rs.long_slot, lane);
+        }
       } else {
         n = coop_merge<SMALL>(T, sm, n, lane);
         for (int base = 0; base < n; base += 32) {
@@ -739,13 +936,14 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
   __syncwarp();
 }
 
-template <bool SMALL>
-__global__ void __launch_bounds__(32, 27) sp_encode_kernel(const uint8_t* __restrict__ text,
-                                                       const int64_t* __restrict__ offsets, int n_req,
-                                                       int32_t* __restrict__ ids, int64_t ids_stride,
-                                                       int32_t* __restrict__ n_ids, int32_t* __restrict__ status,
-                                                       const __grid_constant__ SpDev T,
-                                                       unsigned int* __restrict__ task_counter) {
+// LONG == false: the throughput kernel; a request that needs the long-word path is appended to defer_list.
+// LONG == true : re-runs exactly the deferred requests (work list = defer_list[0 .. *defer_count)).
+template <bool SMALL, bool LONG>
+__global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
+    const uint8_t* __restrict__ text, const int64_t* __restrict__ offsets, int n_req, int32_t* __restrict__ ids,
+    int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status, const __grid_constant__ SpDev T,
+    unsigned int* __restrict__ task_counter, int32_t* __restrict__ defer_list,
+    unsigned int* __restrict__ defer_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = WarpSmemT<SMALL>;
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
@@ -756,7 +954,12 @@ __global__ void __launch_bounds__(32, 27) sp_encode_kernel(const uint8_t* __rest
     unsigned int r = 0;
     if (lane == 0) r = atomicAdd(task_counter, 1u);
     r = __shfl_sync(kFull, r, 0);
-    if (r >= (unsigned)n_req) break;
+    if constexpr (LONG) {
+      if (r >= *defer_count) break;
+      r = (unsigned)defer_list[r];
+    } else {
+      if (r >= (unsigned)n_req) break;
+    }
 
     ReqState rs;
     const int64_t beg = offsets[r];
@@ -773,6 +976,11 @@ __global__ void __launch_bounds__(32, 27) sp_encode_kernel(const uint8_t* __rest
     rs.prev_space = T.remove_extra_ws;
     rs.prev_unk = false;
     rs.too_long = false;
+    rs.deferred = false;
+    rs.long_mode = false;
+    rs.long_last_sp = false;
+    rs.long_slot = -1;
+    rs.long_n = 0;
 
     if (rs.len > 0) {
       if (T.add_dummy_prefix) {
@@ -787,27 +995,66 @@ __global__ void __launch_bounds__(32, 27) sp_encode_kernel(const uint8_t* __rest
           pos += kFastWin;
         } else {
           if (!normalize_window(T, sm, rs, pos, carry_skip, lane)) {
-            drain<SMALL>(T, sm, rs, false, lane);  // make room, then this window must fit
-            if (!normalize_window(T, sm, rs, pos, carry_skip, lane)) {
-              rs.too_long = true;
-              break;
+            // make room, then this window must fit
+            bool consumed = false;
+            if constexpr (LONG) {
+              if (rs.long_mode) { long_consume(T, sm, rs, false, lane); consumed = true; }
             }
+            if (!consumed) drain<SMALL, LONG>(T, sm, rs, false, lane);
+            if (!rs.too_long && !normalize_window(T, sm, rs, pos, carry_skip, lane)) {
+              // still no room: the kept tail is one very long word -> stream it through a scratch slot
+              bool entered = false;
+              if constexpr (LONG) {
+                if (!rs.long_mode) entered = long_enter(T, sm, rs, lane);
+                if (!entered) rs.too_long = true;
+              } else {
+                rs.deferred = true;  // needs the long-word kernel
+              }
+              if (entered && !normalize_window(T, sm, rs, pos, carry_skip, lane)) rs.too_long = true;
+            }
+            if (rs.too_long || rs.deferred) break;
           }
           pos += 32;
         }
-        if (rs.nlen > drain_at) {
-          drain<SMALL>(T, sm, rs, false, lane);
-          if (rs.nlen > drain_at) {  // one pre-token longer than the staging buffer
-            rs.too_long = true;
-            break;
+        bool in_long = false;
+        if constexpr (LONG) {
+          if (rs.long_mode) {
+            in_long = true;
+            if (rs.nlen > kLongFlushAt) long_consume(T, sm, rs, false, lane);
           }
         }
+        if (!in_long && rs.nlen > drain_at) {
+          drain<SMALL, LONG>(T, sm, rs, false, lane);
+          if (rs.nlen > kLongEnterAt) {
+            if constexpr (LONG) {
+              if (!long_enter(T, sm, rs, lane)) rs.too_long = true;
+            } else {
+              rs.deferred = true;
+            }
+          }
+        }
+        if (rs.too_long || rs.deferred) break;
       }
-      if (!rs.too_long) drain<SMALL>(T, sm, rs, true, lane);
+      if constexpr (LONG) {
+        if (!rs.too_long && rs.long_mode) long_consume(T, sm, rs, true, lane);
+      }
+      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG>(T, sm, rs, true, lane);
+    }
+    if constexpr (LONG) {
+      if (rs.long_mode) {  // error exit while a slot is held
+        long_slot_release(T.long_locks, rs.long_slot, lane);
+        rs.long_mode = false;
+      }
     }
     if (lane == 0) {
-      n_ids[r] = rs.too_long ? 0 : (int32_t)rs.n_out;
-      status[r] = rs.too_long ? kEncWordTooLong : (rs.n_out > rs.cap ? kEncTruncated : kEncOk);
+      if (rs.deferred) {
+        defer_list[atomicAdd(defer_count, 1u)] = (int32_t)r;
+        n_ids[r] = 0;
+        status[r] = kEncWordTooLong;  // overwritten by the long-word kernel
+      } else {
+        n_ids[r] = rs.too_long ? 0 : (int32_t)rs.n_out;
+        status[r] = rs.too_long ? kEncWordTooLong : (rs.n_out > rs.cap ? kEncTruncated : kEncOk);
+      }
     }
     __syncwarp();
   }
@@ -872,6 +1119,30 @@ int SpDeviceModel::upload(const SpTables& t) {
     if (e.a != kEmptyKey && e.prio > max_rank) max_rank = e.prio;
   dev_.small_vocab = (t.n_pieces < 65535 && max_rank < 65535) ? 1 : 0;
   if (const char* w = getenv("XLLM_SP_WARPS_PER_SM")) g_warps_per_sm_override = atoi(w);
+  // scratch pool for pre-tokens longer than the shared-memory paths hold
+  uint32_t cap = 1u << 17;
+  int slots = 16;
+  if (const char* w = getenv("XLLM_SP_LONG_CAP")) cap = (uint32_t)atoi(w);
+  if (const char* w = getenv("XLLM_SP_LONG_SLOTS")) slots = atoi(w);
+  cap = (cap + 31) & ~31u;
+  if (slots > 0 && cap > 0) {
+    void* pool = nullptr;
+    void* locks = nullptr;
+    if (cudaMalloc(&pool, long_slot_bytes(cap) * (size_t)slots) != cudaSuccess ||
+        cudaMalloc(&locks, sizeof(int) * (size_t)slots) != cudaSuccess ||
+        cudaMemset(locks, 0, sizeof(int) * (size_t)slots) != cudaSuccess) {
+      set_last_error("cudaMalloc of the long-word scratch pool (%d x %u symbols) failed", slots, cap);
+      if (pool) cudaFree(pool);
+      if (locks) cudaFree(locks);
+      return XLLM_ERR_NOMEM;
+    }
+    allocs_[n_allocs_++] = pool;
+    allocs_[n_allocs_++] = locks;
+    dev_.long_pool = static_cast<uint8_t*>(pool);
+    dev_.long_locks = static_cast<int*>(locks);
+    dev_.long_cap = cap;
+    dev_.long_slots = slots;
+  }
   for (int i = 0; i < 4; ++i) dev_.simple_ascii[i] = t.simple_ascii[i];
   dev_.byte_fallback = t.byte_fallback;
   dev_.add_dummy_prefix = t.add_dummy_prefix;
@@ -881,8 +1152,8 @@ int SpDeviceModel::upload(const SpTables& t) {
 }
 
 cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
-                             int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* task_counter,
-                             cudaStream_t stream) {
+                             int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
+                             int32_t* defer_list, cudaStream_t stream) {
   if (n_req <= 0) return cudaSuccess;
   static int n_sm = 0;
   static bool attr_set = false;
@@ -894,27 +1165,38 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sp_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(WarpSmemT<true>));
+#define XLLM_SET_SMEM(K, B)                                                                          \
+    e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B>)); \
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sp_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(WarpSmemT<false>));
-    if (e != cudaSuccess) return e;
+    XLLM_SET_SMEM((sp_encode_kernel<true, false>), true)
+    XLLM_SET_SMEM((sp_encode_kernel<true, true>), true)
+    XLLM_SET_SMEM((sp_encode_kernel<false, false>), false)
+    XLLM_SET_SMEM((sp_encode_kernel<false, true>), false)
+#undef XLLM_SET_SMEM
     attr_set = true;
   }
-  cudaError_t e = cudaMemsetAsync(task_counter, 0, sizeof(unsigned int), stream);
+  // counters[0]: task counter, [1]: deferred count, [2]: task counter of the long-word pass
+  cudaError_t e = cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
   int warps_per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (warps_per_sm > 32) warps_per_sm = 32;
+  if (warps_per_sm > 27) warps_per_sm = 27;
   if (g_warps_per_sm_override > 0 && g_warps_per_sm_override < warps_per_sm) warps_per_sm = g_warps_per_sm_override;
   int grid = n_sm * warps_per_sm;
   if (grid > n_req) grid = n_req;
-  if (small)
-    sp_encode_kernel<true><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status, dev,
-                                                       task_counter);
-  else
-    sp_encode_kernel<false><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status, dev,
-                                                        task_counter);
+  int grid_long = n_sm * 2;
+  if (grid_long > n_req) grid_long = n_req;
+  if (small) {
+    sp_encode_kernel<true, false><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status,
+                                                              dev, counters, defer_list, counters + 1);
+    sp_encode_kernel<true, true><<<grid_long, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids,
+                                                                  status, dev, counters + 2, defer_list, counters + 1);
+  } else {
+    sp_encode_kernel<false, false><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status,
+                                                               dev, counters, defer_list, counters + 1);
+    sp_encode_kernel<false, true><<<grid_long, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids,
+                                                                   status, dev, counters + 2, defer_list,
+                                                                   counters + 1);
+  }
   return cudaGetLastError();
 }
 

@@ -31,6 +31,11 @@ struct SpDev {
   uint32_t simple_ascii[4];
   uint8_t byte_fallback, add_dummy_prefix, remove_extra_ws, split_mode;
   uint8_t small_vocab;  // ranks and piece ids fit 16 bits: packed merge scratch
+  // global scratch pool for pre-tokens too long for shared memory (sp_long_word.cuh)
+  uint8_t* long_pool;
+  int* long_locks;
+  uint32_t long_cap;   // symbols per slot
+  int32_t long_slots;
 };
 
 // Per-request status written by the kernel.
@@ -46,14 +51,17 @@ class SpDeviceModel {
 
  private:
   SpDev dev_{};
-  void* allocs_[8] = {nullptr};
+  void* allocs_[12] = {nullptr};
   int n_allocs_ = 0;
 };
 
 // text: all prompts back to back; offsets[n_req + 1] (bytes).  Request r's ids go to
 // ids + r * ids_stride (at most ids_stride of them), n_ids[r] = full count, status[r] = kEnc*.
+// counters: 4 zero-initialisable uint32 in device memory; defer_list: n_req int32 of device scratch (requests
+// that need the long-word pass).  Two launches: the throughput kernel, then the long-word kernel over the
+// deferred requests (a no-op grid when there are none).
 cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
-                             int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* task_counter,
-                             cudaStream_t stream);
+                             int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
+                             int32_t* defer_list, cudaStream_t stream);
 
 }  // namespace xllm
