@@ -81,6 +81,14 @@ def lib():
         L.oracle_registry_clear_load.restype = None
         L.oracle_route_car.argtypes = [VP, VP, VP, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, VP, ctypes.c_int,
                                        VP, VP, VP, VP, VP, VP]
+        L.oracle_tik_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.oracle_tik_load.restype = VP
+        L.oracle_tik_free.argtypes = [VP]
+        L.oracle_tik_free.restype = None
+        L.oracle_tik_vocab_size.argtypes = [VP]
+        L.oracle_tik_vocab_size.restype = ctypes.c_long
+        L.oracle_tik_encode.argtypes = [VP, ctypes.c_char_p, ctypes.c_size_t, VP, ctypes.c_size_t]
+        L.oracle_tik_encode.restype = ctypes.c_long
         L.oracle_ingest_batch.argtypes = [VP, VP, VP, VP, VP, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, VP,
                                           ctypes.c_int, ctypes.c_int, VP, ctypes.c_int64, VP, VP, VP, VP]
         _lib = L
@@ -302,3 +310,34 @@ def ingest_batch(sp, prefix, text_u8, offsets, ids_stride, n_threads=1, want_ids
                               ids.ctypes.data if want_ids else None, ids_stride, n_ids.ctypes.data, pid.ctypes.data,
                               did.ctypes.data, ok.ctypes.data)
     return {"ids": ids, "n_ids": n_ids, "prefill_id": pid, "decode_id": did, "ok": ok}
+
+
+class TiktokenOracle:
+    """TiktokenTokenizer as the service configures it (no regex pattern: the whole text is one piece);
+    oracle/tiktoken_oracle.cc restating tiktoken_tokenizer.cpp:115-294."""
+
+    def __init__(self, model_dir_or_file):
+        path = model_dir_or_file
+        if os.path.isdir(path):
+            path = os.path.join(path, "tokenizer.model")  # tokenizer_args.h:37
+        err = ctypes.create_string_buffer(512)
+        self._h = lib().oracle_tik_load(path.encode(), err, 512)
+        if not self._h:
+            raise ValueError(err.value.decode())
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().oracle_tik_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def vocab_size(self):
+        return lib().oracle_tik_vocab_size(self._h)
+
+    def encode(self, text: bytes):
+        cap = len(text) + 8
+        out = np.zeros(cap, dtype=np.int32)
+        n = lib().oracle_tik_encode(self._h, text, len(text), out.ctypes.data, cap)
+        return out[:n].copy()
