@@ -112,7 +112,7 @@ int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
   if (cfg->tokenizer_path && cfg->tokenizer_path[0]) {
     h->tokenizer_path = cfg->tokenizer_path;
     h->sp_tables = std::make_shared<SpTables>();
-    int rc = sp_load_model(h->tokenizer_path, h->sp_tables.get());
+    int rc = load_tokenizer_tables(h->tokenizer_path, h->sp_tables.get());
     if (rc != XLLM_OK) {
       set_last_error("tokenizer %s: %s", cfg->tokenizer_path, h->sp_tables->error.c_str());
       xllm_ingest_destroy(h);
@@ -468,7 +468,7 @@ int xllm_tokenizer_probe(const char* tokenizer_path, xllm_tokenizer_info* out) {
     return XLLM_ERR_INVALID_ARG;
   }
   SpTables t;
-  const int rc = sp_load_model(tokenizer_path, &t);
+  const int rc = load_tokenizer_tables(tokenizer_path, &t);
   if (rc != XLLM_OK) {
     set_last_error("tokenizer %s: %s", tokenizer_path, t.error.c_str());
     return rc;
@@ -493,7 +493,7 @@ int xllm_vocab_size(xllm_ingest_t h, int32_t* out) {
     set_last_error("handle has no tokenizer");
     return XLLM_ERR_UNSUPPORTED;
   }
-  *out = (int32_t)h->sp_tables->n_pieces;
+  *out = h->sp_tables->vocab_size_override >= 0 ? h->sp_tables->vocab_size_override : (int32_t)h->sp_tables->n_pieces;
   return XLLM_OK;
 }
 

@@ -148,7 +148,7 @@ __device__ __forceinline__ uint32_t utf8_unit(const uint8_t* p, uint32_t avail, 
 // Char at p (well-formed by construction: normalized text) -> symbol; *adv = its byte length.
 __device__ __forceinline__ uint32_t char_sym(const SpDev& T, const uint8_t* p, uint32_t* adv) {
   const uint32_t b0 = p[0];
-  if (b0 < 0x80) {
+  if (b0 < 0x80 || T.byte_mode) {  // byte_mode (tiktoken tables): every byte is a symbol, 256-entry table
     *adv = 1;
     return __ldg(T.ascii_sym + b0);
   }
@@ -167,6 +167,7 @@ __device__ __forceinline__ int sym_ids(const SpDev& T, uint32_t sym, int32_t out
   if (!(sym & kSymUnknownFlag)) {
     const int32_t e = __ldg(T.emit + sym);
     if (e >= 0) { out[0] = e; return 1; }
+    if (e == -2) return 0;  // a part without a rank is skipped (tiktoken_tokenizer.cpp:228-229)
     cp = __ldg(T.virt_cp + (sym - T.n_pieces));
   } else {
     cp = sym & 0x1FFFFFu;
@@ -351,15 +352,17 @@ __device__ __forceinline__ bool normalize_fast(const SpDev& T, SM& sm, ReqState&
   for (int k = 0; k < 4; ++k) b[k] = (uint32_t)k < nvalid ? __ldg(p + k) : 0x61u;
   uint32_t nextb = __shfl_down_sync(kFull, b[0], 1);
   if (lane == 31) nextb = base + 4 < rs.len ? __ldg(p + 4) : 0x61u;
-  bool ok = nextb < 0x80 || nvalid < 4;
+  if (!T.byte_mode) {
+    bool ok = nextb < 0x80 || nvalid < 4;
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    ok = ok && ((uint32_t)k >= nvalid || (b[k] < 0x80 && ((T.simple_ascii[(b[k] >> 5) & 3] >> (b[k] & 31)) & 1u)));
-  if (!__all_sync(kFull, ok)) return false;
+    for (int k = 0; k < 4; ++k)
+      ok = ok && ((uint32_t)k >= nvalid || (b[k] < 0x80 && ((T.simple_ascii[(b[k] >> 5) & 3] >> (b[k] & 31)) & 1u)));
+    if (!__all_sync(kFull, ok)) return false;
+  }
 
-  bool sp[4];
+  bool sp[4];  // byte_mode: text is copied verbatim, a space is an ordinary byte
 #pragma unroll
-  for (int k = 0; k < 4; ++k) sp[k] = (uint32_t)k < nvalid && b[k] == ' ';
+  for (int k = 0; k < 4; ++k) sp[k] = !T.byte_mode && (uint32_t)k < nvalid && b[k] == ' ';
   // is the byte before this lane's first byte a space?  (lanes before a valid lane are full)
   const bool last_sp = sp[3];
   bool prev = __shfl_up_sync(kFull, last_sp, 1);
@@ -542,7 +545,7 @@ __device__ __noinline__ bool long_append(const SpDev& T, SM& sm, ReqState& rs, i
   bool ok = true;
   for (int base = from; base < to; base += 32) {
     const int p = base + lane;
-    const bool lead = p < to && (nb[p] & 0xC0) != 0x80;
+    const bool lead = p < to && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
     const uint32_t m = __ballot_sync(kFull, lead);
     const uint32_t idx = rs.long_n + __popc(m & ((1u << lane) - 1));
     if (lead) {
@@ -757,7 +760,7 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
       we = sm.wstart[w + 1];
       if (rs.ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
       else
-        for (int p = ws; p < we; ++p) nsym += (nb[p] & 0xC0) != 0x80;
+        for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
     }
     const uint32_t long_mask = __ballot_sync(kFull, have && nsym > kMaxSym);
     const int first_long = long_mask ? __ffs(long_mask) - 1 : 32;
@@ -788,7 +791,7 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
         const uint32_t sym = sm.S[j * 32 + lane];
         const int c = sym_ids(T, sym, tmp, &unk);
         if (first) { first_unk = unk; first = false; }
-        if (!unk) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
+        if (!unk && c == 1) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
         if (!(unk && pu && !T.byte_fallback)) cnt += c;
         pu = unk;
       }
@@ -851,7 +854,7 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
       bool overflow = false;
       for (int base = lws; base < lwe; base += 32) {
         const int p = base + lane;
-        const bool lead = p < lwe && (nb[p] & 0xC0) != 0x80;
+        const bool lead = p < lwe && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
         const uint32_t m = __ballot_sync(kFull, lead);
         const int idx = n + __popc(m & ((1u << lane) - 1));
         if (lead) {
@@ -925,12 +928,12 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
       bool non_ascii = false;
       const bool lead = tl >= 3 && sm.nbuf[0] == 0xE2 && sm.nbuf[1] == 0x96 && sm.nbuf[2] == 0x81;
       for (int k = lane; k < tl; k += 32) non_ascii |= sm.nbuf[k] >= 0x80 && !(lead && k < 3);
-      rs.ascii = !__any_sync(kFull, non_ascii);
+      rs.ascii = !T.byte_mode && !__any_sync(kFull, non_ascii);
     }
   } else {
     rs.nlen = 0;
     rs.nw = 0;
-    rs.ascii = true;
+    rs.ascii = !T.byte_mode;
   }
   rs.rescan = false;
   __syncwarp();
@@ -972,7 +975,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     rs.trailing_bare = 0;
     rs.nw = 0;
     rs.rescan = false;
-    rs.ascii = true;
+    rs.ascii = !T.byte_mode;
     rs.prev_space = T.remove_extra_ws;
     rs.prev_unk = false;
     rs.too_long = false;
@@ -1148,6 +1151,7 @@ int SpDeviceModel::upload(const SpTables& t) {
   dev_.add_dummy_prefix = t.add_dummy_prefix;
   dev_.remove_extra_ws = t.remove_extra_whitespaces;
   dev_.split_mode = (uint8_t)t.split_mode;
+  dev_.byte_mode = t.byte_mode ? 1 : 0;
   return XLLM_OK;
 }
 

@@ -31,6 +31,7 @@ struct SpDev {
   uint32_t simple_ascii[4];
   uint8_t byte_fallback, add_dummy_prefix, remove_extra_ws, split_mode;
   uint8_t small_vocab;  // ranks and piece ids fit 16 bits: packed merge scratch
+  uint8_t byte_mode;    // tiktoken tables: every byte is a symbol, text is copied verbatim
   // global scratch pool for pre-tokens too long for shared memory (sp_long_word.cuh)
   uint8_t* long_pool;
   int* long_locks;

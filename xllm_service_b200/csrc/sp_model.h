@@ -51,6 +51,10 @@ struct SpTables {
   // 0: no exact pre-split exists (whole text is one word); 1: split before every U+2581;
   // 2: split before a U+2581 unless the previous char is U+2581 too
   int split_mode = 1;
+  // tiktoken tables (tiktoken_model.cc): every BYTE is a symbol (ascii_sym has 256 entries), no normaliser,
+  // no whitespace rules; emit == -2 marks a symbol that produces no id
+  bool byte_mode = false;
+  int32_t vocab_size_override = -1;
   // vocabulary strings for decode / id_to_token / token_to_id
   std::vector<std::string> piece_str;
   std::vector<uint8_t> piece_type;
@@ -60,5 +64,11 @@ struct SpTables {
 // Loads <path> (file, or directory containing tokenizer.model).  Returns XLLM_OK or an error code
 // (message in out->error).
 int sp_load_model(const std::string& path, SpTables* out);
+// tiktoken vocabulary (`base64(token) rank` lines) -> the same tables, byte_mode (tiktoken_model.cc)
+int tiktoken_load_model(const std::string& path, SpTables* out);
+// <dir>/tokenizer_config.json has "tokenizer_class": "TikTokenTokenizer" (tokenizer_factory.cpp:20-25)
+bool tokenizer_dir_is_tiktoken(const std::string& dir);
+// the factory's choice for a tokenizer directory / file
+int load_tokenizer_tables(const std::string& path, SpTables* out);
 
 }  // namespace xllm

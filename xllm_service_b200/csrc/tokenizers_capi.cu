@@ -28,8 +28,12 @@ std::string decode_ids(const xllm::SpTables& t, const uint32_t* ids, size_t n, b
   std::string out;
   bool first = true;
   for (size_t i = 0; i < n; ++i) {
-    if (ids[i] >= t.n_pieces) continue;
+    if (ids[i] >= t.piece_str.size()) continue;
     const std::string& p = t.piece_str[ids[i]];
+    if (t.byte_mode) {  // tiktoken: tokens are raw byte strings (tiktoken_tokenizer.cpp:296-316)
+      out += p;
+      continue;
+    }
     const int type = t.piece_type[ids[i]];
     if (type == 3) {  // CONTROL
       if (!skip_special) out += p;
@@ -69,7 +73,8 @@ LegacyTokenizer* make(const char* path) {
     return nullptr;
   }
   const xllm::SpTables& t = *L->h->sp_tables;
-  for (uint32_t i = 0; i < t.n_pieces; ++i) L->piece_to_id.emplace(t.piece_str[i], (int32_t)i);
+  for (uint32_t i = 0; i < t.piece_str.size(); ++i)
+    if (!t.piece_str[i].empty()) L->piece_to_id.emplace(t.piece_str[i], (int32_t)i);
   return L;
 }
 
@@ -161,7 +166,7 @@ void tokenizers_id_to_token(TokenizerHandle handle, uint32_t id, const char** da
   LegacyTokenizer* L = static_cast<LegacyTokenizer*>(handle);
   if (!L || !data || !len) return;
   const xllm::SpTables& t = *L->h->sp_tables;
-  L->scratch = id < t.n_pieces ? t.piece_str[id] : std::string();
+  L->scratch = id < t.piece_str.size() ? t.piece_str[id] : std::string();
   *data = L->scratch.data();
   *len = L->scratch.size();
 }
@@ -185,7 +190,11 @@ void tokenizers_free(TokenizerHandle handle) {
 void tokenizers_get_vocab_size(TokenizerHandle handle, size_t* size) {
   LegacyTokenizer* L = static_cast<LegacyTokenizer*>(handle);
   if (!size) return;
-  *size = L ? (size_t)L->h->sp_tables->n_pieces : 0;
+  *size = 0;
+  if (L) {
+    const xllm::SpTables& t = *L->h->sp_tables;
+    *size = t.vocab_size_override >= 0 ? (size_t)t.vocab_size_override : (size_t)t.n_pieces;
+  }
 }
 
 }  // extern "C"
