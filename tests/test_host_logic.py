@@ -74,3 +74,22 @@ def test_workload_exact_tokens_and_shared_prefixes(oracle):
         rows = np.nonzero(pid == j)[0]
         L = int(meta["prefix_blocks"][rows[0]]) * 128
         assert (ids[rows, :L] == ids[rows[0], :L]).all()
+
+
+def test_factory_selects_tiktoken_by_tokenizer_class(tmp_path):
+    """TokenizerFactory::create_tokenizer (tokenizer_factory.cpp:9-32): tokenizer_class == TikTokenTokenizer
+    -> tiktoken tables (bytes are symbols, no pre-split, no normaliser); otherwise SentencePiece."""
+    import shutil
+    from xllm_service_b200 import _lib
+    info = _lib.tokenizer_probe(os.path.join(HERE, "golden", "tiktoken_1k"))
+    assert info["split_mode"] == 0 and info["trie_units"] == 0 and info["byte_fallback"] == 0
+    assert info["n_pieces"] == 1453            # 256 bytes + 1200 merges - 3 bytes dropped on purpose
+    assert info["n_symbols"] == 1456           # the 3 rank-less bytes are still symbols (they emit nothing)
+    assert info["n_pairs"] >= 1200
+    # the same vocabulary file without the tokenizer_class hint is NOT silently read as tiktoken
+    d = tmp_path / "plain"
+    d.mkdir()
+    shutil.copy(os.path.join(HERE, "golden", "tiktoken_1k", "tokenizer.model"), d / "tokenizer.model")
+    import xllm_service_b200 as x
+    with pytest.raises(x.IngestError):
+        _lib.tokenizer_probe(str(d))
