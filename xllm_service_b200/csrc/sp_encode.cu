@@ -1124,7 +1124,7 @@ int SpDeviceModel::upload(const SpTables& t) {
   if (const char* w = getenv("XLLM_SP_WARPS_PER_SM")) g_warps_per_sm_override = atoi(w);
   // scratch pool for pre-tokens longer than the shared-memory paths hold
   uint32_t cap = 1u << 17;
-  int slots = 16;
+  int slots = 64;
   if (const char* w = getenv("XLLM_SP_LONG_CAP")) cap = (uint32_t)atoi(w);
   if (const char* w = getenv("XLLM_SP_LONG_SLOTS")) slots = atoi(w);
   cap = (cap + 31) & ~31u;
