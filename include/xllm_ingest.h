@@ -217,6 +217,8 @@ typedef struct {
   int32_t byte_fallback;
   int32_t unk_id;
   int32_t trie_units;
+  int32_t avg_probe_x100; /* mean probes per successful pair lookup, x100 */
+  int32_t max_probe;      /* longest probe chain of a stored pair */
 } xllm_tokenizer_info;
 int xllm_tokenizer_probe(const char* tokenizer_path, xllm_tokenizer_info* out);
 

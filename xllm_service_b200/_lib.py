@@ -36,7 +36,8 @@ class Config(ctypes.Structure):
 class TokenizerInfo(ctypes.Structure):
     """xllm_tokenizer_info (include/xllm_ingest.h)."""
     _fields_ = [(n, ctypes.c_int32) for n in ("n_pieces", "n_symbols", "n_pair_slots", "n_pairs", "split_mode",
-                                              "max_unit_out", "byte_fallback", "unk_id", "trie_units")]
+                                              "max_unit_out", "byte_fallback", "unk_id", "trie_units",
+                                              "avg_probe_x100", "max_probe")]
 
 
 class MatchOut(ctypes.Structure):

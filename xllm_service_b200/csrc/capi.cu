@@ -9,6 +9,8 @@
 
 namespace xllm {
 
+uint32_t sp_pair_slot_fwd(uint32_t a, uint32_t b, uint32_t n_slots);  // sp_model.cc
+
 static thread_local char g_last_error[512] = "";
 
 void set_last_error(const char* fmt, ...) {
@@ -484,6 +486,24 @@ int xllm_tokenizer_probe(const char* tokenizer_path, xllm_tokenizer_info* out) {
   out->byte_fallback = t.byte_fallback;
   out->unk_id = t.unk_id;
   out->trie_units = (int32_t)t.trie.size();
+  {
+    // probe statistics of the pair table under the device's slot function
+
+    const uint32_t n = (uint32_t)t.pair_table.size();
+    uint64_t total = 0;
+    uint32_t mx = 0, cnt = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      const auto& e = t.pair_table[i];
+      if (e.a == kEmptyKey) continue;
+      const uint32_t home = sp_pair_slot_fwd(e.a, e.b, n);
+      const uint32_t d = ((i + n - home) & (n - 1)) + 1;
+      total += d;
+      mx = d > mx ? d : mx;
+      ++cnt;
+    }
+    out->avg_probe_x100 = cnt ? (int32_t)(total * 100 / cnt) : 0;
+    out->max_probe = (int32_t)mx;
+  }
   return XLLM_OK;
 }
 

@@ -55,6 +55,7 @@ struct PMOps<false> {
   static __device__ __forceinline__ T none() { return make_uint2(kNoPrio, 0); }
   static __device__ __forceinline__ uint32_t prio(T v) { return v.x; }
   static __device__ __forceinline__ uint32_t merged(T v) { return v.y; }
+  static __device__ __forceinline__ uint32_t prio_at(const T* p) { return p->x; }
 };
 template <>
 struct PMOps<true> {
@@ -64,6 +65,10 @@ struct PMOps<true> {
   static __device__ __forceinline__ T none() { return 0xFFFF0000u; }
   static __device__ __forceinline__ uint32_t prio(T v) { return v >> 16; }
   static __device__ __forceinline__ uint32_t merged(T v) { return v & 0xFFFFu; }
+  // the priority half alone, straight from shared memory (one LDS.U16, no shift)
+  static __device__ __forceinline__ uint32_t prio_at(const T* p) {
+    return reinterpret_cast<const uint16_t*>(p)[1];
+  }
 };
 
 template <bool SMALL>
@@ -75,11 +80,7 @@ struct WarpSmemT {
 };
 
 __device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) {
-  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
-  h ^= h >> 15;
-  h *= 0x2C1B3C6Du;
-  h ^= h >> 13;
-  return h;
+  return (a * 0x9E3779B1u + b) * 0x85EBCA6Bu;  // multiplicative; the slot is its top bits (sp_model.cc)
 }
 __device__ __forceinline__ uint32_t hash_cp(uint32_t cp) {
   uint32_t h = cp * 0x9E3779B1u;
@@ -95,7 +96,7 @@ struct PairProbe {
 };
 __device__ __forceinline__ PairProbe pair_probe_begin(const SpDev& T, uint32_t a, uint32_t b) {
   PairProbe p;
-  p.h = hash_pair(a, b) & T.pair_mask;
+  p.h = hash_pair(a, b) >> T.pair_shift;
   p.e = ((a | b) & kSymUnknownFlag) ? make_uint4(kEmptyKey, 0, 0, 0)
                                     : __ldg(reinterpret_cast<const uint4*>(T.pair_table) + p.h);
   return p;
@@ -458,7 +459,7 @@ __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, in
     for (uint32_t m = alive; m;) {
       const int j = __ffs(m) - 1;
       m &= m - 1;
-      const uint32_t pr = P::prio(PM[j * 32]);
+      const uint32_t pr = P::prio_at(PM + j * 32);
       if (pr < best) { best = pr; bj = j; }
     }
     if (best == P::kNone) break;
@@ -1113,6 +1114,11 @@ int SpDeviceModel::upload(const SpTables& t) {
   dev_.trie_units = (uint32_t)t.trie.size();
   dev_.cp_mask = (uint32_t)t.cp_table.size() - 1;
   dev_.pair_mask = (uint32_t)t.pair_table.size() - 1;
+  {
+    uint32_t lg = 0;
+    while ((1u << lg) < (uint32_t)t.pair_table.size()) ++lg;
+    dev_.pair_shift = 32 - lg;
+  }
   dev_.n_pieces = t.n_pieces;
   dev_.space_sym = t.space_sym;
   dev_.unk_id = t.unk_id;

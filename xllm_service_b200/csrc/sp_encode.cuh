@@ -24,6 +24,7 @@ struct SpDev {
   uint32_t trie_units;
   uint32_t cp_mask;
   uint32_t pair_mask;
+  uint32_t pair_shift;  // 32 - log2(pair slots): the slot is the hash's top bits
   uint32_t n_pieces;
   uint32_t space_sym;
   int32_t unk_id;

@@ -164,18 +164,21 @@ inline uint32_t pow2_at_least(size_t n) {
 }  // namespace
 
 // Same mixers as the device side (sp_encode.cu); kept in one place via this header-less contract:
-uint32_t sp_hash_pair(uint32_t a, uint32_t b) {
-  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
-  h ^= h >> 15;
-  h *= 0x2C1B3C6Du;
-  h ^= h >> 13;
-  return h;
+// Multiplicative hash of a symbol pair; the table index is its TOP log2(slots) bits (3 instructions on
+// the device: IMAD, IMUL, SHF).  The caller masks with slots - 1 after shifting.
+uint32_t sp_hash_pair(uint32_t a, uint32_t b) { return (a * 0x9E3779B1u + b) * 0x85EBCA6Bu; }
+uint32_t sp_pair_slot(uint32_t a, uint32_t b, uint32_t n_slots) {
+  uint32_t lg = 0;
+  while ((1u << lg) < n_slots) ++lg;
+  return lg ? (sp_hash_pair(a, b) >> (32 - lg)) : 0;
 }
 uint32_t sp_hash_cp(uint32_t cp) {
   uint32_t h = cp * 0x9E3779B1u;
   h ^= h >> 16;
   return h;
 }
+
+uint32_t sp_pair_slot_fwd(uint32_t a, uint32_t b, uint32_t n) { return sp_pair_slot(a, b, n); }
 
 int sp_load_model(const std::string& path_in, SpTables* t) {
   std::string path = path_in;
@@ -398,7 +401,7 @@ int sp_load_model(const std::string& path_in, SpTables* t) {
     const uint32_t n = pow2_at_least(pairs.size() * 4 + 16);
     t->pair_table.assign(n, PairEntry{kEmptyKey, kEmptyKey, kNoPrio, 0});
     for (const auto& e : pairs) {
-      uint32_t h = sp_hash_pair(e.a, e.b) & (n - 1);
+      uint32_t h = sp_pair_slot(e.a, e.b, n);
       while (t->pair_table[h].a != kEmptyKey) {
         if (t->pair_table[h].a == e.a && t->pair_table[h].b == e.b) break;  // cannot happen (A||B is unique)
         h = (h + 1) & (n - 1);

@@ -21,7 +21,7 @@
 
 namespace xllm {
 
-uint32_t sp_hash_pair(uint32_t a, uint32_t b);
+uint32_t sp_pair_slot(uint32_t a, uint32_t b, uint32_t n_slots);
 
 namespace {
 
@@ -152,7 +152,7 @@ int tiktoken_load_model(const std::string& path_in, SpTables* t) {
   while (n < pairs.size() * 4 + 16) n <<= 1;
   t->pair_table.assign(n, PairEntry{kEmptyKey, kEmptyKey, kNoPrio, 0});
   for (const auto& e : pairs) {
-    uint32_t h = sp_hash_pair(e.a, e.b) & (n - 1);
+    uint32_t h = sp_pair_slot(e.a, e.b, n);
     while (t->pair_table[h].a != kEmptyKey) h = (h + 1) & (n - 1);
     t->pair_table[h] = e;
   }
