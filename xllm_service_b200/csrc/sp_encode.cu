@@ -923,6 +923,7 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
       }
     }
     rs.nlen = tl;
+    __syncwarp();  // every lane has read wstart[nwords - 1] (which is wstart[0] when one word is left)
     if (lane == 0) sm.wstart[0] = 0;
     rs.nw = 1;
     if (!rs.ascii) {  // the kept tail decides whether the buffer is ASCII-only again
