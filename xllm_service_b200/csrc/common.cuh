@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 // Error codes returned through the C-ABI (include/xllm_ingest.h mirrors these).
 #define XLLM_OK 0
 #define XLLM_ERR_INVALID_ARG (-1)
@@ -45,5 +47,30 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+
+// Per-device one-time kernel setup (SM count, opt-in shared memory sizes); thread-safe.
+struct DeviceOnce {
+  static constexpr int kMaxDevices = 64;
+  std::once_flag flag[kMaxDevices];
+  int n_sm[kMaxDevices] = {0};
+  cudaError_t err[kMaxDevices] = {cudaSuccess};
+  // runs setup(dev) exactly once per device; returns that device's SM count (0 on error, *e set)
+  template <typename F>
+  int get(F&& setup, cudaError_t* e) {
+    int dev = 0;
+    *e = cudaGetDevice(&dev);
+    if (*e != cudaSuccess) return 0;
+    if (dev < 0 || dev >= kMaxDevices) { *e = cudaErrorInvalidDevice; return 0; }
+    std::call_once(flag[dev], [&] {
+      int n = 0;
+      cudaError_t r = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      if (r == cudaSuccess) r = setup();
+      n_sm[dev] = n;
+      err[dev] = r;
+    });
+    *e = err[dev];
+    return *e == cudaSuccess ? n_sm[dev] : 0;
+  }
+};
 
 }  // namespace xllm

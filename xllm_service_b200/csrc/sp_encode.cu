@@ -1166,26 +1166,25 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
                              int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
                              int32_t* defer_list, cudaStream_t stream) {
   if (n_req <= 0) return cudaSuccess;
-  static int n_sm = 0;
-  static bool attr_set = false;
+  static DeviceOnce once;
   const bool small = dev.small_vocab != 0;
   const size_t smem = small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>);
-  if (!attr_set) {
-    int d = 0;
-    cudaError_t e = cudaGetDevice(&d);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d);
-    if (e != cudaSuccess) return e;
+  cudaError_t e0 = cudaSuccess;
+  const int n_sm = once.get(
+      [&] {
+        cudaError_t r;
 #define XLLM_SET_SMEM(K, B)                                                                          \
-    e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B>)); \
-    if (e != cudaSuccess) return e;
-    XLLM_SET_SMEM((sp_encode_kernel<true, false>), true)
-    XLLM_SET_SMEM((sp_encode_kernel<true, true>), true)
-    XLLM_SET_SMEM((sp_encode_kernel<false, false>), false)
-    XLLM_SET_SMEM((sp_encode_kernel<false, true>), false)
+        r = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B>)); \
+        if (r != cudaSuccess) return r;
+        XLLM_SET_SMEM((sp_encode_kernel<true, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<true, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<false, true>), false)
 #undef XLLM_SET_SMEM
-    attr_set = true;
-  }
+        return cudaSuccess;
+      },
+      &e0);
+  if (e0 != cudaSuccess) return e0;
   // counters[0]: task counter, [1]: deferred count, [2]: task counter of the long-word pass
   cudaError_t e = cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;

@@ -532,20 +532,16 @@ cudaError_t xxh3_chain_launch(const int32_t* tokens, const int64_t* tok_start, c
                               unsigned int* task_counter, cudaStream_t stream) {
   if (n_req <= 0) return cudaSuccess;
   if (block_size == kBlockTokens) {
-    static int n_sm = 0;
-    static bool attr_set = false;
+    static DeviceOnce once;
     const size_t smem = sizeof(FastSmem<kFastStages>);
-    if (!attr_set) {
-      int dev = 0;
-      cudaError_t e = cudaGetDevice(&dev);
-      if (e != cudaSuccess) return e;
-      e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(xxh3_chain128_kernel<kFastStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    cudaError_t e0 = cudaSuccess;
+    const int n_sm = once.get(
+        [&] {
+          return cudaFuncSetAttribute(xxh3_chain128_kernel<kFastStages>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        },
+        &e0);
+    if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaMemsetAsync(task_counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
     const int n_tasks = (n_req + kRowsPerWarp - 1) / kRowsPerWarp;
