@@ -1,0 +1,205 @@
+// oracle/hf_bpe_oracle.cc -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the reference's HF-tokenizers backend for byte-level BPE `tokenizer.json` models:
+//   xllm_service/tokenizer/tokenizer_factory.cpp:14-19    tokenizer.json present -> FastTokenizer
+//   xllm_service/tokenizer/fast_tokenizer.cpp:20-30       encode = tokenizers_encode(text, add_special_tokens = 1); REPLACES *ids
+//   xllm_service/tokenizer/tokenizers/src/lib.rs:38-41,83-99   Tokenizer::encode(text, add_special_tokens)
+// The arithmetic is the Rust crate `tokenizers` 0.21 (Cargo.toml:11, absent from /root/reference); this file
+// restates its published pipeline for the configuration GPT-2 style models use:
+//   added_vocabulary.rs   text is first split on the added (special) tokens, leftmost-longest
+//   pre_tokenizers/byte_level.rs   regex split
+//        's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+   then bytes -> GPT-2 byte chars
+//   models/bpe/word.rs    merge_all: lowest merge rank first, leftmost on ties
+// Pinned against pip `tokenizers` 0.22.2 by tests/test_oracle_hf.py (committed goldens
+// tests/golden/hf_bpe_goldens.json + live fuzz).  The vocabulary / merges are handed over by the test
+// harness (it reads tokenizer.json with Python's json), so no JSON parser lives here.
+#include <stdint.h>
+#include <string.h>
+
+#include <queue>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+#include "unicode_classes.inc"
+
+enum { kOther = 0, kLetter = 1, kNumber = 2, kSpace = 3 };
+inline int uni_class(uint32_t cp) {
+  if (cp >= 0x110000) return kOther;
+  return kUniStage2[(size_t)kUniStage1[cp >> 8] * 256 + (cp & 255)];
+}
+
+struct Hf {
+  int32_t byte_sym[256];                                   // byte -> id of its byte-level char
+  std::unordered_map<uint64_t, std::pair<uint32_t, int32_t>> merges;  // (a << 32 | b) -> (rank, new id)
+  std::vector<std::pair<std::string, int32_t>> added;      // special tokens matched on the raw text
+};
+
+// strict UTF-8 decode; returns length or 0 when malformed (Rust &str cannot hold malformed text:
+// lib.rs:91 unwraps from_utf8 and panics)
+int decode(const uint8_t* p, size_t avail, uint32_t* cp) {
+  const uint8_t b0 = p[0];
+  if (b0 < 0x80) { *cp = b0; return 1; }
+  auto tr = [](uint8_t x) { return (x & 0xC0) == 0x80; };
+  if ((b0 & 0xE0) == 0xC0 && avail >= 2 && tr(p[1])) {
+    *cp = ((b0 & 0x1F) << 6) | (p[1] & 0x3F);
+    return *cp >= 0x80 ? 2 : 0;
+  }
+  if ((b0 & 0xF0) == 0xE0 && avail >= 3 && tr(p[1]) && tr(p[2])) {
+    *cp = ((b0 & 0x0F) << 12) | ((p[1] & 0x3F) << 6) | (p[2] & 0x3F);
+    return (*cp >= 0x800 && !(*cp >= 0xD800 && *cp < 0xE000)) ? 3 : 0;
+  }
+  if ((b0 & 0xF8) == 0xF0 && avail >= 4 && tr(p[1]) && tr(p[2]) && tr(p[3])) {
+    *cp = ((b0 & 0x07) << 18) | ((p[1] & 0x3F) << 12) | ((p[2] & 0x3F) << 6) | (p[3] & 0x3F);
+    return (*cp >= 0x10000 && *cp <= 0x10FFFF) ? 4 : 0;
+  }
+  return 0;
+}
+
+struct Ch {
+  uint32_t cp;
+  int cls;
+  uint32_t off, len;
+};
+
+// The ByteLevel regex, alternative by alternative (leftmost-first; each alternative greedy).
+// chars: decoded text.  Returns piece boundaries as indices into chars.
+void gpt2_split(const std::vector<Ch>& c, std::vector<std::pair<size_t, size_t>>* out) {
+  const size_t n = c.size();
+  size_t i = 0;
+  auto is = [&](size_t k, uint32_t ch) { return k < n && c[k].cp == ch; };
+  while (i < n) {
+    size_t j = i;
+    // 's|'t|'re|'ve|'m|'ll|'d
+    if (c[i].cp == '\'') {
+      if (is(i + 1, 's') || is(i + 1, 't') || is(i + 1, 'm') || is(i + 1, 'd')) j = i + 2;
+      else if ((is(i + 1, 'r') && is(i + 2, 'e')) || (is(i + 1, 'v') && is(i + 2, 'e')) || (is(i + 1, 'l') && is(i + 2, 'l'))) j = i + 3;
+    }
+    if (j == i) {
+      // " ?\p{L}+" | " ?\p{N}+" | " ?[^\s\p{L}\p{N}]+"
+      const size_t s = (c[i].cp == ' ' && i + 1 < n && c[i + 1].cls != kSpace) ? i + 1 : i;
+      if (c[s].cls != kSpace) {
+        const int k = c[s].cls;
+        j = s;
+        while (j < n && c[j].cls == k) ++j;
+      }
+    }
+    if (j == i) {
+      // "\s+(?!\S)" | "\s+"
+      size_t e = i;
+      while (e < n && c[e].cls == kSpace) ++e;
+      if (e == n) j = e;              // run reaches the end: (?!\S) holds after the whole run
+      else if (e - i >= 2) j = e - 1; // backtrack one char so that a space follows
+      else j = e;                     // single whitespace before a non-space: plain \s+
+    }
+    out->emplace_back(i, j);
+    i = j;
+  }
+}
+
+// models/bpe/word.rs merge_all
+struct Sym {
+  int32_t id;
+  int prev, next;
+  bool dead;
+};
+struct Mg {
+  uint32_t rank;
+  int pos;
+  int32_t new_id;
+};
+struct MgCmp {
+  bool operator()(const Mg& a, const Mg& b) const { return a.rank != b.rank ? a.rank > b.rank : a.pos > b.pos; }
+};
+
+void bpe_word(const Hf& h, const uint8_t* bytes, size_t n, std::vector<int32_t>* ids) {
+  std::vector<Sym> s(n);
+  for (size_t i = 0; i < n; ++i) s[i] = Sym{h.byte_sym[bytes[i]], (int)i - 1, i + 1 < n ? (int)i + 1 : -1, false};
+  std::priority_queue<Mg, std::vector<Mg>, MgCmp> q;
+  auto push = [&](int pos) {
+    if (pos < 0 || s[pos].next < 0) return;
+    auto it = h.merges.find(((uint64_t)(uint32_t)s[pos].id << 32) | (uint32_t)s[s[pos].next].id);
+    if (it != h.merges.end()) q.push(Mg{it->second.first, pos, it->second.second});
+  };
+  for (size_t i = 0; i + 1 < n; ++i) push((int)i);
+  while (!q.empty()) {
+    const Mg top = q.top();
+    q.pop();
+    if (s[top.pos].dead || s[top.pos].next < 0) continue;
+    const int r = s[top.pos].next;
+    auto it = h.merges.find(((uint64_t)(uint32_t)s[top.pos].id << 32) | (uint32_t)s[r].id);
+    if (it == h.merges.end() || it->second.second != top.new_id) continue;  // expired entry
+    s[top.pos].id = top.new_id;
+    s[top.pos].next = s[r].next;
+    if (s[r].next >= 0) s[s[r].next].prev = top.pos;
+    s[r].dead = true;
+    push(s[top.pos].prev);
+    push(top.pos);
+  }
+  for (int i = 0; i >= 0 && (size_t)i < n; i = s[i].next) ids->push_back(s[i].id);
+}
+
+long encode(const Hf& h, const uint8_t* text, size_t len, std::vector<int32_t>* ids) {
+  size_t pos = 0;
+  while (pos <= len) {
+    // next added token at or after pos (leftmost, longest at that position)
+    size_t best_at = len, best_len = 0;
+    int32_t best_id = -1;
+    for (size_t p = pos; p < len && best_id < 0; ++p)
+      for (const auto& a : h.added)
+        if (a.first.size() <= len - p && a.first.size() > best_len && memcmp(text + p, a.first.data(), a.first.size()) == 0) {
+          best_at = p; best_len = a.first.size(); best_id = a.second;
+        }
+    // ordinary text [pos, best_at)
+    std::vector<Ch> c;
+    for (size_t p = pos; p < best_at;) {
+      uint32_t cp;
+      const int l = decode(text + p, best_at - p, &cp);
+      if (l == 0) return -1;  // malformed UTF-8: the Rust shim panics
+      c.push_back(Ch{cp, uni_class(cp), (uint32_t)p, (uint32_t)l});
+      p += l;
+    }
+    std::vector<std::pair<size_t, size_t>> pieces;
+    gpt2_split(c, &pieces);
+    for (const auto& pr : pieces) {
+      const size_t b = c[pr.first].off, e = c[pr.second - 1].off + c[pr.second - 1].len;
+      bpe_word(h, text + b, e - b, ids);
+    }
+    if (best_id < 0) break;
+    ids->push_back(best_id);
+    pos = best_at + best_len;
+  }
+  return (long)ids->size();
+}
+
+}  // namespace
+
+extern "C" {
+
+// byte_sym[256]: id of each byte's byte-level char; merges: n x (left id, right id, new id), rank = index;
+// added: n_added strings (blob + offsets) with their ids.
+void* oracle_hf_new(const int32_t* byte_sym, const int32_t* merges, size_t n_merges, const char* added_blob,
+                    const int64_t* added_off, const int32_t* added_ids, size_t n_added) {
+  Hf* h = new Hf();
+  memcpy(h->byte_sym, byte_sym, sizeof(h->byte_sym));
+  for (size_t i = 0; i < n_merges; ++i)
+    h->merges.emplace(((uint64_t)(uint32_t)merges[3 * i] << 32) | (uint32_t)merges[3 * i + 1],
+                      std::make_pair((uint32_t)i, merges[3 * i + 2]));
+  for (size_t i = 0; i < n_added; ++i)
+    h->added.emplace_back(std::string(added_blob + added_off[i], (size_t)(added_off[i + 1] - added_off[i])), added_ids[i]);
+  return h;
+}
+void oracle_hf_free(void* h) { delete (Hf*)h; }
+// FastTokenizer::encode; returns the id count, or -1 for malformed UTF-8 (the reference aborts there).
+long oracle_hf_encode(void* h, const char* text, size_t len, int32_t* out, size_t cap) {
+  std::vector<int32_t> ids;
+  const long n = encode(*(Hf*)h, (const uint8_t*)text, len, &ids);
+  if (n < 0) return -1;
+  memcpy(out, ids.data(), sizeof(int32_t) * (ids.size() < cap ? ids.size() : cap));
+  return n;
+}
+
+}  // extern "C"

@@ -89,6 +89,12 @@ def lib():
         L.oracle_tik_vocab_size.restype = ctypes.c_long
         L.oracle_tik_encode.argtypes = [VP, ctypes.c_char_p, ctypes.c_size_t, VP, ctypes.c_size_t]
         L.oracle_tik_encode.restype = ctypes.c_long
+        L.oracle_hf_new.argtypes = [VP, VP, ctypes.c_size_t, ctypes.c_char_p, VP, VP, ctypes.c_size_t]
+        L.oracle_hf_new.restype = VP
+        L.oracle_hf_free.argtypes = [VP]
+        L.oracle_hf_free.restype = None
+        L.oracle_hf_encode.argtypes = [VP, ctypes.c_char_p, ctypes.c_size_t, VP, ctypes.c_size_t]
+        L.oracle_hf_encode.restype = ctypes.c_long
         L.oracle_ingest_batch.argtypes = [VP, VP, VP, VP, VP, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, VP,
                                           ctypes.c_int, ctypes.c_int, VP, ctypes.c_int64, VP, VP, VP, VP]
         _lib = L
@@ -341,3 +347,64 @@ class TiktokenOracle:
         out = np.zeros(cap, dtype=np.int32)
         n = lib().oracle_tik_encode(self._h, text, len(text), out.ctypes.data, cap)
         return out[:n].copy()
+
+
+def gpt2_bytes_to_unicode():
+    """The GPT-2 byte <-> printable-char table used by HF ByteLevel (byte -> str of one char)."""
+    bs = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAC + 1)) + list(range(0xAE, 0xFF + 1))
+    cs = bs[:]
+    n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b)
+            cs.append(256 + n)
+            n += 1
+    return {b: chr(c) for b, c in zip(bs, cs)}
+
+
+class HfBpeOracle:
+    """FastTokenizer (xllm_service/tokenizer/fast_tokenizer.cpp:20-30 over HF `tokenizers`) for byte-level BPE
+    tokenizer.json files; algorithm in oracle/hf_bpe_oracle.cc, the JSON is read here."""
+
+    def __init__(self, model_dir_or_file):
+        import json
+        path = model_dir_or_file
+        if os.path.isdir(path):
+            path = os.path.join(path, "tokenizer.json")
+        with open(path, encoding="utf-8") as f:
+            d = json.load(f)
+        m = d["model"]
+        assert m["type"] == "BPE" and d["pre_tokenizer"]["type"] == "ByteLevel" and d["normalizer"] is None
+        vocab = m["vocab"]
+        b2u = gpt2_bytes_to_unicode()
+        byte_sym = np.array([vocab[b2u[b]] for b in range(256)], dtype=np.int32)
+        mg = []
+        for e in m["merges"]:
+            a, b = e if isinstance(e, list) else e.split(" ")
+            mg.append((vocab[a], vocab[b], vocab[a + b]))
+        merges = np.array(mg, dtype=np.int32).reshape(-1, 3)
+        added = [(t["content"].encode("utf-8"), t["id"]) for t in d.get("added_tokens", [])]
+        blob = b"".join(a for a, _ in added)
+        off = np.zeros(len(added) + 1, dtype=np.int64)
+        if added:
+            np.cumsum([len(a) for a, _ in added], out=off[1:])
+        ids = np.array([i for _, i in added], dtype=np.int32)
+        self._keep = (byte_sym, merges, blob, off, ids)
+        self._h = lib().oracle_hf_new(byte_sym.ctypes.data, merges.ctypes.data, merges.shape[0],
+                                      ctypes.c_char_p(blob), off.ctypes.data, ids.ctypes.data, len(added))
+        self.vocab_size = max(vocab.values()) + 1
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().oracle_hf_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def encode(self, text: bytes):
+        """ids, or None when the text is not valid UTF-8 (the reference's Rust shim panics there)."""
+        cap = len(text) + 16
+        out = np.zeros(cap, dtype=np.int32)
+        n = lib().oracle_hf_encode(self._h, text, len(text), out.ctypes.data, cap)
+        return None if n < 0 else out[:n].copy()

@@ -1,0 +1,50 @@
+"""Pins the CPU oracle of the reference's HF-tokenizers backend (oracle/hf_bpe_oracle.cc: added-token split,
+ByteLevel GPT-2 regex, BPE by merge rank) against upstream `tokenizers`: committed goldens minted with pip
+tokenizers 0.22.2 (tests/golden/make_hf_fixture.py) + live fuzz / Unicode sweep when the wheel is importable.
+Reference call sites: xllm_service/tokenizer/fast_tokenizer.cpp:20-30, tokenizers/src/lib.rs:83-99."""
+import json
+import os
+import random
+
+import pytest
+
+HERE = os.path.dirname(__file__)
+MODEL_DIR = os.path.join(HERE, "golden", "hf_bpe_8k")
+GOLD = os.path.join(HERE, "golden", "hf_bpe_goldens.json")
+
+
+@pytest.fixture(scope="module")
+def hf(oracle):
+    return oracle.HfBpeOracle(MODEL_DIR)
+
+
+def test_goldens(hf):
+    with open(GOLD) as f:
+        g = json.load(f)
+    assert g["vocab_size"] == hf.vocab_size == 8000 and len(g["cases"]) > 350
+    for c in g["cases"]:
+        t = bytes.fromhex(c["text"])
+        assert hf.encode(t).tolist() == c["ids"], t[:40]
+
+
+def test_contract_details(hf):
+    assert hf.encode(b"").size == 0
+    assert hf.encode(b"<|endoftext|>").tolist() == [0]                    # added token matched on the raw text
+    assert hf.encode(b"a<|endoftext|>b").tolist()[1] == 0
+    assert hf.encode(b"\xff broken") is None                               # Rust &str cannot hold this: lib.rs:91 panics
+    # "\s+(?!\S)": the last space of a run attaches to the following word
+    assert hf.encode(b"x   y").tolist() == hf.encode(b"x").tolist() + hf.encode(b"  ").tolist() + hf.encode(b" y").tolist()
+
+
+def test_live_against_tokenizers_wheel(hf):
+    tokenizers = pytest.importorskip("tokenizers")
+    tok = tokenizers.Tokenizer.from_file(os.path.join(MODEL_DIR, "tokenizer.json"))
+    rnd = random.Random(4)
+    alphabet = list("abcdefghij  \t\n'.,!?012") + ["é", "日", "Σ", "١", " ", "　", "\U0001F600", "'s", "'re",
+                                                   " '", "<|endoftext|>", "\r\n", " ", "_", "²", "", " "]
+    for _ in range(2000):
+        s = "".join(rnd.choice(alphabet) for _ in range(rnd.randrange(0, 70)))
+        assert hf.encode(s.encode()).tolist() == tok.encode(s).ids, repr(s)
+    for cp in list(range(0x80, 0x2100, 3)) + list(range(0x2E80, 0x3100, 5)) + list(range(0x1F600, 0x1F608)):
+        s = "a" + chr(cp) + "b " + chr(cp) + "1"
+        assert hf.encode(s.encode()).tolist() == tok.encode(s).ids, hex(cp)
