@@ -93,3 +93,71 @@ def test_factory_selects_tiktoken_by_tokenizer_class(tmp_path):
     import xllm_service_b200 as x
     with pytest.raises(x.IngestError):
         _lib.tokenizer_probe(str(d))
+
+
+HF_DIR = os.path.join(HERE, "golden", "hf_bpe_8k")
+
+
+def test_hf_tokenizer_json_tables(tmp_path):
+    """tokenizer.json wins the factory's choice (tokenizer_factory.cpp:14-19) and loads as byte-level BPE."""
+    import json
+    import shutil
+    import xllm_service_b200 as x
+    from xllm_service_b200 import _lib
+    info = _lib.tokenizer_probe(HF_DIR)
+    assert info["split_mode"] == 3 and info["trie_units"] == 0 and info["byte_fallback"] == 0
+    assert info["n_pieces"] == 8000 and info["n_symbols"] == 8000
+    assert info["n_pairs"] == 8000 - 256 - 1          # one merge per non-byte, non-special token
+    assert _lib.tokenizer_probe(os.path.join(HF_DIR, "tokenizer.json")) == info
+    # a directory holding BOTH files is an HF tokenizer, as in the reference's factory
+    both = tmp_path / "both"
+    both.mkdir()
+    shutil.copy(os.path.join(HF_DIR, "tokenizer.json"), both / "tokenizer.json")
+    shutil.copy(os.path.join(MODEL_DIR, "tokenizer.model"), both / "tokenizer.model")
+    assert _lib.tokenizer_probe(str(both))["split_mode"] == 3
+    # configurations the device path does not implement are refused, never approximated
+    with open(os.path.join(HF_DIR, "tokenizer.json")) as f:
+        base = json.load(f)
+
+    def variant(name, edit):
+        d = json.loads(json.dumps(base))
+        edit(d)
+        q = tmp_path / name
+        q.mkdir()
+        (q / "tokenizer.json").write_text(json.dumps(d))
+        return str(q)
+
+    def set_(path, value):
+        def f(d):
+            for k in path[:-1]:
+                d = d[k]
+            d[path[-1]] = value
+        return f
+
+    for name, edit in (
+        ("nfc", set_(["normalizer"], {"type": "NFC"})),
+        ("ignore_merges", set_(["model", "ignore_merges"], True)),
+        ("dropout", set_(["model", "dropout"], 0.1)),
+        ("prefix_space", set_(["pre_tokenizer", "add_prefix_space"], True)),
+        ("no_regex", set_(["pre_tokenizer", "use_regex"], False)),
+        ("whitespace", set_(["pre_tokenizer"], {"type": "Whitespace"})),
+        ("wordpiece", set_(["model", "type"], "WordPiece")),
+        ("truncation", set_(["truncation"], {"max_length": 8, "strategy": "LongestFirst", "stride": 0, "direction": "Right"})),
+        ("lstrip", lambda d: d["added_tokens"][0].__setitem__("lstrip", True)),
+        ("roberta", set_(["post_processor"], {"type": "RobertaProcessing", "sep": ["</s>", 2], "cls": ["<s>", 0],
+                                               "trim_offsets": True, "add_prefix_space": True})),
+    ):
+        with pytest.raises(x.IngestError) as e:
+            _lib.tokenizer_probe(variant(name, edit))
+        assert e.value.code == -5, name
+    (tmp_path / "broken").mkdir()
+    (tmp_path / "broken" / "tokenizer.json").write_text('{"model": {"vocab": {"a": 0}, "merges": [')
+    with pytest.raises(x.IngestError) as e:
+        _lib.tokenizer_probe(str(tmp_path / "broken"))
+    assert e.value.code == -4
+    # a template post-processor is accepted (ids are wrapped on device)
+    tp = {"type": "TemplateProcessing",
+          "single": [{"SpecialToken": {"id": "<|endoftext|>", "type_id": 0}}, {"Sequence": {"id": "A", "type_id": 0}}],
+          "pair": [{"Sequence": {"id": "A", "type_id": 0}}, {"Sequence": {"id": "B", "type_id": 1}}],
+          "special_tokens": {"<|endoftext|>": {"id": "<|endoftext|>", "ids": [0], "tokens": ["<|endoftext|>"]}}}
+    assert _lib.tokenizer_probe(variant("template", set_(["post_processor"], tp)))["split_mode"] == 3

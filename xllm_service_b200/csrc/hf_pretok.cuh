@@ -1,0 +1,224 @@
+// hf_pretok.cuh — warp-parallel pre-tokenizer of the HF byte-level BPE backend (included by sp_encode.cu).
+//
+// Device replacement for the two steps the Rust crate runs before BPE inside tokenizers_encode
+// (xllm_service/tokenizer/tokenizers/src/lib.rs:83-99 -> Tokenizer::encode):
+//   added_vocabulary.rs   split the text on the added (special) tokens, leftmost-longest, verbatim
+//   pre_tokenizers/byte_level.rs   split every remaining segment with the GPT-2 pattern
+//        's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+
+// (the oracle's sequential restatement: oracle/hf_bpe_oracle.cc gpt2_split).
+//
+// The leftmost-first regex scan is sequential as written, but every token boundary of THIS pattern is decided by
+// a window of one char back, one char ahead (plus two ASCII bytes after an apostrophe), so the warp decides all
+// positions of the staging buffer at once:
+//   A   class of every char (letter / number / whitespace / other, Unicode tables), UTF-8 validation
+//   A2  added-token starts (first-byte filter, then compare), resolved leftmost-longest / non-overlapping
+//   B1  an apostrophe starts a contraction token iff it is at a token start — i.e. the previous char is neither
+//       "other" class (the [^\s\p{L}\p{N}]+ run would have swallowed it) nor U+0020 (which is then the " ?" prefix
+//       of a punctuation run) — and the bytes after it spell one of s t m d re ve ll
+//   B2  position i starts a token iff: segment start | contraction start | contraction end | (not inside a
+//       contraction and)  whitespace after non-whitespace | whitespace that is the LAST of a run of >= 2 followed
+//       by a non-space in the same segment (the \s+(?!\S) backtrack) | non-whitespace after whitespace other
+//       than U+0020 (a single U+0020 is the " ?" prefix) | class change between two non-whitespace chars.
+// Per-byte scratch (one byte per text byte, in the merge scratch S[] which is idle while scanning):
+//   bits 0-1 class, bit 2 char is U+0020, bit 3 inside an added token, bit 4 added token starts here,
+//   bits 5-6 contraction length - 1 (0 = none), 0x80 = UTF-8 continuation byte.
+#pragma once
+
+enum : uint8_t { kHfOther = 0, kHfLetter = 1, kHfNumber = 2, kHfSpace = 3 };
+constexpr uint8_t kHfIsSp = 0x04, kHfInAdded = 0x08, kHfAddedStart = 0x10, kHfCont = 0x80;
+constexpr uint16_t kHfSpecialWord = 0x8000;  // wstart[] flag: the word is an added token (one id, no BPE)
+constexpr uint16_t kHfPosMask = 0x0FFF;
+
+__device__ __forceinline__ uint8_t hf_class(const SpDev& T, uint32_t cp) {
+  if (cp < 0x80) {
+    const uint32_t l = cp | 0x20;
+    if (l >= 'a' && l <= 'z') return kHfLetter;
+    if (cp >= '0' && cp <= '9') return kHfNumber;
+    if (cp == ' ' || (cp >= 9 && cp <= 13)) return kHfSpace;
+    return kHfOther;
+  }
+  return __ldg(T.uni2 + (uint32_t)__ldg(T.uni1 + (cp >> 8)) * 256u + (cp & 255u));
+}
+
+// longest added token that is a prefix of p[0..avail); 0 = none.  *id = its token id.
+__device__ __forceinline__ int hf_added_len(const SpDev& T, const uint8_t* p, int avail, int32_t* id) {
+  int best = 0;
+  for (uint32_t a = 0; a < T.n_added; ++a) {
+    const int o = __ldg(T.added_off + a), l = (int)__ldg(T.added_off + a + 1) - o;
+    if (l > avail || l <= best) continue;
+    bool eq = true;
+    for (int k = 0; k < l && eq; ++k) eq = p[k] == __ldg(T.added_blob + o + k);
+    if (eq) { best = l; *id = __ldg(T.added_id + a); }
+  }
+  return best;
+}
+
+struct HfScan {
+  int nwords;      // complete pre-tokens listed in wstart[0..nwords); wstart[nwords] = tail_start
+  int tail_start;  // first byte that is not part of a listed pre-token
+  bool capped;     // wstart[] filled up: scan the kept tail again
+  bool bad;        // malformed UTF-8
+};
+
+// nb[0..nlen) starts at a token start.  cls = nlen bytes of scratch.  final: the text ends at nlen.
+template <typename SM>
+__device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane) {
+  const uint8_t* nb = sm.nbuf;
+  uint8_t* cls = reinterpret_cast<uint8_t*>(sm.S);
+  static_assert(sizeof(sm.S) >= kNBuf, "class scratch must cover the staging buffer");
+  bool bad = false;
+  // ---- A: classes + UTF-8 validation
+  for (int base = 0; base < nlen; base += 32) {
+    const int p = base + lane;
+    if (p < nlen) {
+      const uint8_t b0 = nb[p];
+      uint8_t v;
+      if (b0 < 0x80) {
+        v = hf_class(T, b0) | (b0 == ' ' ? kHfIsSp : 0);
+      } else if ((b0 & 0xC0) == 0x80) {
+        v = kHfCont;
+        bool cov = false;  // must belong to a lead byte at most 3 back
+        for (int k = 1; k <= 3 && p - k >= 0; ++k) {
+          const uint8_t x = nb[p - k];
+          if ((x & 0xC0) == 0x80) continue;
+          cov = (x >= 0xF0 ? 4 : (x >= 0xE0 ? 3 : (x >= 0xC0 ? 2 : 1))) > k;
+          break;
+        }
+        bad |= !cov;
+      } else {
+        const int l = b0 >= 0xF0 ? 4 : (b0 >= 0xE0 ? 3 : 2);
+        v = kHfOther;
+        if (p + l > nlen) {
+          bad |= final;  // cut by the end of the text; otherwise the rest arrives with the next window
+        } else {
+          bool valid;
+          utf8_unit(nb + p, (uint32_t)(nlen - p), b0, &valid);
+          if (!valid) bad = true;
+          else {
+            const uint32_t cp = l == 2 ? (((b0 & 0x1Fu) << 6) | (nb[p + 1] & 0x3Fu))
+                              : l == 3 ? (((b0 & 0x0Fu) << 12) | ((nb[p + 1] & 0x3Fu) << 6) | (nb[p + 2] & 0x3Fu))
+                                       : (((b0 & 0x07u) << 18) | ((nb[p + 1] & 0x3Fu) << 12) | ((nb[p + 2] & 0x3Fu) << 6) | (nb[p + 3] & 0x3Fu));
+            v = hf_class(T, cp);
+          }
+        }
+      }
+      cls[p] = v;
+    }
+  }
+  __syncwarp();
+  HfScan r;
+  r.nwords = 0;
+  r.tail_start = 0;
+  r.capped = false;
+  r.bad = __any_sync(kFull, bad);
+  if (r.bad) return r;
+  // ---- A2: added tokens, leftmost-longest, non-overlapping
+  if (T.n_added) {
+    int cover = 0;
+    for (int base = 0; base < nlen; base += 32) {
+      const int p = base + lane;
+      int al = 0;
+      if (p < nlen) {
+        const uint8_t b0 = nb[p];
+        if ((T.added_first[b0 >> 5] >> (b0 & 31)) & 1u) {
+          int32_t id;
+          al = hf_added_len(T, nb + p, nlen - p, &id);
+        }
+      }
+      uint32_t m = __ballot_sync(kFull, al > 0);
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int q = base + bit;
+        const int l = __shfl_sync(kFull, al, bit);
+        if (q >= cover) {
+          for (int k = lane; k < l; k += 32) cls[q + k] = k == 0 ? kHfAddedStart : kHfInAdded;
+          cover = q + l;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // ---- B1: contraction starts
+  for (int base = 0; base < nlen; base += 32) {
+    const int p = base + lane;
+    uint8_t add = 0;
+    if (p < nlen && nb[p] == '\'' && !(cls[p] & (kHfInAdded | kHfAddedStart))) {
+      bool st = p == 0;
+      if (!st) {
+        int q = p - 1;
+        while (q > 0 && cls[q] == kHfCont) --q;
+        const uint8_t a = cls[q];
+        st = (a & (kHfInAdded | kHfAddedStart)) || ((a & 3) != kHfOther && !(a & kHfIsSp));
+      }
+      if (st) {
+        const uint8_t c1 = (p + 1 < nlen && !(cls[p + 1] & (kHfInAdded | kHfAddedStart))) ? nb[p + 1] : 0;
+        const uint8_t c2 = (c1 && p + 2 < nlen && !(cls[p + 2] & (kHfInAdded | kHfAddedStart))) ? nb[p + 2] : 0;
+        if (c1 == 's' || c1 == 't' || c1 == 'm' || c1 == 'd') add = 0x20;
+        else if ((c1 == 'r' && c2 == 'e') || (c1 == 'v' && c2 == 'e') || (c1 == 'l' && c2 == 'l')) add = 0x40;
+      }
+    }
+    __syncwarp();
+    if (add) cls[p] |= add;
+    __syncwarp();
+  }
+  // ---- B2: token starts, compacted into wstart[]
+  // non-final: a token is complete only if everything that decides its end is in the buffer
+  const int limit = final ? nlen : nlen - (int)T.added_max_len - 8;
+  constexpr int kCap = kMaxWords - 1;
+  int count = 0;
+  for (int base = 0; base < nlen && base <= limit && !r.capped; base += 32) {
+    const int p = base + lane;
+    bool st = false, special = false;
+    if (p < nlen && p <= limit) {
+      const uint8_t v = cls[p];
+      if (v == kHfCont || v == kHfInAdded) {
+        st = false;
+      } else if (v & kHfAddedStart) {
+        st = special = true;
+      } else if (p == 0 || (cls[p - 1] & (kHfInAdded | kHfAddedStart)) || (v & 0x60)) {
+        st = true;  // buffer / segment start, contraction start
+      } else {
+        const uint8_t c1 = cls[p - 1] & 0x60, c2 = p >= 2 ? (cls[p - 2] & 0x60) : 0, c3 = p >= 3 ? (cls[p - 3] & 0x60) : 0;
+        if (c1 || c2 == 0x40) st = false;              // inside a contraction
+        else if (c2 == 0x20 || c3 == 0x40) st = true;   // right after one
+        else {
+          int q = p - 1;
+          while (q > 0 && cls[q] == kHfCont) --q;
+          const uint8_t a = cls[q];
+          const bool a_ws = (a & 3) == kHfSpace, b_ws = (v & 3) == kHfSpace;
+          if (b_ws) {
+            if (!a_ws) st = true;
+            else {
+              const uint8_t b0 = nb[p];
+              const int nx = p + (b0 < 0x80 ? 1 : (b0 < 0xE0 ? 2 : (b0 < 0xF0 ? 3 : 4)));
+              st = nx < nlen && !(cls[nx] & kHfAddedStart) && (cls[nx] & 3) != kHfSpace;
+            }
+          } else {
+            st = a_ws ? !(a & kHfIsSp) : ((a & 3) != (v & 3));
+          }
+        }
+      }
+    }
+    const uint32_t m = __ballot_sync(kFull, st);
+    const int idx = count + __popc(m & ((1u << lane) - 1));
+    if (st && idx < kCap) sm.wstart[idx] = (uint16_t)(p | (special ? kHfSpecialWord : 0));
+    count += __popc(m);
+    if (count >= kCap) { count = kCap; r.capped = true; }
+  }
+  __syncwarp();
+  if (final && !r.capped) {
+    r.nwords = count;
+    r.tail_start = nlen;
+    if (lane == 0) sm.wstart[count] = (uint16_t)nlen;
+  } else if (count == 0) {
+    r.nwords = 0;
+    r.tail_start = 0;
+  } else {
+    // the last start listed opens the first token that is not known to be complete
+    r.nwords = count - 1;
+    r.tail_start = sm.wstart[count - 1] & kHfPosMask;
+  }
+  __syncwarp();
+  return r;
+}

@@ -26,6 +26,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "sp_long_word.cuh"
 
@@ -194,6 +196,8 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
+#include "hf_pretok.cuh"
+
 // State of one request while it streams through the warp.
 struct ReqState {
   const uint8_t* src;
@@ -209,6 +213,7 @@ struct ReqState {
   bool prev_space;      // normalizer's is_prev_space
   bool prev_unk;        // last emitted symbol was unknown (byte_fallback off only)
   bool too_long;
+  bool bad_input;      // HF backend: malformed UTF-8
   bool deferred;       // needs the long-word kernel (this one was built without it)
   // long-word mode: the current pre-token is being streamed into a global scratch slot
   bool long_mode;
@@ -711,8 +716,10 @@ __device__ __noinline__ bool long_enter(const SpDev& T, SM& sm, ReqState& rs, in
 }
 
 // Tokenises the complete words held in nbuf (all words when final) and keeps the incomplete tail.
-template <bool SMALL, bool LONG, typename SM>
-__device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane) {
+// HF: word boundaries come from the regex pre-tokenizer (hf_pretok.cuh); returns true when the word list
+// filled up and the kept tail has to be scanned again.
+template <bool SMALL, bool LONG, bool HF, typename SM>
+__device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane) {
   const uint8_t* nb = sm.nbuf;
   int nlen = rs.nlen;
   if (final && T.remove_extra_ws) {
@@ -720,11 +727,19 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
     while (nlen >= 3 && nb[nlen - 3] == 0xE2 && nb[nlen - 2] == 0x96 && nb[nlen - 1] == 0x81) nlen -= 3;
     if (nlen == 0) { rs.n_out -= rs.trailing_bare; rs.trailing_bare = 0; }
   }
-  if (nlen == 0) { rs.nlen = 0; return; }
+  if (nlen == 0) { rs.nlen = 0; return false; }
 
   // 1. word starts: recorded by the fast path, or re-derived after any general-path window
   int nwords = 0;
-  if (!rs.rescan && !(final && nlen != rs.nlen)) {
+  int hf_tail = 0;
+  bool hf_capped = false;
+  if constexpr (HF) {
+    const HfScan sc = hf_scan(T, sm, nlen, final, lane);
+    if (sc.bad) { rs.bad_input = true; return false; }
+    nwords = sc.nwords;
+    hf_tail = sc.tail_start;
+    hf_capped = sc.capped;
+  } else if (!rs.rescan && !(final && nlen != rs.nlen)) {
     nwords = rs.nw;
   } else if (!rs.rescan) {
     // trailing U+2581 were stripped: drop the starts that now lie at or past the end
@@ -746,9 +761,11 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
     }
   }
   __syncwarp();
-  if (lane == 0) sm.wstart[nwords] = (uint16_t)nlen;
-  __syncwarp();
-  const int complete = final ? nwords : nwords - 1;
+  if constexpr (!HF) {
+    if (lane == 0) sm.wstart[nwords] = (uint16_t)nlen;
+    __syncwarp();
+  }
+  const int complete = HF ? nwords : (final ? nwords : nwords - 1);
 
   // 2. rounds of up to 32 consecutive words
   int w0 = 0;
@@ -756,7 +773,16 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
     const int w = w0 + lane;
     const bool have = w < complete;
     int ws = 0, we = 0, nsym = 0;
-    if (have) {
+    bool special = false;  // HF: the word is an added token
+    if constexpr (HF) {
+      if (have) {
+        const uint16_t e = sm.wstart[w];
+        ws = e & kHfPosMask;
+        we = sm.wstart[w + 1] & kHfPosMask;
+        special = (e & kHfSpecialWord) != 0;
+        nsym = special ? 1 : we - ws;  // every byte is a symbol
+      }
+    } else if (have) {
       ws = sm.wstart[w];
       we = sm.wstart[w + 1];
       if (rs.ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
@@ -771,7 +797,13 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
     uint32_t alive = 0;
     int cnt = 0;
     bool first_unk = false, last_unk = false, bare = false;
-    if (active) {
+    if (HF && active && special) {
+      int32_t id = 0;
+      hf_added_len(T, nb + ws, we - ws, &id);
+      sm.S[lane] = kResolvedFlag | (uint32_t)id;
+      alive = 1u;
+      cnt = 1;
+    } else if (active) {
       int n = 0;
       for (int p = ws; p < we;) {
         uint32_t adv;
@@ -850,7 +882,8 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
 
     // --- cooperative path for the long word w0
     {
-      const int lws = sm.wstart[w0], lwe = sm.wstart[w0 + 1];
+      const int lws = HF ? (sm.wstart[w0] & kHfPosMask) : sm.wstart[w0];
+      const int lwe = HF ? (sm.wstart[w0 + 1] & kHfPosMask) : sm.wstart[w0 + 1];
       int n = 0;
       bool overflow = false;
       for (int base = lws; base < lwe; base += 32) {
@@ -909,8 +942,8 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
   }
 
   // 3. keep the incomplete tail at the front of nbuf
-  if (!final) {
-    const int ts = sm.wstart[nwords - 1];
+  if (!final || (HF && hf_tail < nlen)) {
+    const int ts = HF ? hf_tail : sm.wstart[nwords - 1];
     const int tl = nlen - ts;
     if (ts > 0) {
       for (int base = 0; base < tl; base += 32) {
@@ -939,11 +972,22 @@ __device__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane
   }
   rs.rescan = false;
   __syncwarp();
+  return HF && hf_capped && !rs.deferred;
+}
+
+template <bool SMALL, bool LONG, bool HF, typename SM>
+__device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane) {
+  if constexpr (HF) {
+    while (drain_pass<SMALL, LONG, true>(T, sm, rs, final, lane)) {}
+  } else {
+    drain_pass<SMALL, LONG, false>(T, sm, rs, final, lane);
+  }
 }
 
 // LONG == false: the throughput kernel; a request that needs the long-word path is appended to defer_list.
 // LONG == true : re-runs exactly the deferred requests (work list = defer_list[0 .. *defer_count)).
-template <bool SMALL, bool LONG>
+// HF == true : byte-level BPE with the regex pre-tokenizer (split_mode 3).
+template <bool SMALL, bool LONG, bool HF>
 __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ offsets, int n_req, int32_t* __restrict__ ids,
     int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status, const __grid_constant__ SpDev T,
@@ -981,13 +1025,33 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     rs.prev_space = T.remove_extra_ws;
     rs.prev_unk = false;
     rs.too_long = false;
+    rs.bad_input = false;
     rs.deferred = false;
     rs.long_mode = false;
     rs.long_last_sp = false;
     rs.long_slot = -1;
     rs.long_n = 0;
 
-    if (rs.len > 0) {
+    if constexpr (HF) {
+      // TemplateProcessing ids in front (add_special_tokens = 1, fast_tokenizer.cpp:24), also for an empty text
+      if (lane < T.n_prefix) put_id(rs, lane, T.prefix_ids[lane]);
+      rs.n_out = T.n_prefix;
+      if (lane == 0) sm.wstart[0] = 0;
+      for (uint32_t pos = 0; pos < rs.len; pos += kFastWin) {
+        normalize_fast(T, sm, rs, pos, lane);  // byte mode: a verbatim copy
+        if (rs.nlen > drain_at) {
+          drain<SMALL, LONG, true>(T, sm, rs, false, lane);
+          // what is left is one unfinished pre-token (plus the look-ahead margin)
+          if (rs.nlen > kLongEnterAt) rs.too_long = true;
+          if (rs.too_long || rs.deferred || rs.bad_input) break;
+        }
+      }
+      if (!rs.too_long && !rs.deferred && !rs.bad_input) drain<SMALL, LONG, true>(T, sm, rs, true, lane);
+      if (!rs.too_long && !rs.deferred && !rs.bad_input) {
+        if (lane < T.n_suffix) put_id(rs, rs.n_out + lane, T.suffix_ids[lane]);
+        rs.n_out += T.n_suffix;
+      }
+    } else if (rs.len > 0) {
       if (T.add_dummy_prefix) {
         if (lane == 0) { sm.nbuf[0] = 0xE2; sm.nbuf[1] = 0x96; sm.nbuf[2] = 0x81; sm.wstart[0] = 0; }
         rs.nlen = 3;
@@ -1005,7 +1069,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
             if constexpr (LONG) {
               if (rs.long_mode) { long_consume(T, sm, rs, false, lane); consumed = true; }
             }
-            if (!consumed) drain<SMALL, LONG>(T, sm, rs, false, lane);
+            if (!consumed) drain<SMALL, LONG, false>(T, sm, rs, false, lane);
             if (!rs.too_long && !normalize_window(T, sm, rs, pos, carry_skip, lane)) {
               // still no room: the kept tail is one very long word -> stream it through a scratch slot
               bool entered = false;
@@ -1029,7 +1093,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
           }
         }
         if (!in_long && rs.nlen > drain_at) {
-          drain<SMALL, LONG>(T, sm, rs, false, lane);
+          drain<SMALL, LONG, false>(T, sm, rs, false, lane);
           if (rs.nlen > kLongEnterAt) {
             if constexpr (LONG) {
               if (!long_enter(T, sm, rs, lane)) rs.too_long = true;
@@ -1043,7 +1107,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       if constexpr (LONG) {
         if (!rs.too_long && rs.long_mode) long_consume(T, sm, rs, true, lane);
       }
-      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG>(T, sm, rs, true, lane);
+      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG, false>(T, sm, rs, true, lane);
     }
     if constexpr (LONG) {
       if (rs.long_mode) {  // error exit while a slot is held
@@ -1057,8 +1121,10 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
         n_ids[r] = 0;
         status[r] = kEncWordTooLong;  // overwritten by the long-word kernel
       } else {
-        n_ids[r] = rs.too_long ? 0 : (int32_t)rs.n_out;
-        status[r] = rs.too_long ? kEncWordTooLong : (rs.n_out > rs.cap ? kEncTruncated : kEncOk);
+        const bool failed = rs.too_long || rs.bad_input;
+        n_ids[r] = failed ? 0 : (int32_t)rs.n_out;
+        status[r] = rs.bad_input ? kEncBadUtf8
+                                 : (rs.too_long ? kEncWordTooLong : (rs.n_out > rs.cap ? kEncTruncated : kEncOk));
       }
     }
     __syncwarp();
@@ -1075,6 +1141,10 @@ SpDeviceModel::~SpDeviceModel() {
 }
 
 int SpDeviceModel::upload(const SpTables& t) {
+  if (t.split_mode == 3 && (!t.byte_mode || t.added_tokens.size() > 256 || t.uni_stage1.empty())) {
+    set_last_error("split_mode 3 (regex pre-tokenizer) needs byte-mode tables and the Unicode class tables");
+    return XLLM_ERR_UNSUPPORTED;
+  }
   if (32 * t.max_unit_out + 64 > (uint32_t)kNBuf) {
     set_last_error("normalizer replacement of %u bytes exceeds the device staging budget", t.max_unit_out);
     return XLLM_ERR_UNSUPPORTED;
@@ -1111,6 +1181,28 @@ int SpDeviceModel::upload(const SpTables& t) {
   UP(t.emit, emit);
   UP(t.virt_cp, virt_cp);
   UP(t.byte_id, byte_id);
+  UP(t.uni_stage1, uni1);
+  UP(t.uni_stage2, uni2);
+  {
+    std::vector<uint8_t> blob;
+    std::vector<uint16_t> off(1, 0);
+    std::vector<int32_t> aid;
+    for (const auto& a : t.added_tokens) {
+      blob.insert(blob.end(), a.first.begin(), a.first.end());
+      off.push_back((uint16_t)blob.size());
+      aid.push_back(a.second);
+      dev_.added_first[(uint8_t)a.first[0] >> 5] |= 1u << ((uint8_t)a.first[0] & 31);
+      if (a.first.size() > dev_.added_max_len) dev_.added_max_len = (uint32_t)a.first.size();
+    }
+    dev_.n_added = (uint32_t)aid.size();
+    UP(blob, added_blob);
+    UP(off, added_off);
+    UP(aid, added_id);
+  }
+  dev_.n_prefix = (uint8_t)t.prefix_ids.size();
+  dev_.n_suffix = (uint8_t)t.suffix_ids.size();
+  for (size_t i = 0; i < t.prefix_ids.size() && i < 4; ++i) dev_.prefix_ids[i] = t.prefix_ids[i];
+  for (size_t i = 0; i < t.suffix_ids.size() && i < 4; ++i) dev_.suffix_ids[i] = t.suffix_ids[i];
 #undef UP
   dev_.trie_units = (uint32_t)t.trie.size();
   dev_.cp_mask = (uint32_t)t.cp_table.size() - 1;
@@ -1176,10 +1268,14 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
 #define XLLM_SET_SMEM(K, B)                                                                          \
         r = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B>)); \
         if (r != cudaSuccess) return r;
-        XLLM_SET_SMEM((sp_encode_kernel<true, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<true, true>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<false, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<true, true, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<false, true, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<true, true, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<false, true, true>), false)
 #undef XLLM_SET_SMEM
         return cudaSuccess;
       },
@@ -1195,18 +1291,18 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
   if (grid > n_req) grid = n_req;
   int grid_long = n_sm * 2;
   if (grid_long > n_req) grid_long = n_req;
-  if (small) {
-    sp_encode_kernel<true, false><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status,
-                                                              dev, counters, defer_list, counters + 1);
-    sp_encode_kernel<true, true><<<grid_long, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids,
-                                                                  status, dev, counters + 2, defer_list, counters + 1);
-  } else {
-    sp_encode_kernel<false, false><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, status,
-                                                               dev, counters, defer_list, counters + 1);
-    sp_encode_kernel<false, true><<<grid_long, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids,
-                                                                   status, dev, counters + 2, defer_list,
-                                                                   counters + 1);
-  }
+#define XLLM_LAUNCH_PAIR(SMALL_, HF_)                                                                          \
+  sp_encode_kernel<SMALL_, false, HF_><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids,    \
+                                                                   status, dev, counters, defer_list, counters + 1); \
+  sp_encode_kernel<SMALL_, true, HF_><<<grid_long, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, \
+                                                                       status, dev, counters + 2, defer_list,       \
+                                                                       counters + 1);
+  const bool hf = dev.split_mode == 3;
+  if (small && hf) { XLLM_LAUNCH_PAIR(true, true) }
+  else if (small) { XLLM_LAUNCH_PAIR(true, false) }
+  else if (hf) { XLLM_LAUNCH_PAIR(false, true) }
+  else { XLLM_LAUNCH_PAIR(false, false) }
+#undef XLLM_LAUNCH_PAIR
   return cudaGetLastError();
 }
 

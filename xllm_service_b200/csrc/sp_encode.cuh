@@ -34,6 +34,17 @@ struct SpDev {
   uint8_t small_vocab;  // ranks and piece ids fit 16 bits: packed merge scratch
   uint8_t byte_mode;    // tiktoken tables: every byte is a symbol, text is copied verbatim
   // global scratch pool for pre-tokens too long for shared memory (sp_long_word.cuh)
+  // HF byte-level BPE (split_mode 3, hf_model.cc): Unicode classes for the GPT-2 regex, the added (special)
+  // tokens matched verbatim in the text, and the template ids wrapped around every sequence
+  const uint16_t* uni1;
+  const uint8_t* uni2;
+  const uint8_t* added_blob;
+  const uint16_t* added_off;  // [n_added + 1]
+  const int32_t* added_id;
+  uint32_t n_added, added_max_len;
+  uint32_t added_first[8];    // bit b set <=> some added token starts with byte b
+  int32_t prefix_ids[4], suffix_ids[4];
+  uint8_t n_prefix, n_suffix;
   uint8_t* long_pool;
   int* long_locks;
   uint32_t long_cap;   // symbols per slot
@@ -43,6 +54,7 @@ struct SpDev {
 // Per-request status written by the kernel.
 constexpr int32_t kEncOk = 0;
 constexpr int32_t kEncTruncated = 1;     // more ids than ids_stride: n_ids holds the full count, the row its prefix
+constexpr int32_t kEncBadUtf8 = -1;      // HF backend: the text is not valid UTF-8 (the reference's Rust shim panics)
 constexpr int32_t kEncWordTooLong = -6;  // a single pre-token exceeds the on-chip word capacity (XLLM_ERR_CAPACITY)
 
 class SpDeviceModel {
@@ -53,7 +65,7 @@ class SpDeviceModel {
 
  private:
   SpDev dev_{};
-  void* allocs_[12] = {nullptr};
+  void* allocs_[24] = {nullptr};
   int n_allocs_ = 0;
 };
 

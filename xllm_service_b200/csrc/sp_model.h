@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace xllm {
@@ -55,8 +56,15 @@ struct SpTables {
   // no whitespace rules; emit == -2 marks a symbol that produces no id
   bool byte_mode = false;
   int32_t vocab_size_override = -1;
+  // HF byte-level BPE (hf_model.cc): split_mode 3 = the GPT-2 regex pre-tokenizer over the raw bytes;
+  // added (special) tokens are matched verbatim in the text; template ids wrap every sequence
+  std::vector<std::pair<std::string, int32_t>> added_tokens;
+  std::vector<int32_t> prefix_ids, suffix_ids;
+  std::vector<uint16_t> uni_stage1;  // [0x1100]  code point >> 8 -> block
+  std::vector<uint8_t> uni_stage2;   // [blocks * 256] class: 0 other, 1 \p{L}, 2 \p{N}, 3 \s
   // vocabulary strings for decode / id_to_token / token_to_id
   std::vector<std::string> piece_str;
+  std::vector<std::string> piece_raw;  // HF byte-level: the bytes each token decodes to (piece_str keeps the vocab spelling)
   std::vector<uint8_t> piece_type;
   std::string error;
 };
@@ -68,6 +76,10 @@ int sp_load_model(const std::string& path, SpTables* out);
 int tiktoken_load_model(const std::string& path, SpTables* out);
 // <dir>/tokenizer_config.json has "tokenizer_class": "TikTokenTokenizer" (tokenizer_factory.cpp:20-25)
 bool tokenizer_dir_is_tiktoken(const std::string& dir);
+// HF `tokenizer.json` byte-level BPE -> the same tables, byte_mode + split_mode 3 (hf_model.cc)
+int hf_load_model(const std::string& path, SpTables* out);
+// <dir>/tokenizer.json exists (tokenizer_factory.cpp:14-19: it wins over everything else)
+bool tokenizer_dir_has_hf_json(const std::string& dir);
 // the factory's choice for a tokenizer directory / file
 int load_tokenizer_tables(const std::string& path, SpTables* out);
 

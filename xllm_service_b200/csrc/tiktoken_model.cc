@@ -161,9 +161,11 @@ int tiktoken_load_model(const std::string& path_in, SpTables* t) {
 
 int load_tokenizer_tables(const std::string& path, SpTables* out) {
   // TokenizerFactory::create_tokenizer (tokenizer_factory.cpp:9-32): tokenizer.json -> HF fast tokenizer
-  // (not available on device yet), tokenizer_class TikTokenTokenizer -> tiktoken, otherwise SentencePiece
+  // (hf_model.cc), tokenizer_class TikTokenTokenizer -> tiktoken, otherwise SentencePiece
   struct stat st;
   const bool is_dir = stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+  if (is_dir && tokenizer_dir_has_hf_json(path)) return hf_load_model(path, out);
+  if (!is_dir && path.size() > 5 && path.compare(path.size() - 5, 5, ".json") == 0) return hf_load_model(path, out);
   if (is_dir && tokenizer_dir_is_tiktoken(path)) return tiktoken_load_model(path, out);
   return sp_load_model(path, out);
 }

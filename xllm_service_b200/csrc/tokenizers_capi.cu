@@ -30,8 +30,14 @@ std::string decode_ids(const xllm::SpTables& t, const uint32_t* ids, size_t n, b
   for (size_t i = 0; i < n; ++i) {
     if (ids[i] >= t.piece_str.size()) continue;
     const std::string& p = t.piece_str[ids[i]];
-    if (t.byte_mode) {  // tiktoken: tokens are raw byte strings (tiktoken_tokenizer.cpp:296-316)
-      out += p;
+    if (t.byte_mode) {
+      // tiktoken: tokens are raw byte strings (tiktoken_tokenizer.cpp:296-316); HF byte-level: the ByteLevel
+      // decoder maps the vocab spelling back to bytes, special tokens dropped on request (lib.rs:101-113)
+      if (!t.piece_raw.empty()) {
+        if (!(skip_special && t.piece_type[ids[i]] == 3)) out += t.piece_raw[ids[i]];
+      } else {
+        out += p;
+      }
       continue;
     }
     const int type = t.piece_type[ids[i]];
