@@ -162,11 +162,16 @@ int xllm_score_route_device(xllm_ingest_t h, int32_t n_req, const uint64_t* d_ma
  * it once per request at scheduler.cpp:129).  text holds all prompts back to back;
  * offsets[n_req + 1] are byte offsets.  Request r's ids are written to ids + r*ids_stride
  * (at most ids_stride of them); n_ids[r] is the full count; status[r] is 0 (ok),
- * XLLM_ENC_TRUNCATED (count > ids_stride: call again with a larger stride) or
- * XLLM_ERR_CAPACITY (a single whitespace-free run longer than the on-chip word buffer).
- * An empty prompt yields 0 ids (sentencepiece_tokenizer.cpp:117-120).
- * Backend = SentencePiece BPE `<tokenizer_path>/tokenizer.model`
- * (sentencepiece_tokenizer.cpp:47-50); returns XLLM_ERR_UNSUPPORTED if the handle has no tokenizer.
+ * XLLM_ENC_TRUNCATED (count > ids_stride: call again with a larger stride),
+ * XLLM_ERR_CAPACITY (a single pre-token longer than the device scratch holds) or, on the HF backend,
+ * XLLM_ERR_INVALID_ARG (malformed UTF-8: the reference's Rust shim panics there, lib.rs:91).
+ * An empty prompt yields 0 ids (sentencepiece_tokenizer.cpp:117-120) plus, on the HF backend, the
+ * template's special tokens.
+ * Backend, in the order of TokenizerFactory::create_tokenizer (tokenizer_factory.cpp:9-32):
+ * `<tokenizer_path>/tokenizer.json` -> HF byte-level BPE (fast_tokenizer.cpp:8-30); tokenizer_config.json with
+ * tokenizer_class TikTokenTokenizer -> tiktoken (tiktoken_tokenizer.cpp:115-294); else SentencePiece BPE
+ * `<tokenizer_path>/tokenizer.model` (sentencepiece_tokenizer.cpp:47-50).  A model outside the supported
+ * envelope fails xllm_ingest_create with XLLM_ERR_UNSUPPORTED; a handle without a tokenizer returns it here.
  */
 #define XLLM_ENC_TRUNCATED 1
 int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets, int32_t* ids,
@@ -190,7 +195,7 @@ typedef struct {
   int32_t* ids;           /* [n_req][ids_stride] */
   int64_t ids_stride;
   int32_t* n_ids;         /* [n_req] full token counts */
-  int32_t* status;        /* [n_req] 0 / XLLM_ENC_TRUNCATED / XLLM_ERR_CAPACITY */
+  int32_t* status;        /* [n_req] 0 / XLLM_ENC_TRUNCATED / XLLM_ERR_CAPACITY / XLLM_ERR_INVALID_ARG */
   uint8_t* keys;          /* [n_req][keys_stride][16] or NULL */
   int64_t keys_stride;
   xllm_match_out* match;     /* [n_req] or NULL */
