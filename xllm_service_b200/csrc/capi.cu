@@ -120,6 +120,7 @@ int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
       xllm_ingest_destroy(h);
       return rc;
     }
+    h->memo_slots = sp_memo_default_slots();
     h->sp_dev = std::make_shared<SpDeviceModel>();
     rc = h->sp_dev->upload(*h->sp_tables);
     if (rc != XLLM_OK) {
@@ -165,6 +166,7 @@ int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out) {
   // sentencepiece_tokenizer.cpp:254-256)
   (*out)->sp_tables = src->sp_tables;
   (*out)->sp_dev = src->sp_dev;
+  (*out)->memo_slots = src->memo_slots;
   (*out)->tokenizer_path = src->tokenizer_path;
   (*out)->index = src->index;
   (*out)->index_mu = src->index_mu;
@@ -187,6 +189,7 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   h->d_n_ids.release();
   h->d_status.release();
   h->d_defer.release();
+  h->d_memo.release();
   h->d_masks.release();
   h->d_match.release();
   h->d_routing.release();
@@ -533,8 +536,14 @@ int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_te
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
   XLLM_TRY(h->d_defer.reserve((size_t)n_req * 4));
+  SpMemo memo;
+  if (h->memo_slots) {
+    XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
+    memo.table = h->d_memo.p;
+    memo.slots = h->memo_slots;
+  }
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), d_text, d_offsets, n_req, d_ids, ids_stride, d_n_ids, d_status,
-                                 h->d_task_counter + 4, h->d_defer.as<int32_t>(), s));
+                                 h->d_task_counter + 4, h->d_defer.as<int32_t>(), s, memo));
   return XLLM_OK;
 }
 
@@ -567,13 +576,19 @@ int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const
   XLLM_TRY(h->d_status.reserve((size_t)n_req * 4));
   XLLM_TRY(h->d_defer.reserve((size_t)n_req * 4));
   cudaStream_t s = h->stream;
+  SpMemo memo;
+  if (h->memo_slots) {
+    XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
+    memo.table = h->d_memo.p;
+    memo.slots = h->memo_slots;
+  }
   // offsets are rebased on the device copy of the text: ship them relative to offsets[0]
   if (text_bytes)
     XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_text.p, text + offsets[0], text_bytes, cudaMemcpyHostToDevice, s));
   XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_offsets.p, offsets, (size_t)(n_req + 1) * 8, cudaMemcpyHostToDevice, s));
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), h->d_text.as<uint8_t>() - offsets[0], h->d_offsets.as<int64_t>(),
                                  n_req, h->d_ids.as<int32_t>(), ids_stride, h->d_n_ids.as<int32_t>(),
-                                 h->d_status.as<int32_t>(), h->d_task_counter + 4, h->d_defer.as<int32_t>(), s));
+                                 h->d_status.as<int32_t>(), h->d_task_counter + 4, h->d_defer.as<int32_t>(), s, memo));
   if (ids_stride)
     XLLM_CUDA_TRY(cudaMemcpyAsync(ids, h->d_ids.p, (size_t)n_req * (size_t)ids_stride * 4, cudaMemcpyDeviceToHost, s));
   XLLM_CUDA_TRY(cudaMemcpyAsync(n_ids, h->d_n_ids.p, (size_t)n_req * 4, cudaMemcpyDeviceToHost, s));

@@ -38,6 +38,7 @@ constexpr int kPipeSlots = 8;
 struct PipeSlot {
   cudaStream_t stream = nullptr;
   unsigned int* counters = nullptr;
+  DevBuf d_memo;  // this slot's word memo (sp_encode.cuh): cleared by every encode launch on the slot's stream
   DevBuf d_defer, d_text, d_offsets, d_ids, d_n_ids, d_status, d_tok_start, d_n_tok, d_key_start, d_n_blocks, d_keys, d_masks,
       d_match, d_routing;
   int ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_stride);
@@ -73,5 +74,7 @@ struct xllm_ingest {
   int64_t pipe_chunk_bytes = 96ll << 20;
   // scratch for the host-pointer entry points
   xllm::DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status, d_defer;
+  xllm::DevBuf d_memo;      // word memo of the single-launch encode entry points
+  uint32_t memo_slots = 0;  // 0 = memo off
   xllm::DevBuf d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start;
 };

@@ -55,6 +55,7 @@ int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_
 
 void PipeSlot::release() {
   d_defer.release();
+  d_memo.release();
   d_text.release(); d_offsets.release(); d_ids.release(); d_n_ids.release(); d_status.release();
   d_tok_start.release(); d_n_tok.release(); d_key_start.release(); d_n_blocks.release();
   d_keys.release(); d_masks.release(); d_match.release(); d_routing.release();
@@ -149,12 +150,16 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
     cudaStream_t s = sl.stream;
     XLLM_CUDA_TRY(cudaStreamSynchronize(s));  // the slot's previous chunk (and its D2H copies) is done
     if ((rc = sl.ensure(text_bytes, m, io->ids_stride, keys_stride)) != XLLM_OK) break;
+    if (h->memo_slots && (rc = sl.d_memo.reserve((size_t)h->memo_slots * 32)) != XLLM_OK) break;
+    xllm::SpMemo memo;
+    memo.table = h->memo_slots ? sl.d_memo.p : nullptr;
+    memo.slots = h->memo_slots;
     if (text_bytes)
       XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_text.p, io->text + t0, text_bytes, cudaMemcpyHostToDevice, s));
     XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_offsets.p, io->offsets + c0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, s));
     XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), m,
                                    sl.d_ids.as<int32_t>(), io->ids_stride, sl.d_n_ids.as<int32_t>(),
-                                   sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s));
+                                   sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s, memo));
     XLLM_CUDA_TRY(cudaMemcpyAsync(io->ids + (size_t)c0 * io->ids_stride, sl.d_ids.p,
                                   (size_t)m * (size_t)io->ids_stride * 4, cudaMemcpyDeviceToHost, s));
     XLLM_CUDA_TRY(cudaMemcpyAsync(io->n_ids + c0, sl.d_n_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));

@@ -198,6 +198,92 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 
 #include "hf_pretok.cuh"
 
+// ---------------------------------------------------------------------------- word memo
+// Slot = two 16-byte halves, each read / written with ONE morally-strong 128-bit access:
+//   half 0  key: byte 0 = (starts with U+2581) << 7 | n, bytes 1..n = the word's bytes (without that U+2581), 0-padded
+//   half 1  ids: x = 1 << 31 | count << 28 | id0, y z w = id1..id3      (count 1..4, ids < 2^28), or, when every
+//           id fits 16 bits (SMALL tables): eight u16 = {0x8000 | count, id0 .. id6}  (count 1..7)
+// Write-once per launch: a slot is claimed by a 128-bit CAS of its key over zero, then its ids are stored; a reader
+// that finds its key but zero ids treats the word as a miss.  No slot is ever rewritten while a launch runs, so
+// a key match binds the ids to that key exactly (no tags, no probabilistic checks).
+struct U128 {
+  unsigned long long lo, hi;
+};
+__device__ __forceinline__ U128 ld_b128(const void* p) {
+  U128 v;
+  asm volatile("{.reg .b128 t; ld.relaxed.gpu.global.b128 t, [%2]; mov.b128 {%0,%1}, t; }"
+               : "=l"(v.lo), "=l"(v.hi) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_b128(void* p, U128 v) {
+  asm volatile("{.reg .b128 t; mov.b128 t, {%1,%2}; st.relaxed.gpu.global.b128 [%0], t; }"
+               :: "l"(p), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ U128 cas_b128(void* p, U128 cmp, U128 val) {
+  U128 o;
+  asm volatile("{.reg .b128 c, n, o; mov.b128 c, {%3,%4}; mov.b128 n, {%5,%6}; "
+               "atom.relaxed.gpu.global.cas.b128 o, [%2], c, n; mov.b128 {%0,%1}, o; }"
+               : "=l"(o.lo), "=l"(o.hi) : "l"(p), "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi) : "memory");
+  return o;
+}
+template <bool SMALL>
+struct MemoIds {
+  static constexpr int kMax = SMALL ? 7 : 4;
+  static __device__ __forceinline__ bool valid(U128 v) { return SMALL ? ((uint32_t)v.lo >> 15) & 1u : (uint32_t)v.lo >> 31; }
+  static __device__ __forceinline__ int count(U128 v) { return SMALL ? (int)((uint32_t)v.lo & 7u) : (int)(((uint32_t)v.lo >> 28) & 7u); }
+  static __device__ __forceinline__ uint32_t id(U128 v, int q) {  // q < count
+    if (SMALL) {
+      const int f = q + 1;  // u16 field index
+      const unsigned long long w = f < 4 ? v.lo : v.hi;
+      return (uint32_t)(w >> ((f & 3) * 16)) & 0xFFFFu;
+    }
+    return q == 0 ? ((uint32_t)v.lo & 0x0FFFFFFFu) : q == 1 ? (uint32_t)(v.lo >> 32) : q == 2 ? (uint32_t)v.hi : (uint32_t)(v.hi >> 32);
+  }
+  static __device__ __forceinline__ U128 pack(int k, const uint32_t* ids) {
+    U128 v{0ull, 0ull};
+    if (SMALL) {
+      v.lo = 0x8000u | (uint32_t)k;
+      for (int q = 0; q < k; ++q) {
+        const int f = q + 1;
+        if (f < 4) v.lo |= (unsigned long long)ids[q] << (f * 16);
+        else v.hi |= (unsigned long long)ids[q] << ((f & 3) * 16);
+      }
+    } else {
+      v.lo = (unsigned long long)(0x80000000u | ((uint32_t)k << 28) | ids[0]) | ((unsigned long long)ids[1] << 32);
+      v.hi = (unsigned long long)ids[2] | ((unsigned long long)ids[3] << 32);
+    }
+    return v;
+  }
+};
+constexpr int kMemoMaxKeyBytes = 15;
+
+// Key of word nb[ws, we); false when the word cannot be memoised (empty after the prefix, or too long).
+__device__ __forceinline__ bool memo_key(const uint8_t* nb, int ws, int we, bool byte_mode, U128* key) {
+  uint32_t hdr = 0;
+  if (!byte_mode && we - ws >= 3 && nb[ws] == 0xE2 && nb[ws + 1] == 0x96 && nb[ws + 2] == 0x81) { ws += 3; hdr = 0x80; }
+  const int n = we - ws;
+  if (n < 1 || n > kMemoMaxKeyBytes) return false;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(nb) + (ws >> 2);  // 16 bytes from ws (reads past nlen are masked)
+  const uint32_t sh = (ws & 3) * 8;
+  uint32_t b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    b[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    const int nb_i = n - 4 * i;
+    if (nb_i < 4) b[i] = nb_i <= 0 ? 0u : (b[i] & ((1u << (8 * nb_i)) - 1u));
+  }
+  const unsigned long long lo = (unsigned long long)b[0] | ((unsigned long long)b[1] << 32);
+  const unsigned long long hi = (unsigned long long)b[2] | ((unsigned long long)b[3] << 32);
+  key->lo = (lo << 8) | (hdr | (uint32_t)n);
+  key->hi = (hi << 8) | (lo >> 56);
+  return true;
+}
+__device__ __forceinline__ uint32_t memo_slot(U128 k, uint32_t mask) {
+  unsigned long long h = (k.lo ^ (k.hi * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  return (uint32_t)h & mask;
+}
+
 // State of one request while it streams through the warp.
 struct ReqState {
   const uint8_t* src;
@@ -718,8 +804,16 @@ __device__ __noinline__ bool long_enter(const SpDev& T, SM& sm, ReqState& rs, in
 // Tokenises the complete words held in nbuf (all words when final) and keeps the incomplete tail.
 // HF: word boundaries come from the regex pre-tokenizer (hf_pretok.cuh); returns true when the word list
 // filled up and the kept tail has to be scanned again.
-template <bool SMALL, bool LONG, bool HF, typename SM>
-__device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane) {
+#ifdef XLLM_MEMO_STATS
+__device__ unsigned long long g_memo_stats[8];
+#endif
+struct MemoRef {
+  uint8_t* table;
+  uint32_t mask;
+};
+
+template <bool SMALL, bool LONG, bool HF, bool MEMO, typename SM>
+__device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
   const uint8_t* nb = sm.nbuf;
   int nlen = rs.nlen;
   if (final && T.remove_extra_ws) {
@@ -797,7 +891,45 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     uint32_t alive = 0;
     int cnt = 0;
     bool first_unk = false, last_unk = false, bare = false;
-    if (HF && active && special) {
+    bool memo_hit = false;
+    if constexpr (MEMO) {
+      U128 key;
+      if (active && !special && memo_key(nb, ws, we, T.byte_mode, &key)) {
+        uint32_t slot = memo_slot(key, memo.mask);
+#pragma unroll 1
+        for (int way = 0; way < 2; ++way, slot ^= 1u) {
+          const uint8_t* e = memo.table + (size_t)slot * 32;
+          const U128 k = ld_b128(e);
+          const U128 v = ld_b128(e + 16);
+          if (k.lo == key.lo && k.hi == key.hi) {
+            if (MemoIds<SMALL>::valid(v)) {
+              memo_hit = true;
+              cnt = MemoIds<SMALL>::count(v);
+              alive = (1u << cnt) - 1u;
+#pragma unroll
+              for (int q = 0; q < MemoIds<SMALL>::kMax; ++q)
+                if (q < cnt) sm.S[q * 32 + lane] = kResolvedFlag | MemoIds<SMALL>::id(v, q);
+            }
+            break;
+          }
+          if ((k.lo | k.hi) == 0) break;  // empty: the word was not seen yet
+        }
+      }
+    }
+#ifdef XLLM_MEMO_STATS
+    {
+      const uint32_t am = __ballot_sync(kFull, active), hm = __ballot_sync(kFull, memo_hit);
+      if (lane == 0) {
+        atomicAdd(&g_memo_stats[0], 1ull);                       // rounds
+        atomicAdd(&g_memo_stats[1], (unsigned long long)__popc(am));   // active words
+        atomicAdd(&g_memo_stats[2], (unsigned long long)__popc(hm));   // hits
+        if (am & ~hm) atomicAdd(&g_memo_stats[3], 1ull);         // rounds with a slow-path lane
+        if (first_long < 32) atomicAdd(&g_memo_stats[4], 1ull);  // rounds cut by a long word
+      }
+    }
+#endif
+    if (memo_hit) {
+    } else if (HF && active && special) {
       int32_t id = 0;
       hf_added_len(T, nb + ws, we - ws, &id);
       sm.S[lane] = kResolvedFlag | (uint32_t)id;
@@ -829,6 +961,35 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
         pu = unk;
       }
       last_unk = pu;
+      if constexpr (MEMO) {
+        // memoise: every surviving symbol resolved to exactly one id, at most four of them
+        const int k = __popc(alive);
+        U128 key;
+        if (k >= 1 && k <= MemoIds<SMALL>::kMax && k == cnt && !bare && memo_key(nb, ws, we, T.byte_mode, &key)) {
+          uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          bool ok = true;
+          int q = 0;
+          for (uint32_t m = alive; m; ++q) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t sym = sm.S[j * 32 + lane];
+            ok = ok && (sym & 0xC0000000u) == kResolvedFlag && (sym & 0x3FFFFFFFu) < (SMALL ? (1u << 16) : (1u << 28));
+            id[q] = sym & 0x0FFFFFFFu;
+          }
+          if (ok) {
+            const U128 val = MemoIds<SMALL>::pack(k, id);
+            uint32_t slot = memo_slot(key, memo.mask);
+            const U128 zero{0ull, 0ull};
+#pragma unroll 1
+            for (int way = 0; way < 2; ++way, slot ^= 1u) {
+              uint8_t* e = memo.table + (size_t)slot * 32;
+              const U128 old = cas_b128(e, zero, key);
+              if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
+              if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
+            }
+          }
+        }
+      }
     }
     // cross-word unknown merging (byte_fallback off): drop the first id if the previous symbol was unknown too
     bool drop_first = false;
@@ -975,24 +1136,26 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
   return HF && hf_capped && !rs.deferred;
 }
 
-template <bool SMALL, bool LONG, bool HF, typename SM>
-__device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane) {
+template <bool SMALL, bool LONG, bool HF, bool MEMO, typename SM>
+__device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
   if constexpr (HF) {
-    while (drain_pass<SMALL, LONG, true>(T, sm, rs, final, lane)) {}
+    while (drain_pass<SMALL, LONG, true, MEMO>(T, sm, rs, final, lane, memo)) {}
   } else {
-    drain_pass<SMALL, LONG, false>(T, sm, rs, final, lane);
+    drain_pass<SMALL, LONG, false, MEMO>(T, sm, rs, final, lane, memo);
   }
 }
 
 // LONG == false: the throughput kernel; a request that needs the long-word path is appended to defer_list.
 // LONG == true : re-runs exactly the deferred requests (work list = defer_list[0 .. *defer_count)).
 // HF == true : byte-level BPE with the regex pre-tokenizer (split_mode 3).
-template <bool SMALL, bool LONG, bool HF>
+// MEMO == true: words are looked up in / added to the launch's word memo (never built together with LONG).
+template <bool SMALL, bool LONG, bool HF, bool MEMO>
 __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ offsets, int n_req, int32_t* __restrict__ ids,
     int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status, const __grid_constant__ SpDev T,
     unsigned int* __restrict__ task_counter, int32_t* __restrict__ defer_list,
-    unsigned int* __restrict__ defer_count) {
+    unsigned int* __restrict__ defer_count, uint8_t* memo_table, uint32_t memo_mask) {
+  const MemoRef memo{memo_table, memo_mask};
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = WarpSmemT<SMALL>;
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
@@ -1040,13 +1203,13 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       for (uint32_t pos = 0; pos < rs.len; pos += kFastWin) {
         normalize_fast(T, sm, rs, pos, lane);  // byte mode: a verbatim copy
         if (rs.nlen > drain_at) {
-          drain<SMALL, LONG, true>(T, sm, rs, false, lane);
+          drain<SMALL, LONG, true, MEMO>(T, sm, rs, false, lane, memo);
           // what is left is one unfinished pre-token (plus the look-ahead margin)
           if (rs.nlen > kLongEnterAt) rs.too_long = true;
           if (rs.too_long || rs.deferred || rs.bad_input) break;
         }
       }
-      if (!rs.too_long && !rs.deferred && !rs.bad_input) drain<SMALL, LONG, true>(T, sm, rs, true, lane);
+      if (!rs.too_long && !rs.deferred && !rs.bad_input) drain<SMALL, LONG, true, MEMO>(T, sm, rs, true, lane, memo);
       if (!rs.too_long && !rs.deferred && !rs.bad_input) {
         if (lane < T.n_suffix) put_id(rs, rs.n_out + lane, T.suffix_ids[lane]);
         rs.n_out += T.n_suffix;
@@ -1069,7 +1232,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
             if constexpr (LONG) {
               if (rs.long_mode) { long_consume(T, sm, rs, false, lane); consumed = true; }
             }
-            if (!consumed) drain<SMALL, LONG, false>(T, sm, rs, false, lane);
+            if (!consumed) drain<SMALL, LONG, false, MEMO>(T, sm, rs, false, lane, memo);
             if (!rs.too_long && !normalize_window(T, sm, rs, pos, carry_skip, lane)) {
               // still no room: the kept tail is one very long word -> stream it through a scratch slot
               bool entered = false;
@@ -1093,7 +1256,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
           }
         }
         if (!in_long && rs.nlen > drain_at) {
-          drain<SMALL, LONG, false>(T, sm, rs, false, lane);
+          drain<SMALL, LONG, false, MEMO>(T, sm, rs, false, lane, memo);
           if (rs.nlen > kLongEnterAt) {
             if constexpr (LONG) {
               if (!long_enter(T, sm, rs, lane)) rs.too_long = true;
@@ -1107,7 +1270,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       if constexpr (LONG) {
         if (!rs.too_long && rs.long_mode) long_consume(T, sm, rs, true, lane);
       }
-      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG, false>(T, sm, rs, true, lane);
+      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG, false, MEMO>(T, sm, rs, true, lane, memo);
     }
     if constexpr (LONG) {
       if (rs.long_mode) {  // error exit while a slot is held
@@ -1135,6 +1298,24 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
 
 // ------------------------------------------------------------------------------ host side
 int g_warps_per_sm_override = 0;  // tuning knob (XLLM_SP_WARPS_PER_SM), 0 = fill shared memory
+
+#ifdef XLLM_MEMO_STATS
+extern "C" void xllm_debug_memo_stats(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, g_memo_stats, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(g_memo_stats, z, sizeof(z));
+}
+#endif
+uint32_t sp_memo_default_slots() {
+  uint32_t slots = 1u << 18;
+  if (const char* w = getenv("XLLM_SP_MEMO_SLOTS")) {
+    const long v = atol(w);
+    if (v <= 0) return 0;
+    slots = 2;
+    while (slots < (uint32_t)v && slots < (1u << 26)) slots <<= 1;
+  }
+  return slots;
+}
 
 SpDeviceModel::~SpDeviceModel() {
   for (int i = 0; i < n_allocs_; ++i) cudaFree(allocs_[i]);
@@ -1256,7 +1437,7 @@ int SpDeviceModel::upload(const SpTables& t) {
 
 cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
                              int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
-                             int32_t* defer_list, cudaStream_t stream) {
+                             int32_t* defer_list, cudaStream_t stream, SpMemo memo) {
   if (n_req <= 0) return cudaSuccess;
   static DeviceOnce once;
   const bool small = dev.small_vocab != 0;
@@ -1268,14 +1449,18 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
 #define XLLM_SET_SMEM(K, B)                                                                          \
         r = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B>)); \
         if (r != cudaSuccess) return r;
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<true, true, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<false, true, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, true>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<true, true, true>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, true>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<false, true, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, false, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<true, true, false, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, false, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<false, true, false, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, true, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<true, true, true, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, true, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<false, true, true, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, false, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, false, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, true, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, true, true>), false)
 #undef XLLM_SET_SMEM
         return cudaSuccess;
       },
@@ -1291,17 +1476,30 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
   if (grid > n_req) grid = n_req;
   int grid_long = n_sm * 2;
   if (grid_long > n_req) grid_long = n_req;
-#define XLLM_LAUNCH_PAIR(SMALL_, HF_)                                                                          \
-  sp_encode_kernel<SMALL_, false, HF_><<<grid, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids,    \
-                                                                   status, dev, counters, defer_list, counters + 1); \
-  sp_encode_kernel<SMALL_, true, HF_><<<grid_long, 32, smem, stream>>>(text, offsets, n_req, ids, ids_stride, n_ids, \
-                                                                       status, dev, counters + 2, defer_list,       \
-                                                                       counters + 1);
+  const bool use_memo = memo.table != nullptr && memo.slots >= 2 && (memo.slots & (memo.slots - 1)) == 0;
+  if (use_memo) {
+    e = cudaMemsetAsync(memo.table, 0, (size_t)memo.slots * 32, stream);  // the memo lives for this launch only
+    if (e != cudaSuccess) return e;
+  }
+  uint8_t* const mt = use_memo ? static_cast<uint8_t*>(memo.table) : nullptr;
+  const uint32_t mm = use_memo ? memo.slots - 1 : 0;
+#define XLLM_LAUNCH_PAIR(SMALL_, HF_, MEMO_)                                                                     \
+  sp_encode_kernel<SMALL_, false, HF_, MEMO_><<<grid, 32, smem, stream>>>(                                       \
+      text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, mt, mm);    \
+  sp_encode_kernel<SMALL_, true, HF_, false><<<grid_long, 32, smem, stream>>>(                                   \
+      text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters + 2, defer_list, counters + 1, nullptr, 0u);
   const bool hf = dev.split_mode == 3;
-  if (small && hf) { XLLM_LAUNCH_PAIR(true, true) }
-  else if (small) { XLLM_LAUNCH_PAIR(true, false) }
-  else if (hf) { XLLM_LAUNCH_PAIR(false, true) }
-  else { XLLM_LAUNCH_PAIR(false, false) }
+  if (use_memo) {
+    if (small && hf) { XLLM_LAUNCH_PAIR(true, true, true) }
+    else if (small) { XLLM_LAUNCH_PAIR(true, false, true) }
+    else if (hf) { XLLM_LAUNCH_PAIR(false, true, true) }
+    else { XLLM_LAUNCH_PAIR(false, false, true) }
+  } else {
+    if (small && hf) { XLLM_LAUNCH_PAIR(true, true, false) }
+    else if (small) { XLLM_LAUNCH_PAIR(true, false, false) }
+    else if (hf) { XLLM_LAUNCH_PAIR(false, true, false) }
+    else { XLLM_LAUNCH_PAIR(false, false, false) }
+  }
 #undef XLLM_LAUNCH_PAIR
   return cudaGetLastError();
 }

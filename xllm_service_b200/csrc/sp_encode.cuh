@@ -69,6 +69,15 @@ class SpDeviceModel {
   int n_allocs_ = 0;
 };
 
+// Word memo: a write-once hash table word bytes -> token ids that lives for ONE launch (the launcher clears
+// it first), so a word that occurs again in the same batch skips symbol building, pair probes and the merge.
+// 32 bytes per slot; slots = power of two; table == nullptr disables it.
+struct SpMemo {
+  void* table = nullptr;
+  uint32_t slots = 0;
+};
+uint32_t sp_memo_default_slots();  // XLLM_SP_MEMO_SLOTS (0 = off), default 2^18 = 8 MiB
+
 // text: all prompts back to back; offsets[n_req + 1] (bytes).  Request r's ids go to
 // ids + r * ids_stride (at most ids_stride of them), n_ids[r] = full count, status[r] = kEnc*.
 // counters: 4 zero-initialisable uint32 in device memory; defer_list: n_req int32 of device scratch (requests
@@ -76,6 +85,6 @@ class SpDeviceModel {
 // deferred requests (a no-op grid when there are none).
 cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
                              int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
-                             int32_t* defer_list, cudaStream_t stream);
+                             int32_t* defer_list, cudaStream_t stream, SpMemo memo = SpMemo());
 
 }  // namespace xllm
