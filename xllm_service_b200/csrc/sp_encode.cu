@@ -1401,6 +1401,8 @@ int SpDeviceModel::upload(const SpTables& t) {
   for (const auto& e : t.pair_table)
     if (e.a != kEmptyKey && e.prio > max_rank) max_rank = e.prio;
   dev_.small_vocab = (t.n_pieces < 65535 && max_rank < 65535) ? 1 : 0;
+  if (const char* w = getenv("XLLM_SP_FORCE_WIDE"))  // tests: run a small vocabulary through the 32-bit-state kernels
+    if (atoi(w) != 0) dev_.small_vocab = 0;
   if (const char* w = getenv("XLLM_SP_WARPS_PER_SM")) g_warps_per_sm_override = atoi(w);
   // scratch pool for pre-tokens longer than the shared-memory paths hold
   uint32_t cap = 1u << 17;
