@@ -265,7 +265,7 @@ def main():
     import torch
     import torch.distributed as dist
     import xllm_service_b200 as x
-    from xllm_service_b200 import _lib, workload
+    from xllm_service_b200 import HostBuffer, _lib, workload
 
     if not os.path.exists(x.lib_path()):
         import __graft_entry__ as ge
@@ -289,8 +289,19 @@ def main():
     text_bytes = int(batch.text.size)
 
     # ---- page-locked host buffers (the e2e call's inputs / outputs)
+    # xllm_host_alloc: page-locked AND on the GPU's NUMA node (the box has two sockets)
+    class Pinned:
+        def __init__(self, shape, dtype):
+            self.buf = HostBuffer(shape, torch.empty(0, dtype=dtype).numpy().dtype)
+
+        def numpy(self):
+            return self.buf.array
+
+        def data_ptr(self):
+            return self.buf.ptr
+
     def pinned(shape, dtype):
-        return torch.empty(shape, dtype=dtype).pin_memory()
+        return Pinned(shape, dtype)
 
     h_text = pinned((text_bytes,), torch.uint8)
     h_text.numpy()[:] = batch.text
@@ -362,8 +373,8 @@ def main():
     # ---- device-resident buffers
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    d_text = h_text.to(dev, non_blocking=True)
-    d_off = h_off.to(dev, non_blocking=True)
+    d_text = torch.from_numpy(h_text.numpy()).to(dev)
+    d_off = torch.from_numpy(h_off.numpy()).to(dev)
     d_ids = torch.empty((n, T), dtype=torch.int32, device=dev)
     d_nids = torch.empty((n,), dtype=torch.int32, device=dev)
     d_st = torch.empty((n,), dtype=torch.int32, device=dev)
@@ -419,7 +430,8 @@ def main():
     barrier()
     dev_ms = max_over_ranks(t0.elapsed_time(t1))
     k_ms = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in ev]).mean(axis=0)
-    assert torch.equal(d_ids.cpu(), h_ids) and torch.equal(d_keys.cpu(), h_keys), "device-resident != e2e results"
+    assert (torch.equal(d_ids.cpu(), torch.from_numpy(h_ids.numpy())) and
+            torch.equal(d_keys.cpu(), torch.from_numpy(h_keys.numpy()))), "device-resident != e2e results"
 
     # ---- end to end through the C-ABI with host buffers
     for _ in range(max(1, min(args.warmup, 2))):
@@ -473,8 +485,9 @@ def main():
                 "h2d_bytes_per_step": text_bytes + 8 * (n + 1),
                 "d2h_bytes_per_step": 4 * n * T + 8 * n + 16 * n * nb + 420 * n,
                 "api": "xllm_ingest_batch (C-ABI, page-locked host buffers)"},
-        # value region: encode + hash + probe + score per step; e2e region: 5 kernels (+ row prep) per chunk
-        "gpu_launches": args.steps * (4 + 5 * (-(-n // (args.chunk_requests or 1024)))),
+        # value region: encode (throughput + long-word pass) + hash + probe + score per step;
+        # e2e region: the library's own count for one batch (6 kernels per pipeline chunk)
+        "gpu_launches": args.steps * (5 + h.last_batch_stats()[1]),
         "roofline": roofline,
         "kernels": kernels,
     }

@@ -203,8 +203,11 @@ typedef struct {
 } xllm_ingest_io;
 int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io);
 /* Pipeline chunking of xllm_ingest_batch: at most chunk_requests requests and chunk_bytes text bytes
- * per chunk (defaults 1024 / 96 MiB; 8 chunks in flight). */
+ * per chunk (defaults 4096 / 96 MiB; chunk sizes ramp up from chunk_requests/16 and taper off at the end;
+ * 4 chunks in flight over one upload, one kernel and one download stream). */
 int xllm_set_pipeline(xllm_ingest_t h, int32_t chunk_requests, int64_t chunk_bytes);
+/* Chunks and kernel launches of the most recent xllm_ingest_batch on this handle (for launch accounting). */
+int xllm_last_batch_stats(xllm_ingest_t h, int32_t* n_chunks, int32_t* n_kernel_launches);
 /* Page-locked host memory for the batch buffers. */
 int xllm_host_alloc(void** out, size_t bytes);
 void xllm_host_free(void* p);

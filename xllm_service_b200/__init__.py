@@ -9,6 +9,6 @@ path: every compute call goes through the C-ABI and fails loudly if the CUDA
 library or a CUDA device is missing.
 """
 from ._lib import IngestError, lib, lib_path  # noqa: F401
-from .ingest import Ingest  # noqa: F401
+from .ingest import HostBuffer, Ingest  # noqa: F401
 
-__all__ = ["Ingest", "IngestError", "lib", "lib_path"]
+__all__ = ["HostBuffer", "Ingest", "IngestError", "lib", "lib_path"]

@@ -121,6 +121,10 @@ int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
       return rc;
     }
     h->memo_slots = sp_memo_default_slots();
+    if (const char* w = getenv("XLLM_PIPE_SLOTS")) {
+      const int v = atoi(w);
+      if (v >= 1 && v <= kPipeSlots) h->pipe_slots = v;
+    }
     h->sp_dev = std::make_shared<SpDeviceModel>();
     rc = h->sp_dev->upload(*h->sp_tables);
     if (rc != XLLM_OK) {
@@ -167,6 +171,7 @@ int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out) {
   (*out)->sp_tables = src->sp_tables;
   (*out)->sp_dev = src->sp_dev;
   (*out)->memo_slots = src->memo_slots;
+  (*out)->pipe_slots = src->pipe_slots;
   (*out)->tokenizer_path = src->tokenizer_path;
   (*out)->index = src->index;
   (*out)->index_mu = src->index_mu;
@@ -196,6 +201,8 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   h->d_nblk.release();
   if (h->d_inst) cudaFree(h->d_inst);
   for (int i = 0; i < kPipeSlots; ++i) h->pipe[i].release();
+  for (int k = 0; k < 3; ++k)
+    if (h->pipe_stream[k]) cudaStreamDestroy(h->pipe_stream[k]);
   if (h->d_task_counter) cudaFree(h->d_task_counter);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

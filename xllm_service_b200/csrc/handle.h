@@ -34,9 +34,10 @@ struct PinBuf {
 };
 
 // One in-flight chunk of xllm_ingest_batch: its own stream + device buffers.
-constexpr int kPipeSlots = 8;
+constexpr int kPipeSlots = 32;  // upper bound; xllm_ingest::pipe_slots are used
 struct PipeSlot {
-  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // uploaded / kernels done / downloaded
+  bool busy = false;                                // ev[2] of an earlier chunk of this batch is pending
   unsigned int* counters = nullptr;
   DevBuf d_memo;  // this slot's word memo (sp_encode.cuh): cleared by every encode launch on the slot's stream
   DevBuf d_defer, d_text, d_offsets, d_ids, d_n_ids, d_status, d_tok_start, d_n_tok, d_key_start, d_n_blocks, d_keys, d_masks,
@@ -70,7 +71,10 @@ struct xllm_ingest {
   xllm::DevBuf d_masks, d_match, d_routing, d_nblk;
   // xllm_ingest_batch pipeline
   xllm::PipeSlot pipe[xllm::kPipeSlots];
-  int pipe_chunk_req = 1024;
+  cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};  // upload / kernel / download engines of xllm_ingest_batch
+  int pipe_slots = 4;
+  int last_chunks = 0, last_launches = 0;  // of the most recent xllm_ingest_batch  // chunks in flight (XLLM_PIPE_SLOTS): enough to cover one request-per-warp encode latency
+  int pipe_chunk_req = 4096;
   int64_t pipe_chunk_bytes = 96ll << 20;
   // scratch for the host-pointer entry points
   xllm::DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status, d_defer;

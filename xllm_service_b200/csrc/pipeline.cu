@@ -2,14 +2,21 @@
 //   host text -> [H2D] -> tokenize -> block-hash chain -> index probe -> match scan + routing -> [D2H]
 // i.e. what Scheduler::schedule does per request between scheduler.cpp:128 and :135
 // (Tokenizer::encode, then CacheAwareRouting::select_instances_pair -> GlobalKVCacheMgr::match ->
-// cost_function), batched.  The batch is cut into chunks that flow through kPipeSlots independent
-// CUDA streams so the PCIe copies of one chunk overlap the kernels of another; the caller's buffers
-// should be page-locked (xllm_host_alloc) for the copies to be asynchronous.
+// cost_function), batched.  The batch is cut into chunks that flow through an upload, a kernel and a download
+// stream so the PCIe copies of one chunk overlap the kernels of another; the caller's buffers should be
+// page-locked (xllm_host_alloc: also NUMA-local to the GPU) for the copies to be asynchronous.
+#include <ctype.h>
+#include <sched.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 
 #include "../../include/xllm_ingest.h"
+#include <chrono>
+#include <vector>
+
 #include "handle.h"
 
 namespace xllm {
@@ -59,10 +66,13 @@ void PipeSlot::release() {
   d_text.release(); d_offsets.release(); d_ids.release(); d_n_ids.release(); d_status.release();
   d_tok_start.release(); d_n_tok.release(); d_key_start.release(); d_n_blocks.release();
   d_keys.release(); d_masks.release(); d_match.release(); d_routing.release();
-  if (stream) cudaStreamDestroy(stream);
+  for (int k = 0; k < 3; ++k) {
+    if (ev[k]) cudaEventDestroy(ev[k]);
+    ev[k] = nullptr;
+  }
   if (counters) cudaFree(counters);
-  stream = nullptr;
   counters = nullptr;
+  busy = false;
 }
 
 }  // namespace xllm
@@ -77,10 +87,48 @@ using namespace xllm;
 
 extern "C" {
 
+// CPUs local to the current device's PCIe root (sysfs local_cpulist, e.g. "0-31,64-95")
+static bool gpu_local_cpus(cpu_set_t* set) {
+  int dev = 0;
+  char bus[32] = {0};
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != cudaSuccess) return false;
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  char line[512] = {0};
+  const bool got = fgets(line, sizeof(line), f) != nullptr;
+  fclose(f);
+  if (!got) return false;
+  CPU_ZERO(set);
+  int n = 0;
+  for (char* p = line; *p && *p != '\n';) {
+    char* end;
+    const long a = strtol(p, &end, 10);
+    if (end == p) break;
+    long b = a;
+    p = end;
+    if (*p == '-') { b = strtol(p + 1, &end, 10); p = end; }
+    for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++n; }
+    if (*p == ',') ++p;
+  }
+  return n > 0;
+}
+
 int xllm_host_alloc(void** out, size_t bytes) {
   if (!out) return XLLM_ERR_INVALID_ARG;
   *out = nullptr;
+  // Page-locking populates the pages, on the NUMA node of the calling thread: run the allocation on a CPU next to
+  // the GPU so the DMA does not cross the socket interconnect (it costs PCIe bandwidth when both directions are busy)
+  cpu_set_t old_set, local_set, both;
+  bool bound = false;
+  if (sched_getaffinity(0, sizeof(old_set), &old_set) == 0 && gpu_local_cpus(&local_set)) {
+    CPU_AND(&both, &old_set, &local_set);
+    if (CPU_COUNT(&both) > 0 && sched_setaffinity(0, sizeof(both), &both) == 0) bound = true;
+  }
   cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (bound) sched_setaffinity(0, sizeof(old_set), &old_set);
   if (e != cudaSuccess) {
     set_last_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     return XLLM_ERR_NOMEM;
@@ -129,79 +177,155 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
                                   h->stream));
     XLLM_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
-  // chunking: bounded by request count and by text bytes
+  // Three engine streams — uploads, kernels, downloads — joined by events: each hardware engine sees its work in
+  // chunk order (no stream-to-queue aliasing, no kernel waiting behind its own chunk's download), and a chunk's
+  // buffers (slot = chunk mod pipe_slots) are reused only after the chunk that last held them has left the
+  // download engine.
   const int chunk_req = h->pipe_chunk_req;
   const int64_t chunk_bytes = h->pipe_chunk_bytes;
-  for (int s = 0; s < kPipeSlots; ++s) {
+  const int n_slots = h->pipe_slots;
+  for (int k = 0; k < 3; ++k)
+    if (!h->pipe_stream[k]) XLLM_CUDA_TRY(cudaStreamCreateWithFlags(&h->pipe_stream[k], cudaStreamNonBlocking));
+  cudaStream_t s_in = h->pipe_stream[0], s_k = h->pipe_stream[1], s_out = h->pipe_stream[2];
+  for (int s = 0; s < n_slots; ++s) {
     PipeSlot& sl = h->pipe[s];
-    if (!sl.stream) XLLM_CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     if (!sl.counters) XLLM_CUDA_TRY(cudaMalloc(&sl.counters, 64));
+    for (int k = 0; k < 3; ++k)
+      if (!sl.ev[k]) XLLM_CUDA_TRY(cudaEventCreateWithFlags(&sl.ev[k], cudaEventDisableTiming));
+    sl.busy = false;
   }
+  // XLLM_PIPE_TRACE=1: per-chunk device timeline on stderr (debugging aid)
+  static const bool trace = getenv("XLLM_PIPE_TRACE") != nullptr;
+  struct TraceRow { int m; double host_ms; cudaEvent_t e[5]; };
+  std::vector<TraceRow> rows;
+  cudaEvent_t ev_begin = nullptr;
+  const auto host_t0 = std::chrono::steady_clock::now();
+  if (trace) { cudaEventCreate(&ev_begin); cudaEventRecord(ev_begin, s_in); }
+  auto mark = [&](int k, cudaStream_t st) {
+    if (!trace) return;
+    cudaEventCreate(&rows.back().e[k]);
+    cudaEventRecord(rows.back().e[k], st);
+  };
   int slot = 0;
   int32_t c0 = 0;
   int rc = XLLM_OK;
+  h->last_chunks = 0;
+  h->last_launches = 0;
+  // Chunk sizes ramp up from chunk_req / 8 to chunk_req: the first chunk's upload + kernels is a stage nothing
+  // overlaps, so it is kept short; the bulk moves in big chunks (full-GPU kernels, few small copies).  The last
+  // chunk's download is exposed too, but a tiny last chunk would expose its kernels' latency floor (one warp walks
+  // one prompt: ~1 ms) instead, so the tail is one quarter-size chunk behind a chunk big enough to cover it.
+  const int ramp_first = chunk_req / 8 > 64 ? chunk_req / 8 : (chunk_req < 64 ? chunk_req : 64);
+  const int tail = chunk_req / 4 > 0 ? chunk_req / 4 : 1;
+  int64_t ramp = ramp_first;
   while (c0 < n) {
+    int64_t target = ramp < chunk_req ? ramp : chunk_req;
+    const int64_t left = n - c0;
+    if (left <= target) target = left;
+    else if (left <= target + tail) target = left - tail;
+    if (ramp < chunk_req) ramp *= 2;
     int32_t c1 = c0;
-    while (c1 < n && c1 - c0 < chunk_req && (c1 == c0 || io->offsets[c1 + 1] - io->offsets[c0] <= chunk_bytes)) ++c1;
+    while (c1 < n && c1 - c0 < target && (c1 == c0 || io->offsets[c1 + 1] - io->offsets[c0] <= chunk_bytes)) ++c1;
     const int m = c1 - c0;
     const int64_t t0 = io->offsets[c0];
     const size_t text_bytes = (size_t)(io->offsets[c1] - t0);
     PipeSlot& sl = h->pipe[slot];
-    cudaStream_t s = sl.stream;
-    XLLM_CUDA_TRY(cudaStreamSynchronize(s));  // the slot's previous chunk (and its D2H copies) is done
+    // the slot's previous chunk has been downloaded (host wait: ensure() below may reallocate its buffers)
+    if (sl.busy) XLLM_CUDA_TRY(cudaEventSynchronize(sl.ev[2]));
     if ((rc = sl.ensure(text_bytes, m, io->ids_stride, keys_stride)) != XLLM_OK) break;
     if (h->memo_slots && (rc = sl.d_memo.reserve((size_t)h->memo_slots * 32)) != XLLM_OK) break;
     xllm::SpMemo memo;
     memo.table = h->memo_slots ? sl.d_memo.p : nullptr;
     memo.slots = h->memo_slots;
+    if (trace) {
+      rows.push_back(TraceRow{m, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(), {}});
+      mark(0, s_in);
+    }
+    // ---- upload
     if (text_bytes)
-      XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_text.p, io->text + t0, text_bytes, cudaMemcpyHostToDevice, s));
-    XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_offsets.p, io->offsets + c0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, s));
+      XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_text.p, io->text + t0, text_bytes, cudaMemcpyHostToDevice, s_in));
+    XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_offsets.p, io->offsets + c0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, s_in));
+    XLLM_CUDA_TRY(cudaEventRecord(sl.ev[0], s_in));
+    mark(1, s_in);
+    // ---- kernels: tokenize -> row prep -> chained block hash -> index probe -> match scan + routing
+    XLLM_CUDA_TRY(cudaStreamWaitEvent(s_k, sl.ev[0], 0));
     XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), m,
                                    sl.d_ids.as<int32_t>(), io->ids_stride, sl.d_n_ids.as<int32_t>(),
-                                   sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s, memo));
-    XLLM_CUDA_TRY(cudaMemcpyAsync(io->ids + (size_t)c0 * io->ids_stride, sl.d_ids.p,
-                                  (size_t)m * (size_t)io->ids_stride * 4, cudaMemcpyDeviceToHost, s));
-    XLLM_CUDA_TRY(cudaMemcpyAsync(io->n_ids + c0, sl.d_n_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-    XLLM_CUDA_TRY(cudaMemcpyAsync(io->status + c0, sl.d_status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+                                   sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s_k, memo));
+    mark(2, s_k);
     if (keys_stride > 0) {
-      prep_rows_kernel<<<(m + 127) / 128, 128, 0, s>>>(sl.d_n_ids.as<int32_t>(), m, io->ids_stride, keys_stride,
-                                                      h->block_size, sl.d_tok_start.as<int64_t>(),
-                                                      sl.d_n_tok.as<int32_t>(), sl.d_key_start.as<int64_t>(),
-                                                      sl.d_n_blocks.as<int32_t>());
+      prep_rows_kernel<<<(m + 127) / 128, 128, 0, s_k>>>(sl.d_n_ids.as<int32_t>(), m, io->ids_stride, keys_stride,
+                                                        h->block_size, sl.d_tok_start.as<int64_t>(),
+                                                        sl.d_n_tok.as<int32_t>(), sl.d_key_start.as<int64_t>(),
+                                                        sl.d_n_blocks.as<int32_t>());
       XLLM_CUDA_TRY(cudaGetLastError());
-      if (io->keys) XLLM_CUDA_TRY(cudaMemsetAsync(sl.d_keys.p, 0, (size_t)m * (size_t)keys_stride * 16, s));
+      if (io->keys) XLLM_CUDA_TRY(cudaMemsetAsync(sl.d_keys.p, 0, (size_t)m * (size_t)keys_stride * 16, s_k));
       XLLM_CUDA_TRY(xxh3_chain_launch(sl.d_ids.as<int32_t>(), sl.d_tok_start.as<int64_t>(), sl.d_n_tok.as<int32_t>(),
                                       sl.d_keys.as<uint8_t>(), sl.d_key_start.as<int64_t>(), m, h->block_size, h->xxh,
-                                      sl.counters + 8, s));
-      if (io->keys)
-        XLLM_CUDA_TRY(cudaMemcpyAsync(io->keys + (size_t)c0 * (size_t)keys_stride * 16, sl.d_keys.p,
-                                      (size_t)m * (size_t)keys_stride * 16, cudaMemcpyDeviceToHost, s));
+                                      sl.counters + 8, s_k));
       if (want_match) {
-        XLLM_CUDA_TRY(h->index->probe(sl.d_keys.as<uint8_t>(), (int64_t)m * keys_stride, sl.d_masks.as<uint64_t>(), s));
+        XLLM_CUDA_TRY(h->index->probe(sl.d_keys.as<uint8_t>(), (int64_t)m * keys_stride, sl.d_masks.as<uint64_t>(), s_k));
         XLLM_CUDA_TRY(score_route_launch(sl.d_masks.as<uint64_t>(), sl.d_key_start.as<int64_t>(),
                                          sl.d_n_blocks.as<int32_t>(), m, h->d_inst, sl.d_match.as<MatchOut>(),
-                                         sl.d_routing.as<RoutingOut>(), s));
-        if (io->match)
-          XLLM_CUDA_TRY(cudaMemcpyAsync(io->match + c0, sl.d_match.p, (size_t)m * sizeof(MatchOut),
-                                        cudaMemcpyDeviceToHost, s));
-        if (io->routing)
-          XLLM_CUDA_TRY(cudaMemcpyAsync(io->routing + c0, sl.d_routing.p, (size_t)m * sizeof(RoutingOut),
-                                        cudaMemcpyDeviceToHost, s));
+                                         sl.d_routing.as<RoutingOut>(), s_k));
       }
     }
-    slot = (slot + 1) % kPipeSlots;
+    XLLM_CUDA_TRY(cudaEventRecord(sl.ev[1], s_k));
+    // ---- download
+    XLLM_CUDA_TRY(cudaStreamWaitEvent(s_out, sl.ev[1], 0));
+    XLLM_CUDA_TRY(cudaMemcpyAsync(io->ids + (size_t)c0 * io->ids_stride, sl.d_ids.p,
+                                  (size_t)m * (size_t)io->ids_stride * 4, cudaMemcpyDeviceToHost, s_out));
+    mark(3, s_out);
+    XLLM_CUDA_TRY(cudaMemcpyAsync(io->n_ids + c0, sl.d_n_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
+    XLLM_CUDA_TRY(cudaMemcpyAsync(io->status + c0, sl.d_status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
+    if (keys_stride > 0) {
+      if (io->keys)
+        XLLM_CUDA_TRY(cudaMemcpyAsync(io->keys + (size_t)c0 * (size_t)keys_stride * 16, sl.d_keys.p,
+                                      (size_t)m * (size_t)keys_stride * 16, cudaMemcpyDeviceToHost, s_out));
+      if (want_match && io->match)
+        XLLM_CUDA_TRY(cudaMemcpyAsync(io->match + c0, sl.d_match.p, (size_t)m * sizeof(MatchOut),
+                                      cudaMemcpyDeviceToHost, s_out));
+      if (want_match && io->routing)
+        XLLM_CUDA_TRY(cudaMemcpyAsync(io->routing + c0, sl.d_routing.p, (size_t)m * sizeof(RoutingOut),
+                                      cudaMemcpyDeviceToHost, s_out));
+    }
+    XLLM_CUDA_TRY(cudaEventRecord(sl.ev[2], s_out));
+    mark(4, s_out);
+    sl.busy = true;
+    h->last_chunks += 1;
+    h->last_launches += 2 + (keys_stride > 0 ? 2 + (want_match ? 2 : 0) : 0);  // encode x2, prep, hash, probe, score
+    slot = (slot + 1) % n_slots;
     c0 = c1;
   }
-  for (int s = 0; s < kPipeSlots; ++s)
-    if (h->pipe[s].stream) {
-      cudaError_t e = cudaStreamSynchronize(h->pipe[s].stream);
-      if (e != cudaSuccess && rc == XLLM_OK) {
-        set_last_error("xllm_ingest_batch: %s", cudaGetErrorString(e));
-        rc = XLLM_ERR_CUDA;
-      }
+  {
+    cudaError_t e = cudaStreamSynchronize(s_out);
+    cudaError_t e2 = cudaStreamSynchronize(s_k);
+    cudaError_t e3 = cudaStreamSynchronize(s_in);
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) e = e3;
+    if (e != cudaSuccess && rc == XLLM_OK) {
+      set_last_error("xllm_ingest_batch: %s", cudaGetErrorString(e));
+      rc = XLLM_ERR_CUDA;
     }
+  }
+  if (trace && rc == XLLM_OK) {
+    fprintf(stderr, "# chunk m host_enqueue  h2d_begin h2d_end encode_end d2h_ids_end all_end   (ms since batch start)\n");
+    for (size_t i = 0; i < rows.size(); ++i) {
+      float t[5];
+      for (int k = 0; k < 5; ++k) { cudaEventElapsedTime(&t[k], ev_begin, rows[i].e[k]); cudaEventDestroy(rows[i].e[k]); }
+      fprintf(stderr, "%3zu %5d %8.3f  %8.3f %8.3f %8.3f %8.3f %8.3f\n", i, rows[i].m, rows[i].host_ms, t[0], t[1], t[2], t[3], t[4]);
+    }
+    cudaEventDestroy(ev_begin);
+  }
   return rc;
+}
+
+int xllm_last_batch_stats(xllm_ingest_t h, int32_t* n_chunks, int32_t* n_kernel_launches) {
+  if (!h) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (n_chunks) *n_chunks = h->last_chunks;
+  if (n_kernel_launches) *n_kernel_launches = h->last_launches;
+  return XLLM_OK;
 }
 
 int xllm_set_pipeline(xllm_ingest_t h, int32_t chunk_requests, int64_t chunk_bytes) {

@@ -11,6 +11,35 @@ def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data) if a is not None and a.size else None
 
 
+class HostBuffer:
+    """Page-locked host memory from xllm_host_alloc (placed on the GPU's NUMA node), viewed as a numpy array.
+    Call with the device already selected (cudaSetDevice / torch.cuda.set_device)."""
+
+    def __init__(self, shape, dtype):
+        self._L = _lib.lib()
+        self.array = None
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = ctypes.c_void_p()
+        check(self._L.xllm_host_alloc(ctypes.byref(p), n))
+        self.ptr = p.value
+        self.nbytes = n
+        raw = (ctypes.c_uint8 * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self._L.xllm_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Ingest:
     """One xllm_ingest_t handle.  Mirrors the hot-path knobs of the reference's Options
     (block_size, xxh3_128bits_seed, tokenizer_path: global_gflags.cpp:60,114-118)."""
@@ -185,6 +214,12 @@ class Ingest:
     # ------------------------------------------------------- the whole path
     def set_pipeline(self, chunk_requests, chunk_bytes):
         check(self._L.xllm_set_pipeline(self._h, chunk_requests, chunk_bytes))
+
+    def last_batch_stats(self):
+        """(chunks, kernel launches) of the most recent ingest_batch on this handle."""
+        c, k = ctypes.c_int32(), ctypes.c_int32()
+        check(self._L.xllm_last_batch_stats(self._h, ctypes.byref(c), ctypes.byref(k)))
+        return c.value, k.value
 
     def ingest_batch_ptrs(self, n_req, text, offsets, ids, ids_stride, n_ids, status, keys=0, keys_stride=0,
                           match=0, routing=0):
