@@ -467,7 +467,7 @@ def main():
                 "frac": kernels[dom]["frac"], "traffic": traffic_from_profiles(dom), "peak_source": peak_src,
                 "share_of_step": float(k_ms[list(kernels).index(dom)] / k_ms.sum()),
                 "note": "achieved = (text bytes + 4 B/token) / CUDA-event time of the kernel; the tokenizer is "
-                        "bound by L1/L2 table lookups and issue slots, not HBM (DESIGN.md)"}
+                        "bound by instruction issue and shared-memory / L2 latency, not HBM (DESIGN.md 4.2)"}
     line = {
         "metric": METRIC, "value": world * n * args.steps / (dev_ms / 1e3), "unit": "req/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,

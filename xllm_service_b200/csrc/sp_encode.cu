@@ -37,6 +37,8 @@ namespace {
 
 constexpr int kNBuf = 2048;        // normalized-text staging buffer per warp (bytes)
 constexpr int kFastWin = 128;      // source bytes per fast-path step (4 per lane)
+constexpr int kPrefetchFirst = 2;  // fast path: prefetch windows pos + 2 .. pos + 2 + kPrefetchWindows - 1 into L2
+constexpr int kPrefetchWindows = 2;
 constexpr int kLongEnterAt = 1024;   // a kept tail (one incomplete word) longer than this switches to long mode
 constexpr int kLongFlushAt = 1024;   // long mode: move nbuf into the scratch slot once it holds this much
 constexpr int kMaxSym = 16;        // lane-per-word path: chars per word (alive set = 16 bits of a register)
@@ -438,49 +440,67 @@ template <typename SM>
 __device__ __forceinline__ bool normalize_fast(const SpDev& T, SM& sm, ReqState& rs, uint32_t pos, int lane) {
   const uint32_t base = pos + 4u * lane;
   const uint32_t nvalid = base >= rs.len ? 0u : (rs.len - base < 4u ? rs.len - base : 4u);
-  const uint8_t* p = rs.src + base;
-  uint32_t b[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) b[k] = (uint32_t)k < nvalid ? __ldg(p + k) : 0x61u;
-  uint32_t nextb = __shfl_down_sync(kFull, b[0], 1);
-  if (lane == 31) nextb = base + 4 < rs.len ? __ldg(p + 4) : 0x61u;
-  if (!T.byte_mode) {
-    bool ok = nextb < 0x80 || nvalid < 4;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      ok = ok && ((uint32_t)k >= nvalid || (b[k] < 0x80 && ((T.simple_ascii[(b[k] >> 5) & 3] >> (b[k] & 31)) & 1u)));
-    if (!__all_sync(kFull, ok)) return false;
+  // The lane's 4 source bytes as one little-endian word.  Every lane loads the ALIGNED word that holds its first
+  // byte (one coalesced 128-byte request per warp) and borrows the next lane's word for the unaligned remainder;
+  // words are only read while they start before the end of the request (bytes outside it are masked).
+  const uint8_t* win = rs.src + pos;
+  const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(win) & 3u);
+  const uint32_t* aw = reinterpret_cast<const uint32_t*>(win - off) + lane;
+  const uint8_t* src_end = rs.src + rs.len;
+  const uint32_t W = reinterpret_cast<const uint8_t*>(aw) < src_end ? __ldg(aw) : 0x61616161u;
+  // the text is read once, front to back: pull the next windows' lines into L2 while this one is processed
+  if (lane < kPrefetchWindows) {
+    const uint8_t* pf = reinterpret_cast<const uint8_t*>(aw - lane) + (size_t)kFastWin * (kPrefetchFirst + lane);
+    if (pf < src_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
   }
-
-  bool sp[4];  // byte_mode: text is copied verbatim, a space is an ordinary byte
+  uint32_t Wn = __shfl_down_sync(kFull, W, 1);
+  if (lane == 31) Wn = reinterpret_cast<const uint8_t*>(aw + 1) < src_end ? __ldg(aw + 1) : 0x61616161u;
+  uint32_t w = __funnelshift_r(W, Wn, off * 8u);
+  if (nvalid < 4u) w = nvalid == 0u ? 0x61616161u : ((w & ((1u << (8u * nvalid)) - 1u)) | (0x61616161u << (8u * nvalid)));
+  uint32_t nextb = __shfl_down_sync(kFull, w, 1) & 0xFFu;
+  if (lane == 31) nextb = base + 4 < rs.len ? ((Wn >> (off * 8u)) & 0xFFu) : 0x61u;
+  if (!T.byte_mode) {
+    // all four bytes ASCII and "simple"; the byte after them ASCII too.  Printable ASCII is simple for every
+    // ordinary charsmap (host flag): three SWAR tests; anything else takes the per-byte table.
+    const bool ascii4 = (w & 0x80808080u) == 0u;
+    bool ok = (nextb < 0x80 || nvalid < 4) && ascii4;
+    bool fast_ok = false;
+    if (T.printable_simple)
+      fast_ok = ((((w | 0x80808080u) - 0x20202020u) & 0x80808080u) == 0x80808080u) &&  // every byte >= 0x20
+                (((w + 0x01010101u) & 0x80808080u) == 0u);                               // every byte <= 0x7E
+    if (!__all_sync(kFull, ok && fast_ok)) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) sp[k] = !T.byte_mode && (uint32_t)k < nvalid && b[k] == ' ';
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t bk = (w >> (8 * k)) & 0xFFu;
+        ok = ok && ((T.simple_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u);
+      }
+      if (!__all_sync(kFull, ok)) return false;
+    }
+  }
+  // spaces as a 4-bit mask (byte_mode: text is copied verbatim, a space is an ordinary byte)
+  uint32_t sp4 = 0;
+  if (!T.byte_mode) {
+    const uint32_t x = w ^ 0x20202020u;
+    const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);  // 0x80 in every zero byte of x
+    sp4 = (((z >> 7) * 0x01020408u) >> 24) & 0xFu;
+  }
   // is the byte before this lane's first byte a space?  (lanes before a valid lane are full)
-  const bool last_sp = sp[3];
-  bool prev = __shfl_up_sync(kFull, last_sp, 1);
+  uint32_t prev_in = __shfl_up_sync(kFull, sp4 >> 3, 1) & 1u;
   if (lane == 0) {
     // remove_extra_whitespaces: the normalizer's is_prev_space; otherwise "the last emitted char is U+2581"
     const int nl = rs.nlen;
-    prev = T.remove_extra_ws ? rs.prev_space
-                             : (nl >= 3 && sm.nbuf[nl - 3] == 0xE2 && sm.nbuf[nl - 2] == 0x96 && sm.nbuf[nl - 1] == 0x81);
+    prev_in = T.remove_extra_ws ? (uint32_t)rs.prev_space
+                                : (uint32_t)(nl >= 3 && sm.nbuf[nl - 3] == 0xE2 && sm.nbuf[nl - 2] == 0x96 && sm.nbuf[nl - 1] == 0x81);
   }
   const bool buffer_empty = rs.nlen == 0;  // offset 0 is a word start by definition: do not record it twice
-  uint32_t out_len = 0, n_start = 0;
-  uint32_t keep = 0, start = 0;  // bit k: byte k is emitted / starts a word
-  bool pv = prev;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if ((uint32_t)k < nvalid) {
-      const bool drop = T.remove_extra_ws && sp[k] && pv;
-      if (!drop) {
-        keep |= 1u << k;
-        out_len += sp[k] ? 3u : 1u;
-        const bool at_zero = buffer_empty && lane == 0 && out_len == (sp[k] ? 3u : 1u);
-        if (sp[k] && !at_zero && (T.split_mode == 1 || (T.split_mode == 2 && !pv))) { start |= 1u << k; ++n_start; }
-      }
-      pv = sp[k];
-    }
-  }
+  const uint32_t valid4 = (1u << nvalid) - 1u;
+  const uint32_t prevbits = ((sp4 << 1) | prev_in) & 0xFu;            // bit k: the byte before byte k is a space
+  const uint32_t keep4 = valid4 & ~(T.remove_extra_ws ? (sp4 & prevbits) : 0u);   // a space after a space is dropped
+  const uint32_t az4 = (buffer_empty && lane == 0) ? (keep4 & (0u - keep4)) : 0u;  // the byte that lands at offset 0
+  const uint32_t start4 =
+      keep4 & sp4 & ~az4 & (T.split_mode == 1 ? 0xFu : (T.split_mode == 2 ? ~prevbits : 0u));  // kept spaces that start a word
+  const uint32_t out_len = __popc(keep4) + 2u * __popc(keep4 & sp4);
+  const uint32_t n_start = __popc(start4);
   const int packed = (int)(out_len | (n_start << 16));
   const int incl = warp_incl_scan(packed, lane);
   const int total = __shfl_sync(kFull, incl, 31);
@@ -489,26 +509,29 @@ __device__ __forceinline__ bool normalize_fast(const SpDev& T, SM& sm, ReqState&
     rs.nw = 1;
   }
   uint32_t o = (uint32_t)rs.nlen + ((uint32_t)(incl - packed) & 0xFFFFu);
-  uint32_t wi = (uint32_t)rs.nw + ((uint32_t)(incl - packed) >> 16);
   uint8_t* d = sm.nbuf;
+  if (keep4 == 0xFu && sp4 == 0u) {  // four plain bytes
+    d[o] = (uint8_t)w; d[o + 1] = (uint8_t)(w >> 8); d[o + 2] = (uint8_t)(w >> 16); d[o + 3] = (uint8_t)(w >> 24);
+  } else {
+    uint32_t wi = (uint32_t)rs.nw + ((uint32_t)(incl - packed) >> 16);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if ((keep >> k) & 1u) {
-      if (sp[k]) {
-        if ((start >> k) & 1u) sm.wstart[wi++] = (uint16_t)o;
-        d[o] = 0xE2; d[o + 1] = 0x96; d[o + 2] = 0x81;
-        o += 3;
-      } else {
-        d[o++] = (uint8_t)b[k];
+    for (int k = 0; k < 4; ++k) {
+      if ((keep4 >> k) & 1u) {
+        if ((sp4 >> k) & 1u) {
+          if ((start4 >> k) & 1u) sm.wstart[wi++] = (uint16_t)o;
+          d[o] = 0xE2; d[o + 1] = 0x96; d[o + 2] = 0x81;
+          o += 3;
+        } else {
+          d[o++] = (uint8_t)(w >> (8 * k));
+        }
       }
     }
   }
   // is_prev_space after the window = the last source byte is a space (every unit here is non-empty)
-  const uint32_t n_in = rs.len - pos < (uint32_t)kFastWin ? rs.len - pos : (uint32_t)kFastWin;
-  const uint32_t last_lane = (n_in - 1) >> 2, last_k = (n_in - 1) & 3;
-  const bool mine = last_k == 0 ? sp[0] : (last_k == 1 ? sp[1] : (last_k == 2 ? sp[2] : sp[3]));
-  const bool ws = __shfl_sync(kFull, mine, last_lane);
-  if (T.remove_extra_ws) rs.prev_space = ws;
+  if (T.remove_extra_ws) {
+    const uint32_t n_in = rs.len - pos < (uint32_t)kFastWin ? rs.len - pos : (uint32_t)kFastWin;
+    rs.prev_space = (__shfl_sync(kFull, sp4, (n_in - 1) >> 2) >> ((n_in - 1) & 3)) & 1u;
+  }
   rs.nlen += total & 0xFFFF;
   rs.nw += total >> 16;
   __syncwarp();
@@ -1434,6 +1457,11 @@ int SpDeviceModel::upload(const SpTables& t) {
   dev_.remove_extra_ws = t.remove_extra_whitespaces;
   dev_.split_mode = (uint8_t)t.split_mode;
   dev_.byte_mode = t.byte_mode ? 1 : 0;
+  {  // printable ASCII (0x20..0x7E) all "simple": the fast path tests a whole word at once
+    bool all = true;
+    for (uint32_t c = 0x20; c <= 0x7E; ++c) all = all && ((t.simple_ascii[c >> 5] >> (c & 31)) & 1u);
+    dev_.printable_simple = all ? 1 : 0;
+  }
   return XLLM_OK;
 }
 

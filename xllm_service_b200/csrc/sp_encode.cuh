@@ -33,6 +33,7 @@ struct SpDev {
   uint8_t byte_fallback, add_dummy_prefix, remove_extra_ws, split_mode;
   uint8_t small_vocab;  // ranks and piece ids fit 16 bits: packed merge scratch
   uint8_t byte_mode;    // tiktoken tables: every byte is a symbol, text is copied verbatim
+  uint8_t printable_simple;  // every byte 0x20..0x7E is "simple" (simple_ascii): word-at-a-time fast-path test
   // global scratch pool for pre-tokens too long for shared memory (sp_long_word.cuh)
   // HF byte-level BPE (split_mode 3, hf_model.cc): Unicode classes for the GPT-2 regex, the added (special)
   // tokens matched verbatim in the text, and the template ids wrapped around every sequence
