@@ -9,6 +9,11 @@
 //   added_vocabulary.rs   text is first split on the added (special) tokens, leftmost-longest
 //   pre_tokenizers/byte_level.rs   regex split
 //        's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+   then bytes -> GPT-2 byte chars
+//   pre_tokenizers/split.rs + byte_level.rs(use_regex = false)   the newer layout (Llama-3, Qwen2, OLMo-2 ...):
+//        Split(Regex, Isolated) with the cl100k-family pattern
+//        (?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,K}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+
+//        (K = 3 for Llama-3, plain \p{N} i.e. K = 1 for Qwen2), then the byte alphabet
+//   models/bpe/model.rs   ignore_merges: a pre-token that is itself in the vocabulary is emitted as that id
 //   models/bpe/word.rs    merge_all: lowest merge rank first, leftmost on ties
 // Pinned against pip `tokenizers` 0.22.2 by tests/test_oracle_hf.py (committed goldens
 // tests/golden/hf_bpe_goldens.json + live fuzz).  The vocabulary / merges are handed over by the test
@@ -36,6 +41,10 @@ struct Hf {
   int32_t byte_sym[256];                                   // byte -> id of its byte-level char
   std::unordered_map<uint64_t, std::pair<uint32_t, int32_t>> merges;  // (a << 32 | b) -> (rank, new id)
   std::vector<std::pair<std::string, int32_t>> added;      // special tokens matched on the raw text
+  int pattern = 1;                                         // 1: GPT-2 ByteLevel regex, 2: cl100k family
+  int digits = 3;                                          // pattern 2: \p{N}{1,digits}
+  bool ignore_merges = false;
+  std::unordered_map<std::string, int32_t> vocab;          // raw bytes of every token -> id (ignore_merges)
 };
 
 // strict UTF-8 decode; returns length or 0 when malformed (Rust &str cannot hold malformed text:
@@ -94,6 +103,69 @@ void gpt2_split(const std::vector<Ch>& c, std::vector<std::pair<size_t, size_t>>
       if (e == n) j = e;              // run reaches the end: (?!\S) holds after the whole run
       else if (e - i >= 2) j = e - 1; // backtrack one char so that a space follows
       else j = e;                     // single whitespace before a non-space: plain \s+
+    }
+    out->emplace_back(i, j);
+    i = j;
+  }
+}
+
+inline bool is_nl(uint32_t cp) { return cp == '\r' || cp == '\n'; }
+inline uint32_t fold(uint32_t cp) {  // the simple case folds that can hit the contraction letters
+  if (cp >= 'A' && cp <= 'Z') return cp + 32;
+  if (cp == 0x17F) return 's';  // LATIN SMALL LETTER LONG S folds to s
+  return cp;
+}
+
+// The cl100k-family pattern, alternative by alternative (leftmost-first, each alternative greedy with backtracking
+// exactly where the pattern allows it).
+void cl100k_split(const std::vector<Ch>& c, int K, std::vector<std::pair<size_t, size_t>>* out) {
+  const size_t n = c.size();
+  size_t i = 0;
+  auto isf = [&](size_t k, uint32_t ch) { return k < n && fold(c[k].cp) == ch; };
+  while (i < n) {
+    size_t j = i;
+    // (?i:'s|'t|'re|'ve|'m|'ll|'d)
+    if (c[i].cp == '\'') {
+      if (isf(i + 1, 's') || isf(i + 1, 't')) j = i + 2;
+      else if ((isf(i + 1, 'r') && isf(i + 2, 'e')) || (isf(i + 1, 'v') && isf(i + 2, 'e'))) j = i + 3;
+      else if (isf(i + 1, 'm')) j = i + 2;
+      else if (isf(i + 1, 'l') && isf(i + 2, 'l')) j = i + 3;
+      else if (isf(i + 1, 'd')) j = i + 2;
+    }
+    // [^\r\n\p{L}\p{N}]?\p{L}+
+    if (j == i) {
+      size_t s = i;
+      if (c[i].cls != kLetter && c[i].cls != kNumber && !is_nl(c[i].cp) && i + 1 < n && c[i + 1].cls == kLetter) s = i + 1;
+      if (c[s].cls == kLetter) {
+        j = s;
+        while (j < n && c[j].cls == kLetter) ++j;
+      }
+    }
+    // \p{N}{1,K}
+    if (j == i && c[i].cls == kNumber) {
+      j = i;
+      while (j < n && c[j].cls == kNumber && j - i < (size_t)K) ++j;
+    }
+    //  ?[^\s\p{L}\p{N}]+[\r\n]*
+    if (j == i) {
+      const size_t s = (c[i].cp == ' ' && i + 1 < n && c[i + 1].cls == kOther) ? i + 1 : i;
+      if (c[s].cls == kOther) {
+        j = s;
+        while (j < n && c[j].cls == kOther) ++j;
+        while (j < n && is_nl(c[j].cp)) ++j;
+      }
+    }
+    if (j == i) {
+      size_t e = i;
+      while (e < n && c[e].cls == kSpace) ++e;  // the whole whitespace run
+      // \s*[\r\n]+ : up to and including the last CR / LF of the run
+      size_t last_nl = n;
+      for (size_t k = i; k < e; ++k)
+        if (is_nl(c[k].cp)) last_nl = k;
+      if (last_nl != n) j = last_nl + 1;
+      else if (e == n) j = e;              // \s+(?!\S): the run reaches the end
+      else if (e - i >= 2) j = e - 1;      // \s+(?!\S): backtrack one char so that a space follows
+      else j = e;                          // \s+
     }
     out->emplace_back(i, j);
     i = j;
@@ -163,9 +235,14 @@ long encode(const Hf& h, const uint8_t* text, size_t len, std::vector<int32_t>* 
       p += l;
     }
     std::vector<std::pair<size_t, size_t>> pieces;
-    gpt2_split(c, &pieces);
+    if (h.pattern == 2) cl100k_split(c, h.digits, &pieces);
+    else gpt2_split(c, &pieces);
     for (const auto& pr : pieces) {
       const size_t b = c[pr.first].off, e = c[pr.second - 1].off + c[pr.second - 1].len;
+      if (h.ignore_merges) {
+        auto it = h.vocab.find(std::string((const char*)text + b, e - b));
+        if (it != h.vocab.end()) { ids->push_back(it->second); continue; }
+      }
       bpe_word(h, text + b, e - b, ids);
     }
     if (best_id < 0) break;
@@ -191,6 +268,18 @@ void* oracle_hf_new(const int32_t* byte_sym, const int32_t* merges, size_t n_mer
   for (size_t i = 0; i < n_added; ++i)
     h->added.emplace_back(std::string(added_blob + added_off[i], (size_t)(added_off[i + 1] - added_off[i])), added_ids[i]);
   return h;
+}
+// pattern: 1 GPT-2 / 2 cl100k family (digits = K); vocab: raw bytes of every token (blob + offsets) with ids,
+// consulted per pre-token when ignore_merges is set
+void oracle_hf_configure(void* hv, int pattern, int digits, int ignore_merges, const char* vocab_blob,
+                         const int64_t* vocab_off, const int32_t* vocab_ids, size_t n_vocab) {
+  Hf* h = (Hf*)hv;
+  h->pattern = pattern;
+  h->digits = digits;
+  h->ignore_merges = ignore_merges != 0;
+  h->vocab.clear();
+  for (size_t i = 0; i < n_vocab; ++i)
+    h->vocab.emplace(std::string(vocab_blob + vocab_off[i], (size_t)(vocab_off[i + 1] - vocab_off[i])), vocab_ids[i]);
 }
 void oracle_hf_free(void* h) { delete (Hf*)h; }
 // FastTokenizer::encode; returns the id count, or -1 for malformed UTF-8 (the reference aborts there).

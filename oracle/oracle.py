@@ -91,6 +91,9 @@ def lib():
         L.oracle_tik_encode.restype = ctypes.c_long
         L.oracle_hf_new.argtypes = [VP, VP, ctypes.c_size_t, ctypes.c_char_p, VP, VP, ctypes.c_size_t]
         L.oracle_hf_new.restype = VP
+        L.oracle_hf_configure.argtypes = [VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, VP, VP,
+                                          ctypes.c_size_t]
+        L.oracle_hf_configure.restype = None
         L.oracle_hf_free.argtypes = [VP]
         L.oracle_hf_free.restype = None
         L.oracle_hf_encode.argtypes = [VP, ctypes.c_char_p, ctypes.c_size_t, VP, ctypes.c_size_t]
@@ -362,6 +365,25 @@ def gpt2_bytes_to_unicode():
     return {b: chr(c) for b, c in zip(bs, cs)}
 
 
+CL100K_FAMILY = {
+    r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+": 3,
+    r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+": 1,
+}
+
+
+def hf_pattern_of(pre):
+    """(pattern kind, digits) of a tokenizer.json pre_tokenizer: (1, 0) = ByteLevel with its own GPT-2 regex,
+    (2, K) = Sequence[Split(cl100k-family regex, Isolated), ByteLevel(use_regex = false)]."""
+    if pre["type"] == "ByteLevel":
+        assert pre.get("use_regex", True) and not pre.get("add_prefix_space", False)
+        return 1, 0
+    assert pre["type"] == "Sequence" and len(pre["pretokenizers"]) == 2, pre
+    sp, bl = pre["pretokenizers"]
+    assert sp["type"] == "Split" and sp["behavior"] == "Isolated" and not sp.get("invert", False)
+    assert bl["type"] == "ByteLevel" and not bl.get("use_regex", True) and not bl.get("add_prefix_space", False)
+    return 2, CL100K_FAMILY[sp["pattern"]["Regex"]]
+
+
 class HfBpeOracle:
     """FastTokenizer (xllm_service/tokenizer/fast_tokenizer.cpp:20-30 over HF `tokenizers`) for byte-level BPE
     tokenizer.json files; algorithm in oracle/hf_bpe_oracle.cc, the JSON is read here."""
@@ -374,7 +396,12 @@ class HfBpeOracle:
         with open(path, encoding="utf-8") as f:
             d = json.load(f)
         m = d["model"]
-        assert m["type"] == "BPE" and d["pre_tokenizer"]["type"] == "ByteLevel" and d["normalizer"] is None
+        assert m["type"] == "BPE"
+        self.pattern, self.digits = hf_pattern_of(d["pre_tokenizer"])
+        norm = d.get("normalizer")
+        assert norm is None or norm == {"type": "NFC"}, norm
+        self.nfc = norm is not None
+        self.ignore_merges = bool(m.get("ignore_merges", False))
         vocab = m["vocab"]
         b2u = gpt2_bytes_to_unicode()
         byte_sym = np.array([vocab[b2u[b]] for b in range(256)], dtype=np.int32)
@@ -392,6 +419,26 @@ class HfBpeOracle:
         self._keep = (byte_sym, merges, blob, off, ids)
         self._h = lib().oracle_hf_new(byte_sym.ctypes.data, merges.ctypes.data, merges.shape[0],
                                       ctypes.c_char_p(blob), off.ctypes.data, ids.ctypes.data, len(added))
+        u2b = {c: b for b, c in b2u.items()}
+        raw = [(bytes(u2b[ch] for ch in tok), i) for tok, i in vocab.items() if all(ch in u2b for ch in tok)]
+        vblob = b"".join(r for r, _ in raw)
+        voff = np.zeros(len(raw) + 1, dtype=np.int64)
+        np.cumsum([len(r) for r, _ in raw], out=voff[1:])
+        vids = np.array([i for _, i in raw], dtype=np.int32)
+        lib().oracle_hf_configure(self._h, self.pattern, self.digits, int(self.ignore_merges), ctypes.c_char_p(vblob),
+                                  voff.ctypes.data, vids.ctypes.data, len(raw))
+        tp = d.get("post_processor") or {}
+        procs = tp.get("processors", [tp]) if tp else []
+        self.prefix_ids, self.suffix_ids = [], []
+        for pr in procs:
+            if pr.get("type") == "TemplateProcessing":
+                seen = False
+                for it in pr["single"]:
+                    if "Sequence" in it:
+                        seen = True
+                    else:
+                        (self.suffix_ids if seen else self.prefix_ids).extend(
+                            pr["special_tokens"][it["SpecialToken"]["id"]]["ids"])
         self.vocab_size = max(vocab.values()) + 1
 
     def __del__(self):
@@ -403,7 +450,14 @@ class HfBpeOracle:
             pass
 
     def encode(self, text: bytes):
-        """ids, or None when the text is not valid UTF-8 (the reference's Rust shim panics there)."""
+        """ids, or None when the text is not valid UTF-8 (the reference's Rust shim panics there).  A `normalizer:
+        NFC` is applied here (Python's unicodedata); template ids are NOT added (see prefix_ids / suffix_ids)."""
+        if self.nfc:
+            import unicodedata
+            try:
+                text = unicodedata.normalize("NFC", text.decode("utf-8")).encode("utf-8")
+            except UnicodeDecodeError:
+                return None
         cap = len(text) + 16
         out = np.zeros(cap, dtype=np.int32)
         n = lib().oracle_hf_encode(self._h, text, len(text), out.ctypes.data, cap)

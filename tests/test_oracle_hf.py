@@ -48,3 +48,37 @@ def test_live_against_tokenizers_wheel(hf):
     for cp in list(range(0x80, 0x2100, 3)) + list(range(0x2E80, 0x3100, 5)) + list(range(0x1F600, 0x1F608)):
         s = "a" + chr(cp) + "b " + chr(cp) + "1"
         assert hf.encode(s.encode()).tolist() == tok.encode(s).ids, hex(cp)
+
+
+# ---------------------------------------------------------------- the newer layouts (Llama-3 / Qwen2 style)
+GOLD2 = os.path.join(HERE, "golden", "hf_cl100k_goldens.json")
+STYLES = ["hf_llama3_style", "hf_qwen2_style"]
+
+
+@pytest.mark.parametrize("style", STYLES)
+def test_cl100k_family_goldens(oracle, style):
+    """Split(cl100k-family regex) + ByteLevel(use_regex=false); ignore_merges + BOS template (Llama-3 style) and
+    \\p{N} + NFC (Qwen2 style): goldens minted by tests/golden/make_hf_fixture2.py."""
+    h = oracle.HfBpeOracle(os.path.join(HERE, "golden", style))
+    assert h.pattern == 2 and h.digits == (3 if style == "hf_llama3_style" else 1)
+    assert h.ignore_merges == (style == "hf_llama3_style") and h.nfc == (style == "hf_qwen2_style")
+    with open(GOLD2) as f:
+        cases = json.load(f)["cases"][style]
+    assert len(cases) > 350
+    for c in cases:
+        t = bytes.fromhex(c["text"])
+        assert h.prefix_ids + h.encode(t).tolist() + h.suffix_ids == c["ids"], t[:40]
+
+
+@pytest.mark.parametrize("style", STYLES)
+def test_cl100k_family_live(oracle, style):
+    tokenizers = pytest.importorskip("tokenizers")
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_hf_fixture2 as m
+    h = oracle.HfBpeOracle(os.path.join(HERE, "golden", style))
+    tok = tokenizers.Tokenizer.from_file(os.path.join(HERE, "golden", style, "tokenizer.json"))
+    rnd = random.Random(21)
+    for _ in range(2500):
+        s = "".join(rnd.choice(m.ALPHABET) for _ in range(rnd.randrange(0, 50)))
+        assert h.prefix_ids + h.encode(s.encode()).tolist() + h.suffix_ids == tok.encode(s).ids, repr(s)
