@@ -34,7 +34,7 @@ namespace {
 enum { kOther = 0, kLetter = 1, kNumber = 2, kSpace = 3 };
 inline int uni_class(uint32_t cp) {
   if (cp >= 0x110000) return kOther;
-  return kUniStage2[(size_t)kUniStage1[cp >> 8] * 256 + (cp & 255)];
+  return kUniStage2[(size_t)kUniStage1[cp >> 8] * 256 + (cp & 255)] & 3;  // bit 2: NFC-suspect (unused here)
 }
 
 struct Hf {

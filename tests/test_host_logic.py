@@ -135,8 +135,10 @@ def test_hf_tokenizer_json_tables(tmp_path):
         return f
 
     for name, edit in (
-        ("nfc", set_(["normalizer"], {"type": "NFC"})),
-        ("ignore_merges", set_(["model", "ignore_merges"], True)),
+        ("nfkc", set_(["normalizer"], {"type": "NFKC"})),
+        ("other_regex", set_(["pre_tokenizer"], {"type": "Sequence", "pretokenizers": [
+            {"type": "Split", "pattern": {"Regex": "\\p{N}{1,3}"}, "behavior": "Isolated", "invert": False},
+            {"type": "ByteLevel", "add_prefix_space": False, "trim_offsets": True, "use_regex": False}]})),
         ("dropout", set_(["model", "dropout"], 0.1)),
         ("prefix_space", set_(["pre_tokenizer", "add_prefix_space"], True)),
         ("no_regex", set_(["pre_tokenizer", "use_regex"], False)),
@@ -155,6 +157,11 @@ def test_hf_tokenizer_json_tables(tmp_path):
     with pytest.raises(x.IngestError) as e:
         _lib.tokenizer_probe(str(tmp_path / "broken"))
     assert e.value.code == -4
+    # NFC (checked per request on device) and ignore_merges are accepted; so are the Llama-3 / Qwen2 layouts
+    assert _lib.tokenizer_probe(variant("nfc", set_(["normalizer"], {"type": "NFC"})))["split_mode"] == 3
+    assert _lib.tokenizer_probe(variant("im", set_(["model", "ignore_merges"], True)))["split_mode"] == 3
+    for style in ("hf_llama3_style", "hf_qwen2_style"):
+        assert _lib.tokenizer_probe(os.path.join(HERE, "golden", style))["split_mode"] == 3
     # a template post-processor is accepted (ids are wrapped on device)
     tp = {"type": "TemplateProcessing",
           "single": [{"SpecialToken": {"id": "<|endoftext|>", "type_id": 0}}, {"Sequence": {"id": "A", "type_id": 0}}],

@@ -221,23 +221,63 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
     if (v && !v->is_null() && !(v->type == JVal::kStr && v->str.empty()))
       return fail(t, XLLM_ERR_UNSUPPORTED, std::string("tokenizer.json model.") + k + " is not supported on device");
   }
-  for (const char* k : {"fuse_unk", "byte_fallback", "ignore_merges"})
+  t->ignore_merges = !flag_false_or_absent(model, "ignore_merges");
+  for (const char* k : {"fuse_unk", "byte_fallback"})
     if (!flag_false_or_absent(model, k))
       return fail(t, XLLM_ERR_UNSUPPORTED, std::string("tokenizer.json model.") + k + " = true is not supported on device");
   const JVal* norm = root.get("normalizer");
-  if (norm && !norm->is_null()) return fail(t, XLLM_ERR_UNSUPPORTED, "tokenizer.json normalizer is not supported on device yet");
+  if (norm && !norm->is_null()) {
+    // NFC (Qwen2 family): the device proves per request that NFC is the identity (every char NFC-inert) and
+    // fails the request otherwise — it never normalises
+    const JVal* ty = norm->get("type");
+    if (!ty || ty->type != JVal::kStr || ty->str != "NFC")
+      return fail(t, XLLM_ERR_UNSUPPORTED, "tokenizer.json normalizer: only null or NFC is supported on device");
+    t->nfc_check = true;
+  }
   for (const char* k : {"truncation", "padding"}) {
     const JVal* v = root.get(k);
     if (v && !v->is_null()) return fail(t, XLLM_ERR_UNSUPPORTED, std::string("tokenizer.json ") + k + " is not supported on device");
   }
   const JVal* pre = root.get("pre_tokenizer");
   {
+    static const char* kUnsupported =
+        "tokenizer.json pre_tokenizer: supported on device are ByteLevel{add_prefix_space:false, use_regex:true} and "
+        "Sequence[Split{cl100k-family regex, Isolated}, ByteLevel{add_prefix_space:false, use_regex:false}]";
+    static const char* kP3 =
+        "(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\\r\\n\\p{L}\\p{N}]?\\p{L}+|\\p{N}{1,3}| ?[^\\s\\p{L}\\p{N}]+[\\r\\n]*|\\s*[\\r\\n]+|\\s+(?!\\S)|\\s+";
+    static const char* kP1 =
+        "(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\\r\\n\\p{L}\\p{N}]?\\p{L}+|\\p{N}| ?[^\\s\\p{L}\\p{N}]+[\\r\\n]*|\\s*[\\r\\n]+|\\s+(?!\\S)|\\s+";
     const JVal* ty = pre ? pre->get("type") : nullptr;
-    const JVal* rx = pre ? pre->get("use_regex") : nullptr;
-    if (!ty || ty->type != JVal::kStr || ty->str != "ByteLevel" || !flag_false_or_absent(pre, "add_prefix_space") ||
-        (rx && rx->type == JVal::kBool && !rx->b))
-      return fail(t, XLLM_ERR_UNSUPPORTED,
-                  "tokenizer.json pre_tokenizer: only ByteLevel{add_prefix_space:false, use_regex:true} is supported on device");
+    if (!ty || ty->type != JVal::kStr) return fail(t, XLLM_ERR_UNSUPPORTED, kUnsupported);
+    auto byte_level_ok = [&](const JVal* bl, bool want_regex) {
+      const JVal* bt = bl->get("type");
+      const JVal* rx = bl->get("use_regex");
+      const bool use_regex = !(rx && rx->type == JVal::kBool && !rx->b);
+      return bt && bt->type == JVal::kStr && bt->str == "ByteLevel" && flag_false_or_absent(bl, "add_prefix_space") &&
+             use_regex == want_regex;
+    };
+    if (ty->str == "ByteLevel") {
+      if (!byte_level_ok(pre, true)) return fail(t, XLLM_ERR_UNSUPPORTED, kUnsupported);
+      t->hf_pattern = 1;
+    } else if (ty->str == "Sequence") {
+      const JVal* seq = pre->get("pretokenizers");
+      if (!seq || seq->type != JVal::kArr || seq->arr.size() != 2) return fail(t, XLLM_ERR_UNSUPPORTED, kUnsupported);
+      const JVal& sp = seq->arr[0];
+      const JVal* st = sp.get("type");
+      const JVal* pat = sp.get("pattern");
+      const JVal* rx = pat ? pat->get("Regex") : nullptr;
+      const JVal* beh = sp.get("behavior");
+      if (!st || st->type != JVal::kStr || st->str != "Split" || !rx || rx->type != JVal::kStr || !beh ||
+          beh->type != JVal::kStr || beh->str != "Isolated" || !flag_false_or_absent(&sp, "invert") ||
+          !byte_level_ok(&seq->arr[1], false))
+        return fail(t, XLLM_ERR_UNSUPPORTED, kUnsupported);
+      if (rx->str == kP3) t->hf_digits = 3;
+      else if (rx->str == kP1) t->hf_digits = 1;
+      else return fail(t, XLLM_ERR_UNSUPPORTED, std::string(kUnsupported) + "; got regex " + rx->str);
+      t->hf_pattern = 2;
+    } else {
+      return fail(t, XLLM_ERR_UNSUPPORTED, kUnsupported);
+    }
   }
 
   // ---- vocabulary
@@ -300,6 +340,7 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
   // decode table: token string (byte-level chars) -> raw bytes
   t->piece_str.assign(V, std::string());
   t->piece_raw.assign(V, std::string());
+  std::vector<bool> raw_ok(V, false);
   t->piece_type.assign(V, 1);
   for (const auto& kv : id_of) {
     std::string raw;
@@ -318,6 +359,35 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
     }
     t->piece_str[(size_t)kv.second] = kv.first;
     t->piece_raw[(size_t)kv.second] = ok ? raw : kv.first;
+    raw_ok[(size_t)kv.second] = ok;
+  }
+  if (t->ignore_merges) {
+    // raw bytes of every model.vocab entry -> id, probed once per pre-token on device (hf_vocab_lookup)
+    std::vector<std::pair<std::string, int32_t>> ent;
+    for (const auto& kv : id_of) {
+      // an entry spelled with chars outside the byte alphabet can never equal a byte-level pre-token
+      if (raw_ok[(size_t)kv.second]) ent.emplace_back(t->piece_raw[(size_t)kv.second], kv.second);
+    }
+    uint32_t slots = 16;
+    while (slots < ent.size() * 2 + 16) slots <<= 1;
+    t->vocab_table.assign((size_t)slots * 4, 0u);
+    for (const auto& e : ent) {
+      if (e.first.empty()) continue;
+      if (e.first.size() > 512)
+        return fail(t, XLLM_ERR_UNSUPPORTED, "ignore_merges with a vocabulary entry longer than 512 bytes");
+      unsigned long long h = 0xcbf29ce484222325ull;
+      for (unsigned char c : e.first) h = (h ^ c) * 0x100000001b3ull;
+      if (h == 0) h = 1;
+      if (t->vocab_blob.size() + e.first.size() >= (1u << 22))
+        return fail(t, XLLM_ERR_UNSUPPORTED, "ignore_merges vocabulary larger than 4 MiB of token bytes");
+      uint32_t slot = (uint32_t)(h >> 24) & (slots - 1);
+      while (t->vocab_table[(size_t)slot * 4] | t->vocab_table[(size_t)slot * 4 + 1]) slot = (slot + 1) & (slots - 1);
+      t->vocab_table[(size_t)slot * 4 + 0] = (uint32_t)h;
+      t->vocab_table[(size_t)slot * 4 + 1] = (uint32_t)(h >> 32);
+      t->vocab_table[(size_t)slot * 4 + 2] = (uint32_t)e.second;
+      t->vocab_table[(size_t)slot * 4 + 3] = ((uint32_t)t->vocab_blob.size() << 10) | (uint32_t)e.first.size();
+      t->vocab_blob.insert(t->vocab_blob.end(), e.first.begin(), e.first.end());
+    }
   }
   size_t n_extra = 0;
   for (const auto& a : t->added_tokens) {
@@ -364,14 +434,32 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
     }
     if (!dup) t->pair_table[h] = e;
   }
-  // ---- post-processor: ids wrapped around the sequence when add_special_tokens = 1 (fast_tokenizer.cpp:24)
-  const JVal* post = root.get("post_processor");
-  if (post && !post->is_null()) {
-    const JVal* ty = post->get("type");
-    if (!ty || ty->type != JVal::kStr) return fail(t, XLLM_ERR_FORMAT, "post_processor without a type");
-    if (ty->str == "TemplateProcessing") {
-      const JVal* single = post->get("single");
-      const JVal* specials = post->get("special_tokens");
+  // ---- post-processor: ids wrapped around the sequence when add_special_tokens = 1 (fast_tokenizer.cpp:24).
+  // ByteLevel only trims offsets; a Sequence (Llama-3: [ByteLevel, TemplateProcessing]) applies its members in order.
+  {
+    std::vector<const JVal*> procs;
+    const JVal* post = root.get("post_processor");
+    if (post && !post->is_null()) {
+      const JVal* ty = post->get("type");
+      if (!ty || ty->type != JVal::kStr) return fail(t, XLLM_ERR_FORMAT, "post_processor without a type");
+      if (ty->str == "Sequence") {
+        const JVal* list = post->get("processors");
+        if (!list || list->type != JVal::kArr) return fail(t, XLLM_ERR_FORMAT, "post_processor Sequence without processors");
+        for (const JVal& x : list->arr) procs.push_back(&x);
+      } else {
+        procs.push_back(post);
+      }
+    }
+    bool have_template = false;
+    for (const JVal* pr : procs) {
+      const JVal* ty = pr->get("type");
+      if (!ty || ty->type != JVal::kStr) return fail(t, XLLM_ERR_FORMAT, "post_processor without a type");
+      if (ty->str == "ByteLevel") continue;
+      if (ty->str != "TemplateProcessing" || have_template)
+        return fail(t, XLLM_ERR_UNSUPPORTED, "post_processor " + ty->str + " is not supported on device");
+      have_template = true;
+      const JVal* single = pr->get("single");
+      const JVal* specials = pr->get("special_tokens");
       if (!single || single->type != JVal::kArr) return fail(t, XLLM_ERR_FORMAT, "TemplateProcessing without `single`");
       bool seen_seq = false;
       for (const JVal& it : single->arr) {
@@ -393,8 +481,6 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
       if (!seen_seq) return fail(t, XLLM_ERR_UNSUPPORTED, "TemplateProcessing.single without sequence A");
       if (t->prefix_ids.size() > 4 || t->suffix_ids.size() > 4)
         return fail(t, XLLM_ERR_UNSUPPORTED, "more than 4 template tokens on one side");
-    } else if (ty->str != "ByteLevel") {
-      return fail(t, XLLM_ERR_UNSUPPORTED, "post_processor " + ty->str + " is not supported on device");
     }
   }
   // ---- Unicode classes for the regex (\p{L}, \p{N}, \s)

@@ -19,6 +19,20 @@
 //       contraction and)  whitespace after non-whitespace | whitespace that is the LAST of a run of >= 2 followed
 //       by a non-space in the same segment (the \s+(?!\S) backtrack) | non-whitespace after whitespace other
 //       than U+0020 (a single U+0020 is the " ?" prefix) | class change between two non-whitespace chars.
+// hf_pattern 2 is the cl100k-family Split regex of the newer layouts (Llama-3: K = 3, Qwen2: K = 1)
+//        (?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,K}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+
+// (oracle: cl100k_split).  Still decided per position, with three facts that need a scan along the buffer, done
+// 32 bytes at a time with a warp-uniform carry: C1 forward — a CR/LF is "swallowed" when only CR/LFs separate it
+// from a punctuation char (the [\r\n]* tail of the punctuation alternative), and a digit's index inside its run
+// (a token starts every K digits); C2 backward — a non-newline whitespace char has a CR/LF later in its
+// whitespace run (then \s*[\r\n]+ takes the run up to the LAST newline).  With those, position i starts a token iff
+//   letter: the previous char is a number or CR/LF, or a punctuation char that is NOT itself a token start (a
+//           punctuation / space / tab char that IS a token start is the letters' one-char prefix);
+//   number: index in the digit run is a multiple of K;      punctuation: previous char is neither punctuation nor U+0020;
+//   CR/LF : not swallowed and the previous char is not whitespace;
+//   other whitespace: run start | previous char is a CR/LF with no newline left in the run | last char of the run
+//           before a non-space (prefix or single) — and nothing else while a newline still follows in the run;
+// contractions are case-insensitive (incl. U+017F) and otherwise as above.
 // Per-byte scratch (one byte per text byte, in the merge scratch S[] which is idle while scanning):
 //   bits 0-1 class, bit 2 char is U+0020, bit 3 inside an added token, bit 4 added token starts here,
 //   bits 5-6 contraction length - 1 (0 = none), 0x80 = UTF-8 continuation byte.
@@ -28,7 +42,11 @@ enum : uint8_t { kHfOther = 0, kHfLetter = 1, kHfNumber = 2, kHfSpace = 3 };
 constexpr uint8_t kHfIsSp = 0x04, kHfInAdded = 0x08, kHfAddedStart = 0x10, kHfCont = 0x80;
 constexpr uint16_t kHfSpecialWord = 0x8000;  // wstart[] flag: the word is an added token (one id, no BPE)
 constexpr uint16_t kHfPosMask = 0x0FFF;
+// pattern 2, second scratch byte per text byte (in PM[]): CR/LF | swallowed CR/LF | digit starts a token | a CR/LF follows in the run
+constexpr uint8_t kAuxNl = 0x01, kAuxSwallowed = 0x02, kAuxDigitStart = 0x04, kAuxNlAfter = 0x08;
 
+// class in bits 0-1; bit 2 (non-ASCII only): the char is not NFC-inert (scripts/gen_unicode_classes.py)
+constexpr uint8_t kUniNfcSuspect = 0x04;
 __device__ __forceinline__ uint8_t hf_class(const SpDev& T, uint32_t cp) {
   if (cp < 0x80) {
     const uint32_t l = cp | 0x20;
@@ -53,11 +71,32 @@ __device__ __forceinline__ int hf_added_len(const SpDev& T, const uint8_t* p, in
   return best;
 }
 
+// ignore_merges: raw bytes of a pre-token -> id of the vocabulary entry with exactly those bytes, or -1.
+// Table entry (16 B): x,y = FNV-1a 64 of the bytes (0 = empty), z = id, w = blob offset << 10 | length.
+__device__ __forceinline__ int32_t hf_vocab_lookup(const SpDev& T, const uint8_t* w, int n) {
+  if (n > 1023) return -1;
+  unsigned long long h = 0xcbf29ce484222325ull;
+  for (int k = 0; k < n; ++k) h = (h ^ w[k]) * 0x100000001b3ull;
+  if (h == 0) h = 1;
+  uint32_t slot = (uint32_t)(h >> 24) & T.vtab_mask;
+  for (;;) {
+    const uint4 e = __ldg(T.vtab + slot);
+    if ((e.x | e.y) == 0) return -1;
+    if (e.x == (uint32_t)h && e.y == (uint32_t)(h >> 32) && (int)(e.w & 1023u) == n) {
+      const uint8_t* b = T.vblob + (e.w >> 10);
+      bool eq = true;
+      for (int k = 0; k < n && eq; ++k) eq = __ldg(b + k) == w[k];
+      if (eq) return (int32_t)e.z;
+    }
+    slot = (slot + 1) & T.vtab_mask;
+  }
+}
+
 struct HfScan {
   int nwords;      // complete pre-tokens listed in wstart[0..nwords); wstart[nwords] = tail_start
   int tail_start;  // first byte that is not part of a listed pre-token
   bool capped;     // wstart[] filled up: scan the kept tail again
-  bool bad;        // malformed UTF-8
+  int bad;         // 0 ok, 1 malformed UTF-8, 2 the text is not provably in NFC and the tokenizer normalises with NFC
 };
 
 // nb[0..nlen) starts at a token start.  cls = nlen bytes of scratch.  final: the text ends at nlen.
@@ -65,9 +104,11 @@ template <typename SM>
 __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane) {
   const uint8_t* nb = sm.nbuf;
   uint8_t* cls = reinterpret_cast<uint8_t*>(sm.S);
-  static_assert(sizeof(sm.S) >= kNBuf, "class scratch must cover the staging buffer");
-  bool bad = false;
-  // ---- A: classes + UTF-8 validation
+  uint8_t* aux = reinterpret_cast<uint8_t*>(sm.PM);
+  static_assert(sizeof(sm.S) >= kNBuf && sizeof(sm.PM) >= kNBuf, "class scratch must cover the staging buffer");
+  const bool p2 = T.hf_pattern == 2;
+  bool bad = false, nfc_bad = false;
+  // ---- A: classes + UTF-8 validation (+ the NFC quick check: every char NFC-inert => NFC is the identity)
   for (int base = 0; base < nlen; base += 32) {
     const int p = base + lane;
     if (p < nlen) {
@@ -99,10 +140,13 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
                               : l == 3 ? (((b0 & 0x0Fu) << 12) | ((nb[p + 1] & 0x3Fu) << 6) | (nb[p + 2] & 0x3Fu))
                                        : (((b0 & 0x07u) << 18) | ((nb[p + 1] & 0x3Fu) << 12) | ((nb[p + 2] & 0x3Fu) << 6) | (nb[p + 3] & 0x3Fu));
             v = hf_class(T, cp);
+            nfc_bad |= T.nfc_check && (v & kUniNfcSuspect);
+            v &= 3;
           }
         }
       }
       cls[p] = v;
+      if (p2) aux[p] = (b0 == '\n' || b0 == '\r') ? kAuxNl : 0;
     }
   }
   __syncwarp();
@@ -110,7 +154,7 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
   r.nwords = 0;
   r.tail_start = 0;
   r.capped = false;
-  r.bad = __any_sync(kFull, bad);
+  r.bad = __any_sync(kFull, bad) ? 1 : (__any_sync(kFull, nfc_bad) ? 2 : 0);
   if (r.bad) return r;
   // ---- A2: added tokens, leftmost-longest, non-overlapping
   if (T.n_added) {
@@ -152,8 +196,13 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
         st = (a & (kHfInAdded | kHfAddedStart)) || ((a & 3) != kHfOther && !(a & kHfIsSp));
       }
       if (st) {
-        const uint8_t c1 = (p + 1 < nlen && !(cls[p + 1] & (kHfInAdded | kHfAddedStart))) ? nb[p + 1] : 0;
-        const uint8_t c2 = (c1 && p + 2 < nlen && !(cls[p + 2] & (kHfInAdded | kHfAddedStart))) ? nb[p + 2] : 0;
+        uint8_t c1 = (p + 1 < nlen && !(cls[p + 1] & (kHfInAdded | kHfAddedStart))) ? nb[p + 1] : 0;
+        uint8_t c2 = (c1 && p + 2 < nlen && !(cls[p + 2] & (kHfInAdded | kHfAddedStart))) ? nb[p + 2] : 0;
+        if (p2) {  // (?i: ...): ASCII upper case, and U+017F (C5 BF) folds to s
+          if (c1 == 0xC5 && c2 == 0xBF) add = 0x40;
+          if (c1 >= 'A' && c1 <= 'Z') c1 |= 0x20;
+          if (c2 >= 'A' && c2 <= 'Z') c2 |= 0x20;
+        }
         if (c1 == 's' || c1 == 't' || c1 == 'm' || c1 == 'd') add = 0x20;
         else if ((c1 == 'r' && c2 == 'e') || (c1 == 'v' && c2 == 'e') || (c1 == 'l' && c2 == 'l')) add = 0x40;
       }
@@ -162,9 +211,78 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
     if (add) cls[p] |= add;
     __syncwarp();
   }
-  // ---- B2: token starts, compacted into wstart[]
   // non-final: a token is complete only if everything that decides its end is in the buffer
-  const int limit = final ? nlen : nlen - (int)T.added_max_len - 8;
+  int limit = final ? nlen : nlen - (int)T.added_max_len - 8;
+  if (p2) {
+    const uint32_t below = (1u << lane) - 1u;
+    // ---- C1 (forward): swallowed CR/LFs, digit index inside the run
+    bool carry_sw = false;  // the last char that is not CR/LF is a punctuation char
+    int carry_d = 0;        // digits since the last non-digit char
+    const int K = T.hf_digits;
+    for (int base = 0; base < nlen; base += 32) {
+      const int p = base + lane;
+      const uint8_t v = p < nlen ? cls[p] : kHfCont;
+      const bool ch = p < nlen && v != kHfCont;                       // a char starts here (added-token bytes count as chars)
+      const bool plain = ch && !(v & (kHfInAdded | kHfAddedStart));
+      const bool is_nl = plain && (aux[p] & kAuxNl);
+      const bool is_n = plain && (v & 3) == kHfNumber;
+      const uint32_t m_o = __ballot_sync(kFull, plain && (v & 3) == kHfOther);
+      const uint32_t m_n = __ballot_sync(kFull, is_n);
+      const uint32_t m_not_nl = __ballot_sync(kFull, ch && !is_nl);
+      const uint32_t m_not_n = __ballot_sync(kFull, ch && !is_n);
+      uint8_t add = 0;
+      if (is_nl) {
+        const uint32_t m = m_not_nl & below;
+        if (m ? ((m_o >> (31 - __clz(m))) & 1u) : (uint32_t)carry_sw) add |= kAuxSwallowed;
+      }
+      if (is_n) {
+        const uint32_t m = m_not_n & below;
+        const int idx = m ? __popc(m_n & below & ~((2u << (31 - __clz(m))) - 1u)) : carry_d + __popc(m_n & below);
+        if (idx % K == 0) add |= kAuxDigitStart;
+      }
+      if (add) aux[p] |= add;
+      if (m_not_nl) carry_sw = (m_o >> (31 - __clz(m_not_nl))) & 1u;
+      if (m_not_n) carry_d = __popc(m_n & ~((2u << (31 - __clz(m_not_n))) - 1u));
+      else carry_d += __popc(m_n);
+    }
+    // ---- C2 (backward): does a CR/LF follow inside the same whitespace run?
+    bool carry_nl = false;
+    for (int base = ((nlen - 1) >> 5) << 5; base >= 0; base -= 32) {
+      const int p = base + lane;
+      const uint8_t v = p < nlen ? cls[p] : kHfCont;
+      const bool ch = p < nlen && v != kHfCont;
+      const bool plain = ch && !(v & (kHfInAdded | kHfAddedStart));
+      const bool is_ws = plain && (v & 3) == kHfSpace;
+      const bool is_nl = plain && (aux[p] & kAuxNl);
+      const uint32_t m_nl = __ballot_sync(kFull, is_nl);
+      const uint32_t m_not_ws = __ballot_sync(kFull, ch && !is_ws);
+      if (is_ws && !is_nl) {
+        const uint32_t above = ~((2u << lane) - 1u);
+        const uint32_t m = m_not_ws & above;
+        const uint32_t upto = m ? (above & ((1u << (__ffs(m) - 1)) - 1u)) : above;
+        if ((m_nl & upto) || (!m && carry_nl)) aux[p] |= kAuxNlAfter;
+      }
+      if (m_not_ws) carry_nl = (m_nl & ((1u << (__ffs(m_not_ws) - 1)) - 1u)) != 0;
+      else carry_nl = carry_nl || m_nl != 0;
+    }
+    __syncwarp();
+    // a whitespace run that touches the end of a non-final buffer cannot be cut yet (a newline may still come)
+    if (!final) {
+      int q = nlen - 1;
+      while (q > 0 && cls[q] == kHfCont) --q;
+      if (!(cls[q] & (kHfInAdded | kHfAddedStart)) && (cls[q] & 3) == kHfSpace) {
+        int run = q;
+        for (;;) {
+          int t = run - 1;
+          while (t > 0 && cls[t] == kHfCont) --t;
+          if (run == 0 || (cls[t] & (kHfInAdded | kHfAddedStart)) || (cls[t] & 3) != kHfSpace || cls[t] == kHfCont) break;
+          run = t;
+        }
+        if (run < limit) limit = run;
+      }
+    }
+  }
+  // ---- B2: token starts, compacted into wstart[]
   constexpr int kCap = kMaxWords - 1;
   int count = 0;
   for (int base = 0; base < nlen && base <= limit && !r.capped; base += 32) {
@@ -187,7 +305,38 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
           while (q > 0 && cls[q] == kHfCont) --q;
           const uint8_t a = cls[q];
           const bool a_ws = (a & 3) == kHfSpace, b_ws = (v & 3) == kHfSpace;
-          if (b_ws) {
+          if (p2) {
+            const uint8_t a_aux = aux[q], b_aux = aux[p];
+            const uint8_t bc = v & 3, ac = a & 3;
+            if (bc == kHfLetter) {
+              if (ac == kHfLetter) st = false;
+              else if (ac == kHfNumber) st = true;
+              else if (a_ws) st = (a_aux & kAuxNl) != 0;   // a space / tab is the letters' prefix, a newline is not
+              else {
+                // punctuation before letters: it is their prefix iff it is a token start itself
+                bool a_start = q == 0 || (cls[q - 1] & (kHfInAdded | kHfAddedStart));
+                if (!a_start) {
+                  int t = q - 1;
+                  while (t > 0 && cls[t] == kHfCont) --t;
+                  a_start = (cls[t] & 3) != kHfOther && !(cls[t] & kHfIsSp);
+                }
+                st = !a_start;
+              }
+            } else if (bc == kHfNumber) {
+              st = (b_aux & kAuxDigitStart) != 0;
+            } else if (bc == kHfOther) {
+              st = ac != kHfOther && !(a & kHfIsSp);
+            } else if (b_aux & kAuxNl) {
+              st = !(b_aux & kAuxSwallowed) && !a_ws;
+            } else if (b_aux & kAuxNlAfter) {
+              st = !a_ws || ((a_aux & kAuxNl) && (a_aux & kAuxSwallowed));
+            } else {
+              const uint8_t b0 = nb[p];
+              const int nx = p + (b0 < 0x80 ? 1 : (b0 < 0xE0 ? 2 : (b0 < 0xF0 ? 3 : 4)));
+              st = !a_ws || (a_aux & kAuxNl) ||
+                   (nx < nlen && !(cls[nx] & kHfAddedStart) && (cls[nx] & 3) != kHfSpace);
+            }
+          } else if (b_ws) {
             if (!a_ws) st = true;
             else {
               const uint8_t b0 = nb[p];

@@ -301,7 +301,7 @@ struct ReqState {
   bool prev_space;      // normalizer's is_prev_space
   bool prev_unk;        // last emitted symbol was unknown (byte_fallback off only)
   bool too_long;
-  bool bad_input;      // HF backend: malformed UTF-8
+  int8_t bad_input;    // HF backend: 1 malformed UTF-8, 2 not provably NFC under a normalizer NFC
   bool deferred;       // needs the long-word kernel (this one was built without it)
   // long-word mode: the current pre-token is being streamed into a global scratch slot
   bool long_mode;
@@ -852,7 +852,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
   bool hf_capped = false;
   if constexpr (HF) {
     const HfScan sc = hf_scan(T, sm, nlen, final, lane);
-    if (sc.bad) { rs.bad_input = true; return false; }
+    if (sc.bad) { rs.bad_input = (int8_t)sc.bad; return false; }
     nwords = sc.nwords;
     hf_tail = sc.tail_start;
     hf_capped = sc.capped;
@@ -959,19 +959,33 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
       alive = 1u;
       cnt = 1;
     } else if (active) {
-      int n = 0;
-      for (int p = ws; p < we;) {
-        uint32_t adv;
-        sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
-        p += adv;
-        ++n;
+      bool direct = false;
+      if constexpr (HF) {
+        if (T.ignore_merges) {  // models/bpe/model.rs: a pre-token that is a vocabulary entry is that token
+          const int32_t id = hf_vocab_lookup(T, nb + ws, we - ws);
+          if (id >= 0) {
+            sm.S[lane] = kResolvedFlag | (uint32_t)id;
+            alive = 1u;
+            cnt = 1;
+            direct = true;
+          }
+        }
       }
-      bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
-      alive = lane_merge<SMALL>(T, sm, n, lane);
+      bool pu = false, first = true;
+      if (!direct) {
+        int n = 0;
+        for (int p = ws; p < we;) {
+          uint32_t adv;
+          sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
+          p += adv;
+          ++n;
+        }
+        bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
+        alive = lane_merge<SMALL>(T, sm, n, lane);
+      }
       // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
       // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
-      bool pu = false, first = true;
-      for (uint32_t m = alive; m;) {
+      for (uint32_t m = direct ? 0u : alive; m;) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
         int32_t tmp[4];
@@ -1083,7 +1097,18 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
       }
       overflow = __any_sync(kFull, overflow);
       __syncwarp();
-      if (overflow) {
+      int32_t whole = -1;
+      if constexpr (HF) {
+        if (T.ignore_merges && !overflow) {  // no vocabulary entry is longer than the cooperative path (host check)
+          if (lane == 0) whole = hf_vocab_lookup(T, nb + lws, lwe - lws);
+          whole = __shfl_sync(kFull, whole, 0);
+        }
+      }
+      if (whole >= 0) {
+        if (lane == 0) put_id(rs, rs.n_out, whole);
+        rs.n_out += 1;
+        rs.trailing_bare = 0;
+      } else if (overflow) {
         // more chars than the shared-memory scratch holds: merge it in a global scratch slot
         if constexpr (!LONG) {
           rs.deferred = true;
@@ -1211,7 +1236,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     rs.prev_space = T.remove_extra_ws;
     rs.prev_unk = false;
     rs.too_long = false;
-    rs.bad_input = false;
+    rs.bad_input = 0;
     rs.deferred = false;
     rs.long_mode = false;
     rs.long_last_sp = false;
@@ -1309,7 +1334,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       } else {
         const bool failed = rs.too_long || rs.bad_input;
         n_ids[r] = failed ? 0 : (int32_t)rs.n_out;
-        status[r] = rs.bad_input ? kEncBadUtf8
+        status[r] = rs.bad_input ? (rs.bad_input == 1 ? kEncBadUtf8 : kEncNeedsNfc)
                                  : (rs.too_long ? kEncWordTooLong : (rs.n_out > rs.cap ? kEncTruncated : kEncOk));
       }
     }
@@ -1403,6 +1428,15 @@ int SpDeviceModel::upload(const SpTables& t) {
     UP(off, added_off);
     UP(aid, added_id);
   }
+  dev_.ignore_merges = t.ignore_merges ? 1 : 0;
+  if (t.ignore_merges) {
+    UP(t.vocab_table, vtab);
+    UP(t.vocab_blob, vblob);
+    dev_.vtab_mask = (uint32_t)(t.vocab_table.size() / 4) - 1;
+  }
+  dev_.nfc_check = t.nfc_check ? 1 : 0;
+  dev_.hf_pattern = (uint8_t)t.hf_pattern;
+  dev_.hf_digits = (uint8_t)(t.hf_digits > 0 ? t.hf_digits : 1);
   dev_.n_prefix = (uint8_t)t.prefix_ids.size();
   dev_.n_suffix = (uint8_t)t.suffix_ids.size();
   for (size_t i = 0; i < t.prefix_ids.size() && i < 4; ++i) dev_.prefix_ids[i] = t.prefix_ids[i];

@@ -46,6 +46,13 @@ struct SpDev {
   uint32_t added_first[8];    // bit b set <=> some added token starts with byte b
   int32_t prefix_ids[4], suffix_ids[4];
   uint8_t n_prefix, n_suffix;
+  uint8_t ignore_merges;  // a pre-token that is a vocabulary entry is emitted as that id (vtab / vblob)
+  const uint4* vtab;
+  const uint8_t* vblob;
+  uint32_t vtab_mask;
+  uint8_t nfc_check;   // normalizer NFC: a request passes only if every char is NFC-inert (then NFC is the identity)
+  uint8_t hf_pattern;  // 1: ByteLevel's own GPT-2 regex, 2: Split(cl100k-family regex) + ByteLevel(use_regex = false)
+  uint8_t hf_digits;   // pattern 2: \p{N}{1,hf_digits}
   uint8_t* long_pool;
   int* long_locks;
   uint32_t long_cap;   // symbols per slot
@@ -56,6 +63,7 @@ struct SpDev {
 constexpr int32_t kEncOk = 0;
 constexpr int32_t kEncTruncated = 1;     // more ids than ids_stride: n_ids holds the full count, the row its prefix
 constexpr int32_t kEncBadUtf8 = -1;      // HF backend: the text is not valid UTF-8 (the reference's Rust shim panics)
+constexpr int32_t kEncNeedsNfc = -5;     // HF backend with normalizer NFC: the text is not provably in NFC (XLLM_ERR_UNSUPPORTED)
 constexpr int32_t kEncWordTooLong = -6;  // a single pre-token exceeds the on-chip word capacity (XLLM_ERR_CAPACITY)
 
 class SpDeviceModel {

@@ -60,6 +60,12 @@ struct SpTables {
   // added (special) tokens are matched verbatim in the text; template ids wrap every sequence
   std::vector<std::pair<std::string, int32_t>> added_tokens;
   std::vector<int32_t> prefix_ids, suffix_ids;
+  int hf_pattern = 1;   // 1: ByteLevel's own GPT-2 regex, 2: Split(cl100k-family regex) + ByteLevel(use_regex = false)
+  int hf_digits = 3;    // pattern 2: \p{N}{1,hf_digits}
+  bool ignore_merges = false;  // a pre-token that is a vocabulary entry is emitted as that id (models/bpe/model.rs)
+  std::vector<uint32_t> vocab_table;  // ignore_merges: 4 x u32 per slot {hash lo, hash hi, id, blob offset << 10 | length}
+  std::vector<uint8_t> vocab_blob;
+  bool nfc_check = false;      // normalizer NFC: requests are accepted only when NFC leaves them unchanged
   std::vector<uint16_t> uni_stage1;  // [0x1100]  code point >> 8 -> block
   std::vector<uint8_t> uni_stage2;   // [blocks * 256] class: 0 other, 1 \p{L}, 2 \p{N}, 3 \s
   // vocabulary strings for decode / id_to_token / token_to_id
