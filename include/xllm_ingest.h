@@ -164,7 +164,8 @@ int xllm_score_route_device(xllm_ingest_t h, int32_t n_req, const uint64_t* d_ma
  * (at most ids_stride of them); n_ids[r] is the full count; status[r] is 0 (ok),
  * XLLM_ENC_TRUNCATED (count > ids_stride: call again with a larger stride),
  * XLLM_ERR_CAPACITY (a single pre-token longer than the device scratch holds) or, on the HF backend,
- * XLLM_ERR_INVALID_ARG (malformed UTF-8: the reference's Rust shim panics there, lib.rs:91).
+ * XLLM_ERR_INVALID_ARG (malformed UTF-8: the reference's Rust shim panics there, lib.rs:91) or
+ * XLLM_ERR_UNSUPPORTED (tokenizer.json with normalizer NFC and a text that is not provably in NFC already).
  * An empty prompt yields 0 ids (sentencepiece_tokenizer.cpp:117-120) plus, on the HF backend, the
  * template's special tokens.
  * Backend, in the order of TokenizerFactory::create_tokenizer (tokenizer_factory.cpp:9-32):
@@ -195,7 +196,7 @@ typedef struct {
   int32_t* ids;           /* [n_req][ids_stride] */
   int64_t ids_stride;
   int32_t* n_ids;         /* [n_req] full token counts */
-  int32_t* status;        /* [n_req] 0 / XLLM_ENC_TRUNCATED / XLLM_ERR_CAPACITY / XLLM_ERR_INVALID_ARG */
+  int32_t* status;        /* [n_req] 0 / XLLM_ENC_TRUNCATED / XLLM_ERR_CAPACITY / _INVALID_ARG / _UNSUPPORTED */
   uint8_t* keys;          /* [n_req][keys_stride][16] or NULL */
   int64_t keys_stride;
   xllm_match_out* match;     /* [n_req] or NULL */
