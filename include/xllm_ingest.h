@@ -109,6 +109,16 @@ int xllm_index_apply(xllm_ingest_t h, int32_t instance_id, const uint8_t* stored
                      const uint8_t* offload, size_t n_offload, const uint8_t* removed, size_t n_removed);
 int xllm_index_put(xllm_ingest_t h, const uint8_t* key16, uint64_t hbm_mask, uint64_t dram_mask, uint64_t ssd_mask);
 int xllm_index_erase(xllm_ingest_t h, const uint8_t* key16);
+/* Bulk xllm_index_put: what a replica or a restarted master does with the XLLM:CACHE:* pairs it lists from etcd
+ * (global_kvcache_mgr.cpp:47-51 -> etcd_client.cpp:174-198); staged like the single form, publish afterwards. */
+int xllm_index_put_bulk(xllm_ingest_t h, int64_t n, const uint8_t* keys /*[n][16]*/, const uint64_t* hbm_masks,
+                        const uint64_t* dram_masks, const uint64_t* ssd_masks);
+/* Snapshot of the published index: every live key with its three instance masks, in unspecified order — the
+ * content the master holds in etcd under "XLLM:CACHE:" + key (etcd_client.cpp:122-137).  *n_keys = live keys;
+ * returns XLLM_ERR_CAPACITY (with *n_keys set, the first `capacity` rows filled) when capacity is too small.
+ * host/index_wire.h turns rows into / from the reference's etcd keys and CacheLocations JSON (types.h:320-365). */
+int xllm_index_export(xllm_ingest_t h, int64_t capacity, uint8_t* keys /*[capacity][16]*/, uint64_t* hbm_masks,
+                      uint64_t* dram_masks, uint64_t* ssd_masks, int64_t* n_keys);
 int xllm_index_publish(xllm_ingest_t h);
 int xllm_index_size(xllm_ingest_t h, int64_t* n_keys);
 int xllm_index_get(xllm_ingest_t h, const uint8_t* key16, uint64_t masks3[3], int32_t* found);

@@ -95,6 +95,8 @@ def _declare(L):
     L.xllm_index_probe_device.argtypes = [_VP, _VP, ctypes.c_int64, _VP, _VP]
     L.xllm_score_route_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]
     L.xllm_ingest_batch.argtypes = [_VP, ctypes.POINTER(IngestIO)]
+    L.xllm_index_put_bulk.argtypes = [_VP, ctypes.c_int64, _VP, _VP, _VP, _VP]
+    L.xllm_index_export.argtypes = [_VP, ctypes.c_int64, _VP, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_int64)]
     L.xllm_set_pipeline.argtypes = [_VP, ctypes.c_int32, ctypes.c_int64]
     L.xllm_last_batch_stats.argtypes = [_VP, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
     L.xllm_host_alloc.argtypes = [ctypes.POINTER(_VP), ctypes.c_size_t]

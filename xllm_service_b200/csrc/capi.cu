@@ -325,6 +325,23 @@ int xllm_index_put(xllm_ingest_t h, const uint8_t* key16, uint64_t hbm, uint64_t
   h->index->put(key16, hbm, dram, ssd);
   return XLLM_OK;
 }
+int xllm_index_put_bulk(xllm_ingest_t h, int64_t n, const uint8_t* keys, const uint64_t* hbm, const uint64_t* dram,
+                        const uint64_t* ssd) {
+  XLLM_TRY(need_index(h));
+  if (n < 0 || (n > 0 && (!keys || !hbm || !dram || !ssd))) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(*h->index_mu);
+  for (int64_t i = 0; i < n; ++i) h->index->put(keys + 16 * i, hbm[i], dram[i], ssd[i]);
+  return XLLM_OK;
+}
+int xllm_index_export(xllm_ingest_t h, int64_t capacity, uint8_t* keys, uint64_t* hbm, uint64_t* dram, uint64_t* ssd,
+                      int64_t* n_keys) {
+  XLLM_TRY(need_index(h));
+  if (!n_keys || capacity < 0 || (capacity > 0 && (!keys || !hbm || !dram || !ssd))) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::mutex> lock2(*h->index_mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  return h->index->export_all(h->stream, capacity, keys, hbm, dram, ssd, n_keys);
+}
 int xllm_index_erase(xllm_ingest_t h, const uint8_t* key16) {
   XLLM_TRY(need_index(h));
   if (!key16) return XLLM_ERR_INVALID_ARG;

@@ -415,6 +415,66 @@ int PrefixIndex::size(cudaStream_t stream, int64_t* n) {
   return XLLM_OK;
 }
 
+// One thread per slot: live slots are compacted (order = atomic arrival) into a packed array of
+// {key lo, key hi, hbm, dram, ssd} rows.
+__global__ void index_export_kernel(const IndexSlot* __restrict__ slots, uint64_t n_slots, uint64_t* __restrict__ rows,
+                                    long long cap, unsigned long long* __restrict__ counter) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  const IndexSlot s = slots[i];
+  if (s.state != 1) return;
+  const unsigned long long at = atomicAdd(counter, 1ull);
+  if ((long long)at < cap) {
+    uint64_t* r = rows + at * 5;
+    r[0] = s.klo; r[1] = s.khi; r[2] = s.hbm; r[3] = s.dram; r[4] = s.ssd;
+  }
+}
+
+int PrefixIndex::export_all(cudaStream_t stream, int64_t cap, uint8_t* keys16, uint64_t* hbm, uint64_t* dram,
+                            uint64_t* ssd, int64_t* n_out) {
+  if (!ready()) return XLLM_ERR_UNSUPPORTED;
+  if (cap < 0) cap = 0;
+  const size_t need = 64 + (size_t)cap * 40;
+  if (d_stage_cap_ < need) {
+    if (d_stage_) cudaFree(d_stage_);
+    d_stage_ = nullptr;
+    d_stage_cap_ = 0;
+    if (cudaMalloc(&d_stage_, need) != cudaSuccess) {
+      set_last_error("cudaMalloc(%zu) for the index snapshot failed", need);
+      return XLLM_ERR_NOMEM;
+    }
+    d_stage_cap_ = need;
+  }
+  unsigned long long* d_count = static_cast<unsigned long long*>(d_stage_);
+  uint64_t* d_rows = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(d_stage_) + 64);
+  XLLM_CUDA_TRY(cudaMemsetAsync(d_count, 0, 8, stream));
+  const int threads = 256;
+  index_export_kernel<<<(unsigned)((n_slots_ + threads - 1) / threads), threads, 0, stream>>>(
+      slots_, n_slots_, d_rows, (long long)cap, d_count);
+  XLLM_CUDA_TRY(cudaGetLastError());
+  unsigned long long n = 0;
+  XLLM_CUDA_TRY(cudaMemcpyAsync(&n, d_count, 8, cudaMemcpyDeviceToHost, stream));
+  XLLM_CUDA_TRY(cudaStreamSynchronize(stream));
+  *n_out = (int64_t)n;
+  const int64_t take = (int64_t)n < cap ? (int64_t)n : cap;
+  if (take > 0) {
+    std::vector<uint64_t> rows((size_t)take * 5);
+    XLLM_CUDA_TRY(cudaMemcpyAsync(rows.data(), d_rows, rows.size() * 8, cudaMemcpyDeviceToHost, stream));
+    XLLM_CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int64_t i = 0; i < take; ++i) {
+      memcpy(keys16 + 16 * i, &rows[(size_t)i * 5], 16);  // low64 LE || high64 LE, as hashed (hash_util.cpp:26-27)
+      hbm[i] = rows[(size_t)i * 5 + 2];
+      dram[i] = rows[(size_t)i * 5 + 3];
+      ssd[i] = rows[(size_t)i * 5 + 4];
+    }
+  }
+  if ((int64_t)n > cap) {
+    set_last_error("index snapshot: %lld live keys, room for %lld", (long long)n, (long long)cap);
+    return XLLM_ERR_CAPACITY;
+  }
+  return XLLM_OK;
+}
+
 int PrefixIndex::get(cudaStream_t stream, const uint8_t* key16, uint64_t masks3[3], int* found) {
   if (!ready()) return XLLM_ERR_UNSUPPORTED;
   if (d_stage_cap_ < 256) {

@@ -86,6 +86,9 @@ class PrefixIndex {
 
   int size(cudaStream_t stream, int64_t* n);
   int get(cudaStream_t stream, const uint8_t* key16, uint64_t masks3[3], int* found);
+  // snapshot of every live key with its three masks (order unspecified); *n_out = live keys, also when > cap
+  int export_all(cudaStream_t stream, int64_t cap, uint8_t* keys16, uint64_t* hbm, uint64_t* dram, uint64_t* ssd,
+                 int64_t* n_out);
 
   // ---- reads (device pointers, asynchronous on `stream`)
   // masks3[k] = {hbm, dram, ssd} of keys[k], all zero when absent

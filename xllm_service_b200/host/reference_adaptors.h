@@ -21,6 +21,7 @@
 #include "scheduler/loadbalance_policy/loadbalance_policy.h"
 #include "tokenizer/tokenizer.h"
 #include "tokenizers.h"      // this repo: include/tokenizers.h
+#include "index_snapshot.h"
 #include "xllm_ingest.h"     // this repo: include/xllm_ingest.h
 #include "xllm_rpc_service.pb.h"
 
@@ -132,6 +133,22 @@ class GpuGlobalKVCacheIndex {
   }
   // GlobalKVCacheMgr::upload_kvcache's local effect (:227-247); the etcd write stays where it is
   bool upload_kvcache() { return xllm_index_publish(h_) == XLLM_OK; }
+
+  // The table as the pairs the master keeps under XLLM:CACHE: (etcd_client.cpp:122-137), e.g. to seed a new etcd
+  // cluster or to hand the index to a freshly elected master; host/index_snapshot.h.
+  bool snapshot(const std::string& namespace_prefix, std::vector<xllm_host::CacheKv>* out) {
+    std::lock_guard<std::mutex> l(mu_);
+    return xllm_host::snapshot_index(h_, namespace_prefix, names_, out) == XLLM_OK;
+  }
+  // The constructor's start-up load (:47-51) and the replica watch (:133-175): the pairs of one listing / one
+  // watch response (empty value = DELETE).  prefix_len = size of namespace + "XLLM:CACHE:".
+  bool apply_etcd_pairs(const std::vector<xllm_host::CacheKv>& kvs, size_t prefix_len) {
+    size_t skipped = 0;
+    const int rc = xllm_host::apply_etcd_pairs(
+        h_, prefix_len, kvs, [this](const std::string& n) { return instance_id(n); }, &skipped);
+    if (skipped) LOG(ERROR) << skipped << " XLLM:CACHE pairs could not be parsed";
+    return rc == XLLM_OK;
+  }
 
   // GlobalKVCacheMgr::match (:73-131) for one request (the batch path goes through IngestBatcher)
   void match(const Slice<int32_t>& token_ids, int32_t block_size, OverlapScores* out) {

@@ -150,6 +150,27 @@ class Ingest:
             return np.zeros((0, 16), np.uint8)
         return np.ascontiguousarray(np.asarray(keys, dtype=np.uint8).reshape(-1, 16))
 
+    def index_put_bulk(self, keys, hbm, dram, ssd):
+        """Bulk replica PUT (update_kvcache / start-up load, global_kvcache_mgr.cpp:47-51,133-175); staged."""
+        k = self._keys(keys)
+        m = [np.ascontiguousarray(x, dtype=np.uint64) for x in (hbm, dram, ssd)]
+        assert all(x.size == k.shape[0] for x in m)
+        check(self._L.xllm_index_put_bulk(self._h, k.shape[0], _ptr(k), _ptr(m[0]), _ptr(m[1]), _ptr(m[2])))
+
+    def index_export(self):
+        """Snapshot of the published index: (keys uint8[n,16], hbm, dram, ssd uint64[n]), order unspecified."""
+        n = ctypes.c_int64()
+        cap = max(1, self.index_size())
+        while True:
+            keys = np.zeros((cap, 16), np.uint8)
+            m = [np.zeros(cap, np.uint64) for _ in range(3)]
+            rc = self._L.xllm_index_export(self._h, cap, _ptr(keys), _ptr(m[0]), _ptr(m[1]), _ptr(m[2]), ctypes.byref(n))
+            if rc == -6 and n.value > cap:      # grew in between: retry with the reported size
+                cap = n.value
+                continue
+            check(rc)
+            return keys[:n.value], m[0][:n.value], m[1][:n.value], m[2][:n.value]
+
     def index_apply(self, instance_id, stored=None, offload=None, removed=None):
         """GlobalKVCacheMgr::record_updated_kvcaches (global_kvcache_mgr.cpp:177-225); staged."""
         s, o, r = self._keys(stored), self._keys(offload), self._keys(removed)
