@@ -24,12 +24,13 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--check", type=int, default=4)
 ap.add_argument("--backend", choices=["sp", "hf"], default="sp")
+ap.add_argument("--hf-dir", default="hf_bpe_8k", help="fixture under tests/golden: hf_bpe_8k | hf_llama3_style | hf_qwen2_style")
 ap.add_argument("--cpu", type=int, default=0, help="hf: prompts to time through pip tokenizers encode_batch")
 a = ap.parse_args()
 
 model = os.path.join(ROOT, "tests", "golden", "sp_bpe_8k")
 h = x.Ingest(tokenizer_path=model)
-hf_dir = os.path.join(ROOT, "tests", "golden", "hf_bpe_8k")
+hf_dir = os.path.join(ROOT, "tests", "golden", a.hf_dir)
 h_run = x.Ingest(tokenizer_path=hf_dir) if a.backend == "hf" else h
 vocab = workload.make_vocabulary()
 t0 = time.time()
@@ -77,7 +78,7 @@ if a.backend == "hf":
     ids = d_ids[:a.check].cpu().numpy()
     cnt = d_n[:a.check].cpu().numpy()
     for i in range(a.check):
-        assert ids[i, :cnt[i]].tolist() == H.encode(batch.prompt(i)).tolist()
+        assert ids[i, :cnt[i]].tolist() == H.prefix_ids + H.encode(batch.prompt(i)).tolist() + H.suffix_ids
     if a.cpu:
         from tokenizers import Tokenizer
         ref = Tokenizer.from_file(os.path.join(hf_dir, "tokenizer.json"))

@@ -380,7 +380,7 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
       if (h == 0) h = 1;
       if (t->vocab_blob.size() + e.first.size() >= (1u << 22))
         return fail(t, XLLM_ERR_UNSUPPORTED, "ignore_merges vocabulary larger than 4 MiB of token bytes");
-      uint32_t slot = (uint32_t)(h >> 24) & (slots - 1);
+      uint32_t slot = (uint32_t)(((h ^ (h >> 29)) * 0xBF58476D1CE4E5B9ull) >> 32) & (slots - 1);  // as hf_vocab_lookup
       while (t->vocab_table[(size_t)slot * 4] | t->vocab_table[(size_t)slot * 4 + 1]) slot = (slot + 1) & (slots - 1);
       t->vocab_table[(size_t)slot * 4 + 0] = (uint32_t)h;
       t->vocab_table[(size_t)slot * 4 + 1] = (uint32_t)(h >> 32);

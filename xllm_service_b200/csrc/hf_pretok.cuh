@@ -78,7 +78,8 @@ __device__ __forceinline__ int32_t hf_vocab_lookup(const SpDev& T, const uint8_t
   unsigned long long h = 0xcbf29ce484222325ull;
   for (int k = 0; k < n; ++k) h = (h ^ w[k]) * 0x100000001b3ull;
   if (h == 0) h = 1;
-  uint32_t slot = (uint32_t)(h >> 24) & T.vtab_mask;
+  // FNV's upper bits barely move for 1-2 byte keys: mix before taking the slot (same on the host, hf_model.cc)
+  uint32_t slot = (uint32_t)(((h ^ (h >> 29)) * 0xBF58476D1CE4E5B9ull) >> 32) & T.vtab_mask;
   for (;;) {
     const uint4 e = __ldg(T.vtab + slot);
     if ((e.x | e.y) == 0) return -1;
