@@ -272,9 +272,10 @@ def main():
         ge.build()
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: at NCCL_DEBUG=VERSION (set on the GPU boxes) NCCL prints its version
+        # banner on stdout, NCCL_DEBUG_FILE does not move it; VERSION has no other effect, so drop it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
