@@ -68,3 +68,25 @@ def test_pipeline_matches_oracle(oracle):
     o2 = h.ingest_batch(b.text, b.offsets, T, want_keys=True, want_match=False)
     assert (o2["ids"] == out["ids"]).all() and (o2["keys"] == out["keys"]).all()
     h.close()
+
+
+@pytest.mark.parametrize("n_req", [1, 63, 513, 600, 1100, 1537, 4097])
+def test_default_pipeline_any_batch_size(oracle, n_req):
+    """The default chunk schedule (ramp 512 -> 4096, quarter-size tail) on batch sizes around its break points."""
+    import xllm_service_b200 as x
+    from xllm_service_b200 import workload
+    sp = oracle.SentencePieceOracle(MODEL_DIR)
+    texts = [s.encode() for s in workload.sentences(n_req, (1, 12), seed=n_req)]
+    b = workload.pack_prompts(texts)
+    h = x.Ingest(tokenizer_path=MODEL_DIR)
+    try:
+        out = h.ingest_batch(b.text, b.offsets, 128, want_match=False)
+        chunks, launches = h.last_batch_stats()
+        assert chunks >= 1 and launches == 4 * chunks          # encode x2 + row prep + hash per chunk
+        assert (out["status"] == 0).all()
+        ref_ids, ref_n = sp.encode_batch(b.text, b.offsets, 128)
+        assert (out["n_ids"] == ref_n).all()
+        for r in range(n_req):
+            assert (out["ids"][r, :ref_n[r]] == ref_ids[r, :ref_n[r]]).all(), r
+    finally:
+        h.close()

@@ -168,3 +168,13 @@ def test_hf_tokenizer_json_tables(tmp_path):
           "pair": [{"Sequence": {"id": "A", "type_id": 0}}, {"Sequence": {"id": "B", "type_id": 1}}],
           "special_tokens": {"<|endoftext|>": {"id": "<|endoftext|>", "ids": [0], "tokens": ["<|endoftext|>"]}}}
     assert _lib.tokenizer_probe(variant("template", set_(["post_processor"], tp)))["split_mode"] == 3
+
+
+def test_pipeline_chunk_schedule(tmp_path):
+    """csrc/pipeline_schedule.h: every (batch size, chunk bound) is covered exactly by chunks in [1, bound] —
+    including the 513..1536-request batches a first version of the tail rule turned into empty chunks."""
+    import subprocess
+    exe = tmp_path / "pipeline_schedule_main"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(HERE, "cpp", "pipeline_schedule_main.cc"), "-o", str(exe)])
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-1500:]

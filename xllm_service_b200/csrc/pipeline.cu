@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "handle.h"
+#include "pipeline_schedule.h"
 
 namespace xllm {
 
@@ -211,19 +212,9 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
   int rc = XLLM_OK;
   h->last_chunks = 0;
   h->last_launches = 0;
-  // Chunk sizes ramp up from chunk_req / 8 to chunk_req: the first chunk's upload + kernels is a stage nothing
-  // overlaps, so it is kept short; the bulk moves in big chunks (full-GPU kernels, few small copies).  The last
-  // chunk's download is exposed too, but a tiny last chunk would expose its kernels' latency floor (one warp walks
-  // one prompt: ~1 ms) instead, so the tail is one quarter-size chunk behind a chunk big enough to cover it.
-  const int ramp_first = chunk_req / 8 > 64 ? chunk_req / 8 : (chunk_req < 64 ? chunk_req : 64);
-  const int tail = chunk_req / 4 > 0 ? chunk_req / 4 : 1;
-  int64_t ramp = ramp_first;
+  ChunkSchedule sched(chunk_req);  // ramp-up, full-size bulk, quarter-size tail (pipeline_schedule.h)
   while (c0 < n) {
-    int64_t target = ramp < chunk_req ? ramp : chunk_req;
-    const int64_t left = n - c0;
-    if (left <= target) target = left;
-    else if (left <= target + tail) target = left - tail;
-    if (ramp < chunk_req) ramp *= 2;
+    const int64_t target = sched.next((int64_t)n - c0);
     int32_t c1 = c0;
     while (c1 < n && c1 - c0 < target && (c1 == c0 || io->offsets[c1 + 1] - io->offsets[c0] <= chunk_bytes)) ++c1;
     const int m = c1 - c0;
