@@ -23,7 +23,10 @@
 //   tests/test_oracle_sp.py: live when the wheel is importable, and through the committed
 //   vectors tests/golden/sp_bpe_8k_goldens.json.
 //
-// Unsupported (load fails): UNIGRAM/WORD/CHAR models, USER_DEFINED or UNUSED pieces.
+//     unigram_model.cc  Model::EncodeOptimized (UNIGRAM models: Viterbi over the normalized bytes, on-the-fly
+//                    lattice; candidate scores are formed in double and stored as float, the earlier / shorter
+//                    candidate wins ties, a char no piece covers costs min_score - 10)
+// Unsupported (load fails): WORD/CHAR models, USER_DEFINED or UNUSED pieces.
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -113,6 +116,9 @@ struct SpModel {
   std::unordered_map<std::string_view, int> pieces_map;    // NORMAL / USER_DEFINED / UNUSED
   std::unordered_map<std::string_view, int> reserved_map;  // CONTROL / UNKNOWN / BYTE
   int byte_id[256];
+  // unigram_model.cc: min / max over NORMAL pieces, longest piece in bytes
+  float min_score = 0.f, max_score = 0.f;
+  size_t max_piece_len = 0;
   std::string error;
 };
 
@@ -187,6 +193,18 @@ bool init_pieces(SpModel* m) {
     }
   }
   if (m->unk_id < 0) { m->error = "unk is not defined."; return false; }
+  {  // unigram_model.cc Model::PopulateNodes / constructor: score range over the NORMAL pieces
+    float mn = 3.402823466e+38f, mx = 1.175494351e-38f;  // FLT_MAX, FLT_MIN as upstream initialises them
+    for (const Piece& sp : m->pieces) {
+      if (sp.type == NORMAL) {
+        mn = sp.score < mn ? sp.score : mn;
+        mx = sp.score > mx ? sp.score : mx;
+      }
+      if (sp.type == NORMAL && sp.piece.size() > m->max_piece_len) m->max_piece_len = sp.piece.size();
+    }
+    m->min_score = mn;
+    m->max_score = mx;
+  }
   if (m->byte_fallback)
     for (int i = 0; i < 256; ++i)
       if (m->byte_id[i] < 0) { m->error = "there are not 256 byte pieces although `byte_fallback` is true."; return false; }
@@ -352,12 +370,83 @@ struct EncodeScratch {
   std::vector<SymbolPair> heap;
 };
 
+// sentencepiece_processor.cc PopulateSentencePieceText for one (piece, id): byte fallback, merging of
+// consecutive unknown pieces when byte fallback is off
+inline void emit_piece(const SpModel& m, std::string_view w, int id, bool* is_prev_unk, std::vector<int32_t>* ids) {
+  const bool is_unk = m.pieces[id].type == UNKNOWN;
+  if (m.pieces[id].type == CONTROL) {
+    ids->push_back(id);
+  } else if (is_unk && m.byte_fallback) {
+    for (char c : w) ids->push_back(m.byte_id[(uint8_t)c]);
+  } else if (*is_prev_unk && is_unk) {
+    // consecutive unknown pieces are merged into the previous piece: no new id
+  } else {
+    ids->push_back(id);
+  }
+  *is_prev_unk = is_unk;
+}
+
+// unigram_model.cc Model::EncodeOptimized
+void encode_unigram(const SpModel& m, std::string_view normalized, std::vector<int32_t>* ids) {
+  struct Node {
+    int id = -1;
+    float best = 0.f;
+    int starts_at = -1;
+  };
+  const int size = (int)normalized.size();
+  const float unk_score = m.min_score - 10.0f;  // kUnkPenalty
+  std::vector<Node> ends_at((size_t)size + 1);
+  int starts_at = 0;
+  while (starts_at < size) {
+    const float till_here = ends_at[(size_t)starts_at].best;
+    bool has_single_node = false;
+    const int mblen = std::min<int>((int)one_char_len(normalized.data() + starts_at), size - starts_at);
+    // every piece that is a prefix of the rest, shortest first (the order the trie walk meets them)
+    const int max_len = std::min<int>((int)m.max_piece_len, size - starts_at);
+    for (int len = 1; len <= max_len; ++len) {
+      auto it = m.pieces_map.find(normalized.substr((size_t)starts_at, (size_t)len));
+      if (it == m.pieces_map.end()) continue;
+      Node& t = ends_at[(size_t)(starts_at + len)];
+      const double score = (double)m.pieces[(size_t)it->second].score;  // `auto score = cond ? double : float` upstream
+      const double cand = score + (double)till_here;
+      if (t.starts_at == -1 || cand > (double)t.best) {
+        t.best = (float)cand;
+        t.starts_at = starts_at;
+        t.id = it->second;
+      }
+      if (!has_single_node && len == mblen) has_single_node = true;
+    }
+    if (!has_single_node) {
+      Node& t = ends_at[(size_t)(starts_at + mblen)];
+      const float cand = unk_score + till_here;  // both float upstream
+      if (t.starts_at == -1 || cand > t.best) {
+        t.best = cand;
+        t.starts_at = starts_at;
+        t.id = m.unk_id;
+      }
+    }
+    starts_at += mblen;
+  }
+  std::vector<std::pair<int, int>> path;  // (start, end) backwards
+  for (int e = size; e > 0;) {
+    const Node& nd = ends_at[(size_t)e];
+    path.emplace_back(nd.starts_at, e);
+    e = nd.starts_at;
+  }
+  bool is_prev_unk = false;
+  for (size_t i = path.size(); i-- > 0;) {
+    const int b = path[i].first, e = path[i].second;
+    emit_piece(m, normalized.substr((size_t)b, (size_t)(e - b)), ends_at[(size_t)e].id, &is_prev_unk, ids);
+  }
+}
+
 // SentencePieceProcessor::Encode -> ids appended to *ids.
 void encode(const SpModel& m, std::string_view text, EncodeScratch* sc, std::vector<int32_t>* ids) {
   if (text.empty()) return;  // sentencepiece_tokenizer.cpp:117-120
   normalize(m, text, &sc->normalized);
   std::string_view normalized(sc->normalized);
   if (normalized.empty()) return;
+  if (m.model_type == 1) { encode_unigram(m, normalized, ids); return; }
   auto& symbols = sc->symbols;
   symbols.clear();
   std::priority_queue<SymbolPair, std::vector<SymbolPair>, PairCmp> agenda(PairCmp(), std::move(sc->heap));
@@ -401,18 +490,7 @@ void encode(const SpModel& m, std::string_view text, EncodeScratch* sc, std::vec
   bool is_prev_unk = false;
   for (int index = 0; index != -1; index = symbols[index].next) {
     const std::string_view w = symbols[index].piece;
-    const int id = piece_to_id(m, w);
-    const bool is_unk = m.pieces[id].type == UNKNOWN;
-    if (m.pieces[id].type == CONTROL) {
-      ids->push_back(id);
-    } else if (is_unk && m.byte_fallback) {
-      for (char c : w) ids->push_back(m.byte_id[(uint8_t)c]);
-    } else if (is_prev_unk && is_unk) {
-      // consecutive unknown pieces are merged into the previous piece: no new id
-    } else {
-      ids->push_back(id);
-    }
-    is_prev_unk = is_unk;
+    emit_piece(m, w, piece_to_id(m, w), &is_prev_unk, ids);
   }
 }
 
@@ -442,14 +520,15 @@ void* oracle_sp_load(const char* path, char* err, size_t err_cap) {
     delete h;
     return nullptr;
   }
-  if (h->m.model_type != 2) {
-    if (err) snprintf(err, err_cap, "model_type %d is not BPE (2); only BPE is supported", h->m.model_type);
+  if (h->m.model_type != 2 && h->m.model_type != 1) {
+    if (err) snprintf(err, err_cap, "model_type %d is neither UNIGRAM (1) nor BPE (2)", h->m.model_type);
     delete h;
     return nullptr;
   }
   return h;
 }
 void oracle_sp_free(void* h) { delete (SpHandle*)h; }
+int oracle_sp_model_type(void* h) { return ((SpHandle*)h)->m.model_type; }  // 1 UNIGRAM, 2 BPE
 int oracle_sp_piece_count(void* h) { return (int)((SpHandle*)h)->m.pieces.size(); }
 
 // Normalizer::Normalize.  Returns the normalized length (bytes), writes up to cap bytes.

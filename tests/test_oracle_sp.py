@@ -73,3 +73,27 @@ def test_live_against_sentencepiece_wheel(sp):
             "".join(rnd.choice(alphabet) for _ in range(k)).encode()
         assert sp.encode(t).tolist() == ref.EncodeAsIds(t), t
         assert sp.normalize(t) == ref.Normalize(t), t
+
+
+# ---------------------------------------------------------------- Unigram models (oracle first; no device kernel yet)
+@pytest.mark.parametrize("name", ["sp_unigram_4k", "sp_unigram_4k_bf"])
+def test_unigram_goldens_and_live(oracle, name):
+    """unigram_model.cc EncodeOptimized restated in oracle/sp_oracle.cc: committed goldens from pip sentencepiece
+    0.2.1 (tests/golden/make_sp_unigram_fixture.py) + live fuzz when the wheel is importable."""
+    import json
+    import random
+    d = os.path.join(HERE, "golden", name)
+    S = oracle.SentencePieceOracle(d)
+    with open(os.path.join(HERE, "golden", "sp_unigram_goldens.json")) as f:
+        cases = json.load(f)["cases"][name]
+    assert len(cases) > 400
+    for c in cases:
+        t = bytes.fromhex(c["text"])
+        assert S.encode(t).tolist() == c["ids"], t[:40]
+    spm = pytest.importorskip("sentencepiece")
+    sp = spm.SentencePieceProcessor(model_file=os.path.join(d, "tokenizer.model"))
+    rnd = random.Random(31)
+    alphabet = list("abcdefghijklmnopqrstuvwxyz   ") + ["é", "日", " ", "\t", "Q", "7", "▁"]
+    for _ in range(1500):
+        t = "".join(rnd.choice(alphabet) for _ in range(rnd.randrange(0, 50)))
+        assert S.encode(t.encode()).tolist() == sp.encode(t), repr(t)
