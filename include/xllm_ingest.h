@@ -180,8 +180,8 @@ int xllm_score_route_device(xllm_ingest_t h, int32_t n_req, const uint64_t* d_ma
  * template's special tokens.
  * Backend, in the order of TokenizerFactory::create_tokenizer (tokenizer_factory.cpp:9-32):
  * `<tokenizer_path>/tokenizer.json` -> HF byte-level BPE (fast_tokenizer.cpp:8-30); tokenizer_config.json with
- * tokenizer_class TikTokenTokenizer -> tiktoken (tiktoken_tokenizer.cpp:115-294); else SentencePiece BPE
- * `<tokenizer_path>/tokenizer.model` (sentencepiece_tokenizer.cpp:47-50).  A model outside the supported
+ * tokenizer_class TikTokenTokenizer -> tiktoken (tiktoken_tokenizer.cpp:115-294); else SentencePiece (BPE or
+ * Unigram) `<tokenizer_path>/tokenizer.model` (sentencepiece_tokenizer.cpp:47-50).  A model outside the supported
  * envelope fails xllm_ingest_create with XLLM_ERR_UNSUPPORTED; a handle without a tokenizer returns it here.
  */
 #define XLLM_ENC_TRUNCATED 1

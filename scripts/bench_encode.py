@@ -23,7 +23,7 @@ ap.add_argument("--T", type=int, default=4096)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--check", type=int, default=4)
-ap.add_argument("--backend", choices=["sp", "hf"], default="sp")
+ap.add_argument("--backend", choices=["sp", "hf", "unigram"], default="sp")
 ap.add_argument("--hf-dir", default="hf_bpe_8k", help="fixture under tests/golden: hf_bpe_8k | hf_llama3_style | hf_qwen2_style")
 ap.add_argument("--cpu", type=int, default=0, help="hf: prompts to time through pip tokenizers encode_batch")
 a = ap.parse_args()
@@ -31,7 +31,8 @@ a = ap.parse_args()
 model = os.path.join(ROOT, "tests", "golden", "sp_bpe_8k")
 h = x.Ingest(tokenizer_path=model)
 hf_dir = os.path.join(ROOT, "tests", "golden", a.hf_dir)
-h_run = x.Ingest(tokenizer_path=hf_dir) if a.backend == "hf" else h
+uni_dir = os.path.join(ROOT, "tests", "golden", "sp_unigram_4k_bf")
+h_run = x.Ingest(tokenizer_path=hf_dir) if a.backend == "hf" else (x.Ingest(tokenizer_path=uni_dir) if a.backend == "unigram" else h)
 vocab = workload.make_vocabulary()
 t0 = time.time()
 wb = workload.pack_prompts(vocab)
@@ -72,7 +73,14 @@ n_tok = int(d_n.sum().item())
 if a.backend == "sp":
     assert (d_n.cpu().numpy() == a.T).all(), d_n.cpu().numpy()[:10]
 extra = {}
-if a.backend == "hf":
+if a.backend == "unigram":
+    from oracle import oracle as o
+    U = o.SentencePieceOracle(uni_dir)
+    ids = d_ids[:a.check].cpu().numpy()
+    cnt = d_n[:a.check].cpu().numpy()
+    for i in range(a.check):
+        assert ids[i, :cnt[i]].tolist() == U.encode(batch.prompt(i)).tolist()
+elif a.backend == "hf":
     from oracle import oracle as o
     H = o.HfBpeOracle(hf_dir)
     ids = d_ids[:a.check].cpu().numpy()

@@ -39,18 +39,26 @@ def test_tokenizer_probe_errors(tmp_path):
     assert e.value.code in (-4, -5)
 
 
-def test_unigram_model_is_rejected_not_mistokenised(tmp_path):
+def test_unigram_models_load_and_odd_ones_are_rejected(tmp_path):
+    """Unigram models load (Viterbi tables); a model whose pieces span word starts has no exact word split and is
+    refused, as are WORD / CHAR models — never mis-tokenised."""
     spm = pytest.importorskip("sentencepiece")
     import io
     import xllm_service_b200 as x
     from xllm_service_b200 import _lib, workload
-    model = io.BytesIO()
-    spm.SentencePieceTrainer.train(sentence_iterator=iter(workload.sentences(2000, seed=1)), model_writer=model,
-                                   model_type="unigram", vocab_size=400, minloglevel=2)
-    (tmp_path / "tokenizer.model").write_bytes(model.getvalue())
-    with pytest.raises(x.IngestError) as e:
-        _lib.tokenizer_probe(str(tmp_path))
-    assert e.value.code == -5  # XLLM_ERR_UNSUPPORTED
+    info = _lib.tokenizer_probe(os.path.join(HERE, "golden", "sp_unigram_4k"))
+    assert info["n_pieces"] == 4000 and info["split_mode"] == 1 and info["n_pairs"] == 0
+    for name, kw in (("cross", dict(model_type="unigram", split_by_whitespace=False)), ("word", dict(model_type="word")),
+                     ("char", dict(model_type="char"))):
+        model = io.BytesIO()
+        spm.SentencePieceTrainer.train(sentence_iterator=iter(workload.sentences(6000, seed=1)), model_writer=model,
+                                       vocab_size={"cross": 4000, "word": 300, "char": 30}[name], minloglevel=2, **kw)
+        d = tmp_path / name
+        d.mkdir()
+        (d / "tokenizer.model").write_bytes(model.getvalue())
+        with pytest.raises(x.IngestError) as e:
+            _lib.tokenizer_probe(str(d))
+        assert e.value.code == -5, name  # XLLM_ERR_UNSUPPORTED
 
 
 def test_workload_exact_tokens_and_shared_prefixes(oracle):

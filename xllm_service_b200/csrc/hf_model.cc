@@ -368,26 +368,8 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
       // an entry spelled with chars outside the byte alphabet can never equal a byte-level pre-token
       if (raw_ok[(size_t)kv.second]) ent.emplace_back(t->piece_raw[(size_t)kv.second], kv.second);
     }
-    uint32_t slots = 16;
-    while (slots < ent.size() * 2 + 16) slots <<= 1;
-    t->vocab_table.assign((size_t)slots * 4, 0u);
-    for (const auto& e : ent) {
-      if (e.first.empty()) continue;
-      if (e.first.size() > 512)
-        return fail(t, XLLM_ERR_UNSUPPORTED, "ignore_merges with a vocabulary entry longer than 512 bytes");
-      unsigned long long h = 0xcbf29ce484222325ull;
-      for (unsigned char c : e.first) h = (h ^ c) * 0x100000001b3ull;
-      if (h == 0) h = 1;
-      if (t->vocab_blob.size() + e.first.size() >= (1u << 22))
-        return fail(t, XLLM_ERR_UNSUPPORTED, "ignore_merges vocabulary larger than 4 MiB of token bytes");
-      uint32_t slot = (uint32_t)(((h ^ (h >> 29)) * 0xBF58476D1CE4E5B9ull) >> 32) & (slots - 1);  // as hf_vocab_lookup
-      while (t->vocab_table[(size_t)slot * 4] | t->vocab_table[(size_t)slot * 4 + 1]) slot = (slot + 1) & (slots - 1);
-      t->vocab_table[(size_t)slot * 4 + 0] = (uint32_t)h;
-      t->vocab_table[(size_t)slot * 4 + 1] = (uint32_t)(h >> 32);
-      t->vocab_table[(size_t)slot * 4 + 2] = (uint32_t)e.second;
-      t->vocab_table[(size_t)slot * 4 + 3] = ((uint32_t)t->vocab_blob.size() << 10) | (uint32_t)e.first.size();
-      t->vocab_blob.insert(t->vocab_blob.end(), e.first.begin(), e.first.end());
-    }
+    const int rc = build_bytes_table(ent, t);
+    if (rc != XLLM_OK) return rc;
   }
   size_t n_extra = 0;
   for (const auto& a : t->added_tokens) {

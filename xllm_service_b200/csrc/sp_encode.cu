@@ -301,6 +301,7 @@ struct ReqState {
   bool prev_space;      // normalizer's is_prev_space
   bool prev_unk;        // last emitted symbol was unknown (byte_fallback off only)
   bool too_long;
+  float uni_score;     // Unigram: best-path score at the start of the next word (running float, as upstream)
   int8_t bad_input;    // HF backend: 1 malformed UTF-8, 2 not provably NFC under a normalizer NFC
   bool deferred;       // needs the long-word kernel (this one was built without it)
   // long-word mode: the current pre-token is being streamed into a global scratch slot
@@ -835,8 +836,96 @@ struct MemoRef {
   uint32_t mask;
 };
 
-template <bool SMALL, bool LONG, bool HF, bool MEMO, typename SM>
+// ---------------------------------------------------------------------------- Unigram
+// unigram_model.cc Model::EncodeOptimized for ONE word w[0, len) whose best path starts from *score (the best-path
+// score at the word start, carried as a float across words exactly as upstream's best_path_ends_at[].best_path_score).
+// No NORMAL piece spans a word start (split_mode 1/2, checked by the loader), so every path of the sentence passes
+// through it and the sentence's Viterbi factors into per-word ones — but each word has to start from the running
+// float score, because candidates are formed as double(piece score) + double(float score so far) and stored back
+// as float: rounding makes the winner depend on everything before the word.
+// The warp walks the word's end positions; lane L-1 proposes the piece of L bytes that ends there (one probe of the
+// bytes -> id table), the candidates are then folded in upstream's order (ascending start = descending length,
+// strict '>' against the stored float), a char no piece covers costs unk_score.  best[] lives in S[], the back
+// links in PM[].  Returns the symbol count; S[0..n) = kResolvedFlag | piece id, or kSymUnknownFlag | code point.
+constexpr int kUniMaxWord = 511;  // bytes per word (best[] has kCoopMaxSym entries)
+template <typename SM>
+__device__ int unigram_word(const SpDev& T, SM& sm, const uint8_t* w, int len, float* score, int lane) {
+  float* best = reinterpret_cast<float*>(sm.S);
+  uint32_t* back = reinterpret_cast<uint32_t*>(sm.PM);  // id (24 bits, 0xFFFFFF = unknown char) | length << 24
+  static_assert(sizeof(sm.S) >= 4 * (kUniMaxWord + 1) && sizeof(sm.PM) >= 4 * (kUniMaxWord + 1), "lattice scratch");
+  if (lane == 0) best[0] = *score;
+  __syncwarp();
+  const int passes = ((int)T.max_piece_len + 31) / 32;
+  for (int e = 1; e <= len; ++e) {
+    if (e < len && (w[e] & 0xC0) == 0x80) continue;  // not a char boundary
+    int cs = e - 1;
+    while (cs > 0 && (w[cs] & 0xC0) == 0x80) --cs;
+    const int clen = e - cs;  // bytes of the char that ends at e
+    float best_f = 0.f;
+    uint32_t best_link = 0;
+    bool first = true;
+    for (int pass = passes - 1; pass >= 0; --pass) {  // longest pieces (earliest starts) first
+      const int L = pass * 32 + lane + 1;
+      const int s = e - L;
+      int32_t id = -1;
+      if (L <= (int)T.max_piece_len && s >= 0 && (w[s] & 0xC0) != 0x80) id = hf_vocab_lookup(T, w + s, L);
+      const bool unk = id < 0 && L == clen;  // no piece is exactly this char: the unknown candidate of its start
+      double cand = 0.0;
+      if (id >= 0) cand = (double)__ldg(T.piece_score + id) + (double)best[s];
+      else if (unk) cand = (double)(T.unk_score + best[s]);  // float + float upstream
+      uint32_t m = __ballot_sync(kFull, id >= 0 || unk);
+      while (m) {
+        const int src = 31 - __clz(m);
+        m &= ~(1u << src);
+        const double c = __shfl_sync(kFull, cand, src);
+        const int32_t cid = __shfl_sync(kFull, id, src);
+        if (first || c > (double)best_f) {
+          best_f = (float)c;
+          best_link = ((uint32_t)(pass * 32 + src + 1) << 24) | (cid >= 0 ? (uint32_t)cid : 0xFFFFFFu);
+          first = false;
+        }
+      }
+    }
+    if (lane == 0) { best[e] = best_f; back[e] = best_link; }
+    __syncwarp();
+  }
+  const float end_score = best[len];
+  __syncwarp();
+  // backtrack: count the pieces, then write them front to back over best[] (no longer needed)
+  int n = 0;
+  for (int e = len; e > 0; e -= (int)(back[e] >> 24)) ++n;
+  __syncwarp();
+  if (lane == 0) {
+    int k = n;
+    for (int e = len; e > 0;) {
+      const uint32_t link = back[e];
+      const int L = (int)(link >> 24);
+      uint32_t sym;
+      if ((link & 0xFFFFFFu) != 0xFFFFFFu) {
+        sym = kResolvedFlag | (link & 0xFFFFFFu);
+      } else {
+        const uint8_t* p = w + e - L;
+        const uint32_t b0 = p[0];
+        uint32_t cp = b0;
+        if (L == 2) cp = ((b0 & 0x1F) << 6) | (p[1] & 0x3F);
+        else if (L == 3) cp = ((b0 & 0x0F) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3F);
+        else if (L == 4) cp = ((b0 & 0x07) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3F);
+        sym = kSymUnknownFlag | cp;
+      }
+      sm.S[--k] = sym;
+      e -= L;
+    }
+  }
+  *score = end_score;
+  __syncwarp();
+  return n;
+}
+
+// MODE: 0 SentencePiece BPE / tiktoken, 1 HF byte-level BPE (regex pre-tokenizer), 2 SentencePiece Unigram
+template <bool SMALL, bool LONG, int MODE, bool MEMO, typename SM>
 __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
+  constexpr bool HF = MODE == 1;
+  constexpr bool UNI = MODE == 2;
   const uint8_t* nb = sm.nbuf;
   int nlen = rs.nlen;
   if (final && T.remove_extra_ws) {
@@ -906,7 +995,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
       else
         for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
     }
-    const uint32_t long_mask = __ballot_sync(kFull, have && nsym > kMaxSym);
+    const uint32_t long_mask = __ballot_sync(kFull, have && (UNI || nsym > kMaxSym));  // Unigram: one word at a time
     const int first_long = long_mask ? __ffs(long_mask) - 1 : 32;
     const bool active = have && lane < first_long;
 
@@ -1084,7 +1173,44 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
       const int lwe = HF ? (sm.wstart[w0 + 1] & kHfPosMask) : sm.wstart[w0 + 1];
       int n = 0;
       bool overflow = false;
-      for (int base = lws; base < lwe; base += 32) {
+      bool uni_done = false;
+      if constexpr (UNI) {
+        const int len = lwe - lws;
+        const bool bare_word = len == 3 && nb[lws] == 0xE2 && nb[lws + 1] == 0x96 && nb[lws + 2] == 0x81;
+        if (len > kUniMaxWord) {
+          rs.too_long = true;  // the Viterbi lattice of one word lives in shared memory
+        } else {
+          n = unigram_word(T, sm, nb + lws, len, &rs.uni_score, lane);
+          const int64_t before = rs.n_out;
+          for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            int32_t tmp[4];
+            bool unk = false;
+            int c = 0;
+            if (j < n) {
+              const uint32_t sym = sm.S[j];
+              if ((sym & 0xC0000000u) == kResolvedFlag) { tmp[0] = (int32_t)(sym & 0x3FFFFFFFu); c = 1; }
+              else c = sym_ids(T, sym, tmp, &unk);
+            }
+            bool skip = false;
+            if (!T.byte_fallback) {
+              const uint32_t um = __ballot_sync(kFull, j < n && unk);
+              const bool prev = lane == 0 ? rs.prev_unk : ((um >> (lane - 1)) & 1u);
+              skip = unk && prev;
+              const int lastl = (n - base) >= 32 ? 31 : (n - base - 1);
+              rs.prev_unk = (um >> lastl) & 1u;
+            }
+            if (skip) c = 0;
+            const int inc2 = warp_incl_scan(c, lane);
+            int64_t o = rs.n_out + (inc2 - c);
+            for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
+            rs.n_out += __shfl_sync(kFull, inc2, 31);
+          }
+          rs.trailing_bare = bare_word ? rs.trailing_bare + (int32_t)(rs.n_out - before) : 0;
+        }
+        uni_done = true;
+      }
+      for (int base = lws; base < lwe && !uni_done; base += 32) {
         const int p = base + lane;
         const bool lead = p < lwe && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
         const uint32_t m = __ballot_sync(kFull, lead);
@@ -1104,7 +1230,8 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
           whole = __shfl_sync(kFull, whole, 0);
         }
       }
-      if (whole >= 0) {
+      if (uni_done) {
+      } else if (whole >= 0) {
         if (lane == 0) put_id(rs, rs.n_out, whole);
         rs.n_out += 1;
         rs.trailing_bare = 0;
@@ -1184,12 +1311,12 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
   return HF && hf_capped && !rs.deferred;
 }
 
-template <bool SMALL, bool LONG, bool HF, bool MEMO, typename SM>
+template <bool SMALL, bool LONG, int MODE, bool MEMO, typename SM>
 __device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
-  if constexpr (HF) {
-    while (drain_pass<SMALL, LONG, true, MEMO>(T, sm, rs, final, lane, memo)) {}
+  if constexpr (MODE == 1) {
+    while (drain_pass<SMALL, LONG, 1, MEMO>(T, sm, rs, final, lane, memo)) {}
   } else {
-    drain_pass<SMALL, LONG, false, MEMO>(T, sm, rs, final, lane, memo);
+    drain_pass<SMALL, LONG, MODE, MEMO>(T, sm, rs, final, lane, memo);
   }
 }
 
@@ -1197,12 +1324,13 @@ __device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool
 // LONG == true : re-runs exactly the deferred requests (work list = defer_list[0 .. *defer_count)).
 // HF == true : byte-level BPE with the regex pre-tokenizer (split_mode 3).
 // MEMO == true: words are looked up in / added to the launch's word memo (never built together with LONG).
-template <bool SMALL, bool LONG, bool HF, bool MEMO>
+template <bool SMALL, bool LONG, int MODE, bool MEMO>
 __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ offsets, int n_req, int32_t* __restrict__ ids,
     int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status, const __grid_constant__ SpDev T,
     unsigned int* __restrict__ task_counter, int32_t* __restrict__ defer_list,
     unsigned int* __restrict__ defer_count, uint8_t* memo_table, uint32_t memo_mask) {
+  constexpr bool HF = MODE == 1;
   const MemoRef memo{memo_table, memo_mask};
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = WarpSmemT<SMALL>;
@@ -1237,6 +1365,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     rs.prev_unk = false;
     rs.too_long = false;
     rs.bad_input = 0;
+    rs.uni_score = 0.f;
     rs.deferred = false;
     rs.long_mode = false;
     rs.long_last_sp = false;
@@ -1251,13 +1380,13 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       for (uint32_t pos = 0; pos < rs.len; pos += kFastWin) {
         normalize_fast(T, sm, rs, pos, lane);  // byte mode: a verbatim copy
         if (rs.nlen > drain_at) {
-          drain<SMALL, LONG, true, MEMO>(T, sm, rs, false, lane, memo);
+          drain<SMALL, LONG, 1, MEMO>(T, sm, rs, false, lane, memo);
           // what is left is one unfinished pre-token (plus the look-ahead margin)
           if (rs.nlen > kLongEnterAt) rs.too_long = true;
           if (rs.too_long || rs.deferred || rs.bad_input) break;
         }
       }
-      if (!rs.too_long && !rs.deferred && !rs.bad_input) drain<SMALL, LONG, true, MEMO>(T, sm, rs, true, lane, memo);
+      if (!rs.too_long && !rs.deferred && !rs.bad_input) drain<SMALL, LONG, 1, MEMO>(T, sm, rs, true, lane, memo);
       if (!rs.too_long && !rs.deferred && !rs.bad_input) {
         if (lane < T.n_suffix) put_id(rs, rs.n_out + lane, T.suffix_ids[lane]);
         rs.n_out += T.n_suffix;
@@ -1280,7 +1409,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
             if constexpr (LONG) {
               if (rs.long_mode) { long_consume(T, sm, rs, false, lane); consumed = true; }
             }
-            if (!consumed) drain<SMALL, LONG, false, MEMO>(T, sm, rs, false, lane, memo);
+            if (!consumed) drain<SMALL, LONG, MODE, MEMO>(T, sm, rs, false, lane, memo);
             if (!rs.too_long && !normalize_window(T, sm, rs, pos, carry_skip, lane)) {
               // still no room: the kept tail is one very long word -> stream it through a scratch slot
               bool entered = false;
@@ -1304,7 +1433,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
           }
         }
         if (!in_long && rs.nlen > drain_at) {
-          drain<SMALL, LONG, false, MEMO>(T, sm, rs, false, lane, memo);
+          drain<SMALL, LONG, MODE, MEMO>(T, sm, rs, false, lane, memo);
           if (rs.nlen > kLongEnterAt) {
             if constexpr (LONG) {
               if (!long_enter(T, sm, rs, lane)) rs.too_long = true;
@@ -1318,13 +1447,16 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       if constexpr (LONG) {
         if (!rs.too_long && rs.long_mode) long_consume(T, sm, rs, true, lane);
       }
-      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG, false, MEMO>(T, sm, rs, true, lane, memo);
+      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG, MODE, MEMO>(T, sm, rs, true, lane, memo);
     }
     if constexpr (LONG) {
       if (rs.long_mode) {  // error exit while a slot is held
         long_slot_release(T.long_locks, rs.long_slot, lane);
         rs.long_mode = false;
       }
+    }
+    if constexpr (MODE == 2) {
+      if (rs.deferred) { rs.deferred = false; rs.too_long = true; }  // no long-word pass for Unigram
     }
     if (lane == 0) {
       if (rs.deferred) {
@@ -1429,7 +1561,13 @@ int SpDeviceModel::upload(const SpTables& t) {
     UP(aid, added_id);
   }
   dev_.ignore_merges = t.ignore_merges ? 1 : 0;
-  if (t.ignore_merges) {
+  dev_.unigram = t.unigram ? 1 : 0;
+  if (t.unigram) {
+    UP(t.piece_score, piece_score);
+    dev_.unk_score = t.unk_score;
+    dev_.max_piece_len = t.max_piece_len;
+  }
+  if (t.ignore_merges || t.unigram) {
     UP(t.vocab_table, vtab);
     UP(t.vocab_blob, vblob);
     dev_.vtab_mask = (uint32_t)(t.vocab_table.size() / 4) - 1;
@@ -1513,18 +1651,20 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
 #define XLLM_SET_SMEM(K, B)                                                                          \
         r = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B>)); \
         if (r != cudaSuccess) return r;
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, false, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<true, true, false, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, false, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<false, true, false, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, true, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<true, true, true, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, true, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<false, true, true, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, false, true>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, false, true>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, true, true>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, true, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<true, true, 0, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<false, true, 0, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, 1, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<true, true, 1, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, 1, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<false, true, 1, false>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, 1, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, 1, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, 2, false>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, 2, false>), false)
 #undef XLLM_SET_SMEM
         return cudaSuccess;
       },
@@ -1553,16 +1693,24 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
   sp_encode_kernel<SMALL_, true, HF_, false><<<grid_long, 32, smem, stream>>>(                                   \
       text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters + 2, defer_list, counters + 1, nullptr, 0u);
   const bool hf = dev.split_mode == 3;
-  if (use_memo) {
-    if (small && hf) { XLLM_LAUNCH_PAIR(true, true, true) }
-    else if (small) { XLLM_LAUNCH_PAIR(true, false, true) }
-    else if (hf) { XLLM_LAUNCH_PAIR(false, true, true) }
-    else { XLLM_LAUNCH_PAIR(false, false, true) }
+  if (dev.unigram) {
+    // Viterbi per word from a running score: no word memo (the result depends on the prefix), no long-word pass
+    if (small)
+      sp_encode_kernel<true, false, 2, false><<<grid, 32, smem, stream>>>(
+          text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, nullptr, 0u);
+    else
+      sp_encode_kernel<false, false, 2, false><<<grid, 32, smem, stream>>>(
+          text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, nullptr, 0u);
+  } else if (use_memo) {
+    if (small && hf) { XLLM_LAUNCH_PAIR(true, 1, true) }
+    else if (small) { XLLM_LAUNCH_PAIR(true, 0, true) }
+    else if (hf) { XLLM_LAUNCH_PAIR(false, 1, true) }
+    else { XLLM_LAUNCH_PAIR(false, 0, true) }
   } else {
-    if (small && hf) { XLLM_LAUNCH_PAIR(true, true, false) }
-    else if (small) { XLLM_LAUNCH_PAIR(true, false, false) }
-    else if (hf) { XLLM_LAUNCH_PAIR(false, true, false) }
-    else { XLLM_LAUNCH_PAIR(false, false, false) }
+    if (small && hf) { XLLM_LAUNCH_PAIR(true, 1, false) }
+    else if (small) { XLLM_LAUNCH_PAIR(true, 0, false) }
+    else if (hf) { XLLM_LAUNCH_PAIR(false, 1, false) }
+    else { XLLM_LAUNCH_PAIR(false, 0, false) }
   }
 #undef XLLM_LAUNCH_PAIR
   return cudaGetLastError();

@@ -50,6 +50,11 @@ struct SpDev {
   const uint4* vtab;
   const uint8_t* vblob;
   uint32_t vtab_mask;
+  // Unigram SentencePiece: Viterbi over vtab (NORMAL pieces) with piece_score; see unigram_word (sp_encode.cu)
+  uint8_t unigram;
+  const float* piece_score;
+  float unk_score;
+  uint32_t max_piece_len;
   uint8_t nfc_check;   // normalizer NFC: a request passes only if every char is NFC-inert (then NFC is the identity)
   uint8_t hf_pattern;  // 1: ByteLevel's own GPT-2 regex, 2: Split(cl100k-family regex) + ByteLevel(use_regex = false)
   uint8_t hf_digits;   // pattern 2: \p{N}{1,hf_digits}

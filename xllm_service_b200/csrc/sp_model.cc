@@ -180,6 +180,35 @@ uint32_t sp_hash_cp(uint32_t cp) {
 
 uint32_t sp_pair_slot_fwd(uint32_t a, uint32_t b, uint32_t n) { return sp_pair_slot(a, b, n); }
 
+int build_bytes_table(const std::vector<std::pair<std::string, int32_t>>& entries, SpTables* t) {
+  uint32_t slots = 16;
+  while (slots < entries.size() * 2 + 16) slots <<= 1;
+  t->vocab_table.assign((size_t)slots * 4, 0u);
+  t->vocab_blob.clear();
+  for (const auto& e : entries) {
+    if (e.first.empty()) continue;
+    if (e.first.size() > 512) {
+      t->error = "a vocabulary entry is longer than 512 bytes";
+      return XLLM_ERR_UNSUPPORTED;
+    }
+    unsigned long long h = 0xcbf29ce484222325ull;
+    for (unsigned char c : e.first) h = (h ^ c) * 0x100000001b3ull;
+    if (h == 0) h = 1;
+    if (t->vocab_blob.size() + e.first.size() >= (1u << 22)) {
+      t->error = "vocabulary larger than 4 MiB of token bytes";
+      return XLLM_ERR_UNSUPPORTED;
+    }
+    uint32_t slot = (uint32_t)(((h ^ (h >> 29)) * 0xBF58476D1CE4E5B9ull) >> 32) & (slots - 1);  // as hf_vocab_lookup
+    while (t->vocab_table[(size_t)slot * 4] | t->vocab_table[(size_t)slot * 4 + 1]) slot = (slot + 1) & (slots - 1);
+    t->vocab_table[(size_t)slot * 4 + 0] = (uint32_t)h;
+    t->vocab_table[(size_t)slot * 4 + 1] = (uint32_t)(h >> 32);
+    t->vocab_table[(size_t)slot * 4 + 2] = (uint32_t)e.second;
+    t->vocab_table[(size_t)slot * 4 + 3] = ((uint32_t)t->vocab_blob.size() << 10) | (uint32_t)e.first.size();
+    t->vocab_blob.insert(t->vocab_blob.end(), e.first.begin(), e.first.end());
+  }
+  return XLLM_OK;
+}
+
 int sp_load_model(const std::string& path_in, SpTables* t) {
   std::string path = path_in;
   struct stat st;
@@ -200,10 +229,11 @@ int sp_load_model(const std::string& path_in, SpTables* t) {
     t->error = path + ": not a SentencePiece ModelProto";
     return XLLM_ERR_FORMAT;
   }
-  if (m.model_type != 2) {
-    t->error = "SentencePiece model_type " + std::to_string(m.model_type) + ": only BPE (2) is supported on device";
+  if (m.model_type != 2 && m.model_type != 1) {
+    t->error = "SentencePiece model_type " + std::to_string(m.model_type) + ": only BPE (2) and UNIGRAM (1) are supported on device";
     return XLLM_ERR_UNSUPPORTED;
   }
+  t->unigram = m.model_type == 1;
   if (!m.escape_ws || m.suffix_ws) {
     t->error = "escape_whitespaces=false / treat_whitespace_as_suffix=true are not supported on device";
     return XLLM_ERR_UNSUPPORTED;
@@ -359,6 +389,32 @@ int sp_load_model(const std::string& path_in, SpTables* t) {
   }
   t->space_sym = sym_of_char(kSpace);
   t->split_mode = !space_inside ? 1 : (space_only_after_space ? 2 : 0);
+  if (t->unigram) {
+    // unigram_model.cc: Viterbi over the NORMAL pieces; a word is scored on its own because no piece spans a
+    // word start (split_mode), with the running float prefix score carried from word to word by the kernel
+    if (t->split_mode == 0) {
+      t->error = "Unigram model with a piece that holds U+2581 past its first char: no exact word split exists";
+      return XLLM_ERR_UNSUPPORTED;
+    }
+    std::vector<std::pair<std::string, int32_t>> ent;
+    float mn = 3.402823466e+38f;  // FLT_MAX, as upstream initialises min_score_
+    t->piece_score.assign(P, 0.f);
+    for (uint32_t i = 0; i < P; ++i) {
+      t->piece_score[i] = m.pieces[i].score;
+      if (m.pieces[i].type != kNormal) continue;
+      ent.emplace_back(m.pieces[i].s, (int32_t)i);
+      mn = m.pieces[i].score < mn ? m.pieces[i].score : mn;
+      if (m.pieces[i].s.size() > t->max_piece_len) t->max_piece_len = (uint32_t)m.pieces[i].s.size();
+    }
+    if (t->max_piece_len > 64 || t->max_piece_len == 0) {
+      t->error = "Unigram model without NORMAL pieces, or with a piece longer than 64 bytes";
+      return XLLM_ERR_UNSUPPORTED;
+    }
+    t->unk_score = mn - 10.0f;  // min_score() - kUnkPenalty
+    const int rc = build_bytes_table(ent, t);
+    if (rc != XLLM_OK) return rc;
+    pairs.clear();  // no merges in a Unigram model
+  }
   t->n_syms = P + (uint32_t)virt.size();
   t->virt_cp = virt;
 

@@ -65,6 +65,11 @@ struct SpTables {
   bool ignore_merges = false;  // a pre-token that is a vocabulary entry is emitted as that id (models/bpe/model.rs)
   std::vector<uint32_t> vocab_table;  // ignore_merges: 4 x u32 per slot {hash lo, hash hi, id, blob offset << 10 | length}
   std::vector<uint8_t> vocab_blob;
+  // Unigram SentencePiece (sp_model.cc): Viterbi over the vocabulary table above (NORMAL pieces) with these scores
+  bool unigram = false;
+  std::vector<float> piece_score;  // [n_pieces]
+  float unk_score = 0.f;           // min NORMAL score - 10 (unigram_model.cc kUnkPenalty)
+  uint32_t max_piece_len = 0;      // longest NORMAL piece in bytes
   bool nfc_check = false;      // normalizer NFC: requests are accepted only when NFC leaves them unchanged
   std::vector<uint16_t> uni_stage1;  // [0x1100]  code point >> 8 -> block
   std::vector<uint8_t> uni_stage2;   // [blocks * 256] class: 0 other, 1 \p{L}, 2 \p{N}, 3 \s
@@ -75,6 +80,10 @@ struct SpTables {
   std::string error;
 };
 
+// Fills vocab_table / vocab_blob: raw bytes -> id, probed on device by hf_vocab_lookup (hf_pretok.cuh): FNV-1a 64
+// of the bytes, slot from the mixed hash, 16-byte entries {hash lo, hash hi, id, blob offset << 10 | length}.
+// Returns XLLM_OK or XLLM_ERR_UNSUPPORTED (an entry longer than 512 bytes / more than 4 MiB of bytes).
+int build_bytes_table(const std::vector<std::pair<std::string, int32_t>>& entries, SpTables* t);
 // Loads <path> (file, or directory containing tokenizer.model).  Returns XLLM_OK or an error code
 // (message in out->error).
 int sp_load_model(const std::string& path, SpTables* out);
