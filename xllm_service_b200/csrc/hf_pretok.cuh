@@ -85,9 +85,9 @@ __device__ __forceinline__ int32_t hf_vocab_lookup(const SpDev& T, const uint8_t
     if ((e.x | e.y) == 0) return -1;
     if (e.x == (uint32_t)h && e.y == (uint32_t)(h >> 32) && (int)(e.w & 1023u) == n) {
       const uint8_t* b = T.vblob + (e.w >> 10);
-      bool eq = true;
-      for (int k = 0; k < n && eq; ++k) eq = __ldg(b + k) == w[k];
-      if (eq) return (int32_t)e.z;
+      uint32_t diff = 0;  // no early exit: the loads are independent and overlap
+      for (int k = 0; k < n; ++k) diff |= (uint32_t)(__ldg(b + k) ^ w[k]);
+      if (diff == 0) return (int32_t)e.z;
     }
     slot = (slot + 1) & T.vtab_mask;
   }
