@@ -1,24 +1,29 @@
-// sp_encode.cu — batched SentencePiece-BPE encode on sm_100a: one warp per request.
+// sp_encode.cu — the batched tokenizer kernels on sm_100a: one warp per request.
 //
-// Bit-exact target: what SentencePieceTokenizer::encode returns through libsentencepiece
-// (xllm_service/tokenizer/sentencepiece_tokenizer.cpp:115-168 -> sp_processor_.Encode):
-//   normalizer.cc     Normalize(): longest-prefix rewrite through the precompiled charsmap trie,
-//                     invalid UTF-8 -> U+FFFD, whitespace collapse, ' ' -> U+2581, dummy prefix
-//   bpe_model.cc      Encode(): merge the adjacent pair with the best score, leftmost on ties,
-//                     until no adjacent pair concatenates to a NORMAL piece
-//   sentencepiece_processor.cc  byte fallback / consecutive-unknown merging
+// Bit-exact target: what Tokenizer::encode returns on each of the reference's backends —
+//   SentencePiece (sentencepiece_tokenizer.cpp:115-168 -> sp_processor_.Encode):
+//     normalizer.cc     Normalize(): longest-prefix rewrite through the precompiled charsmap trie,
+//                       invalid UTF-8 -> U+FFFD, whitespace collapse, ' ' -> U+2581, dummy prefix
+//     bpe_model.cc      Encode(): merge the adjacent pair with the best score, leftmost on ties,
+//                       until no adjacent pair concatenates to a NORMAL piece
+//     unigram_model.cc  EncodeOptimized(): Viterbi over the piece lattice (unigram_word below)
+//     sentencepiece_processor.cc  byte fallback / consecutive-unknown merging
+//   tiktoken in the service's regex-less mode (tiktoken_tokenizer.cpp:115-294): byte symbols, merges by rank
+//   HF `tokenizer.json` byte-level BPE (fast_tokenizer.cpp:20-30): hf_pretok.cuh in front of the same merges
 //
-// Why this is exact AND parallel: no NORMAL piece of the loaded model holds U+2581 anywhere but
+// Why the BPE merge is exact AND parallel: no NORMAL piece of the loaded model holds U+2581 anywhere but
 // at its first char (checked by the host loader: SpTables::split_mode), so no merge can ever
 // span the boundary in front of a U+2581.  The priority-ordered global merge therefore factors
 // into independent per-"word" merges.  The warp streams the request through shared memory:
-//   1. normalise 32 source bytes per step (every lane walks the trie from its own byte; a
-//      ballot resolves which positions start a unit) into a 4 KB normalized-text buffer;
-//   2. when the buffer fills, split it at U+2581 and hand one word per lane: the lane builds its
-//      symbols (chars -> symbol ids), looks up every adjacent pair in the (left,right) ->
-//      (priority, merged) hash table in L2, and runs the serial best-pair merge over a column
-//      of shared memory (alive bitmask in a register);
-//      words with more than 32 chars are merged by the whole warp cooperatively;
+//   1. normalise into a 2 KB normalized-text buffer: 128 source bytes per step on the ASCII fast path
+//      (one word-at-a-time test per lane), 32 per step on the general path (every lane walks the trie
+//      from its own byte; a ballot resolves which positions start a unit);
+//   2. when the buffer fills, split it at U+2581 and hand one word per lane: the lane first probes the
+//      per-launch word memo (word bytes -> ids); on a miss it builds its symbols (chars -> symbol ids),
+//      looks up every adjacent pair in the (left,right) -> (priority, merged) hash table in L2, runs the
+//      serial best-pair merge over a column of shared memory (alive bitmask in a register) and inserts
+//      the result; words of 17..512 chars are merged by the whole warp cooperatively, longer ones in a
+//      global scratch slot by a second launch;
 //   3. ids are written straight to the request's output row in order.
 // Algorithmic HBM traffic: text bytes read once + 4 B per id written.
 #include "sp_encode.cuh"
