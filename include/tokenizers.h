@@ -34,9 +34,9 @@ typedef struct {
 TokenizerHandle tokenizers_new_from_path(const char* path);
 /* lib.rs:57-62 (exported by the shim, unused by the C++ side): the bytes of a serialized model */
 TokenizerHandle tokenizers_new_from_str(const char* data, size_t len);
-/* tokenizers.h:38-42 / lib.rs:83-99.  add_special_token is accepted and ignored: a tokenizer.json's template
- * ids are always applied (the reference's only caller passes 1, fast_tokenizer.cpp:24); the SentencePiece
- * backend adds no BOS/EOS (sentencepiece_tokenizer.cpp:115-128). */
+/* tokenizers.h:38-42 / lib.rs:83-99.  add_special_token = 0 leaves off the ids a tokenizer.json's template wraps
+ * around the sequence (the reference's only caller passes 1, fast_tokenizer.cpp:24); SentencePiece / tiktoken
+ * models add none either way (sentencepiece_tokenizer.cpp:115-128). */
 void tokenizers_encode(TokenizerHandle handle, const char* data, size_t len, int add_special_token,
                        TokenizerEncodeResult* result);
 /* lib.rs:102-126 */

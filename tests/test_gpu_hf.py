@@ -172,3 +172,14 @@ def test_legacy_abi_round_trip(tok):
     L.tokenizers_token_to_id(h, word.encode(), len(word.encode()), ctypes.byref(out))
     assert out.value == wid
     L.tokenizers_free(h)
+    # add_special_tokens = 0 leaves the template ids off (lib.rs:83-99); the Llama-3-style fixture has a BOS template
+    h3 = L.tokenizers_new_from_path(os.path.join(HERE, "golden", "hf_llama3_style", "tokenizer.json").encode())
+    assert h3
+    got = {}
+    for flag in (1, 0):
+        res = Result()
+        L.tokenizers_encode(h3, b"hello world", 11, flag, ctypes.byref(res))
+        got[flag] = [res.token_ids[i] for i in range(res.len)]
+        L.tokenizers_free_encode_results(ctypes.byref(res), 1)
+    assert got[1][0] == 0 and got[1][1:] == got[0] and len(got[0]) >= 1
+    L.tokenizers_free(h3)

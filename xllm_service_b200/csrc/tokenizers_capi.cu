@@ -84,7 +84,9 @@ LegacyTokenizer* make(const char* path) {
   return L;
 }
 
-void encode_many(LegacyTokenizer* L, const char* const* data, const size_t* len, size_t n,
+// add_special: Tokenizer::encode(text, add_special_tokens) (lib.rs:83-99) — with 0 the template ids a
+// tokenizer.json wraps around the sequence are left off (the device always writes them: the service passes 1)
+void encode_many(LegacyTokenizer* L, const char* const* data, const size_t* len, size_t n, bool add_special,
                  TokenizerEncodeResult* results) {
   for (size_t i = 0; i < n; ++i) { results[i].token_ids = nullptr; results[i].len = 0; }
   if (!L || n == 0) return;
@@ -107,11 +109,15 @@ void encode_many(LegacyTokenizer* L, const char* const* data, const size_t* len,
     if (!need) break;
     stride = need;
   }
+  const xllm::SpTables& t = *L->h->sp_tables;
+  const size_t cut_front = add_special ? 0 : t.prefix_ids.size(), cut_back = add_special ? 0 : t.suffix_ids.size();
   for (size_t i = 0; i < n; ++i) {
     if (status[i] != XLLM_OK) continue;
-    results[i].len = (size_t)n_ids[i];
-    results[i].token_ids = static_cast<int*>(malloc(sizeof(int) * (results[i].len ? results[i].len : 1)));
-    if (results[i].token_ids) memcpy(results[i].token_ids, ids.data() + i * (size_t)stride, sizeof(int) * results[i].len);
+    const size_t total = (size_t)n_ids[i];
+    const size_t keep = total >= cut_front + cut_back ? total - cut_front - cut_back : 0;
+    results[i].len = keep;
+    results[i].token_ids = static_cast<int*>(malloc(sizeof(int) * (keep ? keep : 1)));
+    if (results[i].token_ids) memcpy(results[i].token_ids, ids.data() + i * (size_t)stride + cut_front, sizeof(int) * keep);
     else results[i].len = 0;
   }
 }
@@ -138,16 +144,16 @@ TokenizerHandle tokenizers_new_from_str(const char* data, size_t len) {
   return L;
 }
 
-void tokenizers_encode(TokenizerHandle handle, const char* data, size_t len, int /*add_special_token*/,
+void tokenizers_encode(TokenizerHandle handle, const char* data, size_t len, int add_special_token,
                        TokenizerEncodeResult* result) {
   if (!result) return;
-  encode_many(static_cast<LegacyTokenizer*>(handle), &data, &len, 1, result);
+  encode_many(static_cast<LegacyTokenizer*>(handle), &data, &len, 1, add_special_token != 0, result);
 }
 
 void tokenizers_encode_batch(TokenizerHandle handle, const char* const* data, const size_t* len, size_t num_seqs,
-                             int /*add_special_token*/, TokenizerEncodeResult* results) {
+                             int add_special_token, TokenizerEncodeResult* results) {
   if (!results) return;
-  encode_many(static_cast<LegacyTokenizer*>(handle), data, len, num_seqs, results);
+  encode_many(static_cast<LegacyTokenizer*>(handle), data, len, num_seqs, add_special_token != 0, results);
 }
 
 void tokenizers_free_encode_results(TokenizerEncodeResult* results, size_t num_seqs) {
