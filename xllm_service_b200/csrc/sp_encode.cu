@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -86,6 +87,12 @@ struct WarpSmemT {
   typename PMOps<SMALL>::T PM[kCoopMaxSym];  // pair state at position j
   uint8_t nbuf[kNBuf];                       // normalized text (always starts at a word start)
   uint16_t wstart[kMaxWords];
+};
+// Unigram kernels: plus the pieces found from each of 32 start positions (unigram_word)
+constexpr int kUniMaxMatch = 32;
+template <bool SMALL>
+struct WarpSmemUniT : WarpSmemT<SMALL> {
+  uint32_t mlist[32 * kUniMaxMatch];  // [start lane][k]: piece id (24 bits, 0xFFFFFF = unknown char) | length << 24
 };
 
 __device__ __forceinline__ uint32_t hash_pair(uint32_t a, uint32_t b) {
@@ -853,8 +860,137 @@ struct MemoRef {
 // strict '>' against the stored float), a char no piece covers costs unk_score.  best[] lives in S[], the back
 // links in PM[].  Returns the symbol count; S[0..n) = kResolvedFlag | piece id, or kSymUnknownFlag | code point.
 constexpr int kUniMaxWord = 511;  // bytes per word (best[] has kCoopMaxSym entries)
+
+// (parent node, byte) -> child node and its piece id (-1: a proper prefix only); false: no piece continues this way
+__device__ __forceinline__ bool uni_trie_step(const SpDev& T, uint32_t parent, uint32_t byte, uint32_t* child,
+                                              int32_t* piece) {
+  uint32_t h = (parent * 256u + byte) * 0x9E3779B1u;  // sp_trie_slot (sp_model.cc)
+  h ^= h >> 15;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  uint32_t slot = h & T.utrie_mask;
+  for (;;) {
+    const uint4 e = __ldg(T.utrie + slot);
+    if (e.x == parent && e.y == byte) { *child = e.z; *piece = (int32_t)e.w; return true; }
+    if (e.x == 0xFFFFFFFFu) return false;
+    slot = (slot + 1) & T.utrie_mask;
+  }
+}
+
+template <typename SM>
+__device__ int unigram_backtrack(SM& sm, const uint8_t* w, int len, int lane);
+template <typename SM>
+__device__ int unigram_word_slow(const SpDev& T, SM& sm, const uint8_t* w, int len, float* score, int lane);
+
+// The same lattice built the way upstream builds it — from the START positions: 32 starts at a time, every lane walks
+// the piece trie from its start until no piece continues (a few dependent L2 probes, all lanes in parallel) and
+// lists what it found; then the starts are folded in order (as upstream's outer loop), lane k applying the k-th
+// piece of the current start to best[start + length] — distinct ends, so no conflicts inside a start.
+// Falls back to unigram_word_slow when one start has more than kUniMaxMatch pieces.
 template <typename SM>
 __device__ int unigram_word(const SpDev& T, SM& sm, const uint8_t* w, int len, float* score, int lane) {
+  float* best = reinterpret_cast<float*>(sm.S);
+  uint32_t* back = reinterpret_cast<uint32_t*>(sm.PM);  // 0 = no path ends here yet
+  for (int e = lane; e <= len; e += 32) back[e] = 0;
+  if (lane == 0) best[0] = *score;
+  __syncwarp();
+  for (int s0 = 0; s0 < len; s0 += 32) {
+    // ---- walk the trie from every start of this block
+    const int s = s0 + lane;
+    const bool is_start = s < len && (w[s] & 0xC0) != 0x80;
+    int cnt = 0;
+    bool overflow = false;
+    if (is_start) {
+      const uint8_t b0 = w[s];
+      int clen = b0 < 0x80 ? 1 : (b0 < 0xE0 ? 2 : (b0 < 0xF0 ? 3 : 4));
+      if (clen > len - s) clen = len - s;
+      const int max_l = (int)T.max_piece_len < len - s ? (int)T.max_piece_len : len - s;
+      uint32_t node = 0;
+      bool has_single = false;
+      for (int L = 1; L <= max_l; ++L) {
+        int32_t piece;
+        if (!uni_trie_step(T, node, w[s + L - 1], &node, &piece)) break;
+        if (piece >= 0) {
+          if (cnt < kUniMaxMatch) sm.mlist[lane * kUniMaxMatch + cnt] = ((uint32_t)L << 24) | (uint32_t)piece;
+          else overflow = true;
+          ++cnt;
+          has_single |= L == clen;
+        }
+      }
+      if (!has_single) {  // no piece is exactly this char: the unknown candidate
+        if (cnt < kUniMaxMatch) sm.mlist[lane * kUniMaxMatch + cnt] = ((uint32_t)clen << 24) | 0xFFFFFFu;
+        else overflow = true;
+        ++cnt;
+      }
+    }
+    if (__any_sync(kFull, overflow)) return unigram_word_slow(T, sm, w, len, score, lane);
+    __syncwarp();
+    // ---- fold the starts in order
+    uint32_t starts = __ballot_sync(kFull, is_start);
+    while (starts) {
+      const int b = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const int sb = s0 + b;
+      const int nb_ = __shfl_sync(kFull, cnt, b);
+      const float base = best[sb];
+      if (lane < nb_) {
+        const uint32_t m = sm.mlist[b * kUniMaxMatch + lane];
+        const int L = (int)(m >> 24);
+        const uint32_t id = m & 0xFFFFFFu;
+        const int e = sb + L;
+        const double cand = id == 0xFFFFFFu ? (double)(T.unk_score + base)  // float + float upstream
+                                            : (double)__ldg(T.piece_score + id) + (double)base;
+        if (back[e] == 0 || cand > (double)best[e]) {
+          best[e] = (float)cand;
+          back[e] = m;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  const float end_score = best[len];
+  __syncwarp();
+  const int n = unigram_backtrack(sm, w, len, lane);
+  *score = end_score;
+  __syncwarp();
+  return n;
+}
+
+// back[] -> S[0..n): kResolvedFlag | piece id, or kSymUnknownFlag | code point
+template <typename SM>
+__device__ int unigram_backtrack(SM& sm, const uint8_t* w, int len, int lane) {
+  const uint32_t* back = reinterpret_cast<const uint32_t*>(sm.PM);
+  int n = 0;
+  for (int e = len; e > 0; e -= (int)(back[e] >> 24)) ++n;
+  __syncwarp();
+  if (lane == 0) {
+    int k = n;
+    for (int e = len; e > 0;) {
+      const uint32_t link = back[e];
+      const int L = (int)(link >> 24);
+      uint32_t sym;
+      if ((link & 0xFFFFFFu) != 0xFFFFFFu) {
+        sym = kResolvedFlag | (link & 0xFFFFFFu);
+      } else {
+        const uint8_t* p = w + e - L;
+        const uint32_t b0 = p[0];
+        uint32_t cp = b0;
+        if (L == 2) cp = ((b0 & 0x1F) << 6) | (p[1] & 0x3F);
+        else if (L == 3) cp = ((b0 & 0x0F) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3F);
+        else if (L == 4) cp = ((b0 & 0x07) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3F);
+        sym = kSymUnknownFlag | cp;
+      }
+      sm.S[--k] = sym;
+      e -= L;
+    }
+  }
+  __syncwarp();
+  return n;
+}
+
+// The per-END-position form (kept as the fallback): lane L-1 proposes the piece of L bytes that ends at e.
+template <typename SM>
+__device__ int unigram_word_slow(const SpDev& T, SM& sm, const uint8_t* w, int len, float* score, int lane) {
   float* best = reinterpret_cast<float*>(sm.S);
   uint32_t* back = reinterpret_cast<uint32_t*>(sm.PM);  // id (24 bits, 0xFFFFFF = unknown char) | length << 24
   static_assert(sizeof(sm.S) >= 4 * (kUniMaxWord + 1) && sizeof(sm.PM) >= 4 * (kUniMaxWord + 1), "lattice scratch");
@@ -896,31 +1032,7 @@ __device__ int unigram_word(const SpDev& T, SM& sm, const uint8_t* w, int len, f
   }
   const float end_score = best[len];
   __syncwarp();
-  // backtrack: count the pieces, then write them front to back over best[] (no longer needed)
-  int n = 0;
-  for (int e = len; e > 0; e -= (int)(back[e] >> 24)) ++n;
-  __syncwarp();
-  if (lane == 0) {
-    int k = n;
-    for (int e = len; e > 0;) {
-      const uint32_t link = back[e];
-      const int L = (int)(link >> 24);
-      uint32_t sym;
-      if ((link & 0xFFFFFFu) != 0xFFFFFFu) {
-        sym = kResolvedFlag | (link & 0xFFFFFFu);
-      } else {
-        const uint8_t* p = w + e - L;
-        const uint32_t b0 = p[0];
-        uint32_t cp = b0;
-        if (L == 2) cp = ((b0 & 0x1F) << 6) | (p[1] & 0x3F);
-        else if (L == 3) cp = ((b0 & 0x0F) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3F);
-        else if (L == 4) cp = ((b0 & 0x07) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3F);
-        sym = kSymUnknownFlag | cp;
-      }
-      sm.S[--k] = sym;
-      e -= L;
-    }
-  }
+  const int n = unigram_backtrack(sm, w, len, lane);
   *score = end_score;
   __syncwarp();
   return n;
@@ -1175,13 +1287,26 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     // --- cooperative path for the long word w0
     {
       const int lws = HF ? (sm.wstart[w0] & kHfPosMask) : sm.wstart[w0];
-      const int lwe = HF ? (sm.wstart[w0 + 1] & kHfPosMask) : sm.wstart[w0 + 1];
+      int lwe = HF ? (sm.wstart[w0 + 1] & kHfPosMask) : sm.wstart[w0 + 1];
       int n = 0;
+      int words_taken = 1;
       bool overflow = false;
       bool uni_done = false;
       if constexpr (UNI) {
+        auto is_bare = [&](int a, int b) { return b - a == 3 && nb[a] == 0xE2 && nb[a + 1] == 0x96 && nb[a + 2] == 0x81; };
+        const bool bare_word = is_bare(lws, lwe);
+        // No piece spans a word start, so consecutive words form one lattice: take as many complete words as the
+        // lattice scratch holds — the trie walks then fill all 32 lanes and the per-word overhead is paid once per run.
+        // A bare U+2581 word stays on its own (trailing-space bookkeeping).
+        if (!bare_word) {
+          while (w0 + words_taken < complete) {
+            const int a = sm.wstart[w0 + words_taken], b = sm.wstart[w0 + words_taken + 1];
+            if (b - lws > kUniMaxWord || is_bare(a, b)) break;
+            lwe = b;
+            ++words_taken;
+          }
+        }
         const int len = lwe - lws;
-        const bool bare_word = len == 3 && nb[lws] == 0xE2 && nb[lws + 1] == 0x96 && nb[lws + 2] == 0x81;
         if (len > kUniMaxWord) {
           rs.too_long = true;  // the Viterbi lattice of one word lives in shared memory
         } else {
@@ -1278,7 +1403,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
         rs.trailing_bare = 0;
       }
       __syncwarp();
-      w0 += 1;
+      w0 += words_taken;
     }
   }
 
@@ -1338,7 +1463,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
   constexpr bool HF = MODE == 1;
   const MemoRef memo{memo_table, memo_mask};
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using SM = WarpSmemT<SMALL>;
+  using SM = typename std::conditional<MODE == 2, WarpSmemUniT<SMALL>, WarpSmemT<SMALL>>::type;
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int lane = threadIdx.x;
   const int drain_at = kNBuf - 3 * kFastWin - 8;  // room for one more fast-path step
@@ -1569,6 +1694,8 @@ int SpDeviceModel::upload(const SpTables& t) {
   dev_.unigram = t.unigram ? 1 : 0;
   if (t.unigram) {
     UP(t.piece_score, piece_score);
+    UP(t.uni_trie, utrie);
+    dev_.utrie_mask = (uint32_t)(t.uni_trie.size() / 4) - 1;
     dev_.unk_score = t.unk_score;
     dev_.max_piece_len = t.max_piece_len;
   }
@@ -1668,8 +1795,12 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
         XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, true>), false)
         XLLM_SET_SMEM((sp_encode_kernel<true, false, 1, true>), true)
         XLLM_SET_SMEM((sp_encode_kernel<false, false, 1, true>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, 2, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, 2, false>), false)
+        r = cudaFuncSetAttribute(sp_encode_kernel<true, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(WarpSmemUniT<true>));
+        if (r != cudaSuccess) return r;
+        r = cudaFuncSetAttribute(sp_encode_kernel<false, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(WarpSmemUniT<false>));
+        if (r != cudaSuccess) return r;
 #undef XLLM_SET_SMEM
         return cudaSuccess;
       },
@@ -1700,11 +1831,16 @@ cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_
   const bool hf = dev.split_mode == 3;
   if (dev.unigram) {
     // Viterbi per word from a running score: no word memo (the result depends on the prefix), no long-word pass
+    const size_t usmem = small ? sizeof(WarpSmemUniT<true>) : sizeof(WarpSmemUniT<false>);
+    int uwarps = (int)((227 * 1024) / (usmem + 1024));
+    if (uwarps > 27) uwarps = 27;
+    int ugrid = n_sm * uwarps;
+    if (ugrid > n_req) ugrid = n_req;
     if (small)
-      sp_encode_kernel<true, false, 2, false><<<grid, 32, smem, stream>>>(
+      sp_encode_kernel<true, false, 2, false><<<ugrid, 32, usmem, stream>>>(
           text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, nullptr, 0u);
     else
-      sp_encode_kernel<false, false, 2, false><<<grid, 32, smem, stream>>>(
+      sp_encode_kernel<false, false, 2, false><<<ugrid, 32, usmem, stream>>>(
           text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, nullptr, 0u);
   } else if (use_memo) {
     if (small && hf) { XLLM_LAUNCH_PAIR(true, 1, true) }

@@ -55,6 +55,8 @@ struct SpDev {
   const float* piece_score;
   float unk_score;
   uint32_t max_piece_len;
+  const uint4* utrie;   // byte trie of the pieces: {parent, byte, child, piece id or -1}, parent 0xFFFFFFFF = empty
+  uint32_t utrie_mask;
   uint8_t nfc_check;   // normalizer NFC: a request passes only if every char is NFC-inert (then NFC is the identity)
   uint8_t hf_pattern;  // 1: ByteLevel's own GPT-2 regex, 2: Split(cl100k-family regex) + ByteLevel(use_regex = false)
   uint8_t hf_digits;   // pattern 2: \p{N}{1,hf_digits}

@@ -180,6 +180,15 @@ uint32_t sp_hash_cp(uint32_t cp) {
 
 uint32_t sp_pair_slot_fwd(uint32_t a, uint32_t b, uint32_t n) { return sp_pair_slot(a, b, n); }
 
+// slot of (parent node, byte) in SpTables::uni_trie; the device uses the same arithmetic (sp_encode.cu uni_trie_step)
+uint32_t sp_trie_slot(uint32_t parent, uint32_t byte, uint32_t n_slots) {
+  uint32_t h = (parent * 256u + byte) * 0x9E3779B1u;
+  h ^= h >> 15;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  return h & (n_slots - 1);
+}
+
 int build_bytes_table(const std::vector<std::pair<std::string, int32_t>>& entries, SpTables* t) {
   uint32_t slots = 16;
   while (slots < entries.size() * 2 + 16) slots <<= 1;
@@ -414,6 +423,36 @@ int sp_load_model(const std::string& path_in, SpTables* t) {
     const int rc = build_bytes_table(ent, t);
     if (rc != XLLM_OK) return rc;
     pairs.clear();  // no merges in a Unigram model
+    {
+      // the piece trie upstream walks with Darts (unigram_model.cc trie_->traverse), as (parent, byte) -> child
+      std::unordered_map<uint64_t, uint32_t> child;  // parent << 8 | byte -> node
+      std::vector<int32_t> piece_of(1, -1);
+      for (const auto& e : ent) {
+        uint32_t node = 0;
+        for (unsigned char c : e.first) {
+          const uint64_t k = ((uint64_t)node << 8) | c;
+          auto it = child.find(k);
+          if (it == child.end()) {
+            it = child.emplace(k, (uint32_t)piece_of.size()).first;
+            piece_of.push_back(-1);
+          }
+          node = it->second;
+        }
+        piece_of[node] = e.second;
+      }
+      uint32_t slots = 16;
+      while (slots < child.size() * 2 + 16) slots <<= 1;
+      t->uni_trie.assign((size_t)slots * 4, 0xFFFFFFFFu);
+      for (const auto& kv : child) {
+        const uint32_t parent = (uint32_t)(kv.first >> 8), byte = (uint32_t)(kv.first & 0xFF);
+        uint32_t slot = sp_trie_slot(parent, byte, slots);
+        while (t->uni_trie[(size_t)slot * 4] != 0xFFFFFFFFu) slot = (slot + 1) & (slots - 1);
+        t->uni_trie[(size_t)slot * 4 + 0] = parent;
+        t->uni_trie[(size_t)slot * 4 + 1] = byte;
+        t->uni_trie[(size_t)slot * 4 + 2] = kv.second;
+        t->uni_trie[(size_t)slot * 4 + 3] = (uint32_t)piece_of[kv.second];
+      }
+    }
   }
   t->n_syms = P + (uint32_t)virt.size();
   t->virt_cp = virt;

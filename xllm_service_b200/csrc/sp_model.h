@@ -70,6 +70,9 @@ struct SpTables {
   std::vector<float> piece_score;  // [n_pieces]
   float unk_score = 0.f;           // min NORMAL score - 10 (unigram_model.cc kUnkPenalty)
   uint32_t max_piece_len = 0;      // longest NORMAL piece in bytes
+  // byte trie of the NORMAL pieces as a hash table (parent node, byte) -> (child node, piece id or -1):
+  // 4 x u32 per slot {parent, byte, child, piece}, parent 0xFFFFFFFF = empty; node 0 is the root
+  std::vector<uint32_t> uni_trie;
   bool nfc_check = false;      // normalizer NFC: requests are accepted only when NFC leaves them unchanged
   std::vector<uint16_t> uni_stage1;  // [0x1100]  code point >> 8 -> block
   std::vector<uint8_t> uni_stage2;   // [blocks * 256] class: 0 other, 1 \p{L}, 2 \p{N}, 3 \s
