@@ -26,7 +26,10 @@
 //     unigram_model.cc  Model::EncodeOptimized (UNIGRAM models: Viterbi over the normalized bytes, on-the-fly
 //                    lattice; candidate scores are formed in double and stored as float, the earlier / shorter
 //                    candidate wins ties, a char no piece covers costs min_score - 10)
-// Unsupported (load fails): WORD/CHAR models, USER_DEFINED or UNUSED pieces.
+//     model_interface.cc / normalizer.cc / bpe_model.cc  USER_DEFINED pieces: matched longest-first on the raw
+//                    text (PrefixMatcher), copied through the normalizer verbatim, never merged (BPE: frozen
+//                    symbols) / always preferred (Unigram: score = length * max_score - 0.1)
+// Unsupported (load fails): WORD/CHAR models, UNUSED pieces.
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -119,6 +122,7 @@ struct SpModel {
   // unigram_model.cc: min / max over NORMAL pieces, longest piece in bytes
   float min_score = 0.f, max_score = 0.f;
   size_t max_piece_len = 0;
+  std::vector<std::string_view> user_defined;  // model_interface.cc: the PrefixMatcher's symbols
   std::string error;
 };
 
@@ -174,10 +178,11 @@ bool init_pieces(SpModel* m) {
       m->error = sp.piece + " is already defined.";
       return false;
     }
-    if (sp.type == USER_DEFINED || sp.type == UNUSED) {
-      m->error = "USER_DEFINED / UNUSED pieces are not supported by this oracle";
+    if (sp.type == UNUSED) {
+      m->error = "UNUSED pieces are not supported by this oracle";
       return false;
     }
+    if (sp.type == USER_DEFINED) m->user_defined.push_back(std::string_view(sp.piece));
     if (sp.type == UNKNOWN) {
       if (m->unk_id >= 0) { m->error = "unk is already defined."; return false; }
       m->unk_id = (int)i;
@@ -200,7 +205,8 @@ bool init_pieces(SpModel* m) {
         mn = sp.score < mn ? sp.score : mn;
         mx = sp.score > mx ? sp.score : mx;
       }
-      if (sp.type == NORMAL && sp.piece.size() > m->max_piece_len) m->max_piece_len = sp.piece.size();
+      if ((sp.type == NORMAL || sp.type == USER_DEFINED) && sp.piece.size() > m->max_piece_len)
+        m->max_piece_len = sp.piece.size();
     }
     m->min_score = mn;
     m->max_score = mx;
@@ -256,9 +262,21 @@ inline uint32_t da_value(uint32_t u) { return u & ((1U << 31) - 1); }
 inline uint32_t da_label(uint32_t u) { return u & ((1U << 31) | 0xFF); }
 inline uint32_t da_offset(uint32_t u) { return (u >> 10) << ((u & (1U << 9)) >> 6); }
 
+// normalizer.cc PrefixMatcher::PrefixMatch: the longest user-defined symbol that is a prefix of w (0 = none)
+inline size_t user_prefix_match(const SpModel& m, const char* w, size_t len) {
+  size_t best = 0;
+  for (std::string_view u : m.user_defined)
+    if (u.size() > best && u.size() <= len && memcmp(w, u.data(), u.size()) == 0) best = u.size();
+  return best;
+}
+
 // NormalizePrefix: returns (replacement, consumed bytes)
 inline std::pair<std::string_view, int> normalize_prefix(const SpModel& m, const char* in, size_t len) {
   if (len == 0) return {std::string_view(), 0};
+  if (!m.user_defined.empty()) {  // user-defined symbols pass through verbatim
+    const size_t u = user_prefix_match(m, in, len);
+    if (u) return {std::string_view(in, u), (int)u};
+  }
   size_t longest_length = 0;
   int longest_value = 0;
   if (m.trie) {
@@ -352,6 +370,7 @@ struct PairCmp {
   }
 };
 struct Symbol {
+  bool freeze = false;  // a user-defined symbol: never merged
   int prev, next;
   std::string_view piece;
 };
@@ -407,7 +426,10 @@ void encode_unigram(const SpModel& m, std::string_view normalized, std::vector<i
       auto it = m.pieces_map.find(normalized.substr((size_t)starts_at, (size_t)len));
       if (it == m.pieces_map.end()) continue;
       Node& t = ends_at[(size_t)(starts_at + len)];
-      const double score = (double)m.pieces[(size_t)it->second].score;  // `auto score = cond ? double : float` upstream
+      // `auto score = user_defined ? (length * max_score_ - 0.1) : GetScore(id)` upstream: a double either way
+      const double score = m.pieces[(size_t)it->second].type == USER_DEFINED
+                               ? (double)((float)len * m.max_score) - 0.1
+                               : (double)m.pieces[(size_t)it->second].score;
       const double cand = score + (double)till_here;
       if (t.starts_at == -1 || cand > (double)t.best) {
         t.best = (float)cand;
@@ -451,7 +473,7 @@ void encode(const SpModel& m, std::string_view text, EncodeScratch* sc, std::vec
   symbols.clear();
   std::priority_queue<SymbolPair, std::vector<SymbolPair>, PairCmp> agenda(PairCmp(), std::move(sc->heap));
   auto maybe_add = [&](int left, int right) {
-    if (left == -1 || right == -1) return;
+    if (left == -1 || right == -1 || symbols[left].freeze || symbols[right].freeze) return;
     const std::string_view piece(symbols[left].piece.data(), symbols[left].piece.size() + symbols[right].piece.size());
     auto it = m.pieces_map.find(piece);
     if (it == m.pieces_map.end()) return;
@@ -462,7 +484,9 @@ void encode(const SpModel& m, std::string_view text, EncodeScratch* sc, std::vec
     std::string_view rest = normalized;
     while (!rest.empty()) {
       Symbol s;
-      const size_t mblen = std::min(rest.size(), one_char_len(rest.data()));
+      const size_t ulen = m.user_defined.empty() ? 0 : user_prefix_match(m, rest.data(), rest.size());
+      s.freeze = ulen != 0;
+      const size_t mblen = ulen ? ulen : std::min(rest.size(), one_char_len(rest.data()));
       s.piece = std::string_view(rest.data(), mblen);
       s.prev = index == 0 ? -1 : index - 1;
       rest.remove_prefix(mblen);

@@ -97,3 +97,24 @@ def test_unigram_goldens_and_live(oracle, name):
     for _ in range(1500):
         t = "".join(rnd.choice(alphabet) for _ in range(rnd.randrange(0, 50)))
         assert S.encode(t.encode()).tolist() == sp.encode(t), repr(t)
+
+
+@pytest.mark.parametrize("name", ["sp_userdef_bpe", "sp_userdef_unigram"])
+def test_user_defined_symbols_goldens(oracle, name):
+    """USER_DEFINED pieces (PrefixMatcher: matched on the raw text, passed through the normalizer verbatim, frozen in
+    BPE, always preferred in Unigram): goldens from pip sentencepiece 0.2.1 (make_sp_userdef_fixture.py).  Oracle
+    only — the product refuses these models at load."""
+    import json
+    import xllm_service_b200 as x
+    from xllm_service_b200 import _lib
+    d = os.path.join(HERE, "golden", name)
+    S = oracle.SentencePieceOracle(d)
+    with open(os.path.join(HERE, "golden", "sp_userdef_goldens.json")) as f:
+        cases = json.load(f)["cases"][name]
+    assert len(cases) > 400
+    for c in cases:
+        t = bytes.fromhex(c["text"])
+        assert S.encode(t).tolist() == c["ids"], t[:40]
+    with pytest.raises(x.IngestError) as e:
+        _lib.tokenizer_probe(d)
+    assert e.value.code == -5
