@@ -186,3 +186,16 @@ def test_pipeline_chunk_schedule(tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(HERE, "cpp", "pipeline_schedule_main.cc"), "-o", str(exe)])
     p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-1500:]
+
+
+def test_micro_batcher_threading_against_a_stub(tmp_path):
+    """host/ingest_batcher.h without a GPU: the three C-ABI entry points it calls are stubbed (a prompt "tokenises" to
+    its bytes); 32 threads x 300 requests must each get their own prompt back, be coalesced, never overlap two
+    device calls, and an oversized prompt must be refused rather than queued forever."""
+    import subprocess
+    exe = tmp_path / "batcher_stub_main"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I", os.path.join(os.path.dirname(HERE), "include"),
+                           "-I", os.path.join(os.path.dirname(HERE), "xllm_service_b200", "host"),
+                           os.path.join(HERE, "cpp", "batcher_stub_main.cc"), "-o", str(exe)])
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-1000:]
