@@ -31,3 +31,15 @@ def test_wire_format_against_real_nlohmann(tmp_path):
                            "-o", str(exe)])
     p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-2000:]
+
+
+def test_listing_and_watch_semantics_against_a_stub(tmp_path):
+    """host/index_snapshot.h without a GPU (the index entry points of the C-ABI are an in-memory stub): the PUTs of
+    one etcd response are applied before its DELETEs, the last value of a key wins, unparsable pairs are skipped,
+    and a snapshot reads back into an identical table."""
+    exe = tmp_path / "index_snapshot_stub_main"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "xllm_service_b200", "host"),
+                           os.path.join(HERE, "cpp", "index_snapshot_stub_main.cc"), "-o", str(exe)])
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-1000:]
