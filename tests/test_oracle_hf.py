@@ -82,3 +82,27 @@ def test_cl100k_family_live(oracle, style):
     for _ in range(2500):
         s = "".join(rnd.choice(m.ALPHABET) for _ in range(rnd.randrange(0, 50)))
         assert h.prefix_ids + h.encode(s.encode()).tolist() + h.suffix_ids == tok.encode(s).ids, repr(s)
+
+
+def test_full_unicode_sweep_against_tokenizers_wheel(oracle):
+    """Every code point of planes 0-3 and the assigned ones above (456 K) between letters, after a space, before a
+    digit and after a newline: the class tables (scripts/gen_unicode_classes.py, Unicode 15.0) must split exactly as
+    the regex engine inside pip `tokenizers` does, for both patterns."""
+    tokenizers = pytest.importorskip("tokenizers")
+    import unicodedata
+    for style in ("hf_bpe_8k", "hf_qwen2_style"):
+        h = oracle.HfBpeOracle(os.path.join(HERE, "golden", style))
+        tok = tokenizers.Tokenizer.from_file(os.path.join(HERE, "golden", style, "tokenizer.json"))
+        bad = []
+        for cp in range(0x80, 0x110000):
+            if 0xD800 <= cp < 0xE000:
+                continue
+            ch = chr(cp)
+            if 0x3FFFF < cp < 0xE0000 and unicodedata.category(ch) == "Cn":
+                continue                                    # the empty planes
+            if h.nfc and unicodedata.normalize("NFC", ch) != ch:
+                continue                                    # the wrapper would normalise it away
+            s = "a" + ch + "b " + ch + "1\n" + ch
+            if h.prefix_ids + h.encode(s.encode()).tolist() + h.suffix_ids != tok.encode(s).ids:
+                bad.append(hex(cp))
+        assert not bad, (style, len(bad), bad[:20])
