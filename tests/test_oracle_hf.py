@@ -106,3 +106,31 @@ def test_full_unicode_sweep_against_tokenizers_wheel(oracle):
             if h.prefix_ids + h.encode(s.encode()).tolist() + h.suffix_ids != tok.encode(s).ids:
                 bad.append(hex(cp))
         assert not bad, (style, len(bad), bad[:20])
+
+
+def test_nfc_inert_bit_against_the_crates_nfc():
+    """The device proves "NFC is the identity" from the per-code-point NFC-inert bit of the class table (bit 2).  Every
+    inert code point, alone and in random strings, must be left unchanged by the NFC normalizer of pip `tokenizers`
+    (the crate the reference links)."""
+    tokenizers = pytest.importorskip("tokenizers")
+    import re
+    import unicodedata
+    nfc = tokenizers.normalizers.NFC()
+    with open(os.path.join(HERE, "..", "oracle", "unicode_classes.inc")) as f:
+        txt = f.read()
+    grab = lambda name: [int(x) for x in re.search(name + r"\[\d+\] = \{(.*?)\};", txt, re.S).group(1).replace("\n", "").split(",") if x.strip()]  # noqa: E731
+    s1, s2 = grab("kUniStage1"), grab("kUniStage2")
+    inert = [cp for cp in range(0x80, 0x110000)
+             if not (0xD800 <= cp < 0xE000) and not (s2[s1[cp >> 8] * 256 + (cp & 255)] & 4)]
+    assert len(inert) > 1_000_000
+    for i in range(0, len(inert), 4096):
+        s = "x".join(chr(cp) for cp in inert[i:i + 4096])
+        assert nfc.normalize_str(s) == s, hex(inert[i])
+    rnd = random.Random(3)
+    assigned = [cp for cp in inert if unicodedata.category(chr(cp)) != "Cn"]
+    for _ in range(30000):
+        s = "".join(chr(rnd.choice(assigned)) for _ in range(rnd.randrange(1, 8)))
+        assert nfc.normalize_str(s) == s, [hex(ord(c)) for c in s]
+    # and the usual suspects are NOT inert
+    for cp in (0x301, 0x1161, 0x11A8, 0x212B, 0x340, 0xF900, 0x9BE):
+        assert s2[s1[cp >> 8] * 256 + (cp & 255)] & 4, hex(cp)
