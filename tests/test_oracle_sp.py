@@ -118,3 +118,20 @@ def test_user_defined_symbols_goldens(oracle, name):
     with pytest.raises(x.IngestError) as e:
         _lib.tokenizer_probe(d)
     assert e.value.code == -5
+
+
+def test_full_unicode_sweep_against_the_wheel(oracle):
+    """Every code point (1.1 M) inside a word and after a space through normalisation (the model's nmt_nfkc charsmap),
+    BPE and byte fallback: the oracle must agree with upstream libsentencepiece on all of them."""
+    spm = pytest.importorskip("sentencepiece")
+    d = os.path.join(HERE, "golden", "sp_bpe_8k")
+    sp = spm.SentencePieceProcessor(model_file=os.path.join(d, "tokenizer.model"))
+    S = oracle.SentencePieceOracle(d)
+    bad = []
+    for cp in range(1, 0x110000):
+        if 0xD800 <= cp < 0xE000:
+            continue
+        s = "a" + chr(cp) + "b " + chr(cp)
+        if S.encode(s.encode()).tolist() != sp.encode(s):
+            bad.append(hex(cp))
+    assert not bad, (len(bad), bad[:20])
