@@ -41,10 +41,12 @@ int xllm_ingest_batch(xllm_ingest_t, const xllm_ingest_io* io) {
 
 #include "ingest_batcher.h"
 
-int main() {
-  const int n_threads = 32, per_thread = 300;
-  xllm_host::IngestBatcher batcher(nullptr, 64, 1 << 16, 256, 128, 200, true);
-  if (!batcher.ok()) { printf("alloc failed\n"); return 1; }
+static bool run_config(int n_threads, int per_thread, int max_batch, int max_wait_us) {
+  g_calls = 0;
+  g_max_batch = 0;
+  g_overlap = 0;
+  xllm_host::IngestBatcher batcher(nullptr, max_batch, 1 << 16, 256, 128, max_wait_us, true);
+  if (!batcher.ok()) { printf("alloc failed\n"); return false; }
   std::atomic<int> bad{0};
   std::vector<std::thread> th;
   for (int t = 0; t < n_threads; ++t)
@@ -68,10 +70,17 @@ int main() {
   batcher.submit(std::string((1 << 16) + 1, 'z'), &big);
   const bool big_ok = big.status == XLLM_ERR_CAPACITY;
   const unsigned long long total = (unsigned long long)n_threads * per_thread;
-  printf("requests=%llu batches=%llu calls=%d max_batch=%d overlap=%d bad=%d big_refused=%d\n", total,
-         (unsigned long long)batcher.batches(), g_calls.load(), g_max_batch.load(), g_overlap.load(), bad.load(), (int)big_ok);
-  const bool pass = bad.load() == 0 && g_overlap.load() == 0 && batcher.requests() == total && batcher.batches() < total / 2 &&
-                    g_max_batch.load() <= 64 && g_max_batch.load() > 1 && big_ok;
+  printf("threads=%d max_batch=%d wait=%dus: requests=%llu batches=%llu calls=%d largest=%d overlap=%d bad=%d big_refused=%d\n",
+         n_threads, max_batch, max_wait_us, total, (unsigned long long)batcher.batches(), g_calls.load(), g_max_batch.load(),
+         g_overlap.load(), bad.load(), (int)big_ok);
+  return bad.load() == 0 && g_overlap.load() == 0 && batcher.requests() == total && batcher.batches() < total / 3 &&
+         g_max_batch.load() <= max_batch && g_max_batch.load() > 1 && big_ok;
+}
+
+int main() {
+  bool pass = run_config(32, 300, 64, 200);       // everybody fits one batch
+  pass = run_config(100, 60, 16, 50) && pass;     // far more threads than a batch holds: room waits, two sets busy
+  pass = run_config(48, 100, 8, 0) && pass;       // no wait window at all
   printf(pass ? "OK\n" : "FAILED\n");
   return pass ? 0 : 1;
 }

@@ -190,8 +190,10 @@ def test_pipeline_chunk_schedule(tmp_path):
 
 def test_micro_batcher_threading_against_a_stub(tmp_path):
     """host/ingest_batcher.h without a GPU: the three C-ABI entry points it calls are stubbed (a prompt "tokenises" to
-    its bytes); 32 threads x 300 requests must each get their own prompt back, be coalesced, never overlap two
-    device calls, and an oversized prompt must be refused rather than queued forever."""
+    its bytes); three thread / batch-size / wait-window mixes (32 x 300 requests into batches of 64, 100 threads into
+    batches of 16, 48 threads with no wait window): every caller gets its own prompt back, requests are coalesced
+    into near-full batches while the device is busy, two device calls never overlap, and an oversized prompt is
+    refused rather than queued forever.  (Also run under -fsanitize=thread when the batcher changes.)"""
     import subprocess
     exe = tmp_path / "batcher_stub_main"
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I", os.path.join(os.path.dirname(HERE), "include"),

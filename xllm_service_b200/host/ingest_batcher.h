@@ -7,15 +7,19 @@
 // carries it has gone through the device: the call stays "one request in -> ids + routing out"
 // (SURVEY.md §8f rank 2).  Header-only, depends only on the C-ABI.
 //
-// Policy: the first waiting thread becomes the leader; it collects requests for at most
-// `max_wait_us` or until `max_batch` requests / `max_bytes` text bytes are queued, runs ONE
-// xllm_ingest_batch over page-locked staging buffers, and wakes the others.
+// Policy: the first thread of a batch becomes its leader; it collects requests for at least `max_wait_us` and for as
+// long as the device is still busy with an earlier batch (closing early would only queue a small batch behind it),
+// or until `max_batch` requests / `max_bytes` text bytes are queued; then it copies the prompts into one of TWO
+// page-locked staging sets, runs ONE xllm_ingest_batch (device calls are serialised), hands the results out and
+// wakes its followers.  The next batch assembles meanwhile, and batch k+1 can be on the device while the results
+// of batch k are still being handed out.
 #pragma once
 #include <stdint.h>
 #include <string.h>
 
 #include <chrono>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string_view>
 #include <vector>
@@ -38,17 +42,23 @@ class IngestBatcher {
                 bool want_routing)
       : h_(h), max_batch_(max_batch), max_bytes_(max_bytes), max_tokens_(max_tokens),
         keys_stride_(max_tokens / block_size), max_wait_us_(max_wait_us), want_routing_(want_routing) {
-    ok_ = xllm_host_alloc(reinterpret_cast<void**>(&text_), max_bytes) == XLLM_OK &&
-          xllm_host_alloc(reinterpret_cast<void**>(&offsets_), sizeof(int64_t) * (max_batch + 1)) == XLLM_OK &&
-          xllm_host_alloc(reinterpret_cast<void**>(&ids_), sizeof(int32_t) * (size_t)max_batch * max_tokens) == XLLM_OK &&
-          xllm_host_alloc(reinterpret_cast<void**>(&n_ids_), sizeof(int32_t) * max_batch) == XLLM_OK &&
-          xllm_host_alloc(reinterpret_cast<void**>(&status_), sizeof(int32_t) * max_batch) == XLLM_OK &&
-          xllm_host_alloc(reinterpret_cast<void**>(&match_), sizeof(xllm_match_out) * max_batch) == XLLM_OK &&
-          xllm_host_alloc(reinterpret_cast<void**>(&routing_), sizeof(xllm_routing_out) * max_batch) == XLLM_OK;
+    ok_ = true;
+    for (Staging& s : sets_) {
+      ok_ = ok_ && xllm_host_alloc(reinterpret_cast<void**>(&s.text), max_bytes) == XLLM_OK &&
+            xllm_host_alloc(reinterpret_cast<void**>(&s.offsets), sizeof(int64_t) * (max_batch + 1)) == XLLM_OK &&
+            xllm_host_alloc(reinterpret_cast<void**>(&s.ids), sizeof(int32_t) * (size_t)max_batch * max_tokens) == XLLM_OK &&
+            xllm_host_alloc(reinterpret_cast<void**>(&s.n_ids), sizeof(int32_t) * max_batch) == XLLM_OK &&
+            xllm_host_alloc(reinterpret_cast<void**>(&s.status), sizeof(int32_t) * max_batch) == XLLM_OK &&
+            xllm_host_alloc(reinterpret_cast<void**>(&s.match), sizeof(xllm_match_out) * max_batch) == XLLM_OK &&
+            xllm_host_alloc(reinterpret_cast<void**>(&s.routing), sizeof(xllm_routing_out) * max_batch) == XLLM_OK;
+    }
+    free_sets_ = {0, 1};
   }
   ~IngestBatcher() {
-    xllm_host_free(text_); xllm_host_free(offsets_); xllm_host_free(ids_); xllm_host_free(n_ids_);
-    xllm_host_free(status_); xllm_host_free(match_); xllm_host_free(routing_);
+    for (Staging& s : sets_) {
+      xllm_host_free(s.text); xllm_host_free(s.offsets); xllm_host_free(s.ids); xllm_host_free(s.n_ids);
+      xllm_host_free(s.status); xllm_host_free(s.match); xllm_host_free(s.routing);
+    }
   }
   bool ok() const { return ok_; }
   uint64_t batches() const { return n_batches_; }
@@ -59,19 +69,46 @@ class IngestBatcher {
     std::unique_lock<std::mutex> lk(mu_);
     if (!ok_ || prompt.size() > max_bytes_) { out->status = XLLM_ERR_CAPACITY; return; }
     // wait for room in the batch that is being assembled
-    cv_room_.wait(lk, [&] { return !running_ && (int)pending_.size() < max_batch_ && bytes_ + prompt.size() <= max_bytes_; });
-    const uint64_t my_gen = gen_;
-    pending_.push_back(Item{prompt, out});
+    cv_room_.wait(lk, [&] {
+      return !cur_ || ((int)cur_->items.size() < max_batch_ && bytes_ + prompt.size() <= max_bytes_);
+    });
+    if (!cur_) { cur_ = std::make_shared<Batch>(); bytes_ = 0; }
+    std::shared_ptr<Batch> b = cur_;
+    b->items.push_back(Item{prompt, out});
     bytes_ += prompt.size();
-    if (pending_.size() == 1) {
-      // leader: give followers max_wait_us to join, or go as soon as the batch is full
-      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(max_wait_us_);
-      cv_full_.wait_until(lk, deadline, [&] { return (int)pending_.size() >= max_batch_ || bytes_ >= max_bytes_; });
-      run_batch(lk);
-    } else {
-      if ((int)pending_.size() >= max_batch_ || bytes_ >= max_bytes_) cv_full_.notify_one();
-      cv_done_.wait(lk, [&] { return gen_ != my_gen; });
+    if (b->items.size() > 1) {  // follower
+      if ((int)b->items.size() >= max_batch_ || bytes_ >= max_bytes_) cv_full_.notify_all();
+      cv_done_.wait(lk, [&] { return b->done; });
+      return;
     }
+    // leader: give followers max_wait_us to join — and as long as the device is busy anyway — or go when full
+    auto full = [&] { return (int)b->items.size() >= max_batch_ || bytes_ >= max_bytes_; };
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(max_wait_us_);
+    cv_full_.wait_until(lk, deadline, full);
+    cv_full_.wait(lk, [&] { return full() || (!dev_busy_ && !free_sets_.empty()); });
+    cur_.reset();  // closed: the next batch starts assembling now
+    bytes_ = 0;
+    cv_room_.notify_all();
+    cv_set_.wait(lk, [&] { return !dev_busy_ && !free_sets_.empty(); });
+    const int set = free_sets_.back();
+    free_sets_.pop_back();
+    dev_busy_ = true;
+    lk.unlock();
+    const int rc = device_call(*b, sets_[set]);
+    lk.lock();
+    dev_busy_ = false;  // the next batch may close and go while this one's results are handed out
+    cv_full_.notify_all();
+    cv_set_.notify_all();
+    lk.unlock();
+    hand_out(*b, sets_[set], rc);
+    lk.lock();
+    free_sets_.push_back(set);
+    b->done = true;
+    ++n_batches_;
+    n_requests_ += (uint64_t)b->items.size();
+    cv_done_.notify_all();
+    cv_full_.notify_all();
+    cv_set_.notify_all();
   }
 
  private:
@@ -79,48 +116,54 @@ class IngestBatcher {
     std::string_view prompt;
     IngestResult* out;
   };
-  void run_batch(std::unique_lock<std::mutex>& lk) {
-    std::vector<Item> batch;
-    batch.swap(pending_);
-    bytes_ = 0;
-    running_ = true;
-    lk.unlock();
-    const int n = (int)batch.size();
+  struct Batch {
+    std::vector<Item> items;
+    bool done = false;
+  };
+  struct Staging {  // page-locked buffers of one batch in flight
+    uint8_t* text = nullptr;
+    int64_t* offsets = nullptr;
+    int32_t* ids = nullptr;
+    int32_t* n_ids = nullptr;
+    int32_t* status = nullptr;
+    xllm_match_out* match = nullptr;
+    xllm_routing_out* routing = nullptr;
+  };
+  // copy in + one device call, without the batcher lock (the callers of this batch are all blocked)
+  int device_call(Batch& batch, Staging& s) {
+    const int n = (int)batch.items.size();
     int64_t at = 0;
     for (int i = 0; i < n; ++i) {
-      offsets_[i] = at;
-      memcpy(text_ + at, batch[i].prompt.data(), batch[i].prompt.size());
-      at += (int64_t)batch[i].prompt.size();
+      s.offsets[i] = at;
+      memcpy(s.text + at, batch.items[i].prompt.data(), batch.items[i].prompt.size());
+      at += (int64_t)batch.items[i].prompt.size();
     }
-    offsets_[n] = at;
+    s.offsets[n] = at;
     xllm_ingest_io io;
     memset(&io, 0, sizeof(io));
     io.n_req = n;
-    io.text = text_;
-    io.offsets = offsets_;
-    io.ids = ids_;
+    io.text = s.text;
+    io.offsets = s.offsets;
+    io.ids = s.ids;
     io.ids_stride = max_tokens_;
-    io.n_ids = n_ids_;
-    io.status = status_;
-    io.match = want_routing_ ? match_ : nullptr;
-    io.routing = want_routing_ ? routing_ : nullptr;
-    const int rc = xllm_ingest_batch(h_, &io);
+    io.n_ids = s.n_ids;
+    io.status = s.status;
+    io.match = want_routing_ ? s.match : nullptr;
+    io.routing = want_routing_ ? s.routing : nullptr;
+    std::lock_guard<std::mutex> dev(dev_mu_);  // one launch at a time per handle (dev_busy_ already ensures it)
+    return xllm_ingest_batch(h_, &io);
+  }
+  void hand_out(Batch& batch, Staging& s, int rc) {
+    const int n = (int)batch.items.size();
     for (int i = 0; i < n; ++i) {
-      IngestResult* o = batch[i].out;
-      o->status = rc != XLLM_OK ? rc : status_[i];
-      if (rc == XLLM_OK && status_[i] >= 0) {
-        const int32_t keep = n_ids_[i] < max_tokens_ ? n_ids_[i] : max_tokens_;
-        o->token_ids.assign(ids_ + (size_t)i * max_tokens_, ids_ + (size_t)i * max_tokens_ + keep);
-        if (want_routing_) { o->match = match_[i]; o->routing = routing_[i]; }
+      IngestResult* o = batch.items[i].out;
+      o->status = rc != XLLM_OK ? rc : s.status[i];
+      if (rc == XLLM_OK && s.status[i] >= 0) {
+        const int32_t keep = s.n_ids[i] < max_tokens_ ? s.n_ids[i] : max_tokens_;
+        o->token_ids.assign(s.ids + (size_t)i * max_tokens_, s.ids + (size_t)i * max_tokens_ + keep);
+        if (want_routing_) { o->match = s.match[i]; o->routing = s.routing[i]; }
       }
     }
-    lk.lock();
-    running_ = false;
-    ++gen_;
-    ++n_batches_;
-    n_requests_ += (uint64_t)n;
-    cv_done_.notify_all();
-    cv_room_.notify_all();
   }
 
   xllm_ingest_t h_;
@@ -131,19 +174,14 @@ class IngestBatcher {
   const int max_wait_us_;
   const bool want_routing_;
   bool ok_ = false;
-  uint8_t* text_ = nullptr;
-  int64_t* offsets_ = nullptr;
-  int32_t* ids_ = nullptr;
-  int32_t* n_ids_ = nullptr;
-  int32_t* status_ = nullptr;
-  xllm_match_out* match_ = nullptr;
-  xllm_routing_out* routing_ = nullptr;
-  std::mutex mu_;
-  std::condition_variable cv_room_, cv_full_, cv_done_;
-  std::vector<Item> pending_;
-  size_t bytes_ = 0;
-  bool running_ = false;
-  uint64_t gen_ = 0, n_batches_ = 0, n_requests_ = 0;
+  Staging sets_[2];
+  std::vector<int> free_sets_;
+  std::mutex mu_, dev_mu_;
+  std::condition_variable cv_room_, cv_full_, cv_done_, cv_set_;
+  bool dev_busy_ = false;       // a batch is between copy-in and the return of its device call
+  std::shared_ptr<Batch> cur_;  // the batch being assembled (null: none)
+  size_t bytes_ = 0;            // text bytes queued in cur_
+  uint64_t n_batches_ = 0, n_requests_ = 0;
 };
 
 }  // namespace xllm_host
