@@ -1,6 +1,6 @@
 # Builds the product library (CUDA, sm_100a) and the test oracle (CPU).
 #   make            -> xllm_service_b200/libxllm_ingest.so + oracle/liboracle.so
-#   make lib | oracle | clean
+#   make lib | oracle | ref | clean      (ref = oracle/_ref/libxllm_ref.so, the reference's own files; needs /root/reference)
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 CC        ?= gcc
@@ -19,7 +19,9 @@ ORACLE_C    := $(wildcard oracle/*.c)
 ORACLE_CC   := $(wildcard oracle/*.cc)
 ORACLE_OBJS := $(patsubst oracle/%.c,build/oracle/%.c.o,$(ORACLE_C)) $(patsubst oracle/%.cc,build/oracle/%.cc.o,$(ORACLE_CC))
 
-all: lib oracle
+all: lib oracle ref
+ref:
+	@bash oracle/build_ref.sh
 lib: $(LIB)
 oracle: $(ORACLE_LIB)
 
@@ -43,4 +45,4 @@ $(ORACLE_LIB): $(ORACLE_OBJS)
 
 clean:
 	rm -rf build $(LIB) $(ORACLE_LIB)
-.PHONY: all lib oracle clean
+.PHONY: all lib oracle ref clean
