@@ -32,7 +32,7 @@ build/%.cc.o: $(CSRC)/%.cc $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -x cu -c $< -o $@
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -ldl
 
 build/oracle/%.c.o: oracle/%.c
 	@mkdir -p build/oracle

@@ -62,10 +62,32 @@ typedef struct {
   int32_t max_batch;          /* max requests per batch call (0 => 65536) */
   int64_t max_batch_bytes;    /* max total prompt bytes per batch call (0 => 64 MiB * ...) */
   int32_t max_tokens;         /* max token ids per request (0 => 8192) */
-  int64_t index_capacity;     /* max distinct block keys in the prefix index (0 => no index) */
+  int64_t index_capacity;     /* max distinct block keys in the prefix index (0 => no index); with a sharded index:
+                                 keys held by THIS GPU's shard */
+  /* ---- hash-range-sharded prefix index over the GPUs of one box (all three zero / NULL => not sharded).  One
+   * process per GPU; the GPU owning a block key is low64(key) >> (64 - log2(shard_world)); one NCCL all-to-all of
+   * (hash128, request, block) tuples per batch and one of tier masks back (csrc/shard_exchange.cuh). */
+  int32_t shard_world;        /* GPUs the index is split over: a power of two in [2, 32] (0 or 1 => not sharded) */
+  int32_t shard_rank;         /* this process's rank in [0, shard_world); `device` above is its GPU */
+  const void* nccl_unique_id; /* the 128 bytes xllm_shard_unique_id() produced on one rank, passed to every rank */
 } xllm_ingest_config;
 
 const char* xllm_last_error(void);
+/* Rendezvous for a sharded index: call on ONE rank, hand the 128 bytes to all ranks (over whatever channel the
+ * service already has: etcd, the launcher's env, torch.distributed in bench.py), then every rank calls
+ * xllm_ingest_create with them — that call is collective (ncclCommInitRank).  NCCL is loaded with
+ * dlopen("libnccl.so.2") on first use; XLLM_ERR_UNSUPPORTED when it is not installed. */
+int xllm_shard_unique_id(void* out128);
+/* Owner rank of a block key among `shard_world` GPUs (host-only helper: routing events, tests). */
+int xllm_shard_owner(const uint8_t* key16, int32_t shard_world);
+/* Device time of the last sharded match round on this handle, milliseconds: bucketing, exchange out, owner-side
+ * probe, exchange back, first-miss scan + routing; and the tuples one message can carry / overflow repeats so far. */
+typedef struct {
+  float bucket_ms, exchange_out_ms, probe_ms, exchange_back_ms, score_ms;
+  int64_t bucket_capacity;
+  int64_t overflow_rounds;
+} xllm_shard_stats;
+int xllm_shard_last_stats(xllm_ingest_t h, xllm_shard_stats* out);
 int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out);
 int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out);
 void xllm_ingest_destroy(xllm_ingest_t h);
@@ -104,6 +126,8 @@ int xllm_xxh3_128bits_hash(xllm_ingest_t h, const uint8_t* prev16, const int32_t
  * xllm_index_put / _erase = the replica path update_kvcache PUT / DELETE (:133-175); staged.
  * xllm_index_publish = upload_kvcache's local effect (:227-247): replays the staged events on the
  *                      device table (entries left empty are erased) and makes them visible to match.
+ * With a sharded index every rank is given the same events; each keeps the keys it owns and ignores the rest
+ * (xllm_index_get / _export / _size then report this rank's shard).
  */
 int xllm_index_apply(xllm_ingest_t h, int32_t instance_id, const uint8_t* stored, size_t n_stored,
                      const uint8_t* offload, size_t n_offload, const uint8_t* removed, size_t n_removed);
@@ -120,6 +144,13 @@ int xllm_index_put_bulk(xllm_ingest_t h, int64_t n, const uint8_t* keys /*[n][16
 int xllm_index_export(xllm_ingest_t h, int64_t capacity, uint8_t* keys /*[capacity][16]*/, uint64_t* hbm_masks,
                       uint64_t* dram_masks, uint64_t* ssd_masks, int64_t* n_keys);
 int xllm_index_publish(xllm_ingest_t h);
+/* An instance left the cluster (InstanceMgr::deregister_instance): clears its bit in every entry of the published
+ * index at once — the sum of the removed_cache events the reference would need for each of its blocks — erasing
+ * entries left empty, so the id can be handed to a new instance.  Staged events are not touched. */
+int xllm_index_clear_instance(xllm_ingest_t h, int32_t instance_id);
+/* Table health as of the last publish: live keys, tombstones (erased slots not yet reclaimed) and how many times the
+ * table was rebuilt in place (publish does that when live + tombstones exceed 70 % of the slots). */
+int xllm_index_stats(xllm_ingest_t h, int64_t* live_keys, int64_t* tombstones, int64_t* rebuilds);
 int xllm_index_size(xllm_ingest_t h, int64_t* n_keys);
 int xllm_index_get(xllm_ingest_t h, const uint8_t* key16, uint64_t masks3[3], int32_t* found);
 
@@ -152,7 +183,9 @@ typedef struct {
 } xllm_routing_out;
 
 /* keys: the block keys of all requests; request r owns n_blocks[r] keys starting at key_start[r].
- * match / routing may be NULL.  Host-pointer and device-pointer forms. */
+ * match / routing may be NULL.  Host-pointer and device-pointer forms.
+ * With a sharded index these two calls and xllm_ingest_batch (when match / routing is requested) are COLLECTIVE: every
+ * rank must make the call once per batch (each with its own requests, n_req may be 0); they synchronise the stream. */
 int xllm_match_route(xllm_ingest_t h, int32_t n_req, const uint8_t* keys, int64_t n_keys_total,
                      const int64_t* key_start, const int32_t* n_blocks, xllm_match_out* match,
                      xllm_routing_out* routing);

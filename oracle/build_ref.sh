@@ -15,7 +15,11 @@ JSON_INC="$SITE/include/cudnn_frontend/thirdparty"       # nlohmann/json.hpp
 [ -f "$XXH_INC/arrow/vendored/xxhash/xxhash.h" ] || { echo "build_ref: vendored xxhash.h not found"; exit 1; }
 [ -f "$JSON_INC/nlohmann/json.hpp" ] || { echo "build_ref: nlohmann/json.hpp not found"; exit 1; }
 mkdir -p "$OUT/obj"
-if [ -f "$OUT/libxllm_ref.so" ] && [ -z "$(find "$HERE/ref_shim" "$HERE/build_ref.sh" -newer "$OUT/libxllm_ref.so" -print -quit)" ]; then
+ROOT="$(dirname "$HERE")"
+SEAMS_SRCS=("$ROOT/tests/cpp/reference_seams_main.cc" "$ROOT/xllm_service_b200/host" "$ROOT/include")
+if [ -f "$OUT/libxllm_ref.so" ] && [ -f "$OUT/reference_seams_test" ] &&
+   [ -z "$(find "$HERE/ref_shim" "$HERE/build_ref.sh" "${SEAMS_SRCS[@]}" -newer "$OUT/reference_seams_test" -print -quit)" ] &&
+   [ -z "$(find "$HERE/ref_shim" "$HERE/build_ref.sh" -newer "$OUT/libxllm_ref.so" -print -quit)" ]; then
   exit 0
 fi
 CXXFLAGS="-O2 -std=c++17 -fPIC -w -fno-access-control -I$HERE/ref_shim/stubs -I$REF -I$XXH_INC -I$JSON_INC"
@@ -52,5 +56,18 @@ for s in "${SRCS[@]}"; do
 done
 wait
 g++ -shared -o "$OUT/libxllm_ref.so" "${OBJS[@]}" -lpthread
-rm -rf "$OUT/obj"
 echo "build_ref: built $OUT/libxllm_ref.so"
+# The boundary test: the reference's tokenizer/fast_tokenizer.cpp (unmodified) + host/reference_adaptors.h compiled
+# against the reference's real tokenizer.h / slice.h / types.h / loadbalance_policy.h, linked with the product
+# library and with libxllm_ref.so (the reference's GlobalKVCacheMgr / CacheAwareRouting to compare against).
+if [ -f "$ROOT/xllm_service_b200/libxllm_ingest.so" ]; then
+  g++ $CXXFLAGS -I"$REF/tokenizer" -I"$ROOT/xllm_service_b200/host" -I"$ROOT/include" \
+      "$ROOT/tests/cpp/reference_seams_main.cc" "$REF/tokenizer/fast_tokenizer.cpp" \
+      -o "$OUT/reference_seams_test" \
+      -L"$OUT" -lxllm_ref -L"$ROOT/xllm_service_b200" -lxllm_ingest -lpthread \
+      -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../xllm_service_b200' -Wl,--allow-shlib-undefined
+  echo "build_ref: built $OUT/reference_seams_test"
+else
+  echo "build_ref: libxllm_ingest.so not built yet; skipping reference_seams_test (run make lib first)"
+fi
+rm -rf "$OUT/obj"

@@ -10,8 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "sweep: exhaustive device-vs-oracle sweeps, run on demand on a GPU box with "
-                                       "-m sweep (skipped without CUDA; not part of -m gpu)")
+    config.addinivalue_line("markers", "sweep: exhaustive device-vs-oracle Unicode sweeps (also marked gpu; -m sweep selects "
+                                       "them alone)")
 
 
 @pytest.fixture(scope="session")

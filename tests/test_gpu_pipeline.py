@@ -90,3 +90,42 @@ def test_default_pipeline_any_batch_size(oracle, n_req):
             assert (out["ids"][r, :ref_n[r]] == ref_ids[r, :ref_n[r]]).all(), r
     finally:
         h.close()
+
+
+def test_short_rows_still_get_a_routing_decision(oracle):
+    """ids_stride < block_size with match / routing requested: no request has a full block, so the reference's match
+    leaves OverlapScores untouched (global_kvcache_mgr.cpp:77-79) and routing takes get_load_metrics' least-loaded
+    fallback (instance_mgr.cpp:312-358).  The batch call must return exactly that — zeroed match rows and a real
+    decision — not whatever the output buffers held before."""
+    import xllm_service_b200 as x
+    from xllm_service_b200 import workload
+    h = x.Ingest(tokenizer_path=MODEL_DIR, index_capacity=1024)
+    P = oracle.PrefixOracle(NAMES)
+    for i, n in enumerate(NAMES):
+        t = 2 if i % 2 else 1
+        P.set_instance(n, t)
+        P.set_load(n, i % 5, (i * 7 % 16) / 16.0)
+        h.set_instance(i, t)
+        h.set_load_metrics(i, i % 5, (i * 7 % 16) / 16.0)
+    texts = [s.encode() for s in workload.sentences(50, (1, 8), seed=3)] + [b""]
+    b = workload.pack_prompts(texts)
+    n = b.n
+    ids = np.zeros((n, 64), np.int32)
+    n_ids = np.zeros(n, np.int32)
+    status = np.zeros(n, np.int32)
+    match = np.full(n, 0xAB, dtype=np.uint8).repeat(400).view(x._lib.MATCH_DTYPE)    # poisoned output buffers
+    routing = np.full(n * 20, 0xCD, dtype=np.uint8).view(x._lib.ROUTING_DTYPE)
+    h.ingest_batch_ptrs(n, b.text.ctypes.data, b.offsets.ctypes.data, ids.ctypes.data, 64, n_ids.ctypes.data,
+                        status.ctypes.data, 0, 0, match.ctypes.data, routing.ctypes.data)
+    chunks, launches = h.last_batch_stats()
+    assert launches == 4 * chunks      # encode x2 + row prep + match/route, no hash
+    want = P.route(np.zeros(0, np.int32))
+    assert want["ok"]
+    for r in range(n):
+        assert match["max_block_num"][r] == 0 and match["max_matched_block_num"][r] == 0 and match["instances"][r] == 0
+        assert not match["hbm"][r].any() and not match["dram"][r].any() and not match["ssd"][r].any()
+        assert routing["ok"][r] == 1
+        assert routing["prefill_score"][r] == np.float32(want["prefill_score"])
+        assert (want["prefill_argmax"] >> int(routing["prefill_id"][r])) & 1
+        assert (want["decode_argmax"] >> int(routing["decode_id"][r])) & 1
+    h.close()

@@ -1,12 +1,15 @@
-"""Exhaustive device-vs-oracle sweeps over every Unicode code point (run on demand: `pytest -m sweep` on a GPU box;
-written after the round's GPU budget was spent, so NOT part of `-m gpu`; skipped where there is no CUDA device).
-The oracles themselves are swept against the upstream wheels on CPU (tests/test_oracle_sp.py, tests/test_oracle_hf.py)."""
+"""Exhaustive device-vs-oracle sweeps over every Unicode code point: all 1.1 M scalar values, each in five contexts
+("a<c>b <c>1\n<c>"), through the CUDA normaliser / pre-tokenizers / merge kernels against the CPU oracle — 5 models,
+~30 s on a B200, part of `-m gpu` (also selectable alone with `-m sweep`).  The oracles themselves are swept against
+the upstream wheels on CPU (tests/test_oracle_sp.py, tests/test_oracle_hf.py), so this is what separates the device
+tables from the oracle's although both are generated from one Unicode data file."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.sweep
+pytestmark = [pytest.mark.sweep, pytest.mark.gpu]
+STRIDE = 256   # U+FDFA alone normalises to 18 chars; five copies with byte fallback need > 64 ids
 HERE = os.path.dirname(__file__)
 
 
@@ -35,7 +38,7 @@ def _run(model_dir, oracle_encode, accept_status=(0,)):
     b = workload.pack_prompts(texts)
     h = x.Ingest(tokenizer_path=model_dir)
     try:
-        ids, n_ids, status = h.encode_batch(b.text, b.offsets, 64)
+        ids, n_ids, status = h.encode_batch(b.text, b.offsets, STRIDE)
     finally:
         h.close()
     bad = []
@@ -73,7 +76,7 @@ def test_hf_every_code_point(oracle, name):
     b = workload.pack_prompts(texts)
     h = x.Ingest(tokenizer_path=d)
     try:
-        ids, n_ids, status = h.encode_batch(b.text, b.offsets, 64)
+        ids, n_ids, status = h.encode_batch(b.text, b.offsets, STRIDE)
     finally:
         h.close()
     bad = []

@@ -30,7 +30,17 @@ class Config(ctypes.Structure):
         ("max_batch_bytes", ctypes.c_int64),
         ("max_tokens", ctypes.c_int32),
         ("index_capacity", ctypes.c_int64),
+        ("shard_world", ctypes.c_int32),
+        ("shard_rank", ctypes.c_int32),
+        ("nccl_unique_id", ctypes.c_void_p),
     ]
+
+
+class ShardStats(ctypes.Structure):
+    """xllm_shard_stats (include/xllm_ingest.h)."""
+    _fields_ = [("bucket_ms", ctypes.c_float), ("exchange_out_ms", ctypes.c_float), ("probe_ms", ctypes.c_float),
+                ("exchange_back_ms", ctypes.c_float), ("score_ms", ctypes.c_float),
+                ("bucket_capacity", ctypes.c_int64), ("overflow_rounds", ctypes.c_int64)]
 
 
 class TokenizerInfo(ctypes.Structure):
@@ -73,6 +83,9 @@ def _declare(L):
     L.xllm_last_error.restype = ctypes.c_char_p
     L.xllm_last_error.argtypes = []
     L.xllm_ingest_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(_VP)]
+    L.xllm_shard_unique_id.argtypes = [_VP]
+    L.xllm_shard_owner.argtypes = [_VP, ctypes.c_int32]
+    L.xllm_shard_last_stats.argtypes = [_VP, ctypes.POINTER(ShardStats)]
     L.xllm_ingest_clone.argtypes = [_VP, ctypes.POINTER(_VP)]
     L.xllm_ingest_destroy.argtypes = [_VP]
     L.xllm_ingest_destroy.restype = None
@@ -87,6 +100,8 @@ def _declare(L):
     L.xllm_index_erase.argtypes = [_VP, _VP]
     L.xllm_index_publish.argtypes = [_VP]
     L.xllm_index_size.argtypes = [_VP, ctypes.POINTER(ctypes.c_int64)]
+    L.xllm_index_clear_instance.argtypes = [_VP, ctypes.c_int32]
+    L.xllm_index_stats.argtypes = [_VP] + [ctypes.POINTER(ctypes.c_int64)] * 3
     L.xllm_index_get.argtypes = [_VP, _VP, _VP, ctypes.POINTER(ctypes.c_int32)]
     L.xllm_set_instance.argtypes = [_VP, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
     L.xllm_set_load_metrics.argtypes = [_VP, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, ctypes.c_float]

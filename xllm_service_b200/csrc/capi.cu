@@ -147,6 +147,24 @@ int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
       xllm_ingest_destroy(h);
       return rc;
     }
+    h->index_read_ev = h->index->register_reader();
+  }
+  if (cfg->shard_world > 1) {
+    if (!h->index) {
+      set_last_error("a sharded index needs index_capacity > 0 (keys held by this GPU's shard)");
+      xllm_ingest_destroy(h);
+      return XLLM_ERR_INVALID_ARG;
+    }
+    // tuples one message can carry: 1.5x the mean bucket of the largest batch the config describes.  Every rank
+    // passes the same config, so every rank derives the same capacity (shard_exchange.cuh).
+    const int64_t blocks = (h->max_tokens + bs - 1) / bs;
+    const int64_t cap = (int64_t)h->max_batch * blocks * 3 / (2 * (int64_t)cfg->shard_world) + 1024;
+    h->shard = std::make_shared<ShardExchange>();
+    const int rc = h->shard->init(cfg->shard_world, cfg->shard_rank, cfg->nccl_unique_id, h->device, cap);
+    if (rc != XLLM_OK) {
+      xllm_ingest_destroy(h);
+      return rc;
+    }
   }
   *out = h;
   return XLLM_OK;
@@ -173,7 +191,9 @@ int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out) {
   (*out)->memo_slots = src->memo_slots;
   (*out)->pipe_slots = src->pipe_slots;
   (*out)->tokenizer_path = src->tokenizer_path;
+  (*out)->shard = src->shard;
   (*out)->index = src->index;
+  if (src->index) (*out)->index_read_ev = src->index->register_reader();
   (*out)->index_mu = src->index_mu;
   (*out)->inst_host = src->inst_host;
   return XLLM_OK;
@@ -183,6 +203,10 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int k = 0; k < 3; ++k)
+    if (h->pipe_stream[k]) cudaStreamSynchronize(h->pipe_stream[k]);
+  if (h->index && h->index_read_ev) h->index->unregister_reader(h->index_read_ev);
+  h->index_read_ev = nullptr;
   h->d_tokens.release();
   h->d_tok_start.release();
   h->d_n_tok.release();
@@ -199,6 +223,11 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   h->d_match.release();
   h->d_routing.release();
   h->d_nblk.release();
+  h->d_all_keys.release();
+  h->d_all_key_start.release();
+  h->d_all_n_blocks.release();
+  h->d_all_match.release();
+  h->d_all_routing.release();
   if (h->d_inst) cudaFree(h->d_inst);
   for (int i = 0; i < kPipeSlots; ++i) h->pipe[i].release();
   for (int k = 0; k < 3; ++k)
@@ -294,6 +323,40 @@ int xllm_xxh3_128bits_hash(xllm_ingest_t h, const uint8_t* prev16, const int32_t
 }
 
 // ------------------------------------------------------------------ prefix index
+static inline bool owns_key(xllm_ingest_t h, const uint8_t* key16) {
+  if (!h->shard) return true;
+  uint64_t lo;
+  memcpy(&lo, key16, 8);
+  return h->shard->owns(lo);
+}
+int xllm_shard_unique_id(void* out128) {
+  if (!out128) return XLLM_ERR_INVALID_ARG;
+  return ShardExchange::unique_id(out128);
+}
+int xllm_shard_owner(const uint8_t* key16, int32_t shard_world) {
+  if (!key16 || shard_world < 1 || (shard_world & (shard_world - 1)) != 0) return XLLM_ERR_INVALID_ARG;
+  int l2 = 0;
+  while ((1 << l2) < shard_world) ++l2;
+  uint64_t lo;
+  memcpy(&lo, key16, 8);
+  return shard_owner_of(lo, l2);
+}
+int xllm_shard_last_stats(xllm_ingest_t h, xllm_shard_stats* out) {
+  if (!h || !out) return XLLM_ERR_INVALID_ARG;
+  if (!h->shard) {
+    set_last_error("this handle's index is not sharded");
+    return XLLM_ERR_UNSUPPORTED;
+  }
+  const ShardTimes& t = h->shard->last_times();
+  out->bucket_ms = t.bucket_ms;
+  out->exchange_out_ms = t.exchange_out_ms;
+  out->probe_ms = t.probe_ms;
+  out->exchange_back_ms = t.exchange_back_ms;
+  out->score_ms = t.score_ms;
+  out->bucket_capacity = h->shard->bucket_capacity();
+  out->overflow_rounds = h->shard->overflow_rounds();
+  return XLLM_OK;
+}
 static int need_index(xllm_ingest_t h) {
   if (!h) {
     set_last_error("null handle");
@@ -315,6 +378,17 @@ int xllm_index_apply(xllm_ingest_t h, int32_t instance_id, const uint8_t* stored
     return XLLM_ERR_INVALID_ARG;
   }
   std::lock_guard<std::mutex> lock(*h->index_mu);
+  if (h->shard) {   // this rank keeps the keys of its own hash range
+    std::vector<uint8_t> mine[3];
+    const uint8_t* src[3] = {stored, offload, removed};
+    const size_t cnt[3] = {n_stored, n_offload, n_removed};
+    for (int t = 0; t < 3; ++t)
+      for (size_t i = 0; i < cnt[t]; ++i)
+        if (owns_key(h, src[t] + 16 * i)) mine[t].insert(mine[t].end(), src[t] + 16 * i, src[t] + 16 * i + 16);
+    h->index->record(instance_id, mine[0].data(), mine[0].size() / 16, mine[1].data(), mine[1].size() / 16,
+                     mine[2].data(), mine[2].size() / 16);
+    return XLLM_OK;
+  }
   h->index->record(instance_id, stored, n_stored, offload, n_offload, removed, n_removed);
   return XLLM_OK;
 }
@@ -322,6 +396,7 @@ int xllm_index_put(xllm_ingest_t h, const uint8_t* key16, uint64_t hbm, uint64_t
   XLLM_TRY(need_index(h));
   if (!key16) return XLLM_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(*h->index_mu);
+  if (!owns_key(h, key16)) return XLLM_OK;
   h->index->put(key16, hbm, dram, ssd);
   return XLLM_OK;
 }
@@ -330,7 +405,8 @@ int xllm_index_put_bulk(xllm_ingest_t h, int64_t n, const uint8_t* keys, const u
   XLLM_TRY(need_index(h));
   if (n < 0 || (n > 0 && (!keys || !hbm || !dram || !ssd))) return XLLM_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(*h->index_mu);
-  for (int64_t i = 0; i < n; ++i) h->index->put(keys + 16 * i, hbm[i], dram[i], ssd[i]);
+  for (int64_t i = 0; i < n; ++i)
+    if (owns_key(h, keys + 16 * i)) h->index->put(keys + 16 * i, hbm[i], dram[i], ssd[i]);
   return XLLM_OK;
 }
 int xllm_index_export(xllm_ingest_t h, int64_t capacity, uint8_t* keys, uint64_t* hbm, uint64_t* dram, uint64_t* ssd,
@@ -346,6 +422,7 @@ int xllm_index_erase(xllm_ingest_t h, const uint8_t* key16) {
   XLLM_TRY(need_index(h));
   if (!key16) return XLLM_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(*h->index_mu);
+  if (!owns_key(h, key16)) return XLLM_OK;
   h->index->erase(key16);
   return XLLM_OK;
 }
@@ -355,6 +432,25 @@ int xllm_index_publish(xllm_ingest_t h) {
   std::lock_guard<std::mutex> lock2(*h->index_mu);
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
   return h->index->publish(h->stream);
+}
+int xllm_index_clear_instance(xllm_ingest_t h, int32_t instance_id) {
+  XLLM_TRY(need_index(h));
+  if (instance_id < 0 || instance_id >= kMaxInstances) {
+    set_last_error("xllm_index_clear_instance: invalid instance id %d", instance_id);
+    return XLLM_ERR_INVALID_ARG;
+  }
+  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::mutex> lock2(*h->index_mu);
+  XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  return h->index->clear_instance(h->stream, instance_id);
+}
+int xllm_index_stats(xllm_ingest_t h, int64_t* live_keys, int64_t* tombstones, int64_t* rebuilds) {
+  XLLM_TRY(need_index(h));
+  std::lock_guard<std::mutex> lock2(*h->index_mu);
+  if (live_keys) *live_keys = h->index->live_keys();
+  if (tombstones) *tombstones = h->index->tombstones();
+  if (rebuilds) *rebuilds = h->index->rebuilds();
+  return XLLM_OK;
 }
 int xllm_index_size(xllm_ingest_t h, int64_t* n_keys) {
   XLLM_TRY(need_index(h));
@@ -418,7 +514,10 @@ int xllm_index_probe_device(xllm_ingest_t h, const uint8_t* d_keys, int64_t n_ke
   std::lock_guard<std::mutex> lock(h->mu);
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
-  XLLM_CUDA_TRY(h->index->probe(d_keys, n_keys, d_masks3, s));
+  h->index->begin_read();
+  const cudaError_t e = h->index->probe(d_keys, n_keys, d_masks3, s);
+  h->index->end_read(h->index_read_ev, s);
+  XLLM_CUDA_TRY(e);
   return XLLM_OK;
 }
 
@@ -441,15 +540,21 @@ int xllm_match_route_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_key
   XLLM_TRY(need_index(h));
   if (n_req < 0 || n_keys_total < 0 || (n_req > 0 && (!d_key_start || !d_n_blocks)) || (n_keys_total > 0 && !d_keys))
     return XLLM_ERR_INVALID_ARG;
-  if (n_req == 0) return XLLM_OK;
+  if (n_req == 0 && !h->shard) return XLLM_OK;   // a sharded round is collective: an empty rank still takes part
   std::lock_guard<std::mutex> lock(h->mu);
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
-  XLLM_TRY(h->d_masks.reserve((size_t)n_keys_total * 24 + 64));
-  XLLM_TRY(sync_instances(h, s));
-  XLLM_CUDA_TRY(h->index->probe(d_keys, n_keys_total, h->d_masks.as<uint64_t>(), s));
-  XLLM_CUDA_TRY(score_route_launch(h->d_masks.as<uint64_t>(), d_key_start, d_n_blocks, n_req, h->d_inst,
-                                   reinterpret_cast<MatchOut*>(d_match), reinterpret_cast<RoutingOut*>(d_routing), s));
+  XLLM_TRY(sync_instances(h, s));   // takes index_mu: before begin_read, never inside (publish: index_mu -> writer lock)
+  if (h->shard)   // collective; synchronises `s`
+    return h->shard->match_route(*h->index, h->index_read_ev, d_keys, d_key_start, d_n_blocks, n_req, n_keys_total,
+                                 h->d_inst, reinterpret_cast<MatchOut*>(d_match),
+                                 reinterpret_cast<RoutingOut*>(d_routing), s);
+  h->index->begin_read();
+  const cudaError_t e = h->index->match_route(d_keys, d_key_start, d_n_blocks, n_req, h->d_inst,
+                                              reinterpret_cast<MatchOut*>(d_match),
+                                              reinterpret_cast<RoutingOut*>(d_routing), s);
+  h->index->end_read(h->index_read_ev, s);
+  XLLM_CUDA_TRY(e);
   return XLLM_OK;
 }
 
@@ -459,7 +564,7 @@ int xllm_match_route(xllm_ingest_t h, int32_t n_req, const uint8_t* keys, int64_
   XLLM_TRY(need_index(h));
   if (n_req < 0 || n_keys_total < 0 || (n_req > 0 && (!key_start || !n_blocks)) || (n_keys_total > 0 && !keys))
     return XLLM_ERR_INVALID_ARG;
-  if (n_req == 0) return XLLM_OK;
+  if (n_req == 0 && !h->shard) return XLLM_OK;   // a sharded round is collective: an empty rank still takes part
   for (int32_t r = 0; r < n_req; ++r)
     if (n_blocks[r] < 0 || n_blocks[r] > 65535 || key_start[r] < 0 || key_start[r] + n_blocks[r] > n_keys_total) {
       set_last_error("xllm_match_route: request %d out of bounds", r);
@@ -469,22 +574,32 @@ int xllm_match_route(xllm_ingest_t h, int32_t n_req, const uint8_t* keys, int64_
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   XLLM_TRY(h->d_keys.reserve((size_t)n_keys_total * 16 + 64));
-  XLLM_TRY(h->d_key_start.reserve((size_t)n_req * 8));
-  XLLM_TRY(h->d_nblk.reserve((size_t)n_req * 4));
-  XLLM_TRY(h->d_masks.reserve((size_t)n_keys_total * 24 + 64));
-  XLLM_TRY(h->d_match.reserve((size_t)n_req * sizeof(MatchOut)));
-  XLLM_TRY(h->d_routing.reserve((size_t)n_req * sizeof(RoutingOut)));
+  XLLM_TRY(h->d_key_start.reserve((size_t)n_req * 8 + 8));
+  XLLM_TRY(h->d_nblk.reserve((size_t)n_req * 4 + 8));
+  XLLM_TRY(h->d_match.reserve((size_t)n_req * sizeof(MatchOut) + 8));
+  XLLM_TRY(h->d_routing.reserve((size_t)n_req * sizeof(RoutingOut) + 8));
   if (n_keys_total)
     XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_keys.p, keys, (size_t)n_keys_total * 16, cudaMemcpyHostToDevice, s));
-  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_key_start.p, key_start, (size_t)n_req * 8, cudaMemcpyHostToDevice, s));
-  XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_nblk.p, n_blocks, (size_t)n_req * 4, cudaMemcpyHostToDevice, s));
+  if (n_req) {
+    XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_key_start.p, key_start, (size_t)n_req * 8, cudaMemcpyHostToDevice, s));
+    XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_nblk.p, n_blocks, (size_t)n_req * 4, cudaMemcpyHostToDevice, s));
+  }
   XLLM_TRY(sync_instances(h, s));
-  XLLM_CUDA_TRY(h->index->probe(h->d_keys.as<uint8_t>(), n_keys_total, h->d_masks.as<uint64_t>(), s));
-  XLLM_CUDA_TRY(score_route_launch(h->d_masks.as<uint64_t>(), h->d_key_start.as<int64_t>(), h->d_nblk.as<int32_t>(),
-                                   n_req, h->d_inst, h->d_match.as<MatchOut>(), h->d_routing.as<RoutingOut>(), s));
-  if (match)
+  if (h->shard) {
+    XLLM_TRY(h->shard->match_route(*h->index, h->index_read_ev, h->d_keys.as<uint8_t>(), h->d_key_start.as<int64_t>(),
+                                   h->d_nblk.as<int32_t>(), n_req, n_keys_total, h->d_inst, h->d_match.as<MatchOut>(),
+                                   h->d_routing.as<RoutingOut>(), s));
+  } else {
+    h->index->begin_read();
+    const cudaError_t me = h->index->match_route(h->d_keys.as<uint8_t>(), h->d_key_start.as<int64_t>(),
+                                                 h->d_nblk.as<int32_t>(), n_req, h->d_inst,
+                                                 h->d_match.as<MatchOut>(), h->d_routing.as<RoutingOut>(), s);
+    h->index->end_read(h->index_read_ev, s);
+    XLLM_CUDA_TRY(me);
+  }
+  if (match && n_req)
     XLLM_CUDA_TRY(cudaMemcpyAsync(match, h->d_match.p, (size_t)n_req * sizeof(MatchOut), cudaMemcpyDeviceToHost, s));
-  if (routing)
+  if (routing && n_req)
     XLLM_CUDA_TRY(
         cudaMemcpyAsync(routing, h->d_routing.p, (size_t)n_req * sizeof(RoutingOut), cudaMemcpyDeviceToHost, s));
   XLLM_CUDA_TRY(cudaStreamSynchronize(s));

@@ -30,6 +30,12 @@ void set_last_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
+#define XLLM_TRY_RC(expr)          \
+  do {                             \
+    const int _rc = (expr);        \
+    if (_rc != XLLM_OK) return _rc; \
+  } while (0)
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

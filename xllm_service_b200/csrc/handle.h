@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "prefix_index.cuh"
+#include "shard_exchange.cuh"
 #include "sp_encode.cuh"
 #include "sp_model.h"
 #include "xxh3_chain.cuh"
@@ -65,6 +66,8 @@ struct xllm_ingest {
   // prefix index + instance view (shared between clones)
   std::shared_ptr<xllm::PrefixIndex> index;
   std::shared_ptr<std::mutex> index_mu;
+  std::shared_ptr<xllm::ShardExchange> shard;      // set when the index is hash-range-sharded (shared by clones)
+  cudaEvent_t index_read_ev = nullptr;             // this handle's entry in the index's reader list (prefix_index.cuh)
   std::shared_ptr<xllm::InstanceTable> inst_host;  // host copy
   xllm::InstanceTable* d_inst = nullptr;           // this handle's device copy
   bool inst_dirty = true;
@@ -81,4 +84,6 @@ struct xllm_ingest {
   xllm::DevBuf d_memo;      // word memo of the single-launch encode entry points
   uint32_t memo_slots = 0;  // 0 = memo off
   xllm::DevBuf d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start;
+  // sharded xllm_ingest_batch: the whole batch's keys / row descriptors / results stay resident for the one exchange
+  xllm::DevBuf d_all_keys, d_all_key_start, d_all_n_blocks, d_all_match, d_all_routing;
 };

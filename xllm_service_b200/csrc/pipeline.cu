@@ -40,6 +40,15 @@ __global__ void prep_rows_kernel(const int32_t* __restrict__ n_ids, int n, int64
   n_blocks[r] = (int32_t)nb;
 }
 
+// Sharded index: the exchange runs once per batch, so every chunk also files its rows in batch-wide descriptors.
+__global__ void batch_rows_kernel(const int32_t* __restrict__ chunk_n_blocks, int m, int64_t row0, int64_t keys_stride,
+                                  int64_t* __restrict__ all_key_start, int32_t* __restrict__ all_n_blocks) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  all_key_start[row0 + r] = (row0 + r) * keys_stride;
+  all_n_blocks[row0 + r] = chunk_n_blocks[r];
+}
+
 }  // namespace
 
 int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_stride) {
@@ -55,7 +64,6 @@ int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_
   if ((rc = d_key_start.reserve((size_t)n * 8)) != XLLM_OK) return rc;
   if ((rc = d_n_blocks.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_keys.reserve((size_t)n * (size_t)keys_stride * 16 + 64)) != XLLM_OK) return rc;
-  if ((rc = d_masks.reserve((size_t)n * (size_t)keys_stride * 24 + 64)) != XLLM_OK) return rc;
   if ((rc = d_match.reserve((size_t)n * sizeof(MatchOut))) != XLLM_OK) return rc;
   if ((rc = d_routing.reserve((size_t)n * sizeof(RoutingOut))) != XLLM_OK) return rc;
   return XLLM_OK;
@@ -172,6 +180,16 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
 
   std::lock_guard<std::mutex> lock(h->mu);
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
+  // hash-range-sharded index: the chunks tokenise and hash as usual, their keys stay resident, and ONE exchange round
+  // for the whole batch follows the last chunk (collective: every rank makes this call once per batch)
+  const bool sharded = want_match && h->shard != nullptr;
+  if (sharded) {
+    XLLM_TRY(h->d_all_keys.reserve((size_t)n * (size_t)keys_stride * 16 + 64));
+    XLLM_TRY(h->d_all_key_start.reserve((size_t)n * 8));
+    XLLM_TRY(h->d_all_n_blocks.reserve((size_t)n * 4));
+    XLLM_TRY(h->d_all_match.reserve((size_t)n * sizeof(MatchOut)));
+    XLLM_TRY(h->d_all_routing.reserve((size_t)n * sizeof(RoutingOut)));
+  }
   if (want_match) {
     std::lock_guard<std::mutex> l2(*h->index_mu);
     XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_inst, h->inst_host.get(), sizeof(InstanceTable), cudaMemcpyHostToDevice,
@@ -213,6 +231,15 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
   h->last_chunks = 0;
   h->last_launches = 0;
   ChunkSchedule sched(chunk_req);  // ramp-up, full-size bulk, quarter-size tail (pipeline_schedule.h)
+  // inside the chunk loop a CUDA error must not return at once: copies into the caller's buffers may be in flight, so
+  // leave the loop and synchronise the three streams first
+#define PIPE_CUDA_TRY(expr)                                                                              \
+  if (cudaError_t _pe = (expr); _pe != cudaSuccess) {                                                    \
+    ::xllm::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_pe));       \
+    rc = XLLM_ERR_CUDA;                                                                                  \
+    break;                                                                                               \
+  } else                                                                                                 \
+    (void)0
   while (c0 < n) {
     const int64_t target = sched.next((int64_t)n - c0);
     int32_t c1 = c0;
@@ -221,8 +248,9 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
     const int64_t t0 = io->offsets[c0];
     const size_t text_bytes = (size_t)(io->offsets[c1] - t0);
     PipeSlot& sl = h->pipe[slot];
+    uint8_t* chunk_keys = sl.d_keys.as<uint8_t>();
     // the slot's previous chunk has been downloaded (host wait: ensure() below may reallocate its buffers)
-    if (sl.busy) XLLM_CUDA_TRY(cudaEventSynchronize(sl.ev[2]));
+    if (sl.busy) PIPE_CUDA_TRY(cudaEventSynchronize(sl.ev[2]));
     if ((rc = sl.ensure(text_bytes, m, io->ids_stride, keys_stride)) != XLLM_OK) break;
     if (h->memo_slots && (rc = sl.d_memo.reserve((size_t)h->memo_slots * 32)) != XLLM_OK) break;
     xllm::SpMemo memo;
@@ -234,59 +262,89 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
     }
     // ---- upload
     if (text_bytes)
-      XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_text.p, io->text + t0, text_bytes, cudaMemcpyHostToDevice, s_in));
-    XLLM_CUDA_TRY(cudaMemcpyAsync(sl.d_offsets.p, io->offsets + c0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, s_in));
-    XLLM_CUDA_TRY(cudaEventRecord(sl.ev[0], s_in));
+      PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_text.p, io->text + t0, text_bytes, cudaMemcpyHostToDevice, s_in));
+    PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_offsets.p, io->offsets + c0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, s_in));
+    PIPE_CUDA_TRY(cudaEventRecord(sl.ev[0], s_in));
     mark(1, s_in);
     // ---- kernels: tokenize -> row prep -> chained block hash -> index probe -> match scan + routing
-    XLLM_CUDA_TRY(cudaStreamWaitEvent(s_k, sl.ev[0], 0));
-    XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), m,
+    PIPE_CUDA_TRY(cudaStreamWaitEvent(s_k, sl.ev[0], 0));
+    PIPE_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), m,
                                    sl.d_ids.as<int32_t>(), io->ids_stride, sl.d_n_ids.as<int32_t>(),
                                    sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s_k, memo));
     mark(2, s_k);
-    if (keys_stride > 0) {
+    if (keys_stride > 0 || want_match) {
+      // keys_stride == 0 with match / routing requested (ids_stride < block_size): every request has 0 blocks, the
+      // match is all-zero and routing takes get_load_metrics' least-loaded fallback, as the reference does for a
+      // prompt shorter than one block (global_kvcache_mgr.cpp:77-79, instance_mgr.cpp:312-358)
       prep_rows_kernel<<<(m + 127) / 128, 128, 0, s_k>>>(sl.d_n_ids.as<int32_t>(), m, io->ids_stride, keys_stride,
                                                         h->block_size, sl.d_tok_start.as<int64_t>(),
                                                         sl.d_n_tok.as<int32_t>(), sl.d_key_start.as<int64_t>(),
                                                         sl.d_n_blocks.as<int32_t>());
-      XLLM_CUDA_TRY(cudaGetLastError());
-      if (io->keys) XLLM_CUDA_TRY(cudaMemsetAsync(sl.d_keys.p, 0, (size_t)m * (size_t)keys_stride * 16, s_k));
-      XLLM_CUDA_TRY(xxh3_chain_launch(sl.d_ids.as<int32_t>(), sl.d_tok_start.as<int64_t>(), sl.d_n_tok.as<int32_t>(),
-                                      sl.d_keys.as<uint8_t>(), sl.d_key_start.as<int64_t>(), m, h->block_size, h->xxh,
-                                      sl.counters + 8, s_k));
-      if (want_match) {
-        XLLM_CUDA_TRY(h->index->probe(sl.d_keys.as<uint8_t>(), (int64_t)m * keys_stride, sl.d_masks.as<uint64_t>(), s_k));
-        XLLM_CUDA_TRY(score_route_launch(sl.d_masks.as<uint64_t>(), sl.d_key_start.as<int64_t>(),
-                                         sl.d_n_blocks.as<int32_t>(), m, h->d_inst, sl.d_match.as<MatchOut>(),
-                                         sl.d_routing.as<RoutingOut>(), s_k));
+      PIPE_CUDA_TRY(cudaGetLastError());
+      chunk_keys = sharded ? h->d_all_keys.as<uint8_t>() + (size_t)c0 * (size_t)keys_stride * 16 : sl.d_keys.as<uint8_t>();
+      if (keys_stride > 0) {
+        if (io->keys) PIPE_CUDA_TRY(cudaMemsetAsync(chunk_keys, 0, (size_t)m * (size_t)keys_stride * 16, s_k));
+        PIPE_CUDA_TRY(xxh3_chain_launch(sl.d_ids.as<int32_t>(), sl.d_tok_start.as<int64_t>(), sl.d_n_tok.as<int32_t>(),
+                                        chunk_keys, sl.d_key_start.as<int64_t>(), m, h->block_size, h->xxh,
+                                        sl.counters + 8, s_k));
+      }
+      if (sharded) {
+        batch_rows_kernel<<<(m + 127) / 128, 128, 0, s_k>>>(sl.d_n_blocks.as<int32_t>(), m, (int64_t)c0, keys_stride,
+                                                           h->d_all_key_start.as<int64_t>(),
+                                                           h->d_all_n_blocks.as<int32_t>());
+        PIPE_CUDA_TRY(cudaGetLastError());
+      } else if (want_match) {
+        // probe + first-miss scan + routing in one kernel, between begin_read / end_read so that a publish from
+        // another handle of this index waits for it (prefix_index.cuh)
+        h->index->begin_read();
+        const cudaError_t me = h->index->match_route(sl.d_keys.as<uint8_t>(), sl.d_key_start.as<int64_t>(),
+                                                     sl.d_n_blocks.as<int32_t>(), m, h->d_inst,
+                                                     sl.d_match.as<MatchOut>(), sl.d_routing.as<RoutingOut>(), s_k);
+        h->index->end_read(h->index_read_ev, s_k);
+        PIPE_CUDA_TRY(me);
       }
     }
-    XLLM_CUDA_TRY(cudaEventRecord(sl.ev[1], s_k));
+    PIPE_CUDA_TRY(cudaEventRecord(sl.ev[1], s_k));
     // ---- download
-    XLLM_CUDA_TRY(cudaStreamWaitEvent(s_out, sl.ev[1], 0));
-    XLLM_CUDA_TRY(cudaMemcpyAsync(io->ids + (size_t)c0 * io->ids_stride, sl.d_ids.p,
+    PIPE_CUDA_TRY(cudaStreamWaitEvent(s_out, sl.ev[1], 0));
+    PIPE_CUDA_TRY(cudaMemcpyAsync(io->ids + (size_t)c0 * io->ids_stride, sl.d_ids.p,
                                   (size_t)m * (size_t)io->ids_stride * 4, cudaMemcpyDeviceToHost, s_out));
     mark(3, s_out);
-    XLLM_CUDA_TRY(cudaMemcpyAsync(io->n_ids + c0, sl.d_n_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
-    XLLM_CUDA_TRY(cudaMemcpyAsync(io->status + c0, sl.d_status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
-    if (keys_stride > 0) {
-      if (io->keys)
-        XLLM_CUDA_TRY(cudaMemcpyAsync(io->keys + (size_t)c0 * (size_t)keys_stride * 16, sl.d_keys.p,
-                                      (size_t)m * (size_t)keys_stride * 16, cudaMemcpyDeviceToHost, s_out));
-      if (want_match && io->match)
-        XLLM_CUDA_TRY(cudaMemcpyAsync(io->match + c0, sl.d_match.p, (size_t)m * sizeof(MatchOut),
-                                      cudaMemcpyDeviceToHost, s_out));
-      if (want_match && io->routing)
-        XLLM_CUDA_TRY(cudaMemcpyAsync(io->routing + c0, sl.d_routing.p, (size_t)m * sizeof(RoutingOut),
-                                      cudaMemcpyDeviceToHost, s_out));
-    }
-    XLLM_CUDA_TRY(cudaEventRecord(sl.ev[2], s_out));
+    PIPE_CUDA_TRY(cudaMemcpyAsync(io->n_ids + c0, sl.d_n_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
+    PIPE_CUDA_TRY(cudaMemcpyAsync(io->status + c0, sl.d_status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
+    if (keys_stride > 0 && io->keys)
+      PIPE_CUDA_TRY(cudaMemcpyAsync(io->keys + (size_t)c0 * (size_t)keys_stride * 16, chunk_keys,
+                                    (size_t)m * (size_t)keys_stride * 16, cudaMemcpyDeviceToHost, s_out));
+    if (want_match && !sharded && io->match)
+      PIPE_CUDA_TRY(cudaMemcpyAsync(io->match + c0, sl.d_match.p, (size_t)m * sizeof(MatchOut),
+                                    cudaMemcpyDeviceToHost, s_out));
+    if (want_match && !sharded && io->routing)
+      PIPE_CUDA_TRY(cudaMemcpyAsync(io->routing + c0, sl.d_routing.p, (size_t)m * sizeof(RoutingOut),
+                                    cudaMemcpyDeviceToHost, s_out));
+    PIPE_CUDA_TRY(cudaEventRecord(sl.ev[2], s_out));
     mark(4, s_out);
     sl.busy = true;
     h->last_chunks += 1;
-    h->last_launches += 2 + (keys_stride > 0 ? 2 + (want_match ? 2 : 0) : 0);  // encode x2, prep, hash, probe, score
+    h->last_launches += 2 + (keys_stride > 0 || want_match ? 1 : 0) + (keys_stride > 0 ? 1 : 0) + (want_match ? 1 : 0);  // encode x2, prep, hash, match+route
     slot = (slot + 1) % n_slots;
     c0 = c1;
+  }
+#undef PIPE_CUDA_TRY
+  if (sharded && rc == XLLM_OK) {
+    // every chunk's hash kernel is queued on s_k ahead of this; the round synchronises s_k before it returns
+    rc = h->shard->match_route(*h->index, h->index_read_ev, h->d_all_keys.as<uint8_t>(), h->d_all_key_start.as<int64_t>(),
+                               h->d_all_n_blocks.as<int32_t>(), n, (int64_t)n * keys_stride, h->d_inst,
+                               h->d_all_match.as<MatchOut>(), h->d_all_routing.as<RoutingOut>(), s_k);
+    h->last_launches += 5;   // bucket, headers, owner probe, header gather, scan + route (+ 2 NCCL rounds)
+    cudaError_t ce = cudaSuccess;
+    if (rc == XLLM_OK && io->match)
+      ce = cudaMemcpyAsync(io->match, h->d_all_match.p, (size_t)n * sizeof(MatchOut), cudaMemcpyDeviceToHost, s_k);
+    if (rc == XLLM_OK && ce == cudaSuccess && io->routing)
+      ce = cudaMemcpyAsync(io->routing, h->d_all_routing.p, (size_t)n * sizeof(RoutingOut), cudaMemcpyDeviceToHost, s_k);
+    if (ce != cudaSuccess) {
+      set_last_error("xllm_ingest_batch (sharded match download): %s", cudaGetErrorString(ce));
+      rc = XLLM_ERR_CUDA;
+    }
   }
   {
     cudaError_t e = cudaStreamSynchronize(s_out);

@@ -9,7 +9,7 @@ namespace xllm {
 
 namespace {
 
-constexpr uint32_t kEmpty = 0, kFullSlot = 1, kTomb = 2;
+constexpr uint32_t kEmpty = 0, kFullSlot = 1, kTomb = 2, kBusy = 3;
 
 __device__ __forceinline__ uint64_t home_of(uint64_t lo, uint64_t hi) {
   // keys are XXH3-128 outputs: already uniformly distributed; fold both halves
@@ -44,7 +44,7 @@ struct StageHeader {  // layout of the staged upload
 // rules of record_updated_kvcaches (global_kvcache_mgr.cpp:177-225) / upload_kvcache (:227-247) /
 // update_kvcache (:133-175); updates or tombstones in place; queues keys that must be inserted.
 __global__ void index_apply_kernel(IndexSlot* __restrict__ slots, uint64_t mask, const uint64_t* __restrict__ keys,
-                                   const int64_t* __restrict__ op_off, const uint32_t* __restrict__ ops,
+                                   const int64_t* __restrict__ op_off, const uint64_t* __restrict__ ops,
                                    const uint64_t* __restrict__ payload, int64_t n_keys,
                                    uint64_t* __restrict__ insert_list, int64_t* __restrict__ counters) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,8 +56,8 @@ __global__ void index_apply_kernel(IndexSlot* __restrict__ slots, uint64_t mask,
   uint64_t hbm = 0, dram = 0, ssd = 0;
   if (found) { hbm = slots[s].hbm; dram = slots[s].dram; ssd = slots[s].ssd; }
   for (int64_t i = op_off[k]; i < op_off[k + 1]; ++i) {
-    const uint32_t op = ops[i];
-    const uint32_t type = op & 0xFF;
+    const uint64_t op = ops[i];   // type | instance << 8 | payload index << 32
+    const uint32_t type = (uint32_t)op & 0xFF;
     const uint64_t bit = 1ull << ((op >> 8) & 63);
     if (type == 0) {  // stored
       if (!staged) { staged = true; if (!present) { present = true; hbm = dram = ssd = 0; } }
@@ -70,7 +70,7 @@ __global__ void index_apply_kernel(IndexSlot* __restrict__ slots, uint64_t mask,
       if (!staged) { if (!present) continue; staged = true; }
       hbm &= ~bit; dram &= ~bit; ssd &= ~bit;
     } else if (type == 3) {  // replica PUT: insert_or_assign
-      const uint32_t p = op >> 16;
+      const uint32_t p = (uint32_t)(op >> 32);
       present = true;
       hbm = payload[3 * (size_t)p]; dram = payload[3 * (size_t)p + 1]; ssd = payload[3 * (size_t)p + 2];
     } else {  // replica DELETE
@@ -81,7 +81,11 @@ __global__ void index_apply_kernel(IndexSlot* __restrict__ slots, uint64_t mask,
   if (staged && (hbm | dram | ssd) == 0) present = false;  // upload_kvcache erases empty entries
   if (found) {
     if (present) { slots[s].hbm = hbm; slots[s].dram = dram; slots[s].ssd = ssd; }
-    else { slots[s].state = kTomb; atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll); }
+    else {
+      slots[s].state = kTomb;
+      atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);
+      atomicAdd((unsigned long long*)&counters[3], 1ull);
+    }
   } else if (present) {
     const unsigned long long at = atomicAdd((unsigned long long*)&counters[1], 1ull);
     insert_list[5 * at + 0] = lo; insert_list[5 * at + 1] = hi;
@@ -106,9 +110,13 @@ __global__ void index_insert_kernel(IndexSlot* __restrict__ slots, uint64_t mask
   uint64_t s = home_of(lo, hi) & mask;
   for (uint64_t probes = 0; probes <= mask; ++probes) {
     const uint32_t st = slots[s].state;
-    if (st != kFullSlot && atomicCAS(&slots[s].state, st, kFullSlot) == st) {
+    if ((st == kEmpty || st == kTomb) && atomicCAS(&slots[s].state, st, kBusy) == st) {
+      // claimed: a busy slot is skipped by find_slot, so the key only becomes visible complete
       slots[s].klo = lo; slots[s].khi = hi;
       slots[s].hbm = insert_list[5 * i + 2]; slots[s].dram = insert_list[5 * i + 3]; slots[s].ssd = insert_list[5 * i + 4];
+      __threadfence();
+      atomicExch(&slots[s].state, kFullSlot);
+      if (st == kTomb) atomicAdd((unsigned long long*)&counters[3], (unsigned long long)-1ll);
       return;
     }
     s = (s + 1) & mask;
@@ -130,7 +138,16 @@ __global__ void index_probe_kernel(const IndexSlot* __restrict__ slots, uint64_t
 }
 
 // GlobalKVCacheMgr::match's scan + CacheAwareRouting, one warp per request, lane = block.
-__global__ void __launch_bounds__(128) score_route_kernel(const uint64_t* __restrict__ masks3,
+//   kProbe = true  (replicated index): the lane probes its block's key itself — keys in, decision out, one kernel;
+//                  waves of 32 blocks, and the scan stops after the wave that holds the first miss, so a request is
+//                  never probed past it (the reference's loop breaks there, global_kvcache_mgr.cpp:127-129).
+//   kProbe = false (hash-range-sharded index): the tier masks were probed on the owning GPUs and came back through
+//                  the exchange; the lane reads its block's three masks from masks3.
+template <bool kProbe>
+__global__ void __launch_bounds__(128) match_route_kernel(const IndexSlot* __restrict__ slots, uint64_t slot_mask,
+                                                          const uint64_t* __restrict__ keys,
+                                                          const uint64_t* __restrict__ masks3,
+                                                          const uint32_t* __restrict__ pos,
                                                           const int64_t* __restrict__ key_start,
                                                           const int32_t* __restrict__ n_blocks, int n_req,
                                                           const InstanceTable* __restrict__ inst,
@@ -140,7 +157,7 @@ __global__ void __launch_bounds__(128) score_route_kernel(const uint64_t* __rest
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_req) return;
   const int nb = n_blocks[r];
-  const uint64_t* m = masks3 + 3 * key_start[r];
+  const int64_t k0 = key_start[r];
   // lane i owns instances i and i + 32: score = 1 + last matched block index holding the instance
   uint32_t sc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   uint64_t inst_mask = 0;
@@ -149,7 +166,23 @@ __global__ void __launch_bounds__(128) score_route_kernel(const uint64_t* __rest
   for (int base = 0; base < nb && !stop; base += 32) {
     const int i = base + lane;
     uint64_t t[3] = {0, 0, 0};
-    if (i < nb) { t[0] = m[3 * (size_t)i]; t[1] = m[3 * (size_t)i + 1]; t[2] = m[3 * (size_t)i + 2]; }
+    if (i < nb) {
+      if (kProbe) {
+        const ulonglong2 key = *reinterpret_cast<const ulonglong2*>(keys + 2 * (k0 + i));
+        const uint64_t s = find_slot(slots, slot_mask, key.x, key.y);
+        if (s != ~0ull) {
+          const ulonglong2 hd = *reinterpret_cast<const ulonglong2*>(&slots[s].hbm);
+          t[0] = hd.x; t[1] = hd.y; t[2] = slots[s].ssd;
+        }
+      } else {
+        // sharded: the masks came back in the order the keys were sent; pos maps key index -> that slot
+        const size_t at = pos ? (size_t)pos[k0 + i] : (size_t)(k0 + i);
+        if (at != (size_t)0xFFFFFFFFu) {
+          const uint64_t* m = masks3 + 3 * at;
+          t[0] = m[0]; t[1] = m[1]; t[2] = m[2];
+        }
+      }
+    }
     const bool hit = i < nb && (t[0] | t[1] | t[2]) != 0;  // absent or empty entry => miss (:96,127-129)
     const uint32_t hits = __ballot_sync(0xffffffffu, hit);
     const int n_here = nb - base < 32 ? nb - base : 32;
@@ -326,6 +359,86 @@ void PrefixIndex::erase(const uint8_t* key16) {
   it->second.push_back(Op{4, 0, 0});
 }
 
+cudaEvent_t PrefixIndex::register_reader() {
+  cudaEvent_t ev = nullptr;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> l(ev_mu_);
+  reader_events_.push_back(ev);
+  return ev;
+}
+void PrefixIndex::unregister_reader(cudaEvent_t ev) {
+  if (!ev) return;
+  {
+    std::lock_guard<std::mutex> l(ev_mu_);
+    for (size_t i = 0; i < reader_events_.size(); ++i)
+      if (reader_events_[i] == ev) {
+        reader_events_.erase(reader_events_.begin() + (long)i);
+        break;
+      }
+  }
+  cudaEventDestroy(ev);
+}
+// The writer's stream waits for the last read every handle enqueued (an event that was never recorded is
+// complete).  New reads cannot be enqueued meanwhile: the caller holds rw_ exclusively.
+int PrefixIndex::wait_for_readers(cudaStream_t stream) {
+  std::lock_guard<std::mutex> l(ev_mu_);
+  for (cudaEvent_t ev : reader_events_) XLLM_CUDA_TRY(cudaStreamWaitEvent(stream, ev, 0));
+  return XLLM_OK;
+}
+int PrefixIndex::read_counters(cudaStream_t stream) {
+  int64_t c[4] = {0, 0, 0, 0};
+  XLLM_CUDA_TRY(cudaMemcpyAsync(c, d_counters_, sizeof(c), cudaMemcpyDeviceToHost, stream));
+  XLLM_CUDA_TRY(cudaStreamSynchronize(stream));
+  live_ = c[0];
+  tombs_ = c[3];
+  return c[2] != 0 ? 1 : 0;
+}
+
+// Re-inserts every live slot of `from` into the zeroed table `to` (distinct keys: claim the first empty slot).
+__global__ void index_rehash_kernel(const IndexSlot* __restrict__ from, uint64_t n_from, IndexSlot* __restrict__ to,
+                                    uint64_t to_mask) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_from) return;
+  const IndexSlot src = from[i];
+  if (src.state != kFullSlot) return;
+  uint64_t s = home_of(src.klo, src.khi) & to_mask;
+  for (;;) {
+    if (to[s].state == kEmpty && atomicCAS(&to[s].state, kEmpty, kBusy) == kEmpty) {
+      to[s].klo = src.klo; to[s].khi = src.khi;
+      to[s].hbm = src.hbm; to[s].dram = src.dram; to[s].ssd = src.ssd;
+      __threadfence();
+      atomicExch(&to[s].state, kFullSlot);
+      return;
+    }
+    s = (s + 1) & to_mask;
+  }
+}
+
+// Tombstones never turn back into empty slots on their own, so under churn (store, evict, store ...) the empty
+// slots that end a miss probe would run out and every miss would scan further and further.  When live keys +
+// tombstones pass 70 % of the slots the live entries are re-inserted into a fresh table of the same size (live keys
+// alone never exceed 50 %: capacity <= slots / 2), which drops every tombstone.  Needs a second table for the
+// duration; runs under the exclusive lock.
+int PrefixIndex::rebuild(cudaStream_t stream) {
+  IndexSlot* fresh = nullptr;
+  if (cudaMalloc(&fresh, n_slots_ * sizeof(IndexSlot)) != cudaSuccess) {
+    cudaGetLastError();
+    return XLLM_OK;   // no room for the second table now: keep the old one, try again at the next publish
+  }
+  XLLM_CUDA_TRY(cudaMemsetAsync(fresh, 0, n_slots_ * sizeof(IndexSlot), stream));
+  const int threads = 256;
+  index_rehash_kernel<<<(unsigned)((n_slots_ + threads - 1) / threads), threads, 0, stream>>>(slots_, n_slots_, fresh,
+                                                                                              n_slots_ - 1);
+  XLLM_CUDA_TRY(cudaGetLastError());
+  XLLM_CUDA_TRY(cudaMemsetAsync(d_counters_ + 3, 0, sizeof(int64_t), stream));
+  XLLM_CUDA_TRY(cudaStreamSynchronize(stream));
+  cudaFree(slots_);
+  slots_ = fresh;
+  tombs_ = 0;
+  ++rebuilds_;
+  return XLLM_OK;
+}
+
 int PrefixIndex::publish(cudaStream_t stream) {
   if (!ready()) {
     set_last_error("prefix index not configured (index_capacity == 0)");
@@ -333,40 +446,31 @@ int PrefixIndex::publish(cudaStream_t stream) {
   }
   const int64_t nk = (int64_t)staged_order_.size();
   if (nk == 0) return XLLM_OK;
-  // pack: keys[2*nk] | op_off[nk+1] | ops[n_ops] (u32) | payload | insert_list[5*nk]
+  // whatever happens below, the staged window is consumed: a failed publish must not poison the next one
+  struct ClearStaging {
+    PrefixIndex* p;
+    ~ClearStaging() { p->staged_.clear(); p->staged_order_.clear(); p->payload_.clear(); }
+  } clear_staging{this};
+  // pack: keys[2*nk] | op_off[nk+1] | ops[n_ops] (u64: type | instance << 8 | payload index << 32) | payload |
+  // insert_list[5*nk]
   size_t n_ops = 0;
   for (const auto& k : staged_order_) n_ops += staged_[k].size();
   std::vector<uint64_t> keys(2 * (size_t)nk);
   std::vector<int64_t> op_off((size_t)nk + 1);
-  std::vector<uint32_t> ops(n_ops + 1);
-  std::vector<uint64_t> payload;
+  std::vector<uint64_t> ops(n_ops + 1);
   size_t at = 0;
   for (int64_t i = 0; i < nk; ++i) {
     const Key128& k = staged_order_[(size_t)i];
     keys[2 * (size_t)i] = k.lo;
     keys[2 * (size_t)i + 1] = k.hi;
     op_off[(size_t)i] = (int64_t)at;
-    for (const Op& op : staged_[k]) {
-      uint32_t enc = op.type | ((uint32_t)op.instance << 8);
-      if (op.type == 3) {
-        // re-base the payload so the 16-bit index always fits: one payload triple per assigning key
-        const uint32_t idx = (uint32_t)(payload.size() / 3);
-        payload.push_back(payload_[3 * (size_t)op.payload]);
-        payload.push_back(payload_[3 * (size_t)op.payload + 1]);
-        payload.push_back(payload_[3 * (size_t)op.payload + 2]);
-        enc = 3u | (idx << 16);
-        if (idx > 0xFFFF) {
-          set_last_error("more than 65536 replica PUTs in one publish window: call xllm_index_publish more often");
-          return XLLM_ERR_CAPACITY;
-        }
-      }
-      ops[at++] = enc;
-    }
+    for (const Op& op : staged_[k])
+      ops[at++] = (uint64_t)op.type | ((uint64_t)op.instance << 8) | ((uint64_t)op.payload << 32);
   }
   op_off[(size_t)nk] = (int64_t)at;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  const size_t b_keys = al(keys.size() * 8), b_off = al(op_off.size() * 8), b_ops = al(ops.size() * 4),
-               b_pay = al(payload.size() * 8 + 8), b_ins = al((size_t)nk * 40 + 8);
+  const size_t b_keys = al(keys.size() * 8), b_off = al(op_off.size() * 8), b_ops = al(ops.size() * 8),
+               b_pay = al(payload_.size() * 8 + 8), b_ins = al((size_t)nk * 40 + 8);
   const size_t total = b_keys + b_off + b_ops + b_pay + b_ins;
   if (total > d_stage_cap_) {
     if (d_stage_) cudaFree(d_stage_);
@@ -378,15 +482,18 @@ int PrefixIndex::publish(cudaStream_t stream) {
   uint8_t* base = static_cast<uint8_t*>(d_stage_);
   uint64_t* d_keys = reinterpret_cast<uint64_t*>(base);
   int64_t* d_off = reinterpret_cast<int64_t*>(base + b_keys);
-  uint32_t* d_ops = reinterpret_cast<uint32_t*>(base + b_keys + b_off);
+  uint64_t* d_ops = reinterpret_cast<uint64_t*>(base + b_keys + b_off);
   uint64_t* d_pay = reinterpret_cast<uint64_t*>(base + b_keys + b_off + b_ops);
   uint64_t* d_ins = reinterpret_cast<uint64_t*>(base + b_keys + b_off + b_ops + b_pay);
   // synchronous copies from pageable vectors: publish is the (3 s) control path, not the request path
   XLLM_CUDA_TRY(cudaMemcpyAsync(d_keys, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice, stream));
   XLLM_CUDA_TRY(cudaMemcpyAsync(d_off, op_off.data(), op_off.size() * 8, cudaMemcpyHostToDevice, stream));
-  XLLM_CUDA_TRY(cudaMemcpyAsync(d_ops, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice, stream));
-  if (!payload.empty())
-    XLLM_CUDA_TRY(cudaMemcpyAsync(d_pay, payload.data(), payload.size() * 8, cudaMemcpyHostToDevice, stream));
+  XLLM_CUDA_TRY(cudaMemcpyAsync(d_ops, ops.data(), ops.size() * 8, cudaMemcpyHostToDevice, stream));
+  if (!payload_.empty())
+    XLLM_CUDA_TRY(cudaMemcpyAsync(d_pay, payload_.data(), payload_.size() * 8, cudaMemcpyHostToDevice, stream));
+  // ---- the table changes from here: no reader may be enqueued or in flight
+  std::unique_lock<std::shared_mutex> writer(rw_);
+  XLLM_TRY_RC(wait_for_readers(stream));
   XLLM_CUDA_TRY(cudaMemsetAsync(d_counters_ + 1, 0, 2 * sizeof(int64_t), stream));
   const int threads = 128;
   const int grid = (int)((nk + threads - 1) / threads);
@@ -395,21 +502,50 @@ int PrefixIndex::publish(cudaStream_t stream) {
   XLLM_CUDA_TRY(cudaGetLastError());
   index_insert_kernel<<<grid, threads, 0, stream>>>(slots_, n_slots_ - 1, d_ins, d_counters_, capacity_);
   XLLM_CUDA_TRY(cudaGetLastError());
-  int64_t counters[3] = {0, 0, 0};
-  XLLM_CUDA_TRY(cudaMemcpyAsync(counters, d_counters_, sizeof(counters), cudaMemcpyDeviceToHost, stream));
-  XLLM_CUDA_TRY(cudaStreamSynchronize(stream));
-  staged_.clear();
-  staged_order_.clear();
-  payload_.clear();
-  if (counters[2] != 0) {
+  const int overflow = read_counters(stream);   // synchronises
+  if (overflow < 0) return overflow;
+  if ((live_ + tombs_) * 10 > (int64_t)n_slots_ * 7) XLLM_TRY_RC(rebuild(stream));
+  if (overflow) {
     set_last_error("prefix index is full (capacity %lld keys): some stored keys were dropped", (long long)capacity_);
     return XLLM_ERR_CAPACITY;
   }
   return XLLM_OK;
 }
 
+// One thread per slot: drop instance `bit` from the three tiers; an entry left empty is erased (what the
+// reference's removed_cache events for every block of a departed instance would add up to).
+__global__ void index_clear_instance_kernel(IndexSlot* __restrict__ slots, uint64_t n_slots, uint64_t bit,
+                                            int64_t* __restrict__ counters) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots || slots[i].state != kFullSlot) return;
+  const uint64_t h = slots[i].hbm, d = slots[i].dram, v = slots[i].ssd;
+  if (((h | d | v) & bit) == 0) return;
+  slots[i].hbm = h & ~bit; slots[i].dram = d & ~bit; slots[i].ssd = v & ~bit;
+  if (((h | d | v) & ~bit) == 0) {
+    slots[i].state = kTomb;
+    atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);
+    atomicAdd((unsigned long long*)&counters[3], 1ull);
+  }
+}
+
+int PrefixIndex::clear_instance(cudaStream_t stream, int id) {
+  if (!ready()) return XLLM_ERR_UNSUPPORTED;
+  if (id < 0 || id >= kMaxInstances) return XLLM_ERR_INVALID_ARG;
+  std::unique_lock<std::shared_mutex> writer(rw_);
+  XLLM_TRY_RC(wait_for_readers(stream));
+  const int threads = 256;
+  index_clear_instance_kernel<<<(unsigned)((n_slots_ + threads - 1) / threads), threads, 0, stream>>>(
+      slots_, n_slots_, 1ull << id, d_counters_);
+  XLLM_CUDA_TRY(cudaGetLastError());
+  const int rc = read_counters(stream);
+  if (rc < 0) return rc;
+  if ((live_ + tombs_) * 10 > (int64_t)n_slots_ * 7) XLLM_TRY_RC(rebuild(stream));
+  return XLLM_OK;
+}
+
 int PrefixIndex::size(cudaStream_t stream, int64_t* n) {
   if (!ready()) { *n = 0; return XLLM_OK; }
+  std::shared_lock<std::shared_mutex> reader(rw_);
   XLLM_CUDA_TRY(cudaMemcpyAsync(n, d_counters_, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   XLLM_CUDA_TRY(cudaStreamSynchronize(stream));
   return XLLM_OK;
@@ -433,6 +569,7 @@ __global__ void index_export_kernel(const IndexSlot* __restrict__ slots, uint64_
 int PrefixIndex::export_all(cudaStream_t stream, int64_t cap, uint8_t* keys16, uint64_t* hbm, uint64_t* dram,
                             uint64_t* ssd, int64_t* n_out) {
   if (!ready()) return XLLM_ERR_UNSUPPORTED;
+  std::shared_lock<std::shared_mutex> reader(rw_);   // synchronises before returning: no event needed
   if (cap < 0) cap = 0;
   const size_t need = 64 + (size_t)cap * 40;
   if (d_stage_cap_ < need) {
@@ -477,6 +614,7 @@ int PrefixIndex::export_all(cudaStream_t stream, int64_t cap, uint8_t* keys16, u
 
 int PrefixIndex::get(cudaStream_t stream, const uint8_t* key16, uint64_t masks3[3], int* found) {
   if (!ready()) return XLLM_ERR_UNSUPPORTED;
+  std::shared_lock<std::shared_mutex> reader(rw_);   // synchronises before returning: no event needed
   if (d_stage_cap_ < 256) {
     if (d_stage_) cudaFree(d_stage_);
     d_stage_ = nullptr;
@@ -502,14 +640,57 @@ cudaError_t PrefixIndex::probe(const uint8_t* d_keys, int64_t n_keys, uint64_t* 
   return cudaGetLastError();
 }
 
-cudaError_t score_route_launch(const uint64_t* d_masks3, const int64_t* d_key_start, const int32_t* d_n_blocks,
-                               int n_req, const InstanceTable* d_instances, MatchOut* d_match,
-                               RoutingOut* d_routing, cudaStream_t stream) {
+cudaError_t PrefixIndex::match_route(const uint8_t* d_keys, const int64_t* d_key_start, const int32_t* d_n_blocks,
+                                     int n_req, const InstanceTable* d_instances, MatchOut* d_match,
+                                     RoutingOut* d_routing, cudaStream_t stream) const {
   if (n_req <= 0) return cudaSuccess;
   const int warps = 4;
   const int grid = (n_req + warps - 1) / warps;
-  score_route_kernel<<<grid, warps * 32, 0, stream>>>(d_masks3, d_key_start, d_n_blocks, n_req, d_instances,
-                                                      d_match, d_routing);
+  match_route_kernel<true><<<grid, warps * 32, 0, stream>>>(slots_, n_slots_ - 1,
+                                                            reinterpret_cast<const uint64_t*>(d_keys), nullptr,
+                                                            nullptr, d_key_start, d_n_blocks, n_req, d_instances,
+                                                            d_match, d_routing);
+  return cudaGetLastError();
+}
+
+cudaError_t score_route_launch(const uint64_t* d_masks3, const int64_t* d_key_start, const int32_t* d_n_blocks,
+                               int n_req, const InstanceTable* d_instances, MatchOut* d_match,
+                               RoutingOut* d_routing, cudaStream_t stream, const uint32_t* d_pos) {
+  if (n_req <= 0) return cudaSuccess;
+  const int warps = 4;
+  const int grid = (n_req + warps - 1) / warps;
+  match_route_kernel<false><<<grid, warps * 32, 0, stream>>>(nullptr, 0, nullptr, d_masks3, d_pos, d_key_start,
+                                                             d_n_blocks, n_req, d_instances, d_match, d_routing);
+  return cudaGetLastError();
+}
+
+// Owner side of the sharded index: probes the tuples of `world` received messages ([u32 count | 12 bytes | tuples of
+// 24 bytes, key first] each, shard_exchange.cuh) and writes {hbm, dram, ssd} per tuple in arrival order.
+__global__ void index_probe_messages_kernel(const IndexSlot* __restrict__ slots, uint64_t mask,
+                                            const uint8_t* __restrict__ recv, size_t msg_bytes, int world,
+                                            uint32_t cap, uint64_t* __restrict__ back) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = (uint32_t)(t / cap), j = (uint32_t)(t % cap);
+  if ((int)p >= world) return;
+  const uint8_t* msg = recv + (size_t)p * msg_bytes;
+  uint32_t n = *reinterpret_cast<const uint32_t*>(msg);
+  if (n > cap) n = cap;
+  if (j >= n) return;
+  const uint64_t* key = reinterpret_cast<const uint64_t*>(msg + 16 + (size_t)j * 24);
+  const uint64_t s = find_slot(slots, mask, key[0], key[1]);
+  uint64_t h = 0, d = 0, v = 0;
+  if (s != ~0ull) { h = slots[s].hbm; d = slots[s].dram; v = slots[s].ssd; }
+  uint64_t* o = back + ((size_t)p * cap + j) * 3;
+  o[0] = h; o[1] = d; o[2] = v;
+}
+
+cudaError_t PrefixIndex::probe_messages(const uint8_t* d_recv, size_t msg_bytes, int world, uint32_t cap,
+                                        uint64_t* d_back, cudaStream_t stream) const {
+  const uint64_t total = (uint64_t)world * cap;
+  if (total == 0) return cudaSuccess;
+  const int threads = 256;
+  index_probe_messages_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+      slots_, n_slots_ - 1, d_recv, msg_bytes, world, cap, d_back);
   return cudaGetLastError();
 }
 

@@ -45,7 +45,8 @@ class Ingest:
     (block_size, xxh3_128bits_seed, tokenizer_path: global_gflags.cpp:60,114-118)."""
 
     def __init__(self, tokenizer_path=None, block_size=128, xxh3_seed=1024, device=0, max_batch=0,
-                 max_batch_bytes=0, max_tokens=0, index_capacity=0):
+                 max_batch_bytes=0, max_tokens=0, index_capacity=0, shard_world=0, shard_rank=0,
+                 nccl_unique_id=None):
         self._L = _lib.lib()
         self._h = ctypes.c_void_p()
         cfg = Config()
@@ -57,6 +58,11 @@ class Ingest:
         cfg.max_batch_bytes = max_batch_bytes
         cfg.max_tokens = max_tokens
         cfg.index_capacity = index_capacity
+        # hash-range-sharded index: collective create (every rank, same 128-byte id: sharded.create_sharded)
+        cfg.shard_world = shard_world
+        cfg.shard_rank = shard_rank
+        self._uid = ctypes.create_string_buffer(bytes(nccl_unique_id), 128) if nccl_unique_id is not None else None
+        cfg.nccl_unique_id = ctypes.cast(self._uid, ctypes.c_void_p) if self._uid is not None else None
         self.block_size = block_size or 128
         self.seed = xxh3_seed
         check(self._L.xllm_ingest_create(ctypes.byref(cfg), ctypes.byref(self._h)))
@@ -188,6 +194,22 @@ class Ingest:
     def index_publish(self):
         """upload_kvcache (global_kvcache_mgr.cpp:227-247): staged events become visible to match."""
         check(self._L.xllm_index_publish(self._h))
+
+    def shard_last_stats(self):
+        """Device milliseconds of the last sharded match round + message capacity + overflow repeats."""
+        st = _lib.ShardStats()
+        check(self._L.xllm_shard_last_stats(self._h, ctypes.byref(st)))
+        return {n: getattr(st, n) for n, _ in _lib.ShardStats._fields_}
+
+    def index_clear_instance(self, instance_id):
+        """Drop one instance from every entry of the published index (entries left empty are erased)."""
+        check(self._L.xllm_index_clear_instance(self._h, instance_id))
+
+    def index_stats(self):
+        """(live keys, tombstones, in-place rebuilds) as of the last publish."""
+        v = [ctypes.c_int64() for _ in range(3)]
+        check(self._L.xllm_index_stats(self._h, *[ctypes.byref(x) for x in v]))
+        return tuple(x.value for x in v)
 
     def index_size(self):
         n = ctypes.c_int64()
