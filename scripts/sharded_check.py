@@ -169,8 +169,10 @@ if not a.no_pipeline:
     full.set_pipeline(97, 1 << 20)
     ref = full.ingest_batch(b.text, b.offsets, T)
     got = part.ingest_batch(b.text, b.offsets, T)
-    for f in ("ids", "n_ids", "status", "keys"):
+    for f in ("n_ids", "status", "keys"):
         assert (ref[f] == got[f]).all(), f
+    valid = np.arange(T)[None, :] < ref["n_ids"][:, None]          # ids past n_ids are not part of the result
+    assert (ref["ids"][valid] == got["ids"][valid]).all()
     assert ref["match"].tobytes() == got["match"].tobytes() and ref["routing"].tobytes() == got["routing"].tobytes()
     assert (got["match"]["max_matched_block_num"] > 0).any()
 
