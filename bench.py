@@ -47,7 +47,38 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="prompts in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk-requests", type=int, default=0)
+    ap.add_argument("--index", default="auto", choices=["auto", "replicated", "sharded"],
+                    help="prefix index placement at N > 1: sharded = BASELINE config 4 (hash-range shards, index N x "
+                         "--index-keys, one NCCL all-to-all each way per batch); auto = sharded when N > 1")
     return ap.parse_args()
+
+
+def host_threads():
+    """Threads the CPU arm may really use: the smaller of the scheduler affinity mask and the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the container's share).  Returns (threads, detail dict)."""
+    ncpu = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        aff = ncpu
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                txt = f.read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                        quota = q / float(f2.read().split()[0])
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    use = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return use, {"os_cpu_count": ncpu, "sched_affinity": aff, "cgroup_quota_cpus": quota}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -78,7 +109,9 @@ def index_events(prefix_keys, n_total, rng):
     """The KvCacheEvent stream that populates the index: every shared-prefix block
     is held in HBM by 1-3 instances over a leading part of the prefix, filler keys by one instance;
     then 10 % of the entries are offloaded to DRAM and 10 % on to SSD.  Returns a list of
-    (instance_id, stored, offload, removed) uint8 [k,16] arrays, in order, with publish markers (None)."""
+    ("prefix" | "fill", instance_id, stored, offload, removed) uint8 [k,16] events, in order, with publish markers
+    (None).  Prefix and filler keys are disjoint, so a consumer that only ever looks up prefix keys (the CPU oracle of
+    the sharded gate) may skip the "fill" events."""
     stored = [[] for _ in range(N_INST)]
     used = 0
     for keys in prefix_keys:                      # keys: [L,16] of one shared prefix
@@ -92,16 +125,16 @@ def index_events(prefix_keys, n_total, rng):
     owner = rng.integers(0, N_INST, size=n_fill)
     ev = []
     for i in range(N_INST):
-        parts = stored[i] + [fill[owner == i]]
-        ev.append((i, np.concatenate(parts), None, None))
+        ev.append(("prefix", i, np.concatenate(stored[i]) if stored[i] else np.zeros((0, 16), np.uint8), None, None))
+        ev.append(("fill", i, fill[owner == i], None, None))
+    first = list(ev)
     ev.append(None)
     off1, off2 = [], []
-    for i in range(N_INST):
-        k = ev[i][1]
+    for tag, i, k, _, _ in first:
         sel = rng.random(k.shape[0]) < 0.2
-        off1.append((i, None, k[sel], None))                      # HBM -> DRAM
+        off1.append((tag, i, None, k[sel], None))                      # HBM -> DRAM
         sel2 = sel & (rng.random(k.shape[0]) < 0.5)
-        off2.append((i, None, k[sel2], None))                     # DRAM -> SSD
+        off2.append((tag, i, None, k[sel2], None))                     # DRAM -> SSD
     return ev + off1 + [None] + off2 + [None]
 
 
@@ -189,7 +222,7 @@ def cpu_reference_pass(sp, P, batch, n_sample, threads):
     return n_sample / dt, dt, res
 
 
-def build_cpu_side(names, events, view):
+def build_cpu_side(names, events, view, with_fill=True):
     from oracle import oracle as o
     sp = o.SentencePieceOracle(MODEL_DIR)
     P = o.PrefixOracle(names, BLOCK, SEED)
@@ -199,8 +232,8 @@ def build_cpu_side(names, events, view):
     for e in events:
         if e is None:
             P.upload()
-        else:
-            i, st, of, rm = e
+        elif with_fill or e[0] == "prefix":
+            _, i, st, of, rm = e
             P.record(names[i], st if st is not None else (), of if of is not None else (),
                      rm if rm is not None else ())
     return sp, P
@@ -215,7 +248,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as o
     from xllm_service_b200 import workload
     o.build()
-    threads = os.cpu_count() or 1
+    threads, thread_detail = host_threads()
     rng = np.random.default_rng(2026)
     names = ["instance-%02d" % i for i in range(N_INST)]
     vocab = workload.make_vocabulary()
@@ -245,9 +278,12 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "c2+c3: %d-token prompts, SentencePiece-BPE 8k, 1Mi-key prefix index, 64 instances"
                                    % args.tokens, "sample_prompts_per_step": n_sample},
-            "cpu_baseline": {"value": v, "unit": "req/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": "req/s", "cores": threads, "kind": "port", "host": thread_detail,
                              "sample": "%d prompts x %d tokens per step, %d threads, one request per thread at a time"
-                                       % (n_sample, args.tokens, threads)},
+                                       % (n_sample, args.tokens, threads),
+                             "note": "tokenizer = the CPU port (libsentencepiece is not in the image); the port's "
+                                     "hash / match / routing are pinned to the reference's own code compiled "
+                                     "unmodified (oracle/_ref, tests/test_ref_parity.py)"},
             "e2e": {"value": v, "unit": "req/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -281,8 +317,20 @@ def main():
 
     n, T = args.requests, args.tokens
     nb = T // BLOCK
-    h = x.Ingest(tokenizer_path=MODEL_DIR, block_size=BLOCK, xxh3_seed=SEED, device=local,
-                 index_capacity=args.index_keys + (1 << 16))
+    # BASELINE config 4: at N > 1 the index is N x the single-GPU one and hash-range-sharded over the N GPUs (one NCCL
+    # all-to-all of (hash, request, block) tuples per batch and one of tier masks back, csrc/shard_exchange.cu); a
+    # replicated twin of the whole index on every GPU serves the "sharded == replicated == oracle" gate only.
+    sharded_mode = world > 1 and args.index != "replicated"
+    total_keys = args.index_keys * (world if sharded_mode else 1)
+    h_full = None
+    if sharded_mode:
+        from xllm_service_b200 import sharded
+        h = sharded.create_sharded(tokenizer_path=MODEL_DIR, block_size=BLOCK, xxh3_seed=SEED, device=local,
+                                   index_capacity=total_keys // world * 5 // 4 + (1 << 16), max_batch=n, max_tokens=T)
+        h_full = x.Ingest(block_size=BLOCK, xxh3_seed=SEED, device=local, index_capacity=total_keys + (1 << 16))
+    else:
+        h = x.Ingest(tokenizer_path=MODEL_DIR, block_size=BLOCK, xxh3_seed=SEED, device=local,
+                     index_capacity=args.index_keys + (1 << 16))
     if args.chunk_requests:
         h.set_pipeline(args.chunk_requests, 1 << 40)
     vocab = workload.make_vocabulary()
@@ -336,26 +384,63 @@ def main():
     for j, idx in zip(*first):
         r = rows_with[idx]
         pref[int(j)] = keys_np[r, :meta["prefix_blocks"][r]].copy()
-    events = index_events([pref[j] for j in sorted(pref)], args.index_keys, rng)
+    prefix_list = [pref[j] for j in sorted(pref)]
+    if sharded_mode:   # one global event stream: every rank's shared prefixes, in rank order (identical on all ranks)
+        box = [None] * world
+        dist.all_gather_object(box, prefix_list)
+        prefix_list = [p for part in box for p in part]
+    events = index_events(prefix_list, total_keys, rng)
     view = instance_view(rng)
-    for i, (t, s, w, u) in enumerate(view):
-        h.set_instance(i, t, s)
-        h.set_load_metrics(i, w, u)
-    for e in events:
-        if e is None:
-            h.index_publish()
-        else:
-            h.index_apply(e[0], e[1], e[2], e[3])
+    handles = [h] + ([h_full] if h_full is not None else [])
+    for hh in handles:
+        for i, (t, s, w, u) in enumerate(view):
+            hh.set_instance(i, t, s)
+            hh.set_load_metrics(i, w, u)
+        for e in events:          # every rank is given every event; a sharded handle keeps the keys it owns
+            if e is None:
+                hh.index_publish()
+            else:
+                hh.index_apply(e[1], e[2], e[3], e[4])
     index_size = h.index_size()
+    if sharded_mode:
+        t_sz = torch.tensor([index_size], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_sz)
+        assert int(t_sz.item()) == h_full.index_size(), "the shards do not add up to the replicated index"
+        index_size = int(t_sz.item())
 
-    # ---- parity gate (rank 0): a sample of the batch against the CPU oracle, bit for bit
+    # ---- parity gate, part 1 (every rank, whole batch): the sharded index answers exactly like a replicated one
+    shard_gate = None
+    if sharded_mode:
+        e2e_step(with_match=True)                                   # collective
+        d_k = torch.from_numpy(h_keys.numpy().reshape(-1, 16)).to(dev)
+        d_ks0 = torch.arange(n, device=dev, dtype=torch.int64) * nb
+        d_nb0 = torch.full((n,), nb, dtype=torch.int32, device=dev)
+        d_m0 = torch.empty((n, 400), dtype=torch.uint8, device=dev)
+        d_r0 = torch.empty((n, 20), dtype=torch.uint8, device=dev)
+        h_full.match_route_device(n, d_k.data_ptr(), n * nb, d_ks0.data_ptr(), d_nb0.data_ptr(), d_m0.data_ptr(),
+                                  d_r0.data_ptr(), None)
+        torch.cuda.synchronize()
+        same = (torch.equal(d_m0.cpu(), torch.from_numpy(h_match.numpy())) and
+                torch.equal(d_r0.cpu(), torch.from_numpy(h_route.numpy())))
+        t_ok = torch.tensor([1 if same else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        assert int(t_ok.item()) == 1, "sharded match / routing differs from the replicated index"
+        shard_gate = "sharded == replicated on all %d requests of every rank (match + routing, bit for bit)" % n
+        del d_k, d_m0, d_r0
+        h_full.close()
+        h_full = None
+        torch.cuda.empty_cache()
+    # ---- parity gate, part 2 (rank 0): a sample of the batch against the CPU oracle, bit for bit
     gate = {"checked": 0}
     if rank == 0:
         from oracle import oracle as o
         o.build()
-        threads = os.cpu_count() or 1
-        sp, P = build_cpu_side(names, events, view)
-        e2e_step(with_match=True)
+        threads, thread_detail = host_threads()
+        # the oracle of the sharded run holds the prefix entries only (filler keys are disjoint and never looked up):
+        # N x 1 Mi string-set entries would take minutes and gigabytes on the host
+        sp, P = build_cpu_side(names, events, view, with_fill=not sharded_mode)
+        if not sharded_mode:
+            e2e_step(with_match=True)
         n_chk = min(n, 64)
         res = o.ingest_batch(sp, P, batch.text, batch.offsets[:n_chk + 1], T, n_threads=threads)
         assert (res["ids"] == h_ids.numpy()[:n_chk]).all(), "token ids differ from the CPU oracle"
@@ -373,6 +458,8 @@ def main():
             assert (ro["prefill_argmax"] >> int(routing["prefill_id"][r])) & 1
         gate = {"checked": n_chk, "ids": "bit-exact", "keys": "bit-exact", "routing": "score-exact, choice in argmax set",
                 "mean_matched_blocks": float(match["max_matched_block_num"].mean())}
+        if shard_gate:
+            gate["sharded"] = shard_gate
 
     # ---- device-resident buffers
     stream = torch.cuda.Stream(device=dev)
@@ -437,6 +524,41 @@ def main():
     assert (torch.equal(d_ids.cpu(), torch.from_numpy(h_ids.numpy())) and
             torch.equal(d_keys.cpu(), torch.from_numpy(h_keys.numpy()))), "device-resident != e2e results"
 
+    shard_stats = h.shard_last_stats() if sharded_mode else None   # the last device-resident step's round
+
+    # ---- the box's copy floor for this step's bytes: the same page-locked buffers, H2D and D2H at once on two
+    # streams, every rank at the same time, nothing else running — what the e2e step cannot beat
+    h2d_bytes = text_bytes + 8 * (n + 1)
+    d2h_bytes = 4 * n * T + 8 * n + 16 * n * nb + 420 * n
+    cp_in, cp_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_sink = torch.empty(text_bytes, dtype=torch.uint8, device=dev)
+    import ctypes
+
+    def bare_copies():
+        rt = ctypes.CDLL("libcudart.so.12")     # the runtime libxllm_ingest.so already brought into the process
+        rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        cp = lambda dst, src, nbytes, kind, st: rt.cudaMemcpyAsync(dst, src, nbytes, kind, st.cuda_stream)  # noqa: E731
+        rc = cp(d_sink.data_ptr(), h_text.data_ptr(), text_bytes, 1, cp_in)
+        rc |= cp(h_ids.data_ptr(), d_ids.data_ptr(), 4 * n * T, 2, cp_out)
+        rc |= cp(h_keys.data_ptr(), d_keys.data_ptr(), 16 * n * nb, 2, cp_out)
+        rc |= cp(h_match.data_ptr(), d_match.data_ptr(), 400 * n, 2, cp_out)
+        if rc:
+            raise RuntimeError("cudaMemcpyAsync failed")
+
+    floor_ms = None
+    try:
+        bare_copies()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(3):
+            bare_copies()
+        torch.cuda.synchronize()
+        floor_ms = max_over_ranks(time.perf_counter() - w0) / 3 * 1e3
+    except Exception:   # noqa: BLE001  (cudart binding differences: the floor is informative only)
+        floor_ms = None
+    del d_sink
+    barrier()
+
     # ---- end to end through the C-ABI with host buffers
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -461,8 +583,8 @@ def main():
     kernels = {
         "sp_encode": {"ms": float(k_ms[0]), "algo_bytes": enc_bytes, "GBps": enc_bytes / k_ms[0] / 1e6},
         "xxh3_chain128": {"ms": float(k_ms[1]), "algo_bytes": hash_bytes, "GBps": hash_bytes / k_ms[1] / 1e6},
-        "index_probe+score_route": {"ms": float(k_ms[2]), "algo_bytes": match_bytes,
-                                    "GBps": match_bytes / k_ms[2] / 1e6},
+        ("shard_round(bucket+a2a+probe+a2a+scan)" if sharded_mode else "match_route(probe+scan+route)"):
+            {"ms": float(k_ms[2]), "algo_bytes": match_bytes, "GBps": match_bytes / k_ms[2] / 1e6},
     }
     for k in kernels.values():
         k["frac"] = k["GBps"] / peak
@@ -479,30 +601,38 @@ def main():
         "config": {"workload": "c2+c3: %d prompts x %d tokens per GPU, SentencePiece-BPE 8k (byte fallback), "
                                "block 128 seed 1024, %d-key prefix index over %d instances, 80%% shared-prefix "
                                "Zipf-0.9" % (n, T, index_size, N_INST),
-                   "text_bytes_per_step": text_bytes, "parallelism": "dp%d (requests sharded, index replicated, "
-                   "no collective)" % world,
+                   "text_bytes_per_step": text_bytes,
+                   "parallelism": ("dp%d requests + prefix index hash-range-sharded over %d GPUs (%d keys each): one "
+                                   "NCCL all-to-all of 24-B (hash128, req, blk) tuples per batch and one of tier "
+                                   "masks back" % (world, world, index_size // world)) if sharded_mode else
+                                  ("dp%d (requests sharded, index replicated, no collective)" % world),
                    "l2": "inputs larger than L2 (%.2f GB text + %.2f GB ids per step): no flush" %
                          (text_bytes / 1e9, 4 * n * T / 1e9),
                    "parity_gate": gate, "generation_s": round(t_gen, 1)},
         "clocks": clk,
         "e2e": {"value": world * n * args.steps / e2e_s, "unit": "req/s", "ms_per_step": e2e_s / args.steps * 1e3,
-                "h2d_bytes_per_step": text_bytes + 8 * (n + 1),
-                "d2h_bytes_per_step": 4 * n * T + 8 * n + 16 * n * nb + 420 * n,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "copy_floor_ms": floor_ms,
+                "frac_of_copy_floor": (floor_ms / (e2e_s / args.steps * 1e3)) if floor_ms else None,
                 "api": "xllm_ingest_batch (C-ABI, page-locked host buffers)"},
-        # value region: encode (throughput + long-word pass) + hash + probe + score per step;
-        # e2e region: the library's own count for one batch (6 kernels per pipeline chunk)
-        "gpu_launches": args.steps * (5 + h.last_batch_stats()[1]),
+        # value region: encode (throughput + long-word pass) + hash + match/route (sharded: bucket, headers, owner
+        # probe, header gather, scan) per step; e2e region: the library's own count for one batch
+        "gpu_launches": args.steps * ((9 if sharded_mode else 4) + h.last_batch_stats()[1]),
         "roofline": roofline,
         "kernels": kernels,
     }
+    if shard_stats:
+        line["shard_round_us"] = {k[:-3]: round(v * 1e3, 1) for k, v in shard_stats.items() if k.endswith("_ms")}
+        line["shard_round_us"]["bucket_capacity"] = shard_stats["bucket_capacity"]
+        line["shard_round_us"]["overflow_rounds"] = shard_stats["overflow_rounds"]
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as o
-        threads = os.cpu_count() or 1
+        threads, thread_detail = host_threads()
         n_sample = args.cpu_sample or max(256, min(n, threads * 24))
         v, dt, res = cpu_reference_pass(sp, P, batch, n_sample, threads)
         rr = h_route.numpy().view(_lib.ROUTING_DTYPE)[:, 0]
         assert (res["n_ids"] == T).all() and (res["ok"] == rr["ok"][:n_sample]).all()
-        line["cpu_baseline"] = {"value": v, "unit": "req/s", "cores": threads, "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": "req/s", "cores": threads, "kind": "port", "host": thread_detail,
                                 "sample": "%d of this step's prompts, %d threads, one request per thread at a time "
                                           "(encode + select_instances_pair), %.1f s" % (n_sample, threads, dt)}
     print(json.dumps(line))
