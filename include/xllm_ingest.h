@@ -246,6 +246,28 @@ typedef struct {
   xllm_routing_out* routing; /* [n_req] or NULL */
 } xllm_ingest_io;
 int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io);
+
+/* ---------------------------------------------- requests made of text pieces AND ready-made token ids (config 5)
+ * A multimodal request reaches the scheduler as text interleaved with spans that are already token ids — runs of
+ * image-placeholder ids expanded by the front end (the reference only carries a "mm place holder" string through the
+ * chat template, jinja_chat_template.cpp:119-137, and appends whatever Tokenizer::encode returns to
+ * Request::token_ids, scheduler.cpp:128-132, sentencepiece_tokenizer.cpp:122-126).  This entry point keeps that
+ * append semantics: a request is a list of segments; a text segment is tokenised exactly like one
+ * Tokenizer::encode call on that piece (own dummy prefix / whitespace rules / template ids), an id segment is copied
+ * verbatim; the request's token ids are the concatenation, and block keys / match / routing are computed over it as
+ * usual — the id spans bypass BPE but are hashed and matched.
+ *   io->text / io->offsets describe the TEXT PIECES of all requests back to back, in request order
+ *   (offsets[n_pieces + 1]); every other field of io keeps its per-request meaning (n_req, ids rows, n_ids, ...).
+ *   seg_len[s] >= 0: an id segment of that many ids, taken in order from span_ids; seg_len[s] == -1: the next text
+ *   piece.  status[r]: the first failing piece's error, else XLLM_ENC_TRUNCATED / 0. */
+typedef struct {
+  int64_t n_segments;           /* segments of all requests */
+  const int32_t* req_seg_start; /* [n_req + 1]: request r owns segments [req_seg_start[r], req_seg_start[r + 1]) */
+  const int32_t* seg_len;       /* [n_segments] */
+  const int32_t* span_ids;      /* [n_span_ids] all ready-made ids back to back, in segment order */
+  int64_t n_span_ids;
+} xllm_segments;
+int xllm_ingest_batch_segments(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_segments* seg);
 /* Pipeline chunking of xllm_ingest_batch: at most chunk_requests requests and chunk_bytes text bytes
  * per chunk (defaults 4096 / 96 MiB; chunk sizes ramp up from chunk_requests/16 and taper off at the end;
  * 4 chunks in flight over one upload, one kernel and one download stream). */

@@ -41,11 +41,14 @@ int xllm_ingest_batch(xllm_ingest_t, const xllm_ingest_io* io) {
 
 #include "ingest_batcher.h"
 
-static bool run_config(int n_threads, int per_thread, int max_batch, int max_wait_us) {
+// offline_pct: share of the requests submitted as offline (best effort, deferred behind online ones); 100 = offline
+// only (nobody to ride with: every request must fall back to the front door after its defer window)
+static bool run_config(int n_threads, int per_thread, int max_batch, int max_wait_us, int offline_pct = 0,
+                       int offline_defer_us = 3000) {
   g_calls = 0;
   g_max_batch = 0;
   g_overlap = 0;
-  xllm_host::IngestBatcher batcher(nullptr, max_batch, 1 << 16, 256, 128, max_wait_us, true);
+  xllm_host::IngestBatcher batcher(nullptr, max_batch, 1 << 16, 256, 128, max_wait_us, true, offline_defer_us);
   if (!batcher.ok()) { printf("alloc failed\n"); return false; }
   std::atomic<int> bad{0};
   std::vector<std::thread> th;
@@ -56,7 +59,7 @@ static bool run_config(int n_threads, int per_thread, int max_batch, int max_wai
         if (i % 97 == 0) p.assign(300, 'y');          // longer than max_tokens: truncated result
         if (i % 131 == 0) p.clear();                  // empty prompt
         xllm_host::IngestResult r;
-        batcher.submit(p, &r);
+        batcher.submit(p, &r, /*offline=*/(t * 31 + i * 17) % 100 < offline_pct);
         const size_t keep = p.size() < 256 ? p.size() : 256;
         bool ok = r.status == (p.size() > 256 ? XLLM_ENC_TRUNCATED : XLLM_OK) && r.token_ids.size() == keep &&
                   r.routing.ok == 1 && r.routing.prefill_id == (int32_t)(p.size() % 7);
@@ -70,17 +73,22 @@ static bool run_config(int n_threads, int per_thread, int max_batch, int max_wai
   batcher.submit(std::string((1 << 16) + 1, 'z'), &big);
   const bool big_ok = big.status == XLLM_ERR_CAPACITY;
   const unsigned long long total = (unsigned long long)n_threads * per_thread;
-  printf("threads=%d max_batch=%d wait=%dus: requests=%llu batches=%llu calls=%d largest=%d overlap=%d bad=%d big_refused=%d\n",
-         n_threads, max_batch, max_wait_us, total, (unsigned long long)batcher.batches(), g_calls.load(), g_max_batch.load(),
-         g_overlap.load(), bad.load(), (int)big_ok);
+  printf("threads=%d max_batch=%d wait=%dus offline=%d%%: requests=%llu batches=%llu calls=%d largest=%d overlap=%d bad=%d "
+         "big_refused=%d piggybacked=%llu\n",
+         n_threads, max_batch, max_wait_us, offline_pct, total, (unsigned long long)batcher.batches(), g_calls.load(),
+         g_max_batch.load(), g_overlap.load(), bad.load(), (int)big_ok, (unsigned long long)batcher.offline_piggybacked());
+  const bool mix_ok = offline_pct == 0 ? batcher.offline_piggybacked() == 0
+                                       : (offline_pct == 100 ? true : batcher.offline_piggybacked() > 0);
   return bad.load() == 0 && g_overlap.load() == 0 && batcher.requests() == total && batcher.batches() < total / 3 &&
-         g_max_batch.load() <= max_batch && g_max_batch.load() > 1 && big_ok;
+         g_max_batch.load() <= max_batch && g_max_batch.load() > 1 && big_ok && mix_ok;
 }
 
 int main() {
   bool pass = run_config(32, 300, 64, 200);       // everybody fits one batch
   pass = run_config(100, 60, 16, 50) && pass;     // far more threads than a batch holds: room waits, two sets busy
   pass = run_config(48, 100, 8, 0) && pass;       // no wait window at all
+  pass = run_config(64, 120, 32, 100, 30) && pass;        // config 5's 70:30 online / offline mix: offline ones ride along
+  pass = run_config(32, 40, 16, 50, 100, 1000) && pass;   // offline only: nobody to ride with, no starvation
   printf(pass ? "OK\n" : "FAILED\n");
   return pass ? 0 : 1;
 }

@@ -76,6 +76,12 @@ class IngestIO(ctypes.Structure):
                 ("match", ctypes.c_void_p), ("routing", ctypes.c_void_p)]
 
 
+class Segments(ctypes.Structure):
+    """xllm_segments (include/xllm_ingest.h)."""
+    _fields_ = [("n_segments", ctypes.c_int64), ("req_seg_start", ctypes.c_void_p), ("seg_len", ctypes.c_void_p),
+                ("span_ids", ctypes.c_void_p), ("n_span_ids", ctypes.c_int64)]
+
+
 _VP = ctypes.c_void_p
 
 
@@ -110,6 +116,7 @@ def _declare(L):
     L.xllm_index_probe_device.argtypes = [_VP, _VP, ctypes.c_int64, _VP, _VP]
     L.xllm_score_route_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]
     L.xllm_ingest_batch.argtypes = [_VP, ctypes.POINTER(IngestIO)]
+    L.xllm_ingest_batch_segments.argtypes = [_VP, ctypes.POINTER(IngestIO), ctypes.POINTER(Segments)]
     L.xllm_index_put_bulk.argtypes = [_VP, ctypes.c_int64, _VP, _VP, _VP, _VP]
     L.xllm_index_export.argtypes = [_VP, ctypes.c_int64, _VP, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_int64)]
     L.xllm_set_pipeline.argtypes = [_VP, ctypes.c_int32, ctypes.c_int64]

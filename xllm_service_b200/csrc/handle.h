@@ -6,6 +6,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "prefix_index.cuh"
@@ -43,7 +44,14 @@ struct PipeSlot {
   DevBuf d_memo;  // this slot's word memo (sp_encode.cuh): cleared by every encode launch on the slot's stream
   DevBuf d_defer, d_text, d_offsets, d_ids, d_n_ids, d_status, d_tok_start, d_n_tok, d_key_start, d_n_blocks, d_keys, d_masks,
       d_match, d_routing;
-  int ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_stride);
+  // segmented requests (xllm_ingest_batch_segments): text pieces encode into ragged temporary rows, then the
+  // assemble kernel splices pieces and id spans into the request's row
+  DevBuf d_piece_ids, d_piece_n, d_piece_status, d_piece_out_start, d_piece_out_cap, d_seg_len, d_seg_src, d_req_seg,
+      d_span;
+  int ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_stride, int n_req = -1);
+  // host staging of a segmented chunk's small tables: must outlive the asynchronous uploads, so they live in the slot
+  std::vector<int64_t> h_piece_out_start, h_seg_src;
+  std::vector<int32_t> h_piece_out_cap, h_req_seg;
   void release();
 };
 

@@ -40,6 +40,52 @@ __global__ void prep_rows_kernel(const int32_t* __restrict__ n_ids, int n, int64
   n_blocks[r] = (int32_t)nb;
 }
 
+// Segmented requests: one warp per request walks its segments in order and splices the ids of encoded text pieces
+// (ragged temporary rows) and of ready-made id spans into the request's row.  n_ids = the full count even when it
+// exceeds the row; status = the first failing piece's code, else truncated / ok.
+__global__ void __launch_bounds__(128) assemble_segments_kernel(
+    const int32_t* __restrict__ req_seg, const int32_t* __restrict__ seg_len, const int64_t* __restrict__ seg_src,
+    const int32_t* __restrict__ piece_ids, const int64_t* __restrict__ piece_out_start,
+    const int32_t* __restrict__ piece_out_cap, const int32_t* __restrict__ piece_n,
+    const int32_t* __restrict__ piece_status, const int32_t* __restrict__ span, int m, int32_t* __restrict__ ids,
+    int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= m) return;
+  int32_t* row = ids + (int64_t)r * ids_stride;
+  int64_t at = 0;
+  int32_t st = 0;
+  for (int s = req_seg[r]; s < req_seg[r + 1]; ++s) {
+    const int32_t len = seg_len[s];
+    const int32_t* src;
+    int64_t n, have;
+    if (len < 0) {   // a text piece
+      const int64_t p = seg_src[s];
+      int32_t ps = piece_status[p];
+      n = piece_n[p];
+      // a piece whose ids outgrew its temporary row (a normaliser expansion of more than one id per input byte, e.g.
+      // U+FDFA): the row holds only a prefix, so the request fails loudly instead of being spliced with a hole
+      if (ps >= 0 && n > piece_out_cap[p]) ps = XLLM_ERR_CAPACITY;
+      if (ps < 0 && st >= 0) st = ps;
+      have = n < piece_out_cap[p] ? n : piece_out_cap[p];   // ids actually present in the temporary row
+      src = piece_ids + piece_out_start[p];
+      if (ps < 0) { n = 0; have = 0; }
+    } else {
+      n = have = len;
+      src = span + seg_src[s];
+    }
+    int64_t room = ids_stride - at;
+    if (room < 0) room = 0;
+    const int64_t copy = have < room ? have : room;
+    for (int64_t i = lane; i < copy; i += 32) row[at + i] = src[i];
+    at += n;
+  }
+  if (lane == 0) {
+    n_ids[r] = st < 0 ? 0 : (int32_t)at;
+    status[r] = st < 0 ? st : (at > ids_stride ? 1 : 0);
+  }
+}
+
 // Sharded index: the exchange runs once per batch, so every chunk also files its rows in batch-wide descriptors.
 __global__ void batch_rows_kernel(const int32_t* __restrict__ chunk_n_blocks, int m, int64_t row0, int64_t keys_stride,
                                   int64_t* __restrict__ all_key_start, int32_t* __restrict__ all_n_blocks) {
@@ -51,11 +97,13 @@ __global__ void batch_rows_kernel(const int32_t* __restrict__ chunk_n_blocks, in
 
 }  // namespace
 
-int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_stride) {
+// n: rows of the offsets table (requests, or text pieces of segmented requests); n_req: request rows of the outputs
+int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_stride, int n_req) {
   int rc;
+  if (n_req < 0) n_req = n;
   if ((rc = d_text.reserve(text_bytes + 64)) != XLLM_OK) return rc;
   if ((rc = d_offsets.reserve((size_t)(n + 1) * 8)) != XLLM_OK) return rc;
-  if ((rc = d_ids.reserve((size_t)n * (size_t)ids_stride * 4 + 64)) != XLLM_OK) return rc;
+  if ((rc = d_ids.reserve((size_t)n_req * (size_t)ids_stride * 4 + 64)) != XLLM_OK) return rc;
   if ((rc = d_n_ids.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_status.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_defer.reserve((size_t)n * 4)) != XLLM_OK) return rc;
@@ -63,7 +111,7 @@ int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_
   if ((rc = d_n_tok.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_key_start.reserve((size_t)n * 8)) != XLLM_OK) return rc;
   if ((rc = d_n_blocks.reserve((size_t)n * 4)) != XLLM_OK) return rc;
-  if ((rc = d_keys.reserve((size_t)n * (size_t)keys_stride * 16 + 64)) != XLLM_OK) return rc;
+  if ((rc = d_keys.reserve((size_t)n_req * (size_t)keys_stride * 16 + 64)) != XLLM_OK) return rc;
   if ((rc = d_match.reserve((size_t)n * sizeof(MatchOut))) != XLLM_OK) return rc;
   if ((rc = d_routing.reserve((size_t)n * sizeof(RoutingOut))) != XLLM_OK) return rc;
   return XLLM_OK;
@@ -75,6 +123,8 @@ void PipeSlot::release() {
   d_text.release(); d_offsets.release(); d_ids.release(); d_n_ids.release(); d_status.release();
   d_tok_start.release(); d_n_tok.release(); d_key_start.release(); d_n_blocks.release();
   d_keys.release(); d_masks.release(); d_match.release(); d_routing.release();
+  d_piece_ids.release(); d_piece_n.release(); d_piece_status.release(); d_piece_out_start.release();
+  d_piece_out_cap.release(); d_seg_len.release(); d_seg_src.release(); d_req_seg.release(); d_span.release();
   for (int k = 0; k < 3; ++k) {
     if (ev[k]) cudaEventDestroy(ev[k]);
     ev[k] = nullptr;
@@ -148,7 +198,17 @@ void xllm_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
-int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
+static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_segments* seg);
+int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) { return ingest_core(h, io, nullptr); }
+int xllm_ingest_batch_segments(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_segments* seg) {
+  if (!seg) {
+    set_last_error("xllm_ingest_batch_segments: null segment table");
+    return XLLM_ERR_INVALID_ARG;
+  }
+  return ingest_core(h, io, seg);
+}
+
+static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_segments* seg) {
   if (!h || !io || io->n_req < 0) {
     set_last_error("xllm_ingest_batch: invalid argument");
     return XLLM_ERR_INVALID_ARG;
@@ -170,13 +230,50 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
     return XLLM_ERR_UNSUPPORTED;
   }
   const int64_t keys_stride = io->keys_stride > 0 ? io->keys_stride : (want_match ? io->ids_stride / h->block_size : 0);
-  for (int32_t r = 0; r < n; ++r)
-    if (io->offsets[r + 1] < io->offsets[r] || io->offsets[r] < 0 ||
-        io->offsets[r + 1] - io->offsets[r] > 0x7fffffffLL) {
-      set_last_error("xllm_ingest_batch: bad offsets at request %d", r);
+  // ---- segmented requests: where each request's text pieces and id spans start (host prefix sums)
+  int64_t n_pieces = n;                    // rows of io->offsets: requests, or text pieces
+  std::vector<int64_t> piece_of_req, span_of_req, seg_src;   // [n + 1], [n + 1], [n_segments]
+  if (seg) {
+    if (seg->n_segments < 0 || seg->n_span_ids < 0 || !seg->req_seg_start || (seg->n_segments > 0 && !seg->seg_len) ||
+        (seg->n_span_ids > 0 && !seg->span_ids) || seg->req_seg_start[0] != 0 ||
+        seg->req_seg_start[n] != seg->n_segments) {
+      set_last_error("xllm_ingest_batch_segments: inconsistent segment table");
       return XLLM_ERR_INVALID_ARG;
     }
-  if (io->offsets[n] > io->offsets[0] && !io->text) return XLLM_ERR_INVALID_ARG;
+    piece_of_req.assign((size_t)n + 1, 0);
+    span_of_req.assign((size_t)n + 1, 0);
+    seg_src.assign((size_t)seg->n_segments, 0);
+    int64_t pieces = 0, spans = 0;
+    for (int32_t r = 0; r < n; ++r) {
+      piece_of_req[(size_t)r] = pieces;
+      span_of_req[(size_t)r] = spans;
+      if (seg->req_seg_start[r + 1] < seg->req_seg_start[r]) {
+        set_last_error("xllm_ingest_batch_segments: req_seg_start not ascending at request %d", r);
+        return XLLM_ERR_INVALID_ARG;
+      }
+      for (int32_t s2 = seg->req_seg_start[r]; s2 < seg->req_seg_start[r + 1]; ++s2) {
+        const int32_t len = seg->seg_len[s2];
+        if (len < 0) seg_src[(size_t)s2] = pieces++;
+        else { seg_src[(size_t)s2] = spans; spans += len; }
+      }
+    }
+    piece_of_req[(size_t)n] = pieces;
+    span_of_req[(size_t)n] = spans;
+    if (spans != seg->n_span_ids) {
+      set_last_error("xllm_ingest_batch_segments: id segments add up to %lld ids, n_span_ids says %lld", (long long)spans,
+                     (long long)seg->n_span_ids);
+      return XLLM_ERR_INVALID_ARG;
+    }
+    n_pieces = pieces;
+  }
+  for (int64_t r = 0; r < n_pieces; ++r)
+    if (io->offsets[r + 1] < io->offsets[r] || io->offsets[r] < 0 ||
+        io->offsets[r + 1] - io->offsets[r] > 0x7fffffffLL) {
+      set_last_error("xllm_ingest_batch: bad offsets at row %lld", (long long)r);
+      return XLLM_ERR_INVALID_ARG;
+    }
+  if (io->offsets[n_pieces] > io->offsets[0] && !io->text) return XLLM_ERR_INVALID_ARG;
+  const int tmpl_ids = h->sp_dev ? (int)h->sp_dev->dev().n_prefix + (int)h->sp_dev->dev().n_suffix : 0;
 
   std::lock_guard<std::mutex> lock(h->mu);
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
@@ -243,15 +340,21 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
   while (c0 < n) {
     const int64_t target = sched.next((int64_t)n - c0);
     int32_t c1 = c0;
-    while (c1 < n && c1 - c0 < target && (c1 == c0 || io->offsets[c1 + 1] - io->offsets[c0] <= chunk_bytes)) ++c1;
+    // first / one-past-last row of io->offsets a request range covers (requests themselves, or their text pieces)
+    auto row_of = [&](int32_t r) { return seg ? piece_of_req[(size_t)r] : (int64_t)r; };
+    while (c1 < n && c1 - c0 < target &&
+           (c1 == c0 || io->offsets[row_of(c1 + 1)] - io->offsets[row_of(c0)] <= chunk_bytes))
+      ++c1;
     const int m = c1 - c0;
-    const int64_t t0 = io->offsets[c0];
-    const size_t text_bytes = (size_t)(io->offsets[c1] - t0);
+    const int64_t p0 = row_of(c0), p1 = row_of(c1);
+    const int mp = (int)(p1 - p0);                     // rows the encode kernel sees: m requests, or mp text pieces
+    const int64_t t0 = io->offsets[p0];
+    const size_t text_bytes = (size_t)(io->offsets[p1] - t0);
     PipeSlot& sl = h->pipe[slot];
     uint8_t* chunk_keys = sl.d_keys.as<uint8_t>();
     // the slot's previous chunk has been downloaded (host wait: ensure() below may reallocate its buffers)
     if (sl.busy) PIPE_CUDA_TRY(cudaEventSynchronize(sl.ev[2]));
-    if ((rc = sl.ensure(text_bytes, m, io->ids_stride, keys_stride)) != XLLM_OK) break;
+    if ((rc = sl.ensure(text_bytes, m > mp ? m : mp, io->ids_stride, keys_stride, m)) != XLLM_OK) break;
     if (h->memo_slots && (rc = sl.d_memo.reserve((size_t)h->memo_slots * 32)) != XLLM_OK) break;
     xllm::SpMemo memo;
     memo.table = h->memo_slots ? sl.d_memo.p : nullptr;
@@ -263,14 +366,74 @@ int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io) {
     // ---- upload
     if (text_bytes)
       PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_text.p, io->text + t0, text_bytes, cudaMemcpyHostToDevice, s_in));
-    PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_offsets.p, io->offsets + c0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, s_in));
+    PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_offsets.p, io->offsets + p0, (size_t)(mp + 1) * 8, cudaMemcpyHostToDevice, s_in));
+    int64_t piece_ids_total = 0;
+    if (seg) {
+      // ragged temporary rows for the pieces: a piece of b bytes yields at most b + 1 ids (+ template ids)
+      const int32_t s0 = seg->req_seg_start[c0], s1 = seg->req_seg_start[c1];
+      const int64_t sp0 = span_of_req[(size_t)c0], sp1 = span_of_req[(size_t)c1];
+      std::vector<int64_t>& ostart = sl.h_piece_out_start;
+      std::vector<int32_t>& ocap = sl.h_piece_out_cap;
+      std::vector<int32_t>& rseg = sl.h_req_seg;
+      std::vector<int64_t>& ssrc = sl.h_seg_src;
+      ostart.resize((size_t)mp + 1);
+      ocap.resize((size_t)mp + 1);
+      for (int k = 0; k < mp; ++k) {
+        ostart[(size_t)k] = piece_ids_total;
+        ocap[(size_t)k] = (int32_t)(io->offsets[p0 + k + 1] - io->offsets[p0 + k]) + 2 + tmpl_ids;
+        piece_ids_total += ocap[(size_t)k];
+      }
+      rseg.resize((size_t)m + 1);
+      for (int k = 0; k <= m; ++k) rseg[(size_t)k] = seg->req_seg_start[c0 + k] - s0;
+      ssrc.resize((size_t)(s1 - s0) + 1);
+      for (int32_t k = s0; k < s1; ++k)   // chunk-local: piece index / span offset
+        ssrc[(size_t)(k - s0)] = seg_src[(size_t)k] - (seg->seg_len[k] < 0 ? p0 : sp0);
+      if ((rc = sl.d_piece_ids.reserve((size_t)piece_ids_total * 4 + 64)) != XLLM_OK) break;
+      if ((rc = sl.d_piece_n.reserve((size_t)mp * 4 + 4)) != XLLM_OK) break;
+      if ((rc = sl.d_piece_status.reserve((size_t)mp * 4 + 4)) != XLLM_OK) break;
+      if ((rc = sl.d_piece_out_start.reserve((size_t)mp * 8 + 8)) != XLLM_OK) break;
+      if ((rc = sl.d_piece_out_cap.reserve((size_t)mp * 4 + 4)) != XLLM_OK) break;
+      if ((rc = sl.d_seg_len.reserve((size_t)(s1 - s0) * 4 + 4)) != XLLM_OK) break;
+      if ((rc = sl.d_seg_src.reserve((size_t)(s1 - s0) * 8 + 8)) != XLLM_OK) break;
+      if ((rc = sl.d_req_seg.reserve((size_t)(m + 1) * 4)) != XLLM_OK) break;
+      if ((rc = sl.d_span.reserve((size_t)(sp1 - sp0) * 4 + 4)) != XLLM_OK) break;
+      if ((rc = sl.d_defer.reserve((size_t)mp * 4 + 4)) != XLLM_OK) break;
+      if (mp) {
+        PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_piece_out_start.p, ostart.data(), (size_t)mp * 8, cudaMemcpyHostToDevice, s_in));
+        PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_piece_out_cap.p, ocap.data(), (size_t)mp * 4, cudaMemcpyHostToDevice, s_in));
+      }
+      if (s1 > s0) {
+        PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_seg_len.p, seg->seg_len + s0, (size_t)(s1 - s0) * 4, cudaMemcpyHostToDevice, s_in));
+        PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_seg_src.p, ssrc.data(), (size_t)(s1 - s0) * 8, cudaMemcpyHostToDevice, s_in));
+      }
+      PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_req_seg.p, rseg.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice, s_in));
+      if (sp1 > sp0)
+        PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_span.p, seg->span_ids + sp0, (size_t)(sp1 - sp0) * 4, cudaMemcpyHostToDevice, s_in));
+    }
     PIPE_CUDA_TRY(cudaEventRecord(sl.ev[0], s_in));
     mark(1, s_in);
     // ---- kernels: tokenize -> row prep -> chained block hash -> index probe -> match scan + routing
     PIPE_CUDA_TRY(cudaStreamWaitEvent(s_k, sl.ev[0], 0));
-    PIPE_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), m,
-                                   sl.d_ids.as<int32_t>(), io->ids_stride, sl.d_n_ids.as<int32_t>(),
-                                   sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s_k, memo));
+    if (!seg) {
+      PIPE_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), m,
+                                     sl.d_ids.as<int32_t>(), io->ids_stride, sl.d_n_ids.as<int32_t>(),
+                                     sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s_k, memo));
+    } else {
+      xllm::SpLaunchOpts opts;
+      opts.out_start = sl.d_piece_out_start.as<int64_t>();
+      opts.out_cap = sl.d_piece_out_cap.as<int32_t>();
+      PIPE_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), mp,
+                                     sl.d_piece_ids.as<int32_t>(), 0, sl.d_piece_n.as<int32_t>(),
+                                     sl.d_piece_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s_k, memo,
+                                     opts));
+      assemble_segments_kernel<<<(m + 3) / 4, 128, 0, s_k>>>(
+          sl.d_req_seg.as<int32_t>(), sl.d_seg_len.as<int32_t>(), sl.d_seg_src.as<int64_t>(),
+          sl.d_piece_ids.as<int32_t>(), sl.d_piece_out_start.as<int64_t>(), sl.d_piece_out_cap.as<int32_t>(),
+          sl.d_piece_n.as<int32_t>(), sl.d_piece_status.as<int32_t>(), sl.d_span.as<int32_t>(), m,
+          sl.d_ids.as<int32_t>(), io->ids_stride, sl.d_n_ids.as<int32_t>(), sl.d_status.as<int32_t>());
+      PIPE_CUDA_TRY(cudaGetLastError());
+      h->last_launches += 1;
+    }
     mark(2, s_k);
     if (keys_stride > 0 || want_match) {
       // keys_stride == 0 with match / routing requested (ids_stride < block_size): every request has 0 blocks, the

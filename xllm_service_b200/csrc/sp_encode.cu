@@ -1467,6 +1467,10 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int lane = threadIdx.x;
   const int drain_at = kNBuf - 3 * kFastWin - 8;  // room for one more fast-path step
+  unsigned long long warp_t0 = 0;
+  if constexpr (!LONG) {
+    if (T.warp_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(warp_t0));
+  }
 
   for (;;) {
     unsigned int r = 0;
@@ -1483,8 +1487,8 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     const int64_t beg = offsets[r];
     rs.src = text + beg;
     rs.len = (uint32_t)(offsets[r + 1] - beg);
-    rs.out = ids + (int64_t)r * ids_stride;
-    rs.cap = ids_stride;
+    rs.out = T.out_start ? ids + T.out_start[r] : ids + (int64_t)r * ids_stride;
+    rs.cap = T.out_cap ? (int64_t)T.out_cap[r] : ids_stride;
     rs.n_out = 0;
     rs.nlen = 0;
     rs.trailing_bare = 0;
@@ -1601,6 +1605,13 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       }
     }
     __syncwarp();
+  }
+  if constexpr (!LONG) {
+    if (T.warp_ns && lane == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      T.warp_ns[blockIdx.x] = t1 - warp_t0;
+    }
   }
 }
 
@@ -1769,11 +1780,35 @@ int SpDeviceModel::upload(const SpTables& t) {
   return XLLM_OK;
 }
 
-cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
+static DeviceOnce g_sp_once;
+
+static int sp_warps_per_sm(const SpDev& dev) {
+  const bool small = dev.small_vocab != 0;
+  const size_t smem = dev.unigram ? (small ? sizeof(WarpSmemUniT<true>) : sizeof(WarpSmemUniT<false>))
+                                  : (small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>));
+  int w = (int)((227 * 1024) / (smem + 1024));
+  if (w > 27) w = 27;
+  if (!dev.unigram && g_warps_per_sm_override > 0 && g_warps_per_sm_override < w) w = g_warps_per_sm_override;
+  return w;
+}
+
+int sp_encode_grid(const SpDev& dev, int n_req) {
+  int n_sm = 0, d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d) != cudaSuccess)
+    return 0;
+  const int grid = n_sm * sp_warps_per_sm(dev);
+  return grid > n_req ? n_req : grid;
+}
+
+cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
                              int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
-                             int32_t* defer_list, cudaStream_t stream, SpMemo memo) {
+                             int32_t* defer_list, cudaStream_t stream, SpMemo memo, SpLaunchOpts opts) {
   if (n_req <= 0) return cudaSuccess;
-  static DeviceOnce once;
+  DeviceOnce& once = g_sp_once;
+  SpDev dev = dev_in;   // the kernel takes the table descriptor by value: the per-launch options ride along
+  dev.out_start = opts.out_start;
+  dev.out_cap = opts.out_cap;
+  dev.warp_ns = opts.warp_ns;
   const bool small = dev.small_vocab != 0;
   const size_t smem = small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>);
   cudaError_t e0 = cudaSuccess;

@@ -60,6 +60,10 @@ struct SpDev {
   uint8_t nfc_check;   // normalizer NFC: a request passes only if every char is NFC-inert (then NFC is the identity)
   uint8_t hf_pattern;  // 1: ByteLevel's own GPT-2 regex, 2: Split(cl100k-family regex) + ByteLevel(use_regex = false)
   uint8_t hf_digits;   // pattern 2: \p{N}{1,hf_digits}
+  // per-launch options (set by sp_encode_launch from SpLaunchOpts; null = off)
+  const int64_t* out_start;      // request r's ids go to ids + out_start[r] (at most out_cap[r]) instead of r * ids_stride
+  const int32_t* out_cap;
+  unsigned long long* warp_ns;   // [grid]: nanoseconds each warp of the throughput kernel spent from start to exit
   uint8_t* long_pool;
   int* long_locks;
   uint32_t long_cap;   // symbols per slot
@@ -99,8 +103,18 @@ uint32_t sp_memo_default_slots();  // XLLM_SP_MEMO_SLOTS (0 = off), default 2^18
 // counters: 4 zero-initialisable uint32 in device memory; defer_list: n_req int32 of device scratch (requests
 // that need the long-word pass).  Two launches: the throughput kernel, then the long-word kernel over the
 // deferred requests (a no-op grid when there are none).
+struct SpLaunchOpts {
+  // ragged output rows (text pieces of segmented requests, pipeline.cu): ids + out_start[r], capacity out_cap[r]
+  const int64_t* out_start = nullptr;
+  const int32_t* out_cap = nullptr;
+  // diagnostics: per-warp busy time of the throughput kernel's persistent grid ([grid] entries, see
+  // sp_encode_grid()); used by bench.py to report the length tail of variable-length batches
+  unsigned long long* warp_ns = nullptr;
+};
+int sp_encode_grid(const SpDev& dev, int n_req);   // warps (= blocks) the throughput kernel launches for n_req requests
 cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
                              int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
-                             int32_t* defer_list, cudaStream_t stream, SpMemo memo = SpMemo());
+                             int32_t* defer_list, cudaStream_t stream, SpMemo memo = SpMemo(),
+                             SpLaunchOpts opts = SpLaunchOpts());
 
 }  // namespace xllm

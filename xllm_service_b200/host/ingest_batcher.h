@@ -13,12 +13,21 @@
 // page-locked staging sets, runs ONE xllm_ingest_batch (device calls are serialised), hands the results out and
 // wakes its followers.  The next batch assembles meanwhile, and batch k+1 can be on the device while the results
 // of batch k are still being handed out.
+//
+// Online / offline mix (BASELINE config 5; Request::offline, request/request.h:41 — "preemptive execution for online
+// requests and best-effort execution for offline requests", README.md:40): submit(prompt, out, /*offline=*/true) parks
+// the request in a deferred queue instead of opening or extending a batch.  Whenever a batch of online requests
+// closes, the room it has left (requests and bytes) is filled with deferred offline requests, oldest first, so they
+// ride along for free and never delay an online request; an offline request nobody picked up within
+// `offline_defer_us` stops waiting and goes through the online path itself (no starvation when there is no online
+// traffic).
 #pragma once
 #include <stdint.h>
 #include <string.h>
 
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string_view>
@@ -39,9 +48,10 @@ class IngestBatcher {
  public:
   // `h` must outlive the batcher.  max_tokens bounds the ids returned per request.
   IngestBatcher(xllm_ingest_t h, int max_batch, size_t max_bytes, int max_tokens, int block_size, int max_wait_us,
-                bool want_routing)
+                bool want_routing, int offline_defer_us = 20000)
       : h_(h), max_batch_(max_batch), max_bytes_(max_bytes), max_tokens_(max_tokens),
-        keys_stride_(max_tokens / block_size), max_wait_us_(max_wait_us), want_routing_(want_routing) {
+        keys_stride_(max_tokens / block_size), max_wait_us_(max_wait_us), want_routing_(want_routing),
+        offline_defer_us_(offline_defer_us) {
     ok_ = true;
     for (Staging& s : sets_) {
       ok_ = ok_ && xllm_host_alloc(reinterpret_cast<void**>(&s.text), max_bytes) == XLLM_OK &&
@@ -63,11 +73,27 @@ class IngestBatcher {
   bool ok() const { return ok_; }
   uint64_t batches() const { return n_batches_; }
   uint64_t requests() const { return n_requests_; }
+  uint64_t offline_piggybacked() const { return n_piggyback_; }   // offline requests that rode in an online batch
 
-  // Blocks until the request has been tokenised (+ matched and routed).  Thread-safe.
-  void submit(std::string_view prompt, IngestResult* out) {
+  // Blocks until the request has been tokenised (+ matched and routed).  Thread-safe.  offline = best effort: see
+  // the header comment.
+  void submit(std::string_view prompt, IngestResult* out, bool offline = false) {
     std::unique_lock<std::mutex> lk(mu_);
     if (!ok_ || prompt.size() > max_bytes_) { out->status = XLLM_ERR_CAPACITY; return; }
+    if (offline && offline_defer_us_ > 0) {
+      auto d = std::make_shared<Deferred>();
+      d->item = Item{prompt, out};
+      deferred_.push_back(d);
+      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(offline_defer_us_);
+      cv_done_.wait_until(lk, deadline, [&] { return d->batch != nullptr; });
+      if (d->batch) {   // an online batch took it along
+        std::shared_ptr<Batch> b = d->batch;
+        cv_done_.wait(lk, [&] { return b->done; });
+        return;
+      }
+      for (auto it = deferred_.begin(); it != deferred_.end(); ++it)   // nobody came: go through the front door
+        if (*it == d) { deferred_.erase(it); break; }
+    }
     // wait for room in the batch that is being assembled
     cv_room_.wait(lk, [&] {
       return !cur_ || ((int)cur_->items.size() < max_batch_ && bytes_ + prompt.size() <= max_bytes_);
@@ -86,6 +112,17 @@ class IngestBatcher {
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(max_wait_us_);
     cv_full_.wait_until(lk, deadline, full);
     cv_full_.wait(lk, [&] { return full() || (!dev_busy_ && !free_sets_.empty()); });
+    // closing: deferred offline requests fill whatever room is left, oldest first
+    while (!deferred_.empty() && (int)b->items.size() < max_batch_ &&
+           bytes_ + deferred_.front()->item.prompt.size() <= max_bytes_) {
+      std::shared_ptr<Deferred> d = deferred_.front();
+      deferred_.pop_front();
+      b->items.push_back(d->item);
+      bytes_ += d->item.prompt.size();
+      d->batch = b;
+      ++n_piggyback_;
+    }
+    cv_done_.notify_all();   // the riders stop watching their deadline
     cur_.reset();  // closed: the next batch starts assembling now
     bytes_ = 0;
     cv_room_.notify_all();
@@ -119,6 +156,10 @@ class IngestBatcher {
   struct Batch {
     std::vector<Item> items;
     bool done = false;
+  };
+  struct Deferred {   // an offline request waiting for a ride
+    Item item;
+    std::shared_ptr<Batch> batch;   // set when an online batch took it
   };
   struct Staging {  // page-locked buffers of one batch in flight
     uint8_t* text = nullptr;
@@ -173,6 +214,9 @@ class IngestBatcher {
   const int keys_stride_;
   const int max_wait_us_;
   const bool want_routing_;
+  const int offline_defer_us_;
+  std::deque<std::shared_ptr<Deferred>> deferred_;
+  uint64_t n_piggyback_ = 0;
   bool ok_ = false;
   Staging sets_[2];
   std::vector<int> free_sets_;

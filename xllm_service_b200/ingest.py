@@ -289,3 +289,37 @@ class Ingest:
         self.ingest_batch_ptrs(n, a(text), a(offsets), a(out["ids"]), ids_stride, a(out["n_ids"]), a(out["status"]),
                                a(out["keys"]), ks if want_keys else 0, a(out["match"]), a(out["routing"]))
         return out
+
+    def ingest_batch_segments_ptrs(self, n_req, text, offsets, ids, ids_stride, n_ids, status, n_segments,
+                                   req_seg_start, seg_len, span_ids, n_span_ids, keys=0, keys_stride=0, match=0,
+                                   routing=0):
+        """xllm_ingest_batch_segments over raw host addresses (ints)."""
+        io = _lib.IngestIO(n_req, text, offsets, ids, ids_stride, n_ids, status, keys or None, keys_stride,
+                           match or None, routing or None)
+        sg = _lib.Segments(n_segments, req_seg_start, seg_len, span_ids or None, n_span_ids)
+        check(self._L.xllm_ingest_batch_segments(self._h, ctypes.byref(io), ctypes.byref(sg)))
+
+    def ingest_batch_segments(self, seg_batch, ids_stride, want_keys=True, want_match=True):
+        """Requests made of text pieces and ready-made id spans (workload.SegmentBatch) -> the same dict as
+        ingest_batch.  Text pieces are tokenised like independent Tokenizer::encode calls and appended; id spans are
+        copied; keys / match / routing run over the concatenation."""
+        b = seg_batch
+        text = np.ascontiguousarray(b.text, dtype=np.uint8)
+        offsets = np.ascontiguousarray(b.offsets, dtype=np.int64)
+        rss = np.ascontiguousarray(b.req_seg_start, dtype=np.int32)
+        sl = np.ascontiguousarray(b.seg_len, dtype=np.int32)
+        span = np.ascontiguousarray(b.span_ids, dtype=np.int32)
+        n = rss.size - 1
+        ks = ids_stride // self.block_size
+        out = {"ids": np.zeros((n, ids_stride), np.int32), "n_ids": np.zeros(n, np.int32),
+               "status": np.zeros(n, np.int32), "keys": None, "match": None, "routing": None}
+        if want_keys:
+            out["keys"] = np.zeros((n, ks, 16), np.uint8)
+        if want_match:
+            out["match"] = np.zeros(n, dtype=_lib.MATCH_DTYPE)
+            out["routing"] = np.zeros(n, dtype=_lib.ROUTING_DTYPE)
+        a = lambda x: x.ctypes.data if x is not None and x.size else 0  # noqa: E731
+        self.ingest_batch_segments_ptrs(n, a(text), offsets.ctypes.data, a(out["ids"]), ids_stride, a(out["n_ids"]),
+                                        a(out["status"]), sl.size, rss.ctypes.data, a(sl), a(span), span.size,
+                                        a(out["keys"]), ks if want_keys else 0, a(out["match"]), a(out["routing"]))
+        return out

@@ -229,3 +229,117 @@ def make_prompts_exact_tokens(n_prompts, n_tokens, word_token_counts, seed=0, vo
         pb[prefix_id >= 0] = pref_blk_np[prefix_id[prefix_id >= 0]]
     meta = {"prefix_id": prefix_id, "prefix_blocks": pb, "n_prefixes": n_pref}
     return PromptBatch(text, offsets), meta
+
+
+class SegmentBatch:
+    """A batch of segmented requests in the layout xllm_ingest_batch_segments takes (include/xllm_ingest.h):
+    text pieces back to back (text, offsets[n_pieces + 1]) + the segment table + the ready-made id spans."""
+
+    def __init__(self, text, offsets, req_seg_start, seg_len, span_ids, offline, n_tokens):
+        self.text, self.offsets = text, offsets
+        self.req_seg_start, self.seg_len, self.span_ids = req_seg_start, seg_len, span_ids
+        self.offline = offline            # bool [n_req]: best-effort requests (request/request.h:41)
+        self.n_tokens = n_tokens          # int32 [n_req]: tokens each request must come out at
+
+    @property
+    def n(self):
+        return self.req_seg_start.size - 1
+
+    def select(self, rows):
+        """The sub-batch of the given request rows (in that order), same layout."""
+        rows = np.asarray(rows, dtype=np.int64)
+        piece_of_seg = np.cumsum(self.seg_len < 0) - (self.seg_len < 0)          # piece index of a text segment
+        span_of_seg = np.cumsum(np.maximum(self.seg_len, 0)) - np.maximum(self.seg_len, 0)
+        texts, seg_len, spans, rss = [], [], [], [0]
+        for r in rows:
+            for s in range(self.req_seg_start[r], self.req_seg_start[r + 1]):
+                ln = int(self.seg_len[s])
+                seg_len.append(ln)
+                if ln < 0:
+                    p = piece_of_seg[s]
+                    texts.append(self.text[self.offsets[p]:self.offsets[p + 1]])
+                else:
+                    spans.append(self.span_ids[span_of_seg[s]:span_of_seg[s] + ln])
+            rss.append(len(seg_len))
+        off = np.zeros(len(texts) + 1, np.int64)
+        if texts:
+            np.cumsum([t.size for t in texts], out=off[1:])
+        return SegmentBatch(np.concatenate(texts) if texts else np.zeros(0, np.uint8), off,
+                            np.asarray(rss, np.int32), np.asarray(seg_len, np.int32),
+                            np.concatenate(spans).astype(np.int32) if spans else np.zeros(0, np.int32),
+                            self.offline[rows], self.n_tokens[rows])
+
+
+def make_c5_batch(n_requests, word_token_counts, seed=0, vocabulary=None, min_tokens=64, max_tokens=8192,
+                  mm_frac=0.3, span_tokens=(256, 1024), max_spans=4, placeholder_ids=(7001, 7002, 7003),
+                  offline_frac=0.3, shared_prefix=None):
+    """BASELINE config 5 (SURVEY.md §8d C5 — synthetic, no reference semantics): the EPD multimodal mix.
+      * request length log-uniform in [min_tokens, max_tokens] tokens;
+      * mm_frac of the requests carry 1..max_spans runs of span_tokens[0]..span_tokens[1] repeated image-placeholder
+        ids — already-tokenised spans that bypass BPE but are hashed and matched — between their text pieces;
+      * offline_frac of the requests are offline (best effort; the batcher defers them behind online ones);
+      * shared_prefix: optional dict(n_prefixes, frac, min_blocks, max_blocks, block_tokens): that fraction of the
+        requests start their first text piece with one of the shared prefixes (Zipf-0.9 popularity).
+    Every text piece is built from whole vocabulary words whose token counts (word_token_counts, measured with the
+    tokenizer) add up exactly, so request r encodes to exactly n_tokens[r] tokens.  numpy only; deterministic."""
+    vocab = vocabulary or make_vocabulary()
+    V = len(vocab)
+    wtc = np.asarray(word_token_counts, dtype=np.int64)
+    rng = np.random.default_rng(seed)
+    max_cnt = int(wtc.max())
+    by_count = {c: np.nonzero(wtc == c)[0] for c in range(1, max_cnt + 1)}
+    mean_tok = float(wtc[sample_word_ids(rng, 1, 4096, V)[0]].mean())
+    pref_rows, pref_tok, pref_p = [], [], None
+    if shared_prefix:
+        sp = shared_prefix
+        blocks = rng.integers(sp["min_blocks"], sp["max_blocks"] + 1, size=sp["n_prefixes"])
+        for b in blocks:
+            t = int(b) * sp["block_tokens"]
+            pref_rows.append(_exact_row(rng, t, wtc, by_count, max_cnt, V, int(t / mean_tok * 1.2) + 64))
+            pref_tok.append(t)
+        pref_p = zipf_probs(sp["n_prefixes"])
+    lengths = np.exp(rng.uniform(np.log(min_tokens), np.log(max_tokens + 1), size=n_requests)).astype(np.int64)
+    lengths = np.clip(lengths, min_tokens, max_tokens)
+    pieces, seg_len, spans, rss = [], [], [], [0]
+    offline = rng.random(n_requests) < offline_frac
+    prefix_id = np.full(n_requests, -1, np.int32)
+    for r in range(n_requests):
+        L = int(lengths[r])
+        span_lens = []
+        if rng.random() < mm_frac:
+            for _ in range(int(rng.integers(1, max_spans + 1))):
+                ln = int(rng.integers(span_tokens[0], span_tokens[1] + 1))
+                if sum(span_lens) + ln <= L - 16:          # keep at least a little text
+                    span_lens.append(ln)
+        text_tok = L - sum(span_lens)
+        # text budget split over len(span_lens) + 1 pieces (a piece may come out empty and is then left out)
+        cuts = np.sort(rng.integers(0, text_tok + 1, size=len(span_lens)))
+        piece_tok = np.diff(np.concatenate([[0], cuts, [text_tok]]))
+        lead = None
+        if shared_prefix and rng.random() < shared_prefix["frac"]:
+            j = int(rng.choice(len(pref_rows), p=pref_p))
+            if pref_tok[j] <= piece_tok[0]:
+                lead, prefix_id[r] = j, j
+        for k, t in enumerate(piece_tok):
+            t = int(t)
+            if t > 0:
+                words = []
+                if k == 0 and lead is not None:
+                    words.append(pref_rows[lead])
+                    t -= pref_tok[lead]
+                if t > 0:
+                    words.append(_exact_row(rng, t, wtc, by_count, max_cnt, V, int(t / mean_tok * 1.2) + 64))
+                ids = np.concatenate(words)
+                pieces.append(b" ".join(vocab[i] for i in ids))
+                seg_len.append(-1)
+            if k < len(span_lens):
+                spans.append(np.full(span_lens[k], placeholder_ids[int(rng.integers(0, len(placeholder_ids)))], np.int32))
+                seg_len.append(span_lens[k])
+        rss.append(len(seg_len))
+    pb = pack_prompts(pieces)
+    b = SegmentBatch(pb.text, pb.offsets, np.asarray(rss, np.int32), np.asarray(seg_len, np.int32),
+                     np.concatenate(spans).astype(np.int32) if spans else np.zeros(0, np.int32), offline,
+                     lengths.astype(np.int32))
+    b.prefix_id = prefix_id
+    b.prefix_tokens = np.array([pref_tok[j] if j >= 0 else 0 for j in prefix_id], np.int32)
+    return b
