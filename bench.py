@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="prompts in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk-requests", type=int, default=0)
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 (EPD mix) side measurement at N = 1")
+    ap.add_argument("--c5-requests", type=int, default=8192)
     ap.add_argument("--index", default="auto", choices=["auto", "replicated", "sharded"],
                     help="prefix index placement at N > 1: sharded = BASELINE config 4 (hash-range shards, index N x "
                          "--index-keys, one NCCL all-to-all each way per batch); auto = sharded when N > 1")
@@ -212,6 +214,118 @@ def traffic_from_profiles(kernel):
 
 
 # ----------------------------------------------------------------------------------------------
+def run_c5(h, wcnt, n_req, steps, rank_seed=0):
+    """BASELINE config 5 (EPD multimodal mix; synthetic, no reference semantics — SURVEY.md §8d C5): requests of
+    log-uniform 64-8192 tokens, 30 % with 1-4 spans of 256-1024 ready-made image-placeholder ids between their text
+    pieces (the spans bypass BPE but are hashed and matched), 70:30 online / offline.  Measured end to end through
+    xllm_ingest_batch_segments with page-locked host buffers: the online requests go first, the offline ones are
+    batch-deferred behind them.  Returns the dict that becomes the bench line's "c5" key."""
+    from oracle import oracle as o
+    from xllm_service_b200 import HostBuffer, workload
+    T, nbk = 8192, 8192 // BLOCK
+    b = workload.make_c5_batch(n_req, wcnt, seed=555 + rank_seed,
+                               shared_prefix=dict(n_prefixes=256, frac=0.5, min_blocks=1, max_blocks=8,
+                                                  block_tokens=BLOCK))
+    parts = {"online": b.select(np.nonzero(~b.offline)[0]), "offline": b.select(np.nonzero(b.offline)[0])}
+
+    def pin(arr):
+        hb = HostBuffer(arr.shape, arr.dtype)
+        hb.array[...] = arr
+        return hb
+
+    bufs = {}
+    for name, sb in parts.items():
+        n = sb.n
+        bufs[name] = dict(text=pin(sb.text), off=pin(sb.offsets), rss=pin(sb.req_seg_start), sl=pin(sb.seg_len),
+                          span=pin(sb.span_ids if sb.span_ids.size else np.zeros(1, np.int32)),
+                          ids=HostBuffer((n, T), np.int32), nids=HostBuffer((n,), np.int32),
+                          st=HostBuffer((n,), np.int32), keys=HostBuffer((n, nbk, 16), np.uint8),
+                          match=HostBuffer((n, 400), np.uint8), route=HostBuffer((n, 20), np.uint8))
+
+    def call(name, with_match=True):
+        sb, B = parts[name], bufs[name]
+        h.ingest_batch_segments_ptrs(sb.n, B["text"].ptr, B["off"].ptr, B["ids"].ptr, T, B["nids"].ptr, B["st"].ptr,
+                                     sb.seg_len.size, B["rss"].ptr, B["sl"].ptr, B["span"].ptr if sb.span_ids.size else 0,
+                                     sb.span_ids.size, B["keys"].ptr, nbk, B["match"].ptr if with_match else 0,
+                                     B["route"].ptr if with_match else 0)
+
+    # first pass: ids + keys; every request must come out at exactly the length the generator promised
+    for name in parts:
+        call(name, with_match=False)
+        assert (bufs[name]["st"].array == 0).all() and (bufs[name]["nids"].array == parts[name].n_tokens).all()
+    # the shared prefixes of this workload enter the index (instance = prefix id mod 64), then one publish
+    on = parts["online"]
+    seen = {}
+    pid = b.prefix_id[np.nonzero(~b.offline)[0]]
+    ptk = b.prefix_tokens[np.nonzero(~b.offline)[0]]
+    for r in range(on.n):
+        j = int(pid[r])
+        if j >= 0 and j not in seen:
+            seen[j] = bufs["online"]["keys"].array[r, :ptk[r] // BLOCK].copy()
+            h.index_apply(j % N_INST, seen[j])
+    h.index_publish()
+    # parity gate on a sample: ids = per-piece oracle encodes + spans appended; keys = the oracle's hash chain
+    sp = o.SentencePieceOracle(MODEL_DIR)
+    piece_of_seg = np.cumsum(on.seg_len < 0) - (on.seg_len < 0)
+    span_of_seg = np.cumsum(np.maximum(on.seg_len, 0)) - np.maximum(on.seg_len, 0)
+    n_chk = min(24, on.n)
+    for r in range(n_chk):
+        want = []
+        for sg in range(on.req_seg_start[r], on.req_seg_start[r + 1]):
+            ln = int(on.seg_len[sg])
+            if ln < 0:
+                p = piece_of_seg[sg]
+                want.extend(sp.encode(on.text[on.offsets[p]:on.offsets[p + 1]].tobytes()).tolist())
+            else:
+                want.extend(on.span_ids[span_of_seg[sg]:span_of_seg[sg] + ln].tolist())
+        want = np.asarray(want, np.int32)
+        assert (bufs["online"]["ids"].array[r, :want.size] == want).all(), "c5: token ids differ from the oracle"
+        wk = o.block_hash_chain(want, BLOCK, SEED)
+        assert (bufs["online"]["keys"].array[r, :wk.shape[0]] == wk).all(), "c5: block keys differ from the oracle"
+    # timed: online batch, then the deferred offline batch
+    import torch
+    for name in parts:
+        call(name)
+    torch.cuda.synchronize()
+    t_on = t_all = 0.0
+    for _ in range(steps):
+        w0 = time.perf_counter()
+        call("online")
+        w1 = time.perf_counter()
+        call("offline")
+        w2 = time.perf_counter()
+        t_on += w1 - w0
+        t_all += w2 - w0
+    from xllm_service_b200 import _lib
+    mt = bufs["online"]["match"].array.view(_lib.MATCH_DTYPE)[:, 0]
+    # the persistent grid's tail: per-warp busy time of the tokenizer over this batch's text pieces
+    _, st, warp_ns = h.encode_batch_profile(b.text, b.offsets, 0)
+    warp_ms = warp_ns.astype(np.float64) / 1e6
+    tokens = int(b.n_tokens.sum())
+    return {
+        "workload": "c5: %d requests, log-uniform %d-%d tokens (mean %.0f), %.0f%% with 1-4 spans of 256-1024 "
+                    "placeholder ids (%d text pieces + %d id spans, %.0f%% of all tokens pre-tokenised), "
+                    "%d online + %d offline (offline batch-deferred behind online)"
+                    % (b.n, int(b.n_tokens.min()), int(b.n_tokens.max()), b.n_tokens.mean(),
+                       100.0 * np.mean([(b.seg_len[b.req_seg_start[r]:b.req_seg_start[r + 1]] >= 0).any()
+                                        for r in range(b.n)]),
+                       int((b.seg_len < 0).sum()), int((b.seg_len >= 0).sum()), 100.0 * b.span_ids.size / tokens,
+                       parts["online"].n, parts["offline"].n),
+        "api": "xllm_ingest_batch_segments (C-ABI, page-locked host buffers, ids rows of 8192)",
+        "e2e_req_per_s": b.n * steps / t_all, "e2e_tokens_per_s": tokens * steps / t_all,
+        "ms_per_step": t_all / steps * 1e3, "online_batch_ms": t_on / steps * 1e3,
+        "offline_batch_ms": (t_all - t_on) / steps * 1e3,
+        "text_bytes": int(b.text.size),
+        "parity_gate": {"checked": n_chk, "ids": "bit-exact", "keys": "bit-exact",
+                        "lengths": "all %d requests encode to exactly the generated length" % b.n},
+        "mean_matched_blocks_online": float(mt["max_matched_block_num"].mean()),
+        "persistent_grid_tail": {"warps": int(warp_ms.size), "max_ms": float(warp_ms.max()),
+                                 "mean_ms": float(warp_ms.mean()), "max_over_mean": float(warp_ms.max() / warp_ms.mean()),
+                                 "note": "busy time per warp of sp_encode_kernel over all text pieces of the batch "
+                                         "(one warp takes one piece at a time from a shared counter)"},
+    }
+
+
 def cpu_reference_pass(sp, P, batch, n_sample, threads):
     """One bounded pass of the reference's per-request path (encode + select_instances_pair) on the host."""
     from oracle import oracle as o
@@ -625,6 +739,8 @@ def main():
         line["shard_round_us"] = {k[:-3]: round(v * 1e3, 1) for k, v in shard_stats.items() if k.endswith("_ms")}
         line["shard_round_us"]["bucket_capacity"] = shard_stats["bucket_capacity"]
         line["shard_round_us"]["overflow_rounds"] = shard_stats["overflow_rounds"]
+    if world == 1 and not args.no_c5:
+        line["c5"] = run_c5(h, wcnt, args.c5_requests, max(2, min(args.steps, 5)))
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as o
         threads, thread_detail = host_threads()

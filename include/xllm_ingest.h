@@ -220,6 +220,13 @@ int xllm_score_route_device(xllm_ingest_t h, int32_t n_req, const uint64_t* d_ma
 #define XLLM_ENC_TRUNCATED 1
 int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets, int32_t* ids,
                       int64_t ids_stride, int32_t* n_ids, int32_t* status);
+/* Diagnostics: xllm_encode_batch without the id download, plus how long every warp of the tokenizer's persistent
+ * grid (one warp takes one request at a time from a shared counter) stayed busy, in nanoseconds; *n_warps = warps
+ * launched (the first min(n_warps, warp_cap) entries of warp_ns are filled).  max / mean of those numbers is the
+ * length tail a variable-length batch leaves at the end of the kernel. */
+int xllm_encode_batch_profile(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets,
+                              int64_t ids_stride, int32_t* n_ids, int32_t* status, uint64_t* warp_ns, int32_t warp_cap,
+                              int32_t* n_warps);
 int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_text, const int64_t* d_offsets,
                              int32_t* d_ids, int64_t ids_stride, int32_t* d_n_ids, int32_t* d_status,
                              void* cuda_stream);

@@ -99,6 +99,8 @@ def _declare(L):
     L.xllm_hash_blocks_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]
     L.xllm_xxh3_128bits_hash.argtypes = [_VP, _VP, _VP, ctypes.c_size_t, _VP]
     L.xllm_encode_batch.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, ctypes.c_int64, _VP, _VP]
+    L.xllm_encode_batch_profile.argtypes = [_VP, ctypes.c_int32, _VP, _VP, ctypes.c_int64, _VP, _VP, _VP, ctypes.c_int32,
+                                            ctypes.POINTER(ctypes.c_int32)]
     L.xllm_encode_batch_device.argtypes = [_VP, ctypes.c_int32, _VP, _VP, _VP, ctypes.c_int64, _VP, _VP, _VP]
     SZ = ctypes.c_size_t
     L.xllm_index_apply.argtypes = [_VP, ctypes.c_int32, _VP, SZ, _VP, SZ, _VP, SZ]

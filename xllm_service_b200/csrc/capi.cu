@@ -686,10 +686,11 @@ int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_te
   return XLLM_OK;
 }
 
-int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets, int32_t* ids,
-                      int64_t ids_stride, int32_t* n_ids, int32_t* status) {
+static int encode_batch_impl(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets, int32_t* ids,
+                             int64_t ids_stride, int32_t* n_ids, int32_t* status, uint64_t* warp_ns, int32_t warp_cap,
+                             int32_t* n_warps) {
   if (!h || n_req < 0 || ids_stride < 0 || (n_req > 0 && (!offsets || !n_ids || !status)) ||
-      (n_req > 0 && ids_stride > 0 && !ids)) {
+      (n_req > 0 && ids_stride > 0 && !ids && !warp_ns)) {
     set_last_error("xllm_encode_batch: invalid argument");
     return XLLM_ERR_INVALID_ARG;
   }
@@ -725,15 +726,40 @@ int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const
   if (text_bytes)
     XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_text.p, text + offsets[0], text_bytes, cudaMemcpyHostToDevice, s));
   XLLM_CUDA_TRY(cudaMemcpyAsync(h->d_offsets.p, offsets, (size_t)(n_req + 1) * 8, cudaMemcpyHostToDevice, s));
+  SpLaunchOpts opts;
+  int grid = 0;
+  if (warp_ns) {   // diagnostics: per-warp busy time of the persistent grid
+    grid = sp_encode_grid(h->sp_dev->dev(), n_req);
+    XLLM_TRY(h->d_masks.reserve((size_t)grid * 8 + 8));
+    XLLM_CUDA_TRY(cudaMemsetAsync(h->d_masks.p, 0, (size_t)grid * 8, s));
+    opts.warp_ns = h->d_masks.as<unsigned long long>();
+  }
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), h->d_text.as<uint8_t>() - offsets[0], h->d_offsets.as<int64_t>(),
                                  n_req, h->d_ids.as<int32_t>(), ids_stride, h->d_n_ids.as<int32_t>(),
-                                 h->d_status.as<int32_t>(), h->d_task_counter + 4, h->d_defer.as<int32_t>(), s, memo));
-  if (ids_stride)
+                                 h->d_status.as<int32_t>(), h->d_task_counter + 4, h->d_defer.as<int32_t>(), s, memo,
+                                 opts));
+  if (warp_ns) {
+    const int take = grid < warp_cap ? grid : warp_cap;
+    if (take > 0) XLLM_CUDA_TRY(cudaMemcpyAsync(warp_ns, h->d_masks.p, (size_t)take * 8, cudaMemcpyDeviceToHost, s));
+    if (n_warps) *n_warps = grid;
+  }
+  if (ids_stride && ids)
     XLLM_CUDA_TRY(cudaMemcpyAsync(ids, h->d_ids.p, (size_t)n_req * (size_t)ids_stride * 4, cudaMemcpyDeviceToHost, s));
   XLLM_CUDA_TRY(cudaMemcpyAsync(n_ids, h->d_n_ids.p, (size_t)n_req * 4, cudaMemcpyDeviceToHost, s));
   XLLM_CUDA_TRY(cudaMemcpyAsync(status, h->d_status.p, (size_t)n_req * 4, cudaMemcpyDeviceToHost, s));
   XLLM_CUDA_TRY(cudaStreamSynchronize(s));
   return XLLM_OK;
+}
+
+int xllm_encode_batch(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets, int32_t* ids,
+                      int64_t ids_stride, int32_t* n_ids, int32_t* status) {
+  return encode_batch_impl(h, n_req, text, offsets, ids, ids_stride, n_ids, status, nullptr, 0, nullptr);
+}
+int xllm_encode_batch_profile(xllm_ingest_t h, int32_t n_req, const uint8_t* text, const int64_t* offsets,
+                              int64_t ids_stride, int32_t* n_ids, int32_t* status, uint64_t* warp_ns, int32_t warp_cap,
+                              int32_t* n_warps) {
+  if (!warp_ns || warp_cap <= 0) return XLLM_ERR_INVALID_ARG;
+  return encode_batch_impl(h, n_req, text, offsets, nullptr, ids_stride, n_ids, status, warp_ns, warp_cap, n_warps);
 }
 
 }  // extern "C"

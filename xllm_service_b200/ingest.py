@@ -130,6 +130,20 @@ class Ingest:
                                         _ptr(status)))
         return ids, n_ids, status
 
+    def encode_batch_profile(self, text, offsets, ids_stride):
+        """xllm_encode_batch_profile -> (n_ids, status, warp_ns uint64[n_warps]): per-warp busy time of the tokenizer's
+        persistent grid for this batch."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        n_ids, status = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        cap = 1 << 16
+        warp = np.zeros(cap, np.uint64)
+        nw = ctypes.c_int32()
+        check(self._L.xllm_encode_batch_profile(self._h, n, _ptr(text), _ptr(offsets), ids_stride, _ptr(n_ids),
+                                                _ptr(status), _ptr(warp), cap, ctypes.byref(nw)))
+        return n_ids, status, warp[:min(nw.value, cap)].copy()
+
     def encode(self, text: bytes):
         """Single-request Tokenizer::encode (tokenizer.h:32-33): returns the id list; raises on failure
         (the reference returns false, scheduler.cpp:129-132)."""
