@@ -251,6 +251,11 @@ typedef struct {
   int64_t keys_stride;
   xllm_match_out* match;     /* [n_req] or NULL */
   xllm_routing_out* routing; /* [n_req] or NULL */
+  /* Opt-in narrow download: when non-NULL the token ids are delivered HERE as uint16 rows [n_req][ids_stride] and
+   * `ids` is not written (it may be NULL).  Only for vocabularies below 65 536 pieces (XLLM_ERR_UNSUPPORTED
+   * otherwise).  Token ids are half of the bytes that cross PCIe on the way back; a caller that copies them into its
+   * own std::vector<int32_t> anyway (Request::token_ids — host/ingest_batcher.h does) widens during that copy. */
+  uint16_t* ids_u16;
 } xllm_ingest_io;
 int xllm_ingest_batch(xllm_ingest_t h, const xllm_ingest_io* io);
 

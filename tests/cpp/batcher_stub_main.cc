@@ -19,6 +19,8 @@ static std::atomic<int> g_inside{0}, g_overlap{0}, g_calls{0}, g_max_batch{0};
 extern "C" {
 int xllm_host_alloc(void** out, size_t bytes) { *out = malloc(bytes ? bytes : 1); return *out ? XLLM_OK : XLLM_ERR_NOMEM; }
 void xllm_host_free(void* p) { free(p); }
+static int g_vocab = 8000;   // < 65536: the batcher takes the narrow (uint16) id download; 0x20000: the int32 one
+int xllm_vocab_size(xllm_ingest_t, int32_t* out) { *out = g_vocab; return XLLM_OK; }
 int xllm_ingest_batch(xllm_ingest_t, const xllm_ingest_io* io) {
   if (g_inside.fetch_add(1) != 0) g_overlap.fetch_add(1);
   g_calls.fetch_add(1);
@@ -29,7 +31,10 @@ int xllm_ingest_batch(xllm_ingest_t, const xllm_ingest_io* io) {
     const int64_t n = e - b;
     io->n_ids[r] = (int32_t)n;
     io->status[r] = n > io->ids_stride ? XLLM_ENC_TRUNCATED : XLLM_OK;
-    for (int64_t k = 0; k < n && k < io->ids_stride; ++k) io->ids[(size_t)r * io->ids_stride + k] = io->text[b + k];
+    for (int64_t k = 0; k < n && k < io->ids_stride; ++k) {
+      if (io->ids_u16) io->ids_u16[(size_t)r * io->ids_stride + k] = io->text[b + k];
+      else io->ids[(size_t)r * io->ids_stride + k] = io->text[b + k];
+    }
     if (io->routing) { io->routing[r].ok = 1; io->routing[r].prefill_id = (int32_t)(n % 7); io->routing[r].decode_id = -1; }
     if (io->match) io->match[r].max_block_num = (uint32_t)(n / 128);
   }
@@ -89,6 +94,8 @@ int main() {
   pass = run_config(48, 100, 8, 0) && pass;       // no wait window at all
   pass = run_config(64, 120, 32, 100, 30) && pass;        // config 5's 70:30 online / offline mix: offline ones ride along
   pass = run_config(32, 40, 16, 50, 100, 1000) && pass;   // offline only: nobody to ride with, no starvation
+  g_vocab = 0x20000;                                      // large vocabulary: int32 ids end to end
+  pass = run_config(32, 100, 64, 200, 30) && pass;
   printf(pass ? "OK\n" : "FAILED\n");
   return pass ? 0 : 1;
 }

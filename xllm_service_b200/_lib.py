@@ -73,7 +73,7 @@ class IngestIO(ctypes.Structure):
     _fields_ = [("n_req", ctypes.c_int32), ("text", ctypes.c_void_p), ("offsets", ctypes.c_void_p),
                 ("ids", ctypes.c_void_p), ("ids_stride", ctypes.c_int64), ("n_ids", ctypes.c_void_p),
                 ("status", ctypes.c_void_p), ("keys", ctypes.c_void_p), ("keys_stride", ctypes.c_int64),
-                ("match", ctypes.c_void_p), ("routing", ctypes.c_void_p)]
+                ("match", ctypes.c_void_p), ("routing", ctypes.c_void_p), ("ids_u16", ctypes.c_void_p)]
 
 
 class Segments(ctypes.Structure):

@@ -46,6 +46,7 @@ struct PipeSlot {
       d_match, d_routing;
   // segmented requests (xllm_ingest_batch_segments): text pieces encode into ragged temporary rows, then the
   // assemble kernel splices pieces and id spans into the request's row
+  DevBuf d_ids16;   // narrow download (xllm_ingest_io::ids_u16)
   DevBuf d_piece_ids, d_piece_n, d_piece_status, d_piece_out_start, d_piece_out_cap, d_seg_len, d_seg_src, d_req_seg,
       d_span;
   int ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_stride, int n_req = -1);

@@ -40,6 +40,23 @@ __global__ void prep_rows_kernel(const int32_t* __restrict__ n_ids, int n, int64
   n_blocks[r] = (int32_t)nb;
 }
 
+// Narrow download (xllm_ingest_io::ids_u16): int32 ids -> uint16, 8 ids per thread (rows are 16-byte aligned when
+// ids_stride is a multiple of 8; the tail of an odd-sized buffer goes one id at a time).
+__global__ void narrow_ids_kernel(const int32_t* __restrict__ ids, uint16_t* __restrict__ out, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const int4 a = *reinterpret_cast<const int4*>(ids + i), b = *reinterpret_cast<const int4*>(ids + i + 4);
+    uint4 o;
+    o.x = (uint32_t)(uint16_t)a.x | ((uint32_t)(uint16_t)a.y << 16);
+    o.y = (uint32_t)(uint16_t)a.z | ((uint32_t)(uint16_t)a.w << 16);
+    o.z = (uint32_t)(uint16_t)b.x | ((uint32_t)(uint16_t)b.y << 16);
+    o.w = (uint32_t)(uint16_t)b.z | ((uint32_t)(uint16_t)b.w << 16);
+    *reinterpret_cast<uint4*>(out + i) = o;
+  } else {
+    for (size_t k = i; k < n; ++k) out[k] = (uint16_t)ids[k];
+  }
+}
+
 // Segmented requests: one warp per request walks its segments in order and splices the ids of encoded text pieces
 // (ragged temporary rows) and of ready-made id spans into the request's row.  n_ids = the full count even when it
 // exceeds the row; status = the first failing piece's code, else truncated / ok.
@@ -123,6 +140,7 @@ void PipeSlot::release() {
   d_text.release(); d_offsets.release(); d_ids.release(); d_n_ids.release(); d_status.release();
   d_tok_start.release(); d_n_tok.release(); d_key_start.release(); d_n_blocks.release();
   d_keys.release(); d_masks.release(); d_match.release(); d_routing.release();
+  d_ids16.release();
   d_piece_ids.release(); d_piece_n.release(); d_piece_status.release(); d_piece_out_start.release();
   d_piece_out_cap.release(); d_seg_len.release(); d_seg_src.release(); d_req_seg.release(); d_span.release();
   for (int k = 0; k < 3; ++k) {
@@ -215,13 +233,17 @@ static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_seg
   }
   const int32_t n = io->n_req;
   if (n == 0) return XLLM_OK;
-  if (!io->offsets || !io->n_ids || !io->status || io->ids_stride <= 0 || !io->ids || io->keys_stride < 0 ||
-      (io->keys_stride > 0 && !io->keys)) {
+  if (!io->offsets || !io->n_ids || !io->status || io->ids_stride <= 0 || (!io->ids && !io->ids_u16) ||
+      io->keys_stride < 0 || (io->keys_stride > 0 && !io->keys)) {
     set_last_error("xllm_ingest_batch: missing buffer");
     return XLLM_ERR_INVALID_ARG;
   }
   if (!h->sp_dev) {
     set_last_error("handle has no tokenizer (tokenizer_path was not set)");
+    return XLLM_ERR_UNSUPPORTED;
+  }
+  if (io->ids_u16 && h->sp_dev->dev().n_pieces > 65535u) {
+    set_last_error("ids_u16 needs a vocabulary below 65536 pieces (this one has %u)", h->sp_dev->dev().n_pieces);
     return XLLM_ERR_UNSUPPORTED;
   }
   const bool want_match = io->match != nullptr || io->routing != nullptr;
@@ -467,11 +489,23 @@ static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_seg
         PIPE_CUDA_TRY(me);
       }
     }
+    if (io->ids_u16) {
+      const size_t n_ids_chunk = (size_t)m * (size_t)io->ids_stride;
+      if ((rc = sl.d_ids16.reserve(n_ids_chunk * 2 + 64)) != XLLM_OK) break;
+      narrow_ids_kernel<<<(unsigned)((n_ids_chunk / 8 + 256) / 256), 256, 0, s_k>>>(sl.d_ids.as<int32_t>(),
+                                                                                  sl.d_ids16.as<uint16_t>(), n_ids_chunk);
+      PIPE_CUDA_TRY(cudaGetLastError());
+      h->last_launches += 1;
+    }
     PIPE_CUDA_TRY(cudaEventRecord(sl.ev[1], s_k));
     // ---- download
     PIPE_CUDA_TRY(cudaStreamWaitEvent(s_out, sl.ev[1], 0));
-    PIPE_CUDA_TRY(cudaMemcpyAsync(io->ids + (size_t)c0 * io->ids_stride, sl.d_ids.p,
-                                  (size_t)m * (size_t)io->ids_stride * 4, cudaMemcpyDeviceToHost, s_out));
+    if (io->ids_u16)
+      PIPE_CUDA_TRY(cudaMemcpyAsync(io->ids_u16 + (size_t)c0 * io->ids_stride, sl.d_ids16.p,
+                                    (size_t)m * (size_t)io->ids_stride * 2, cudaMemcpyDeviceToHost, s_out));
+    else
+      PIPE_CUDA_TRY(cudaMemcpyAsync(io->ids + (size_t)c0 * io->ids_stride, sl.d_ids.p,
+                                    (size_t)m * (size_t)io->ids_stride * 4, cudaMemcpyDeviceToHost, s_out));
     mark(3, s_out);
     PIPE_CUDA_TRY(cudaMemcpyAsync(io->n_ids + c0, sl.d_n_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));
     PIPE_CUDA_TRY(cudaMemcpyAsync(io->status + c0, sl.d_status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s_out));

@@ -53,10 +53,15 @@ class IngestBatcher {
         keys_stride_(max_tokens / block_size), max_wait_us_(max_wait_us), want_routing_(want_routing),
         offline_defer_us_(offline_defer_us) {
     ok_ = true;
+    // vocabularies below 65 536 pieces: take the ids as uint16 (half the bytes over PCIe) and widen them in hand_out,
+    // during the copy into the caller's std::vector<int32_t> that happens anyway
+    int32_t vocab = 0;
+    narrow_ids_ = xllm_vocab_size(h, &vocab) == XLLM_OK && vocab > 0 && vocab < 65536;
     for (Staging& s : sets_) {
       ok_ = ok_ && xllm_host_alloc(reinterpret_cast<void**>(&s.text), max_bytes) == XLLM_OK &&
             xllm_host_alloc(reinterpret_cast<void**>(&s.offsets), sizeof(int64_t) * (max_batch + 1)) == XLLM_OK &&
-            xllm_host_alloc(reinterpret_cast<void**>(&s.ids), sizeof(int32_t) * (size_t)max_batch * max_tokens) == XLLM_OK &&
+            xllm_host_alloc(reinterpret_cast<void**>(&s.ids), (narrow_ids_ ? sizeof(uint16_t) : sizeof(int32_t)) *
+                                                                   (size_t)max_batch * max_tokens) == XLLM_OK &&
             xllm_host_alloc(reinterpret_cast<void**>(&s.n_ids), sizeof(int32_t) * max_batch) == XLLM_OK &&
             xllm_host_alloc(reinterpret_cast<void**>(&s.status), sizeof(int32_t) * max_batch) == XLLM_OK &&
             xllm_host_alloc(reinterpret_cast<void**>(&s.match), sizeof(xllm_match_out) * max_batch) == XLLM_OK &&
@@ -185,7 +190,8 @@ class IngestBatcher {
     io.n_req = n;
     io.text = s.text;
     io.offsets = s.offsets;
-    io.ids = s.ids;
+    if (narrow_ids_) io.ids_u16 = reinterpret_cast<uint16_t*>(s.ids);
+    else io.ids = s.ids;
     io.ids_stride = max_tokens_;
     io.n_ids = s.n_ids;
     io.status = s.status;
@@ -201,7 +207,12 @@ class IngestBatcher {
       o->status = rc != XLLM_OK ? rc : s.status[i];
       if (rc == XLLM_OK && s.status[i] >= 0) {
         const int32_t keep = s.n_ids[i] < max_tokens_ ? s.n_ids[i] : max_tokens_;
-        o->token_ids.assign(s.ids + (size_t)i * max_tokens_, s.ids + (size_t)i * max_tokens_ + keep);
+        if (narrow_ids_) {
+          const uint16_t* row = reinterpret_cast<const uint16_t*>(s.ids) + (size_t)i * max_tokens_;
+          o->token_ids.assign(row, row + keep);   // widens uint16 -> int32
+        } else {
+          o->token_ids.assign(s.ids + (size_t)i * max_tokens_, s.ids + (size_t)i * max_tokens_ + keep);
+        }
         if (want_routing_) { o->match = s.match[i]; o->routing = s.routing[i]; }
       }
     }
@@ -215,6 +226,7 @@ class IngestBatcher {
   const int max_wait_us_;
   const bool want_routing_;
   const int offline_defer_us_;
+  bool narrow_ids_ = false;
   std::deque<std::shared_ptr<Deferred>> deferred_;
   uint64_t n_piggyback_ = 0;
   bool ok_ = false;

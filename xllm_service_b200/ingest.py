@@ -279,20 +279,22 @@ class Ingest:
         return c.value, k.value
 
     def ingest_batch_ptrs(self, n_req, text, offsets, ids, ids_stride, n_ids, status, keys=0, keys_stride=0,
-                          match=0, routing=0):
-        """xllm_ingest_batch over raw host addresses (ints), e.g. pinned torch tensors' data_ptr()."""
-        io = _lib.IngestIO(n_req, text, offsets, ids, ids_stride, n_ids, status, keys or None, keys_stride,
-                           match or None, routing or None)
+                          match=0, routing=0, ids_u16=0):
+        """xllm_ingest_batch over raw host addresses (ints), e.g. pinned torch tensors' data_ptr().  ids_u16: address
+        of a uint16 [n_req, ids_stride] buffer for the narrow download (then `ids` may be 0)."""
+        io = _lib.IngestIO(n_req, text, offsets, ids or None, ids_stride, n_ids, status, keys or None, keys_stride,
+                           match or None, routing or None, ids_u16 or None)
         check(self._L.xllm_ingest_batch(self._h, ctypes.byref(io)))
 
-    def ingest_batch(self, text, offsets, ids_stride, want_keys=True, want_match=True):
+    def ingest_batch(self, text, offsets, ids_stride, want_keys=True, want_match=True, ids_u16=False):
         """tokenize + block-hash + match + route for a batch of prompts (numpy host buffers).
-        Returns dict(ids, n_ids, status, keys, match, routing)."""
+        Returns dict(ids, n_ids, status, keys, match, routing); ids_u16=True takes the narrow download (ids is then a
+        uint16 array)."""
         text = np.ascontiguousarray(text, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n = offsets.size - 1
         ks = ids_stride // self.block_size
-        out = {"ids": np.zeros((n, ids_stride), np.int32), "n_ids": np.zeros(n, np.int32),
+        out = {"ids": np.zeros((n, ids_stride), np.uint16 if ids_u16 else np.int32), "n_ids": np.zeros(n, np.int32),
                "status": np.zeros(n, np.int32), "keys": None, "match": None, "routing": None}
         if want_keys:
             out["keys"] = np.zeros((n, ks, 16), np.uint8)
@@ -300,8 +302,9 @@ class Ingest:
             out["match"] = np.zeros(n, dtype=_lib.MATCH_DTYPE)
             out["routing"] = np.zeros(n, dtype=_lib.ROUTING_DTYPE)
         a = lambda x: x.ctypes.data if x is not None and x.size else 0  # noqa: E731
-        self.ingest_batch_ptrs(n, a(text), a(offsets), a(out["ids"]), ids_stride, a(out["n_ids"]), a(out["status"]),
-                               a(out["keys"]), ks if want_keys else 0, a(out["match"]), a(out["routing"]))
+        self.ingest_batch_ptrs(n, a(text), a(offsets), 0 if ids_u16 else a(out["ids"]), ids_stride, a(out["n_ids"]),
+                               a(out["status"]), a(out["keys"]), ks if want_keys else 0, a(out["match"]),
+                               a(out["routing"]), a(out["ids"]) if ids_u16 else 0)
         return out
 
     def ingest_batch_segments_ptrs(self, n_req, text, offsets, ids, ids_stride, n_ids, status, n_segments,

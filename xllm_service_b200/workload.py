@@ -307,6 +307,10 @@ def make_c5_batch(n_requests, word_token_counts, seed=0, vocabulary=None, min_to
         L = int(lengths[r])
         span_lens = []
         if rng.random() < mm_frac:
+            if L < span_tokens[0] + 32:      # too short to hold a span: a multimodal request is at least one span long
+                L = int(np.exp(rng.uniform(np.log(span_tokens[0] + 32), np.log(max_tokens + 1))))
+                L = min(L, max_tokens)
+                lengths[r] = L
             for _ in range(int(rng.integers(1, max_spans + 1))):
                 ln = int(rng.integers(span_tokens[0], span_tokens[1] + 1))
                 if sum(span_lens) + ln <= L - 16:          # keep at least a little text
