@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--chunk-requests", type=int, default=0)
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 (EPD mix) side measurement at N = 1")
     ap.add_argument("--c5-requests", type=int, default=8192)
+    ap.add_argument("--no-latency", action="store_true", help="skip the service-shaped latency side measurement")
     ap.add_argument("--index", default="auto", choices=["auto", "replicated", "sharded"],
                     help="prefix index placement at N > 1: sharded = BASELINE config 4 (hash-range shards, index N x "
                          "--index-keys, one NCCL all-to-all each way per batch); auto = sharded when N > 1")
@@ -324,6 +325,39 @@ def run_c5(h, wcnt, n_req, steps, rank_seed=0):
                                  "note": "busy time per warp of sp_encode_kernel over all text pieces of the batch "
                                          "(one warp takes one piece at a time from a shared counter)"},
     }
+
+
+def service_latency(batch, n_prompts=256, seconds=2.5):
+    """p50 / p99 of one request through the micro-batcher at the reference's concurrency (32 worker threads and 128
+    concurrent requests, global_gflags.cpp:32-36): tests/cpp/latency_main.cc, compiled here with g++ against the
+    C-ABI, one 4 K-token prompt per submit, token ids + routing back.  Returns a list of result dicts (or an error)."""
+    import struct
+    import tempfile
+    import xllm_service_b200 as x
+    tmp = tempfile.mkdtemp(prefix="xllm_lat_")
+    exe = os.path.join(tmp, "latency_main")
+    pf = os.path.join(tmp, "prompts.bin")
+    libdir = os.path.dirname(x.lib_path())
+    try:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-I",
+                               os.path.join(ROOT, "xllm_service_b200", "host"),
+                               os.path.join(ROOT, "tests", "cpp", "latency_main.cc"), "-o", exe, "-L", libdir,
+                               "-lxllm_ingest", "-Wl,-rpath," + libdir, "-Wl,--allow-shlib-undefined"],
+                              stderr=subprocess.DEVNULL)
+        with open(pf, "wb") as f:
+            for i in range(min(n_prompts, batch.n)):
+                t = batch.prompt(i)
+                f.write(struct.pack("<I", len(t)) + t)
+        out = []
+        for threads, max_batch, wait_us in ((1, 1, 0), (32, 32, 50), (128, 128, 50)):
+            p = subprocess.run([exe, MODEL_DIR, pf, str(threads), str(seconds), str(max_batch), str(wait_us)],
+                               capture_output=True, text=True, timeout=120)
+            if p.returncode != 0:
+                return {"error": "latency_main rc %d: %s" % (p.returncode, p.stderr[-300:])}
+            out.append(json.loads(p.stdout.strip().split("\n")[-1]))
+        return out
+    except (OSError, subprocess.SubprocessError, ValueError) as e:
+        return {"error": repr(e)[:300]}
 
 
 def cpu_reference_pass(sp, P, batch, n_sample, threads):
@@ -683,6 +717,23 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - w0)
     barrier()
+    # the same end-to-end step with the opt-in narrow id download (xllm_ingest_io::ids_u16: uint16 ids for this
+    # 8 000-piece vocabulary, what host/ingest_batcher.h takes and widens while it hands results out)
+    h_ids16 = pinned((n, T), torch.int16)
+
+    def e2e_step_u16():
+        h.ingest_batch_ptrs(n, h_text.data_ptr(), h_off.data_ptr(), 0, T, h_nids.data_ptr(), h_st.data_ptr(),
+                            h_keys.data_ptr(), nb, h_match.data_ptr(), h_route.data_ptr(), ids_u16=h_ids16.data_ptr())
+
+    e2e_step_u16()
+    assert (h_ids16.numpy().view(np.uint16) == h_ids.numpy()).all(), "uint16 ids differ from the int32 ids"
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step_u16()
+    torch.cuda.synchronize()
+    e2e16_s = max_over_ranks(time.perf_counter() - w0)
+    barrier()
     clk = clocks.stop()
 
     if rank != 0:
@@ -729,6 +780,11 @@ def main():
                 "copy_floor_ms": floor_ms,
                 "frac_of_copy_floor": (floor_ms / (e2e_s / args.steps * 1e3)) if floor_ms else None,
                 "api": "xllm_ingest_batch (C-ABI, page-locked host buffers)"},
+        "e2e_ids_u16": {"value": world * n * args.steps / e2e16_s, "unit": "req/s",
+                        "ms_per_step": e2e16_s / args.steps * 1e3, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes - 2 * n * T,
+                        "note": "same call with xllm_ingest_io::ids_u16 (opt-in; vocabulary < 65536): token ids come "
+                                "back as uint16, checked equal to the int32 ids"},
         # value region: encode (throughput + long-word pass) + hash + match/route (sharded: bucket, headers, owner
         # probe, header gather, scan) per step; e2e region: the library's own count for one batch
         "gpu_launches": args.steps * ((9 if sharded_mode else 4) + h.last_batch_stats()[1]),
@@ -739,6 +795,11 @@ def main():
         line["shard_round_us"] = {k[:-3]: round(v * 1e3, 1) for k, v in shard_stats.items() if k.endswith("_ms")}
         line["shard_round_us"]["bucket_capacity"] = shard_stats["bucket_capacity"]
         line["shard_round_us"]["overflow_rounds"] = shard_stats["overflow_rounds"]
+    if world == 1 and not args.no_latency:
+        line["service_latency"] = {
+            "what": "per-request submit latency through host/ingest_batcher.h (one 4K-token prompt per call, ids + "
+                    "routing back) at the reference's concurrency; 1 thread = an idle service's single request",
+            "runs": service_latency(batch)}
     if world == 1 and not args.no_c5:
         line["c5"] = run_c5(h, wcnt, args.c5_requests, max(2, min(args.steps, 5)))
     if world == 1 and not args.no_cpu_baseline:

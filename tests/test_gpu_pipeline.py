@@ -129,3 +129,35 @@ def test_short_rows_still_get_a_routing_decision(oracle):
         assert (want["prefill_argmax"] >> int(routing["prefill_id"][r])) & 1
         assert (want["decode_argmax"] >> int(routing["decode_id"][r])) & 1
     h.close()
+
+
+def test_narrow_id_download_equals_int32(oracle):
+    """xllm_ingest_io::ids_u16: the same batch with uint16 ids — every other output identical, ids equal after
+    widening; refused for a vocabulary that does not fit 16 bits."""
+    import xllm_service_b200 as x
+    from xllm_service_b200 import workload
+    texts = [s.encode() for s in workload.sentences(700, (1, 90), seed=8)] + [b"", "日本語 text".encode()]
+    b = workload.pack_prompts(texts)
+    h = x.Ingest(tokenizer_path=MODEL_DIR, index_capacity=1024)
+    h.set_pipeline(53, 1 << 20)
+    h.set_instance(0, 1)
+    h.set_instance(1, 2)
+    h.set_load_metrics(0, 1, 0.5)
+    h.set_load_metrics(1, 2, 0.25)
+    a = h.ingest_batch(b.text, b.offsets, 200)
+    c = h.ingest_batch(b.text, b.offsets, 200, ids_u16=True)
+    assert c["ids"].dtype == np.uint16
+    valid = np.arange(200)[None, :] < np.minimum(a["n_ids"], 200)[:, None]
+    assert (a["ids"][valid] == c["ids"][valid]).all()
+    for f in ("n_ids", "status", "keys"):
+        assert (a[f] == c[f]).all(), f
+    assert a["match"].tobytes() == c["match"].tobytes() and a["routing"].tobytes() == c["routing"].tobytes()
+    h.close()
+    os.environ["XLLM_SP_FORCE_WIDE"] = "1"      # kernels built for > 16-bit ids keep working with the narrow download
+    try:
+        hw = x.Ingest(tokenizer_path=MODEL_DIR)
+        d = hw.ingest_batch(b.text, b.offsets, 200, want_match=False, ids_u16=True)
+        assert (d["ids"][valid] == a["ids"][valid]).all()
+        hw.close()
+    finally:
+        del os.environ["XLLM_SP_FORCE_WIDE"]
