@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--chunk-requests", type=int, default=0)
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 (EPD mix) side measurement at N = 1")
     ap.add_argument("--c5-requests", type=int, default=8192)
+    ap.add_argument("--no-honest-text", action="store_true", help="skip the natural-text / memo-off / large-vocabulary "
+                                                                   "tokenizer side measurements")
     ap.add_argument("--no-latency", action="store_true", help="skip the service-shaped latency side measurement")
     ap.add_argument("--index", default="auto", choices=["auto", "replicated", "sharded"],
                     help="prefix index placement at N > 1: sharded = BASELINE config 4 (hash-range shards, index N x "
@@ -358,6 +360,89 @@ def service_latency(batch, n_prompts=256, seconds=2.5):
         return out
     except (OSError, subprocess.SubprocessError, ValueError) as e:
         return {"error": repr(e)[:300]}
+
+
+def honest_text(local, headline_batch, iters=3, corpus_bytes=256 << 20):
+    """The tokenizer kernel away from the headline's comfort zone, device-resident, CUDA events:
+      natural_sp32k   real text (this image's site-packages sources and docs, workload.natural_corpus) cut into 16 KB
+                      prompts, SentencePiece BPE 32 000 trained on that kind of text, word memo on
+      natural_hf128k  the same prompts through an HF byte-level BPE with 128 471 entries: ids beyond 16 bits, i.e. the
+                      non-SMALL kernel variants (12-byte pair state, 4-id memo payload)
+      headline_memo_off  the headline workload with the word memo disabled (XLLM_SP_MEMO_SLOTS=0)
+    Each with a bit-exact gate of 24 prompts against the CPU oracle."""
+    import torch
+    import xllm_service_b200 as x
+    from oracle import oracle as o
+    from xllm_service_b200 import workload
+    dev = torch.device("cuda", local)
+    t0 = time.time()
+    corpus = workload.natural_corpus(corpus_bytes)
+    pb = workload.cut_prompts(corpus, 16384)
+    words = corpus[: 32 << 20].split()
+    out = {"corpus": {"bytes": len(corpus), "prompts": pb.n, "read_s": round(time.time() - t0, 1),
+                      "what": "*.py/*.md/*.rst/*.txt/*.h/*.hpp of site-packages in path order, UTF-8 files only "
+                              "(all there is in the image: no repetition, so less than 1 GB)",
+                      "distinct_whitespace_words_ratio_first_32MB": round(len(set(words)) / max(1, len(words)), 4)}}
+    stream = torch.cuda.current_stream()
+
+    def timed(h, text_np, off_np, stride, check_encode, n_check=24):
+        n = off_np.size - 1
+        d_text = torch.from_numpy(text_np).to(dev)
+        d_off = torch.from_numpy(off_np).to(dev)
+        d_ids = torch.empty((n, stride), dtype=torch.int32, device=dev)
+        d_n = torch.empty((n,), dtype=torch.int32, device=dev)
+        d_st = torch.empty((n,), dtype=torch.int32, device=dev)
+        run = lambda: h.encode_batch_device(n, d_text.data_ptr(), d_off.data_ptr(), d_ids.data_ptr(), stride,  # noqa: E731
+                                            d_n.data_ptr(), d_st.data_ptr(), stream.cuda_stream or None)
+        run()
+        torch.cuda.synchronize()
+        st = d_st.cpu().numpy()
+        nid = d_n.cpu().numpy()
+        assert (st == 0).all(), np.unique(st)
+        ids = d_ids[:n_check].cpu().numpy()
+        for r in range(min(n_check, n)):
+            want = check_encode(text_np[off_np[r]:off_np[r + 1]].tobytes())
+            assert ids[r, :nid[r]].tolist() == want, "honest_text: ids differ from the oracle"
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            run()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        tokens = int(nid.sum())
+        return {"prompts": int(n), "text_bytes": int(text_np.size), "tokens": tokens, "ms": round(ms, 3),
+                "prompts_per_s": round(n / ms * 1e3), "MB_per_s": round(text_np.size / ms / 1e3),
+                "tokens_per_s": round(tokens / ms * 1e3), "bytes_per_token": round(text_np.size / max(1, tokens), 2),
+                "algo_GBps": round((text_np.size + 4 * tokens) / ms / 1e6, 1), "oracle_gate": "bit-exact on 24 prompts"}
+
+    d_sp = os.path.join(ROOT, "tests", "golden", "sp_natural_32k")
+    d_hf = os.path.join(ROOT, "tests", "golden", "hf_natural_128k")
+    h1 = x.Ingest(tokenizer_path=d_sp, device=local)
+    S = o.SentencePieceOracle(d_sp)
+    out["natural_sp32k"] = timed(h1, pb.text, pb.offsets, 16384, lambda t: S.encode(t).tolist())
+    out["natural_sp32k"]["tokenizer"] = "SentencePiece BPE 32000 (byte fallback, nmt_nfkc), memo on"
+    h1.close()
+    h2 = x.Ingest(tokenizer_path=d_hf, device=local)
+    H = o.HfBpeOracle(d_hf)
+    out["natural_hf128k"] = timed(h2, pb.text, pb.offsets, 16384,
+                                  lambda t: H.prefix_ids + H.encode(t).tolist() + H.suffix_ids)
+    out["natural_hf128k"]["tokenizer"] = ("HF byte-level BPE, GPT-2 regex, 128471 entries (non-SMALL kernels: ids "
+                                          "beyond 16 bits), memo on")
+    h2.close()
+    os.environ["XLLM_SP_MEMO_SLOTS"] = "0"
+    try:
+        h3 = x.Ingest(tokenizer_path=MODEL_DIR, device=local)
+    finally:
+        del os.environ["XLLM_SP_MEMO_SLOTS"]
+    S8 = o.SentencePieceOracle(MODEL_DIR)
+    n3 = min(headline_batch.n, 16384)
+    off3 = headline_batch.offsets[: n3 + 1]
+    out["headline_memo_off"] = timed(h3, headline_batch.text[: off3[-1]], off3, 4096 + 64,
+                                     lambda t: S8.encode(t).tolist())
+    out["headline_memo_off"]["tokenizer"] = "the headline's SentencePiece BPE 8000 and prompts, word memo disabled"
+    h3.close()
+    return out
 
 
 def cpu_reference_pass(sp, P, batch, n_sample, threads):
@@ -795,6 +880,8 @@ def main():
         line["shard_round_us"] = {k[:-3]: round(v * 1e3, 1) for k, v in shard_stats.items() if k.endswith("_ms")}
         line["shard_round_us"]["bucket_capacity"] = shard_stats["bucket_capacity"]
         line["shard_round_us"]["overflow_rounds"] = shard_stats["overflow_rounds"]
+    if world == 1 and not args.no_honest_text:
+        line["honest_text"] = honest_text(local, batch)
     if world == 1 and not args.no_latency:
         line["service_latency"] = {
             "what": "per-request submit latency through host/ingest_batcher.h (one 4K-token prompt per call, ids + "

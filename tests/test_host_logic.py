@@ -94,6 +94,22 @@ def test_factory_selects_tiktoken_by_tokenizer_class(tmp_path):
     assert info["n_pieces"] == 1453            # 256 bytes + 1200 merges - 3 bytes dropped on purpose
     assert info["n_symbols"] == 1456           # the 3 rank-less bytes are still symbols (they emit nothing)
     assert info["n_pairs"] >= 1200
+    # only the TOP-LEVEL key counts (tokenizer_args.cpp:49-51 reads "tokenizer_class" from the root object): a nested
+    # one — here inside auto_map, placed first in the file — must not select the tiktoken backend
+    d2 = tmp_path / "nested"
+    d2.mkdir()
+    shutil.copy(os.path.join(HERE, "golden", "tiktoken_1k", "tokenizer.model"), d2 / "tokenizer.model")
+    (d2 / "tokenizer_config.json").write_text(
+        '{"auto_map": {"tokenizer_class": "TikTokenTokenizer"}, "tokenizer_class": "LlamaTokenizer"}')
+    with pytest.raises(_lib.IngestError):
+        _lib.tokenizer_probe(str(d2))          # falls through to SentencePiece, which cannot read a tiktoken file
+    d3 = tmp_path / "toplevel_last"
+    d3.mkdir()
+    shutil.copy(os.path.join(HERE, "golden", "tiktoken_1k", "tokenizer.model"), d3 / "tokenizer.model")
+    (d3 / "tokenizer_config.json").write_text(
+        '{"auto_map": {"tokenizer_class": "Other"}, "x": [1, {"tokenizer_class": "Nope"}], '
+        '"tokenizer_class": "TikTokenTokenizer"}')
+    assert _lib.tokenizer_probe(str(d3))["n_pieces"] == info["n_pieces"]
     # the same vocabulary file without the tokenizer_class hint is NOT silently read as tiktoken
     d = tmp_path / "plain"
     d.mkdir()

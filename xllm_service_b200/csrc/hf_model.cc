@@ -191,6 +191,25 @@ bool flag_false_or_absent(const JVal* o, const char* key) {
 
 }  // namespace
 
+// The top-level string member `key` of a JSON file, as the reference's JsonReader::value<std::string>(key) reads it
+// (tokenizer_args.cpp:49-51): a key of that name nested in another object (auto_map, processor ...) does not count.
+bool json_file_top_level_string(const std::string& path, const char* key, std::string* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::string js;
+  char buf[4096];
+  size_t got;
+  while ((got = fread(buf, 1, sizeof(buf), f)) > 0) js.append(buf, got);
+  fclose(f);
+  JVal root;
+  JParser parser(js.data(), js.data() + js.size());
+  if (!parser.parse(&root) || root.type != JVal::kObj) return false;
+  const JVal* v = root.get(key);
+  if (!v || v->type != JVal::kStr) return false;
+  *out = v->str;
+  return true;
+}
+
 bool tokenizer_dir_has_hf_json(const std::string& dir) {
   struct stat st;
   return stat((dir + "/tokenizer.json").c_str(), &st) == 0 && S_ISREG(st.st_mode);

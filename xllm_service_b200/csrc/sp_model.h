@@ -94,6 +94,7 @@ int sp_load_model(const std::string& path, SpTables* out);
 int tiktoken_load_model(const std::string& path, SpTables* out);
 // <dir>/tokenizer_config.json has "tokenizer_class": "TikTokenTokenizer" (tokenizer_factory.cpp:20-25)
 bool tokenizer_dir_is_tiktoken(const std::string& dir);
+bool json_file_top_level_string(const std::string& path, const char* key, std::string* out);   // hf_model.cc
 // HF `tokenizer.json` byte-level BPE -> the same tables, byte_mode + split_mode 3 (hf_model.cc)
 int hf_load_model(const std::string& path, SpTables* out);
 // <dir>/tokenizer.json exists (tokenizer_factory.cpp:14-19: it wins over everything else)

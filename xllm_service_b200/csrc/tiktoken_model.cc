@@ -52,21 +52,9 @@ bool b64_decode(std::string_view in, std::string* out) {
 // True when <dir>/tokenizer_config.json names the tiktoken backend
 // (tokenizer_factory.cpp:20-25: tokenizer_class == "TikTokenTokenizer").
 bool tokenizer_dir_is_tiktoken(const std::string& dir) {
-  FILE* f = fopen((dir + "/tokenizer_config.json").c_str(), "rb");
-  if (!f) return false;
-  std::string js;
-  char buf[4096];
-  size_t got;
-  while ((got = fread(buf, 1, sizeof(buf), f)) > 0) js.append(buf, got);
-  fclose(f);
-  const size_t k = js.find("\"tokenizer_class\"");
-  if (k == std::string::npos) return false;
-  const size_t colon = js.find(':', k);
-  if (colon == std::string::npos) return false;
-  const size_t q1 = js.find('"', colon);
-  if (q1 == std::string::npos) return false;
-  const size_t q2 = js.find('"', q1 + 1);
-  return q2 != std::string::npos && js.compare(q1 + 1, q2 - q1 - 1, "TikTokenTokenizer") == 0;
+  std::string cls;
+  return json_file_top_level_string(dir + "/tokenizer_config.json", "tokenizer_class", &cls) &&
+         cls == "TikTokenTokenizer";
 }
 
 int tiktoken_load_model(const std::string& path_in, SpTables* t) {

@@ -347,3 +347,53 @@ def make_c5_batch(n_requests, word_token_counts, seed=0, vocabulary=None, min_to
     b.prefix_id = prefix_id
     b.prefix_tokens = np.array([pref_tok[j] if j >= 0 else 0 for j in prefix_id], np.int32)
     return b
+
+
+def natural_corpus(max_bytes, exts=(".py", ".md", ".rst", ".txt", ".h", ".hpp", ".cuh"), min_file=4096, roots=None):
+    """Real text already present in this image (SURVEY.md has no corpus; there is no network): the source and doc files
+    under the Python site-packages tree, in sorted path order, UTF-8 only, concatenated until max_bytes.  Deterministic
+    for a given image.  Returns one bytes object (files separated by a blank line)."""
+    import os
+    import sysconfig
+    roots = roots or [sysconfig.get_paths()["purelib"]]
+    files = []
+    for root in roots:
+        for dp, dn, fn in os.walk(root):
+            dn.sort()
+            for f in sorted(fn):
+                if f.endswith(exts):
+                    files.append(os.path.join(dp, f))
+    out, total = [], 0
+    for path in files:
+        try:
+            if os.path.getsize(path) < min_file:
+                continue
+            with open(path, "rb") as fh:
+                data = fh.read()
+            data.decode("utf-8")
+        except (OSError, UnicodeDecodeError):
+            continue
+        if b"\x00" in data:
+            continue
+        out.append(data)
+        total += len(data) + 2
+        if total >= max_bytes:
+            break
+    return b"\n\n".join(out)[:max_bytes]
+
+
+def cut_prompts(corpus: bytes, prompt_bytes=16384):
+    """Slices of about prompt_bytes, cut at line ends (never inside a UTF-8 sequence) -> PromptBatch."""
+    cuts, pos, n = [0], 0, len(corpus)
+    while pos < n:
+        end = min(pos + prompt_bytes, n)
+        if end < n:
+            nl = corpus.rfind(b"\n", pos + prompt_bytes // 2, end)
+            if nl > pos:
+                end = nl + 1
+            else:
+                while end < n and (corpus[end] & 0xC0) == 0x80:
+                    end += 1
+        cuts.append(end)
+        pos = end
+    return PromptBatch(np.frombuffer(corpus, dtype=np.uint8).copy(), np.asarray(cuts, dtype=np.int64))
