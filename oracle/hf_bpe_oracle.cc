@@ -36,12 +36,18 @@ inline int uni_class(uint32_t cp) {
   if (cp >= 0x110000) return kOther;
   return kUniStage2[(size_t)kUniStage1[cp >> 8] * 256 + (cp & 255)] & 3;  // bit 2: NFC-suspect (unused here)
 }
+// what a class-0 ("other") char is: 1 = \p{P}, 2 = \p{S}, 3 = \p{M}, 0 = the rest (C*, unassigned ...)
+enum { kSubNone = 0, kSubP = 1, kSubS = 2, kSubM = 3 };
+int uni_sub(uint32_t cp) {
+  if (cp >= 0x110000) return kSubNone;
+  return (kUniStage2[(size_t)kUniStage1[cp >> 8] * 256 + (cp & 255)] >> 3) & 3;
+}
 
 struct Hf {
   int32_t byte_sym[256];                                   // byte -> id of its byte-level char
   std::unordered_map<uint64_t, std::pair<uint32_t, int32_t>> merges;  // (a << 32 | b) -> (rank, new id)
   std::vector<std::pair<std::string, int32_t>> added;      // special tokens matched on the raw text
-  int pattern = 1;                                         // 1: GPT-2 ByteLevel regex, 2: cl100k family
+  int pattern = 1;                                         // 1: GPT-2 ByteLevel regex, 2: cl100k family, 3: DeepSeek-V3
   int digits = 3;                                          // pattern 2: \p{N}{1,digits}
   bool ignore_merges = false;
   std::unordered_map<std::string, int32_t> vocab;          // raw bytes of every token -> id (ignore_merges)
@@ -172,6 +178,103 @@ void cl100k_split(const std::vector<Ch>& c, int K, std::vector<std::pair<size_t,
   }
 }
 
+// The DeepSeek-V3 / R1 pre-tokenizer: Sequence[Split(\p{N}{1,3}), Split([一-龥぀-ゟ゠-ヿ]+), Split(main regex)], every
+// Split with behaviour Isolated — matches AND the text between matches become pieces, and the next Split runs inside
+// each piece separately (pre_tokenizers/split.rs, pre_tokenizers/sequence.rs).
+//   main regex = [!-/:-@\[-`{-~][A-Za-z]+ | [^\r\n\p{L}\p{P}\p{S}]?[\p{L}\p{M}]+ | " ?"[\p{P}\p{S}]+[\r\n]* | \s*[\r\n]+
+//                | \s+(?!\S) | \s+          (leftmost-first; a char no alternative matches stays unmatched text)
+inline bool ds_cjk(uint32_t cp) {
+  return (cp >= 0x4E00 && cp <= 0x9FA5) || (cp >= 0x3040 && cp <= 0x309F) || (cp >= 0x30A0 && cp <= 0x30FF);
+}
+inline bool ds_ascii_punct(uint32_t cp) {
+  return (cp >= 0x21 && cp <= 0x2F) || (cp >= 0x3A && cp <= 0x40) || (cp >= 0x5B && cp <= 0x60) || (cp >= 0x7B && cp <= 0x7E);
+}
+inline bool ds_ascii_alpha(uint32_t cp) { return (cp >= 'A' && cp <= 'Z') || (cp >= 'a' && cp <= 'z'); }
+
+// one match attempt of the main regex at position i of the piece [b, e); returns the end, or i when nothing matches
+size_t ds3_match_at(const std::vector<Ch>& c, const std::vector<int>& sub, size_t i, size_t e) {
+  auto is_lm = [&](size_t k) { return c[k].cls == kLetter || (c[k].cls == kOther && sub[k] == kSubM); };
+  auto is_ps = [&](size_t k) { return c[k].cls == kOther && (sub[k] == kSubP || sub[k] == kSubS); };
+  // [!-/:-@\[-`{-~][A-Za-z]+
+  if (ds_ascii_punct(c[i].cp) && i + 1 < e && ds_ascii_alpha(c[i + 1].cp)) {
+    size_t j = i + 2;
+    while (j < e && ds_ascii_alpha(c[j].cp)) ++j;
+    return j;
+  }
+  // [^\r\n\p{L}\p{P}\p{S}]?[\p{L}\p{M}]+
+  {
+    size_t s = i;
+    if (!is_nl(c[i].cp) && c[i].cls != kLetter && !is_ps(i) && i + 1 < e && is_lm(i + 1)) s = i + 1;
+    if (is_lm(s)) {
+      size_t j = s;
+      while (j < e && is_lm(j)) ++j;
+      return j;
+    }
+  }
+  // " ?"[\p{P}\p{S}]+[\r\n]*
+  {
+    const size_t s = (c[i].cp == ' ' && i + 1 < e && is_ps(i + 1)) ? i + 1 : i;
+    if (is_ps(s)) {
+      size_t j = s;
+      while (j < e && is_ps(j)) ++j;
+      while (j < e && is_nl(c[j].cp)) ++j;
+      return j;
+    }
+  }
+  if (c[i].cls == kSpace) {
+    size_t w = i;
+    while (w < e && c[w].cls == kSpace) ++w;  // the whole whitespace run (inside this piece)
+    size_t last_nl = e;
+    for (size_t k = i; k < w; ++k)
+      if (is_nl(c[k].cp)) last_nl = k;
+    if (last_nl != e) return last_nl + 1;     // \s*[\r\n]+ : up to and including the last CR / LF of the run
+    if (w == e) return w;                     // \s+(?!\S): the run reaches the end of the piece
+    if (w - i >= 2) return w - 1;             // \s+(?!\S): backtrack one char so that whitespace follows
+    return w;                                 // \s+
+  }
+  return i;
+}
+
+void ds3_split(const std::vector<Ch>& c, std::vector<std::pair<size_t, size_t>>* out) {
+  const size_t n = c.size();
+  std::vector<int> sub(n);
+  for (size_t k = 0; k < n; ++k) sub[k] = uni_sub(c[k].cp);
+  size_t i = 0;
+  while (i < n) {
+    if (c[i].cls == kNumber) {          // stage 1: \p{N}{1,3}, Isolated
+      size_t j = i;
+      while (j < n && c[j].cls == kNumber && j - i < 3) ++j;
+      out->emplace_back(i, j);
+      i = j;
+      continue;
+    }
+    if (ds_cjk(c[i].cp)) {              // stage 2: the CJK / kana run, Isolated
+      size_t j = i;
+      while (j < n && ds_cjk(c[j].cp) && c[j].cls != kNumber) ++j;
+      out->emplace_back(i, j);
+      i = j;
+      continue;
+    }
+    // stage 3 inside the piece [i, e): up to the next number or CJK char
+    size_t e = i;
+    while (e < n && c[e].cls != kNumber && !ds_cjk(c[e].cp)) ++e;
+    size_t k = i;
+    while (k < e) {
+      const size_t j = ds3_match_at(c, sub, k, e);
+      if (j > k) {
+        out->emplace_back(k, j);
+        k = j;
+      } else {                          // unmatched text up to the next match start = one piece
+        size_t u = k + 1;
+        while (u < e && ds3_match_at(c, sub, u, e) == u) ++u;
+        out->emplace_back(k, u);
+        k = u;
+      }
+    }
+    i = e;
+  }
+}
+
 // models/bpe/word.rs merge_all
 struct Sym {
   int32_t id;
@@ -235,7 +338,8 @@ long encode(const Hf& h, const uint8_t* text, size_t len, std::vector<int32_t>* 
       p += l;
     }
     std::vector<std::pair<size_t, size_t>> pieces;
-    if (h.pattern == 2) cl100k_split(c, h.digits, &pieces);
+    if (h.pattern == 3) ds3_split(c, &pieces);
+    else if (h.pattern == 2) cl100k_split(c, h.digits, &pieces);
     else gpt2_split(c, &pieces);
     for (const auto& pr : pieces) {
       const size_t b = c[pr.first].off, e = c[pr.second - 1].off + c[pr.second - 1].len;
@@ -269,7 +373,7 @@ void* oracle_hf_new(const int32_t* byte_sym, const int32_t* merges, size_t n_mer
     h->added.emplace_back(std::string(added_blob + added_off[i], (size_t)(added_off[i + 1] - added_off[i])), added_ids[i]);
   return h;
 }
-// pattern: 1 GPT-2 / 2 cl100k family (digits = K); vocab: raw bytes of every token (blob + offsets) with ids,
+// pattern: 1 GPT-2 / 2 cl100k family (digits = K) / 3 DeepSeek-V3 three-stage split; vocab: raw bytes of every token (blob + offsets) with ids,
 // consulted per pre-token when ignore_merges is set
 void oracle_hf_configure(void* hv, int pattern, int digits, int ignore_merges, const char* vocab_blob,
                          const int64_t* vocab_off, const int32_t* vocab_ids, size_t n_vocab) {

@@ -371,13 +371,27 @@ CL100K_FAMILY = {
 }
 
 
+DEEPSEEK_V3_SPLITS = (
+    r"\p{N}{1,3}", "[一-龥぀-ゟ゠-ヿ]+",
+    "[!\"#$%&'()*+,\\-./:;<=>?@\\[\\\\\\]^_`{|}~][A-Za-z]+|[^\r\n\\p{L}\\p{P}\\p{S}]?[\\p{L}\\p{M}]+|"
+    " ?[\\p{P}\\p{S}]+[\r\n]*|\\s*[\r\n]+|\\s+(?!\\S)|\\s+")
+
+
 def hf_pattern_of(pre):
     """(pattern kind, digits) of a tokenizer.json pre_tokenizer: (1, 0) = ByteLevel with its own GPT-2 regex,
     (2, K) = Sequence[Split(cl100k-family regex, Isolated), ByteLevel(use_regex = false)]."""
     if pre["type"] == "ByteLevel":
         assert pre.get("use_regex", True) and not pre.get("add_prefix_space", False)
         return 1, 0
-    assert pre["type"] == "Sequence" and len(pre["pretokenizers"]) == 2, pre
+    assert pre["type"] == "Sequence", pre
+    if len(pre["pretokenizers"]) == 4:       # DeepSeek-V3 / R1: three Isolated splits, then ByteLevel(use_regex = false)
+        s1, s2, s3, bl = pre["pretokenizers"]
+        for sp in (s1, s2, s3):
+            assert sp["type"] == "Split" and sp["behavior"] == "Isolated" and not sp.get("invert", False)
+        assert (s1["pattern"]["Regex"], s2["pattern"]["Regex"], s3["pattern"]["Regex"]) == DEEPSEEK_V3_SPLITS
+        assert bl["type"] == "ByteLevel" and not bl.get("use_regex", True) and not bl.get("add_prefix_space", False)
+        return 3, 3
+    assert len(pre["pretokenizers"]) == 2, pre
     sp, bl = pre["pretokenizers"]
     assert sp["type"] == "Split" and sp["behavior"] == "Isolated" and not sp.get("invert", False)
     assert bl["type"] == "ByteLevel" and not bl.get("use_regex", True) and not bl.get("add_prefix_space", False)
@@ -399,6 +413,8 @@ class HfBpeOracle:
         assert m["type"] == "BPE"
         self.pattern, self.digits = hf_pattern_of(d["pre_tokenizer"])
         norm = d.get("normalizer")
+        if norm == {"type": "Sequence", "normalizers": []}:   # DeepSeek-V3 ships an empty normalizer sequence
+            norm = None
         assert norm is None or norm == {"type": "NFC"}, norm
         self.nfc = norm is not None
         self.ignore_merges = bool(m.get("ignore_merges", False))

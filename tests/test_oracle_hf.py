@@ -84,13 +84,37 @@ def test_cl100k_family_live(oracle, style):
         assert h.prefix_ids + h.encode(s.encode()).tolist() + h.suffix_ids == tok.encode(s).ids, repr(s)
 
 
+def test_deepseek_v3_layout_goldens_and_live(oracle):
+    """DeepSeek-V3 / R1: Sequence[Split(\\p{N}{1,3}), Split(CJK + kana runs), Split(main regex), ByteLevel], all
+    Isolated (tests/golden/make_hf_fixture3.py); goldens from pip `tokenizers`, then live fuzz over an alphabet with
+    marks, symbols, control chars, CJK, kana, full-width forms and non-decimal numbers."""
+    d = os.path.join(HERE, "golden", "hf_deepseek_style")
+    h = oracle.HfBpeOracle(d)
+    assert h.pattern == 3 and not h.nfc and not h.ignore_merges and h.prefix_ids == [] and h.suffix_ids == []
+    with open(os.path.join(HERE, "golden", "hf_deepseek_goldens.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) > 450
+    for c in cases:
+        t = bytes.fromhex(c["text"])
+        assert h.encode(t).tolist() == c["ids"], t[:40]
+    tokenizers = pytest.importorskip("tokenizers")
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_hf_fixture3 as m
+    tok = tokenizers.Tokenizer.from_file(os.path.join(d, "tokenizer.json"))
+    rnd = random.Random(31)
+    for _ in range(4000):
+        s = "".join(rnd.choice(m.ALPHABET) for _ in range(rnd.randrange(0, 60)))
+        assert h.encode(s.encode()).tolist() == tok.encode(s).ids, repr(s)
+
+
 def test_full_unicode_sweep_against_tokenizers_wheel(oracle):
     """Every code point of planes 0-3 and the assigned ones above (456 K) between letters, after a space, before a
     digit and after a newline: the class tables (scripts/gen_unicode_classes.py, Unicode 15.0) must split exactly as
     the regex engine inside pip `tokenizers` does, for both patterns."""
     tokenizers = pytest.importorskip("tokenizers")
     import unicodedata
-    for style in ("hf_bpe_8k", "hf_qwen2_style"):
+    for style in ("hf_bpe_8k", "hf_qwen2_style", "hf_deepseek_style"):
         h = oracle.HfBpeOracle(os.path.join(HERE, "golden", style))
         tok = tokenizers.Tokenizer.from_file(os.path.join(HERE, "golden", style, "tokenizer.json"))
         bad = []
@@ -103,6 +127,8 @@ def test_full_unicode_sweep_against_tokenizers_wheel(oracle):
             if h.nfc and unicodedata.normalize("NFC", ch) != ch:
                 continue                                    # the wrapper would normalise it away
             s = "a" + ch + "b " + ch + "1\n" + ch
+            if style == "hf_deepseek_style":               # \p{P} / \p{S} / \p{M} contexts of its main regex too
+                s += "!" + ch + "x " + ch + ch + "\n.\x01" + ch + "z"
             if h.prefix_ids + h.encode(s.encode()).tolist() + h.suffix_ids != tok.encode(s).ids:
                 bad.append(hex(cp))
         assert not bad, (style, len(bad), bad[:20])
