@@ -60,7 +60,7 @@ def test_sentencepiece_every_code_point(oracle, name):
 
 
 @pytest.mark.skipif(not _cuda(), reason="needs a CUDA device")
-@pytest.mark.parametrize("name", ["hf_bpe_8k", "hf_llama3_style", "hf_qwen2_style"])
+@pytest.mark.parametrize("name", ["hf_bpe_8k", "hf_llama3_style", "hf_qwen2_style", "hf_deepseek_style"])
 def test_hf_every_code_point(oracle, name):
     import unicodedata
     d = os.path.join(HERE, "golden", name)

@@ -249,9 +249,14 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
     // NFC (Qwen2 family): the device proves per request that NFC is the identity (every char NFC-inert) and
     // fails the request otherwise — it never normalises
     const JVal* ty = norm->get("type");
-    if (!ty || ty->type != JVal::kStr || ty->str != "NFC")
-      return fail(t, XLLM_ERR_UNSUPPORTED, "tokenizer.json normalizer: only null or NFC is supported on device");
-    t->nfc_check = true;
+    const JVal* members = norm->get("normalizers");
+    const bool empty_sequence = ty && ty->type == JVal::kStr && ty->str == "Sequence" && members &&
+                                members->type == JVal::kArr && members->arr.empty();   // DeepSeek-V3 ships this no-op
+    if (!empty_sequence) {
+      if (!ty || ty->type != JVal::kStr || ty->str != "NFC")
+        return fail(t, XLLM_ERR_UNSUPPORTED, "tokenizer.json normalizer: only null, an empty Sequence or NFC is supported on device");
+      t->nfc_check = true;
+    }
   }
   for (const char* k : {"truncation", "padding"}) {
     const JVal* v = root.get(k);
@@ -260,8 +265,15 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
   const JVal* pre = root.get("pre_tokenizer");
   {
     static const char* kUnsupported =
-        "tokenizer.json pre_tokenizer: supported on device are ByteLevel{add_prefix_space:false, use_regex:true} and "
-        "Sequence[Split{cl100k-family regex, Isolated}, ByteLevel{add_prefix_space:false, use_regex:false}]";
+        "tokenizer.json pre_tokenizer: supported on device are ByteLevel{add_prefix_space:false, use_regex:true}, "
+        "Sequence[Split{cl100k-family regex, Isolated}, ByteLevel{add_prefix_space:false, use_regex:false}] and the "
+        "DeepSeek-V3 Sequence[Split{\\p{N}{1,3}}, Split{CJK/kana runs}, Split{main regex}, ByteLevel{use_regex:false}]";
+    // DeepSeek-V3 / R1 (scheduler/xllm_chat_parse_bridge.cpp:49-78 names the family): three Isolated splits
+    static const char* kDs1 = "\\p{N}{1,3}";
+    static const char* kDs2 = "[\xe4\xb8\x80-\xe9\xbe\xa5\xe3\x81\x80-\xe3\x82\x9f\xe3\x82\xa0-\xe3\x83\xbf]+";
+    static const char* kDs3 =
+        "[!\"#$%&'()*+,\\-./:;<=>?@\\[\\\\\\]^_`{|}~][A-Za-z]+|[^\r\n\\p{L}\\p{P}\\p{S}]?[\\p{L}\\p{M}]+| ?[\\p{P}\\p{S}]+[\r\n]*|"
+        "\\s*[\r\n]+|\\s+(?!\\S)|\\s+";
     static const char* kP3 =
         "(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\\r\\n\\p{L}\\p{N}]?\\p{L}+|\\p{N}{1,3}| ?[^\\s\\p{L}\\p{N}]+[\\r\\n]*|\\s*[\\r\\n]+|\\s+(?!\\S)|\\s+";
     static const char* kP1 =
@@ -280,6 +292,23 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
       t->hf_pattern = 1;
     } else if (ty->str == "Sequence") {
       const JVal* seq = pre->get("pretokenizers");
+      if (seq && seq->type == JVal::kArr && seq->arr.size() == 4) {
+        const char* want[3] = {kDs1, kDs2, kDs3};
+        for (int k = 0; k < 3; ++k) {
+          const JVal& sp = seq->arr[(size_t)k];
+          const JVal* st = sp.get("type");
+          const JVal* pat = sp.get("pattern");
+          const JVal* rx = pat ? pat->get("Regex") : nullptr;
+          const JVal* beh = sp.get("behavior");
+          if (!st || st->type != JVal::kStr || st->str != "Split" || !rx || rx->type != JVal::kStr || !beh ||
+              beh->type != JVal::kStr || beh->str != "Isolated" || !flag_false_or_absent(&sp, "invert") ||
+              rx->str != want[k])
+            return fail(t, XLLM_ERR_UNSUPPORTED, std::string(kUnsupported) + (rx && rx->type == JVal::kStr ? "; got regex " + rx->str : ""));
+        }
+        if (!byte_level_ok(&seq->arr[3], false)) return fail(t, XLLM_ERR_UNSUPPORTED, kUnsupported);
+        t->hf_pattern = 3;
+        t->hf_digits = 3;
+      } else {
       if (!seq || seq->type != JVal::kArr || seq->arr.size() != 2) return fail(t, XLLM_ERR_UNSUPPORTED, kUnsupported);
       const JVal& sp = seq->arr[0];
       const JVal* st = sp.get("type");
@@ -294,6 +323,7 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
       else if (rx->str == kP1) t->hf_digits = 1;
       else return fail(t, XLLM_ERR_UNSUPPORTED, std::string(kUnsupported) + "; got regex " + rx->str);
       t->hf_pattern = 2;
+      }
     } else {
       return fail(t, XLLM_ERR_UNSUPPORTED, kUnsupported);
     }
@@ -327,7 +357,12 @@ int hf_load_model(const std::string& path_in, SpTables* t) {
       t->added_tokens.emplace_back(content->str, (int32_t)id->num);
       max_id = (int32_t)id->num > max_id ? (int32_t)id->num : max_id;
     }
-    if (t->added_tokens.size() > 256) return fail(t, XLLM_ERR_UNSUPPORTED, "more than 256 added tokens");
+    {   // the device keeps them in one blob addressed by 16-bit offsets (DeepSeek-V3: ~820 tokens, ~25 KB)
+      size_t blob = 0;
+      for (const auto& a : t->added_tokens) blob += a.first.size();
+      if (t->added_tokens.size() > 2048 || blob > 65535)
+        return fail(t, XLLM_ERR_UNSUPPORTED, "added tokens: more than 2048 of them or more than 65535 bytes in total");
+    }
   }
   const uint32_t V = (uint32_t)max_id + 1;
   t->byte_mode = true;

@@ -33,6 +33,21 @@
 //   other whitespace: run start | previous char is a CR/LF with no newline left in the run | last char of the run
 //           before a non-space (prefix or single) — and nothing else while a newline still follows in the run;
 // contractions are case-insensitive (incl. U+017F) and otherwise as above.
+// hf_pattern 3 is DeepSeek-V3 / R1: Sequence[Split(\p{N}{1,3}), Split([一-龥぀-ゟ゠-ヿ]+), Split(main regex)], all Isolated —
+// numbers (groups of 3) and CJK / kana runs are cut out first and bound everything else; inside the remaining pieces
+//        [!-/:-@\[-`{-~][A-Za-z]+|[^\r\n\p{L}\p{P}\p{S}]?[\p{L}\p{M}]+| ?[\p{P}\p{S}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+
+// (oracle: ds3_split; the rule set below is checked against the sequential scan in tests/test_hf_rules_equivalence.py).
+// Kinds: letter (\p{L} or \p{M}), number, CJK, whitespace, P/S, rest.  The scanned facts of pattern 2 carry over (with
+// "punctuation" = P/S) plus one more forward scan: an ASCII letter lies inside a "punct + ASCII letters" token when
+// the nearest preceding char that is not an ASCII letter is an ASCII punctuation char that starts a token and is
+// followed by an ASCII letter.  Position i starts a token iff
+//   number: index in the run is a multiple of 3;   CJK: previous char is not CJK;   anything after a number / CJK char;
+//   letter: after a letter only where a "punct + ASCII letters" token ends (this char is not an ASCII letter); after
+//           P/S unless that char opens such a token and this is an ASCII letter; after whitespace only if it is a CR/LF
+//           (any other whitespace or "rest" char is the letters' one-char prefix);
+//   P/S   : previous char is neither P/S nor U+0020;
+//   rest  : previous char is not "rest", or a letter follows (then this char is the letters' prefix);
+//   whitespace: as in pattern 2, where a following number / CJK char ends the piece like the end of the text.
 // Per-byte scratch (one byte per text byte, in the merge scratch S[] which is idle while scanning):
 //   bits 0-1 class, bit 2 char is U+0020, bit 3 inside an added token, bit 4 added token starts here,
 //   bits 5-6 contraction length - 1 (0 = none), 0x80 = UTF-8 continuation byte.
@@ -44,6 +59,16 @@ constexpr uint16_t kHfSpecialWord = 0x8000;  // wstart[] flag: the word is an ad
 constexpr uint16_t kHfPosMask = 0x0FFF;
 // pattern 2, second scratch byte per text byte (in PM[]): CR/LF | swallowed CR/LF | digit starts a token | a CR/LF follows in the run
 constexpr uint8_t kAuxNl = 0x01, kAuxSwallowed = 0x02, kAuxDigitStart = 0x04, kAuxNlAfter = 0x08;
+// pattern 3 (DeepSeek-V3), same byte: \p{P}|\p{S} char | char of the CJK / kana ranges | ASCII punctuation that opens a
+// "punct + ASCII letters" token | ASCII letter inside such a token
+constexpr uint8_t kAuxPS = 0x10, kAuxCjk = 0x20, kAuxAStart = 0x40, kAuxAIn = 0x80;
+__device__ __forceinline__ bool hf_ascii_alpha(uint8_t b) { return (uint8_t)((b | 0x20) - 'a') < 26; }
+__device__ __forceinline__ bool hf_ascii_punct(uint8_t b) {
+  return (b >= 0x21 && b <= 0x2F) || (b >= 0x3A && b <= 0x40) || (b >= 0x5B && b <= 0x60) || (b >= 0x7B && b <= 0x7E);
+}
+__device__ __forceinline__ bool hf_cjk(uint32_t cp) {   // [一-龥぀-ゟ゠-ヿ]
+  return (cp >= 0x4E00 && cp <= 0x9FA5) || (cp >= 0x3040 && cp <= 0x30FF);
+}
 
 // class in bits 0-1; bit 2 (non-ASCII only): the char is not NFC-inert (scripts/gen_unicode_classes.py)
 constexpr uint8_t kUniNfcSuspect = 0x04;
@@ -107,7 +132,7 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
   uint8_t* cls = reinterpret_cast<uint8_t*>(sm.S);
   uint8_t* aux = reinterpret_cast<uint8_t*>(sm.PM);
   static_assert(sizeof(sm.S) >= kNBuf && sizeof(sm.PM) >= kNBuf, "class scratch must cover the staging buffer");
-  const bool p2 = T.hf_pattern == 2;
+  const bool p2 = T.hf_pattern == 2, p3 = T.hf_pattern == 3;
   bool bad = false, nfc_bad = false;
   // ---- A: classes + UTF-8 validation (+ the NFC quick check: every char NFC-inert => NFC is the identity)
   for (int base = 0; base < nlen; base += 32) {
@@ -115,8 +140,10 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
     if (p < nlen) {
       const uint8_t b0 = nb[p];
       uint8_t v;
+      uint8_t ax = (b0 == '\n' || b0 == '\r') ? kAuxNl : 0;
       if (b0 < 0x80) {
         v = hf_class(T, b0) | (b0 == ' ' ? kHfIsSp : 0);
+        if (p3 && hf_ascii_punct(b0)) ax |= kAuxPS;
       } else if ((b0 & 0xC0) == 0x80) {
         v = kHfCont;
         bool cov = false;  // must belong to a lead byte at most 3 back
@@ -140,14 +167,20 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
             const uint32_t cp = l == 2 ? (((b0 & 0x1Fu) << 6) | (nb[p + 1] & 0x3Fu))
                               : l == 3 ? (((b0 & 0x0Fu) << 12) | ((nb[p + 1] & 0x3Fu) << 6) | (nb[p + 2] & 0x3Fu))
                                        : (((b0 & 0x07u) << 18) | ((nb[p + 1] & 0x3Fu) << 12) | ((nb[p + 2] & 0x3Fu) << 6) | (nb[p + 3] & 0x3Fu));
-            v = hf_class(T, cp);
-            nfc_bad |= T.nfc_check && (v & kUniNfcSuspect);
-            v &= 3;
+            const uint8_t tb = hf_class(T, cp);   // bits 0-1 class, 2 NFC-suspect, 3-4: 1 P, 2 S, 3 M (class 0 only)
+            nfc_bad |= T.nfc_check && (tb & kUniNfcSuspect);
+            v = tb & 3;
+            if (p3) {
+              const uint8_t sub = (tb >> 3) & 3;
+              if (hf_cjk(cp)) { v = kHfOther; ax = kAuxCjk; }
+              else if (v == kHfOther && sub == 3) v = kHfLetter;          // \p{M} runs with the letters
+              else if (v == kHfOther && sub != 0) ax |= kAuxPS;
+            }
           }
         }
       }
       cls[p] = v;
-      if (p2) aux[p] = (b0 == '\n' || b0 == '\r') ? kAuxNl : 0;
+      if (p2 || p3) aux[p] = ax;
     }
   }
   __syncwarp();
@@ -188,7 +221,7 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
   for (int base = 0; base < nlen; base += 32) {
     const int p = base + lane;
     uint8_t add = 0;
-    if (p < nlen && nb[p] == '\'' && !(cls[p] & (kHfInAdded | kHfAddedStart))) {
+    if (!p3 && p < nlen && nb[p] == '\'' && !(cls[p] & (kHfInAdded | kHfAddedStart))) {
       bool st = p == 0;
       if (!st) {
         int q = p - 1;
@@ -214,7 +247,7 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
   }
   // non-final: a token is complete only if everything that decides its end is in the buffer
   int limit = final ? nlen : nlen - (int)T.added_max_len - 8;
-  if (p2) {
+  if (p2 || p3) {
     const uint32_t below = (1u << lane) - 1u;
     // ---- C1 (forward): swallowed CR/LFs, digit index inside the run
     bool carry_sw = false;  // the last char that is not CR/LF is a punctuation char
@@ -227,7 +260,8 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
       const bool plain = ch && !(v & (kHfInAdded | kHfAddedStart));
       const bool is_nl = plain && (aux[p] & kAuxNl);
       const bool is_n = plain && (v & 3) == kHfNumber;
-      const uint32_t m_o = __ballot_sync(kFull, plain && (v & 3) == kHfOther);
+      // the char class whose run swallows following CR/LFs: pattern 2 [^\s\p{L}\p{N}], pattern 3 [\p{P}\p{S}]
+      const uint32_t m_o = __ballot_sync(kFull, plain && (p3 ? (aux[p < nlen ? p : 0] & kAuxPS) != 0 : (v & 3) == kHfOther));
       const uint32_t m_n = __ballot_sync(kFull, is_n);
       const uint32_t m_not_nl = __ballot_sync(kFull, ch && !is_nl);
       const uint32_t m_not_n = __ballot_sync(kFull, ch && !is_n);
@@ -283,6 +317,44 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
       }
     }
   }
+  if (p3) {
+    // ---- D1: ASCII punctuation that opens a "punct + ASCII letters" token: followed by an ASCII letter, and a token
+    // start itself (previous char neither P/S — its run would have taken this one — nor U+0020, the " ?" prefix)
+    for (int base = 0; base < nlen; base += 32) {
+      const int p = base + lane;
+      bool as = false;
+      if (p + 1 < nlen && !(cls[p] & (kHfInAdded | kHfAddedStart)) && hf_ascii_punct(nb[p]) &&
+          !(cls[p + 1] & (kHfInAdded | kHfAddedStart)) && hf_ascii_alpha(nb[p + 1])) {
+        as = p == 0;
+        if (!as) {
+          int q = p - 1;
+          while (q > 0 && cls[q] == kHfCont) --q;
+          as = (cls[q] & (kHfInAdded | kHfAddedStart)) || (!(aux[q] & kAuxPS) && nb[q] != ' ');
+        }
+      }
+      if (as) aux[p] |= kAuxAStart;
+    }
+    __syncwarp();
+    // ---- D2 (forward): an ASCII letter belongs to such a token iff the nearest preceding char that is not an ASCII
+    // letter is one of those openers
+    const uint32_t below = (1u << lane) - 1u;
+    bool carry_a = false;
+    for (int base = 0; base < nlen; base += 32) {
+      const int p = base + lane;
+      const uint8_t v = p < nlen ? cls[p] : kHfCont;
+      const bool ch = p < nlen && v != kHfCont;
+      const bool plain = ch && !(v & (kHfInAdded | kHfAddedStart));
+      const bool alpha = plain && hf_ascii_alpha(nb[p]);
+      const uint32_t m_not_alpha = __ballot_sync(kFull, ch && !alpha);
+      const uint32_t m_astart = __ballot_sync(kFull, plain && (aux[p < nlen ? p : 0] & kAuxAStart));
+      if (alpha) {
+        const uint32_t m = m_not_alpha & below;
+        if (m ? ((m_astart >> (31 - __clz(m))) & 1u) : (uint32_t)carry_a) aux[p] |= kAuxAIn;
+      }
+      if (m_not_alpha) carry_a = (m_astart >> (31 - __clz(m_not_alpha))) & 1u;
+    }
+    __syncwarp();
+  }
   // ---- B2: token starts, compacted into wstart[]
   constexpr int kCap = kMaxWords - 1;
   int count = 0;
@@ -306,7 +378,41 @@ __device__ HfScan hf_scan(const SpDev& T, SM& sm, int nlen, bool final, int lane
           while (q > 0 && cls[q] == kHfCont) --q;
           const uint8_t a = cls[q];
           const bool a_ws = (a & 3) == kHfSpace, b_ws = (v & 3) == kHfSpace;
-          if (p2) {
+          if (p3) {
+            const uint8_t a_aux = aux[q], b_aux = aux[p];
+            const uint8_t bc = v & 3, ac = a & 3;
+            const bool a_bound = ac == kHfNumber || (a_aux & kAuxCjk);     // the previous char closed a piece
+            if (bc == kHfNumber) {
+              st = (b_aux & kAuxDigitStart) != 0;
+            } else if (b_aux & kAuxCjk) {
+              st = !(a_aux & kAuxCjk);
+            } else if (a_bound) {
+              st = true;
+            } else if (bc == kHfLetter) {
+              if (ac == kHfLetter) st = (a_aux & kAuxAIn) && !hf_ascii_alpha(nb[p]);
+              else if (a_aux & kAuxPS) st = !((a_aux & kAuxAStart) && hf_ascii_alpha(nb[p]));
+              else if (a_ws) st = (a_aux & kAuxNl) != 0;
+              else st = false;                                             // a "rest" char is the letters' prefix
+            } else if (b_aux & kAuxPS) {
+              st = !(a_aux & kAuxPS) && !(a & kHfIsSp);
+            } else if (bc == kHfOther) {                                   // "rest": control / format / unassigned
+              const uint8_t b0 = nb[p];
+              const int nx = p + (b0 < 0x80 ? 1 : (b0 < 0xE0 ? 2 : (b0 < 0xF0 ? 3 : 4)));
+              const bool a_rest = ac == kHfOther && !(a_aux & (kAuxPS | kAuxCjk));
+              st = !a_rest || (nx < nlen && !(cls[nx] & (kHfInAdded | kHfAddedStart)) && (cls[nx] & 3) == kHfLetter);
+            } else if (b_aux & kAuxNl) {
+              st = !(b_aux & kAuxSwallowed) && !a_ws;
+            } else if (b_aux & kAuxNlAfter) {
+              st = !a_ws || ((a_aux & kAuxNl) && (a_aux & kAuxSwallowed));
+            } else {
+              const uint8_t b0 = nb[p];
+              const int nx = p + (b0 < 0x80 ? 1 : (b0 < 0xE0 ? 2 : (b0 < 0xF0 ? 3 : 4)));
+              // a non-space char of the same piece follows (a number / CJK char ends the piece like the end of text)
+              const bool nxt_open = nx < nlen && !(cls[nx] & kHfAddedStart) && (cls[nx] & 3) != kHfSpace &&
+                                    (cls[nx] & 3) != kHfNumber && !(aux[nx] & kAuxCjk);
+              st = !a_ws || (a_aux & kAuxNl) || nxt_open;
+            }
+          } else if (p2) {
             const uint8_t a_aux = aux[q], b_aux = aux[p];
             const uint8_t bc = v & 3, ac = a & 3;
             if (bc == kHfLetter) {

@@ -482,10 +482,14 @@ __device__ __forceinline__ bool normalize_fast(const SpDev& T, SM& sm, ReqState&
       fast_ok = ((((w | 0x80808080u) - 0x20202020u) & 0x80808080u) == 0x80808080u) &&  // every byte >= 0x20
                 (((w + 0x01010101u) & 0x80808080u) == 0u);                               // every byte <= 0x7E
     if (!__all_sync(kFull, ok && fast_ok)) {
+      // per byte: simple, or "space-like" (the charsmap rewrites it to exactly one space: tab / LF / CR under
+      // nmt_nfkc) — a space-like byte is turned into 0x20 here and from then on IS a source space
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t bk = (w >> (8 * k)) & 0xFFu;
-        ok = ok && ((T.simple_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u);
+        const bool spl = (T.spacelike_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u;
+        ok = ok && (spl || ((T.simple_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u));
+        if (spl && k < (int)nvalid) w = (w & ~(0xFFu << (8 * k))) | (0x20u << (8 * k));
       }
       if (!__all_sync(kFull, ok)) return false;
     }
@@ -1767,6 +1771,7 @@ int SpDeviceModel::upload(const SpTables& t) {
     dev_.long_slots = slots;
   }
   for (int i = 0; i < 4; ++i) dev_.simple_ascii[i] = t.simple_ascii[i];
+  for (int i = 0; i < 4; ++i) dev_.spacelike_ascii[i] = t.spacelike_ascii[i];
   dev_.byte_fallback = t.byte_fallback;
   dev_.add_dummy_prefix = t.add_dummy_prefix;
   dev_.remove_extra_ws = t.remove_extra_whitespaces;

@@ -30,6 +30,7 @@ struct SpDev {
   int32_t unk_id;
   uint32_t max_unit_out;
   uint32_t simple_ascii[4];
+  uint32_t spacelike_ascii[4];  // bytes the charsmap turns into exactly one space (SpTables::spacelike_ascii)
   uint8_t byte_fallback, add_dummy_prefix, remove_extra_ws, split_mode;
   uint8_t small_vocab;  // ranks and piece ids fit 16 bits: packed merge scratch
   uint8_t byte_mode;    // tiktoken tables: every byte is a symbol, text is copied verbatim

@@ -325,6 +325,22 @@ int sp_load_model(const std::string& path_in, SpTables* t) {
       }
       if (b == 0) simple = false;  // NUL always takes the general path
       if (!simple) t->simple_ascii[b >> 5] &= ~(1u << (b & 31));
+      // "space-like": b alone is a key whose replacement is exactly " ", and no longer key continues with ASCII —
+      // then, followed by an ASCII byte, b normalises exactly like a source space (nmt_nfkc: \t \n \r ...)
+      if (!simple && b != 0 && node < tr.size() && (tr[node] & 0x800000FFu) == b && ((tr[node] >> 8) & 1u)) {
+        const uint32_t u = tr[node];
+        const uint32_t next = node ^ off(u);
+        bool longer_ascii = false;
+        for (uint32_t c = 1; c < 128; ++c) {
+          const uint32_t ch = next ^ c;
+          if (ch < tr.size() && (tr[ch] & 0x800000FFu) == c) longer_ascii = true;
+        }
+        if (!longer_ascii && next < tr.size()) {
+          const uint32_t val = tr[next] & 0x7FFFFFFFu;
+          if ((size_t)val + 1 < t->blob.size() && t->blob[val] == ' ' && t->blob[val + 1] == 0)
+            t->spacelike_ascii[b >> 5] |= 1u << (b & 31);
+        }
+      }
     }
   }
   {

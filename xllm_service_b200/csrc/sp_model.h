@@ -35,6 +35,9 @@ struct SpTables {
   // bit b set <=> ASCII byte b is "simple": the charsmap has no key that is exactly b and every longer key
   // starting with b continues with a byte >= 0x80, so b followed by an ASCII byte normalises to itself
   uint32_t simple_ascii[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  // ASCII bytes the charsmap rewrites to exactly one space (tab, LF, CR ... under nmt_nfkc) and that start no longer
+  // key continuing with an ASCII byte: the fast path treats them as a source space (bit b of word b >> 5)
+  uint32_t spacelike_ascii[4] = {0, 0, 0, 0};
   bool add_dummy_prefix = true;
   bool remove_extra_whitespaces = true;
   // symbols: [0, n_pieces) = piece ids; [n_pieces, n_syms) = single chars that occur inside
