@@ -73,14 +73,16 @@ def test_long_texts_cross_the_staging_buffer(setup):
     texts.append(("x \n \n  y!\n\n" * 500).encode())
     texts.append(("  \n" * 30 + "z" + " " * 300 + "\n" + " " * 299 + "q").encode())
     texts.append((".com@user#tag !x.y " * 500).encode())
-    texts.append(("." + "abcdefghij" * 700 + "é").encode())        # a 7000-letter "punct + letters" token, then a break
+    texts.append((("." + "abcdefghij" * 90 + "é ") * 8).encode())  # 900-letter "punct + letters" tokens, then a break
+    big = ("." + "abcdefghij" * 700 + "é").encode()                # one 7 KB pre-token: over the ~1 KB device scratch
     texts.append(("日本語テキスト123 ひらがな " * 700).encode())
     texts.append(("日" * 9000).encode())                            # one CJK run across many buffers
     texts.append(("x <|endoftext|>\n" * 600).encode())
     texts.append(("\x01\x02a \x01 b\x7f\x7fc " * 700).encode())
     for pad in range(1550, 1600):
         texts.append(("ab " * (pad // 3) + "x" * (pad % 3) + " \n \n!ab 12345\t!a<|endoftext|> é　　y日本.z\x01q").encode())
-    got, status = _encode_all(tok, texts)
+    got, status = _encode_all(tok, texts + [big])
+    assert status[-1] == -6                                        # refused loudly (XLLM_ERR_CAPACITY), never split wrongly
     for i, (t, a) in enumerate(zip(texts, got)):
         assert status[i] == 0, (i, len(t), t[:30])
         assert a == hf.encode(t).tolist(), (i, len(t), t[:30])
