@@ -37,8 +37,8 @@ n, nb = a.requests, a.blocks
 MODEL = os.path.join(ROOT, "tests", "golden", "sp_bpe_8k")
 NAMES = ["inst%02d" % i for i in range(64)]
 
-full = x.Ingest(tokenizer_path=MODEL, device=local, index_capacity=a.index_keys + 4096)   # replica: the whole index
-part = sharded.create_sharded(tokenizer_path=MODEL, device=local, index_capacity=a.index_keys // world * 2 + 4096,
+full = x.Ingest(tokenizer_path=MODEL, device=local, index_capacity=a.index_keys + (1 << 16))   # replica: the whole index
+part = sharded.create_sharded(tokenizer_path=MODEL, device=local, index_capacity=a.index_keys // world * 2 + (1 << 16),
                               max_batch=n, max_tokens=nb * 128)                           # this rank's hash range
 assert part.shard_last_stats()["bucket_capacity"] == n * nb * 3 // (2 * world) + 1024
 
