@@ -442,6 +442,27 @@ def honest_text(local, headline_batch, iters=3, corpus_bytes=256 << 20):
                                      lambda t: S8.encode(t).tolist())
     out["headline_memo_off"]["tokenizer"] = "the headline's SentencePiece BPE 8000 and prompts, word memo disabled"
     h3.close()
+    # the two backends rows a2 / a3 count on parity only: SentencePiece Unigram (Viterbi per word from a running
+    # score, no memo) and tiktoken as the service runs it (no regex: the whole prompt is one piece -> long-word path)
+    d_uni = os.path.join(ROOT, "tests", "golden", "sp_unigram_4k_bf")
+    h4 = x.Ingest(tokenizer_path=d_uni, device=local)
+    SU = o.SentencePieceOracle(d_uni)
+    n4 = min(headline_batch.n, 4096)
+    off4 = headline_batch.offsets[: n4 + 1]
+    out["unigram_4k_headline_text"] = timed(h4, headline_batch.text[: off4[-1]], off4, 8192,
+                                            lambda t: SU.encode(t).tolist(), n_check=8)
+    out["unigram_4k_headline_text"]["tokenizer"] = "SentencePiece Unigram 4000 (byte fallback) on the headline prompts"
+    h4.close()
+    d_tik = os.path.join(ROOT, "tests", "golden", "tiktoken_1k")
+    h5 = x.Ingest(tokenizer_path=d_tik, device=local)
+    TK = o.TiktokenOracle(d_tik)
+    n5 = min(headline_batch.n, 256)
+    off5 = headline_batch.offsets[: n5 + 1]
+    out["tiktoken_1k_regexless"] = timed(h5, headline_batch.text[: off5[-1]], off5, 20480,
+                                         lambda t: TK.encode(t).tolist(), n_check=2)
+    out["tiktoken_1k_regexless"]["tokenizer"] = ("tiktoken 1453 ranks, regex-less as the service configures it: every "
+                                                 "16 KB prompt is ONE piece (tiktoken_tokenizer.cpp:238-241)")
+    h5.close()
     return out
 
 

@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(128) match_route_kernel(const IndexSlot* __res
         const ulonglong2 key = *reinterpret_cast<const ulonglong2*>(keys + 2 * (k0 + i));
         const uint64_t s = find_slot(slots, slot_mask, key.x, key.y);
         if (s != ~0ull) {
-          const ulonglong2 hd = *reinterpret_cast<const ulonglong2*>(&slots[s].hbm);
-          t[0] = hd.x; t[1] = hd.y; t[2] = slots[s].ssd;
+          const ulonglong2 ds = *reinterpret_cast<const ulonglong2*>(&slots[s].dram);   // the slot's second sector
+          t[0] = slots[s].hbm; t[1] = ds.x; t[2] = ds.y;
         }
       } else {
         // sharded: the masks came back in the order the keys were sent; pos maps key index -> that slot

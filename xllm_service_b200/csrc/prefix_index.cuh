@@ -10,7 +10,7 @@
 //   CacheAwareRouting::cost_function      xllm_service/scheduler/loadbalance_policy/cache_aware_routing.cpp:59-85
 //
 // Layout in HBM: open-addressing table of 64-byte slots
-//   { key low64, key high64, hbm mask, dram mask, ssd mask, state }   (instance sets -> 64-bit masks)
+//   { key low64, key high64, state, hbm mask | dram mask, ssd mask }   (instance sets -> 64-bit masks; two sectors)
 // sized to >= 2x the configured key capacity (power of two), linear probing from the key's low64.
 //
 // Readers and writers (the reference: shared_lock in match, unique_lock in upload_kvcache / update_kvcache,
@@ -31,11 +31,14 @@ namespace xllm {
 
 constexpr int kMaxInstances = 64;
 
+// Field order = sector order: key, state and the HBM mask share the first 32-byte sector, so a probe that does not
+// match (another key, a tombstone, the empty slot that ends a miss) costs one DRAM sector, a hit two.
 struct IndexSlot {
   uint64_t klo, khi;
-  uint64_t hbm, dram, ssd;
   uint32_t state;  // 0 empty, 1 full, 2 tombstone, 3 busy (claimed by an insert, key not yet visible)
   uint32_t pad0;
+  uint64_t hbm;
+  uint64_t dram, ssd;
   uint64_t pad1[2];
 };
 static_assert(sizeof(IndexSlot) == 64, "one slot = one 64-byte line");
