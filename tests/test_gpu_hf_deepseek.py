@@ -76,7 +76,7 @@ def test_long_texts_cross_the_staging_buffer(setup):
     texts.append((("." + "abcdefghij" * 90 + "é ") * 8).encode())  # 900-letter "punct + letters" tokens, then a break
     big = ("." + "abcdefghij" * 700 + "é").encode()                # one 7 KB pre-token: over the ~1 KB device scratch
     texts.append(("日本語テキスト123 ひらがな " * 700).encode())
-    texts.append(("日" * 9000).encode())                            # one CJK run across many buffers
+    texts.append((("日" * 300 + "ab") * 30).encode())               # 900-byte CJK runs (one token each) across buffers
     texts.append(("x <|endoftext|>\n" * 600).encode())
     texts.append(("\x01\x02a \x01 b\x7f\x7fc " * 700).encode())
     for pad in range(1550, 1600):
