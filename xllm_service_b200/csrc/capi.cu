@@ -219,6 +219,7 @@ void xllm_ingest_destroy(xllm_ingest_t h) {
   h->d_status.release();
   h->d_defer.release();
   h->d_memo.release();
+  h->d_arena.release();
   h->d_masks.release();
   h->d_match.release();
   h->d_routing.release();
@@ -680,6 +681,9 @@ int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_te
     XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
     memo.table = h->d_memo.p;
     memo.slots = h->memo_slots;
+    memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
+    XLLM_TRY(h->d_arena.reserve(memo.arena_bytes));
+    memo.arena = h->d_arena.p;
   }
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), d_text, d_offsets, n_req, d_ids, ids_stride, d_n_ids, d_status,
                                  h->d_task_counter + 4, h->d_defer.as<int32_t>(), s, memo));
@@ -721,6 +725,9 @@ static int encode_batch_impl(xllm_ingest_t h, int32_t n_req, const uint8_t* text
     XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
     memo.table = h->d_memo.p;
     memo.slots = h->memo_slots;
+    memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
+    XLLM_TRY(h->d_arena.reserve(memo.arena_bytes));
+    memo.arena = h->d_arena.p;
   }
   // offsets are rebased on the device copy of the text: ship them relative to offsets[0]
   if (text_bytes)

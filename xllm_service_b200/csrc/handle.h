@@ -91,6 +91,7 @@ struct xllm_ingest {
   // scratch for the host-pointer entry points
   xllm::DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status, d_defer;
   xllm::DevBuf d_memo;      // word memo of the single-launch encode entry points
+  xllm::DevBuf d_arena;     // warm-up scratch of the encode kernel (per handle: launches on one handle are serialised)
   uint32_t memo_slots = 0;  // 0 = memo off
   xllm::DevBuf d_tokens, d_tok_start, d_n_tok, d_keys, d_key_start;
   // sharded xllm_ingest_batch: the whole batch's keys / row descriptors / results stay resident for the one exchange

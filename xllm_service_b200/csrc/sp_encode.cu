@@ -51,6 +51,10 @@ constexpr int kMaxSym = 16;        // lane-per-word path: chars per word (alive 
 constexpr int kCoopMaxSym = 512;   // warp-cooperative path: chars per word (= 32 * kMaxSym scratch entries)
 constexpr int kMaxWords = 704;     // >= kNBuf / 3 + 2 word starts
 constexpr uint32_t kFull = 0xffffffffu;
+// per-warp slice of the launch's warm-up scratch (global, L2-resident): ids of pre-resolved long words, addressed by
+// the word's byte offset in nbuf (a word never yields more ids than it has bytes), + their id counts per word index
+constexpr size_t kWarmSliceBytes = (size_t)kNBuf * 4 + (size_t)kMaxWords * 2;
+constexpr uint16_t kNotPre = 0xFFFFu;
 constexpr uint32_t kResolvedFlag = 0x40000000u;  // S[] entry holds a token id, not a symbol (bit 31 clear)
 
 // (priority, merged symbol) of the pair starting at a position.  SMALL (ranks and piece ids < 65535):
@@ -87,6 +91,7 @@ struct WarpSmemT {
   typename PMOps<SMALL>::T PM[kCoopMaxSym];  // pair state at position j
   uint8_t nbuf[kNBuf];                       // normalized text (always starts at a word start)
   uint16_t wstart[kMaxWords];
+  uint16_t pend[32];                         // warm-up pre-pass: words that missed the memo, waiting for a full round
 };
 // Unigram kernels: plus the pieces found from each of 32 start positions (unigram_word)
 constexpr int kUniMaxMatch = 32;
@@ -316,6 +321,8 @@ struct ReqState {
   float uni_score;     // Unigram: best-path score at the start of the next word (running float, as upstream)
   int8_t bad_input;    // HF backend: 1 malformed UTF-8, 2 not provably NFC under a normalizer NFC
   bool deferred;       // needs the long-word kernel (this one was built without it)
+  bool warm;           // the last drain had several memo misses: warm the memo before the next drain's rounds
+  bool had_long;       // the last drain had words beyond the lane columns: resolve those ahead of the rounds
   // long-word mode: the current pre-token is being streamed into a global scratch slot
   bool long_mode;
   bool long_last_sp;   // the last char appended to the slot is U+2581
@@ -1094,29 +1101,249 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
   }
   const int complete = HF ? nwords : (final ? nwords : nwords - 1);
 
-  // 2. rounds of up to 32 consecutive words
-  int w0 = 0;
-  while (w0 < complete && !rs.deferred) {
-    const int w = w0 + lane;
-    const bool have = w < complete;
-    int ws = 0, we = 0, nsym = 0;
-    bool special = false;  // HF: the word is an added token
+  // byte range, symbol count and kind of word w (w < complete)
+  auto word_of = [&](int w, int& ws, int& we, int& nsym, bool& special) {
+    ws = we = nsym = 0;
+    special = false;
     if constexpr (HF) {
-      if (have) {
-        const uint16_t e = sm.wstart[w];
-        ws = e & kHfPosMask;
-        we = sm.wstart[w + 1] & kHfPosMask;
-        special = (e & kHfSpecialWord) != 0;
-        nsym = special ? 1 : we - ws;  // every byte is a symbol
-      }
-    } else if (have) {
+      const uint16_t e = sm.wstart[w];
+      ws = e & kHfPosMask;
+      we = sm.wstart[w + 1] & kHfPosMask;
+      special = (e & kHfSpecialWord) != 0;  // the word is an added token
+      nsym = special ? 1 : we - ws;         // every byte is a symbol
+    } else {
       ws = sm.wstart[w];
       we = sm.wstart[w + 1];
       if (rs.ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
       else
         for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
     }
-    const uint32_t long_mask = __ballot_sync(kFull, have && (UNI || nsym > kMaxSym));  // Unigram: one word at a time
+  };
+  // The merge path of one word per lane: symbols -> lane_merge -> resolve single-id symbols in place -> (MEMO) insert.
+  // Used by the rounds below for memo misses and by the warm-up pre-pass.  Outputs: alive set in the lane's S column,
+  // id count, unknown-symbol flags for the cross-word rule, bare-U+2581 flag.
+  auto merge_word = [&](int ws, int we, bool special, uint32_t& alive, int& cnt, bool& first_unk, bool& last_unk,
+                        bool& bare) {
+    alive = 0;
+    cnt = 0;
+    first_unk = last_unk = bare = false;
+    if (HF && special) {
+      int32_t id = 0;
+      hf_added_len(T, nb + ws, we - ws, &id);
+      sm.S[lane] = kResolvedFlag | (uint32_t)id;
+      alive = 1u;
+      cnt = 1;
+      return;
+    }
+    bool direct = false;
+    if constexpr (HF) {
+      if (T.ignore_merges) {  // models/bpe/model.rs: a pre-token that is a vocabulary entry is that token
+        const int32_t id = hf_vocab_lookup(T, nb + ws, we - ws);
+        if (id >= 0) {
+          sm.S[lane] = kResolvedFlag | (uint32_t)id;
+          alive = 1u;
+          cnt = 1;
+          direct = true;
+        }
+      }
+    }
+    bool pu = false, first = true;
+    if (!direct) {
+      int n = 0;
+      for (int p = ws; p < we;) {
+        uint32_t adv;
+        sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
+        p += adv;
+        ++n;
+      }
+      bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
+      alive = lane_merge<SMALL>(T, sm, n, lane);
+    }
+    // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
+    // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
+    for (uint32_t m = direct ? 0u : alive; m;) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      int32_t tmp[4];
+      bool unk;
+      const uint32_t sym = sm.S[j * 32 + lane];
+      const int c = sym_ids(T, sym, tmp, &unk);
+      if (first) { first_unk = unk; first = false; }
+      if (!unk && c == 1) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
+      if (!(unk && pu && !T.byte_fallback)) cnt += c;
+      pu = unk;
+    }
+    last_unk = pu;
+    if constexpr (MEMO) {
+      // memoise: every surviving symbol resolved to exactly one id, at most kMax of them
+      const int k = __popc(alive);
+      U128 key;
+      if (k >= 1 && k <= MemoIds<SMALL>::kMax && k == cnt && !bare && memo_key(nb, ws, we, T.byte_mode, &key)) {
+        uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool ok = true;
+        int q = 0;
+        for (uint32_t m = alive; m; ++q) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t sym = sm.S[j * 32 + lane];
+          ok = ok && (sym & 0xC0000000u) == kResolvedFlag && (sym & 0x3FFFFFFFu) < (SMALL ? (1u << 16) : (1u << 28));
+          id[q] = sym & 0x0FFFFFFFu;
+        }
+        if (ok) {
+          const U128 val = MemoIds<SMALL>::pack(k, id);
+          uint32_t slot = memo_slot(key, memo.mask);
+          const U128 zero{0ull, 0ull};
+#pragma unroll 1
+          for (int way = 0; way < 2; ++way, slot ^= 1u) {
+            uint8_t* e = memo.table + (size_t)slot * 32;
+            const U128 old = cas_b128(e, zero, key);
+            if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
+            if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
+          }
+        }
+      }
+    }
+  };
+
+  // 1b. warm-up pre-passes (throughput kernel with a memo; natural text).  The rounds below go through the words in
+  // order, 32 at a time, and a round runs at the speed of its slowest lane: ONE memo miss costs the whole round a merge,
+  // and a word beyond the lane columns cuts the round short and is merged by the whole warp on its own.  On the
+  // synthetic headline text both are rare; on real text 91 % of the rounds hold a miss and every tenth word is long.
+  // So, when the previous drain looked like that:
+  //   A1  probe the memo for every short word of the drain first, collect the misses and merge them 32 at a time in FULL
+  //       rounds (results go to the memo only); the in-order rounds then find them there;
+  //   A2  merge every long word (17..512 symbols) ahead of the rounds and park its ids in a per-warp global scratch
+  //       (slot = the word's byte offset: ids never outnumber bytes); in the rounds such a word is an ordinary lane
+  //       whose ids are read back from there, so the rounds are no longer cut.  Only for vocabularies without
+  //       cross-word unknown merging (byte fallback, or byte-level), where a word's ids do not depend on its neighbours.
+  int32_t* arena = nullptr;
+  uint16_t* lcnt = nullptr;
+  int a1_misses = 0;
+  if constexpr (MEMO && !UNI && !LONG) {
+    if (T.warm_arena != nullptr && (rs.warm || rs.had_long)) {
+      uint8_t* slice = T.warm_arena + (size_t)blockIdx.x * kWarmSliceBytes;
+      const bool do_long = rs.had_long && (T.byte_fallback || T.byte_mode);
+      if (do_long) {
+        arena = reinterpret_cast<int32_t*>(slice);
+        lcnt = reinterpret_cast<uint16_t*>(slice + (size_t)kNBuf * 4);
+      }
+      int np = 0;  // words waiting in sm.pend[0 .. np)
+      auto flush = [&]() {
+        __syncwarp();
+        int ws = 0, we = 0, nsym = 0;
+        bool special = false;
+        if (lane < np) word_of(sm.pend[lane], ws, we, nsym, special);
+        uint32_t alive;
+        int cnt;
+        bool fu, lu, bare;
+        if (lane < np) merge_word(ws, we, special, alive, cnt, fu, lu, bare);
+        np = 0;
+        __syncwarp();
+      };
+      for (int base = 0; base < complete; base += 32) {
+        const int w = base + lane;
+        const bool have = w < complete;
+        int ws = 0, we = 0, nsym = 0;
+        bool special = false;
+        if (have) word_of(w, ws, we, nsym, special);
+        const bool is_long = have && !special && nsym > kMaxSym;
+        // ---- A2: the long words of this block, one at a time, whole warp
+        uint32_t lm = __ballot_sync(kFull, do_long && is_long);
+        while (lm) {
+          const int b = __ffs(lm) - 1;
+          lm &= lm - 1;
+          const int lws = __shfl_sync(kFull, ws, b), lwe = __shfl_sync(kFull, we, b);
+          int n = 0;
+          bool overflow = false;
+          for (int pb = lws; pb < lwe; pb += 32) {
+            const int p = pb + lane;
+            const bool lead = p < lwe && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
+            const uint32_t m = __ballot_sync(kFull, lead);
+            const int idx = n + __popc(m & ((1u << lane) - 1));
+            if (lead) {
+              if (idx < kCoopMaxSym) { uint32_t adv; sm.S[idx] = char_sym(T, nb + p, &adv); }
+              else overflow = true;
+            }
+            n += __popc(m);
+          }
+          overflow = __any_sync(kFull, overflow);
+          __syncwarp();
+          int total = -1;   // ids written for this word, -1: left to the in-order cooperative path
+          if (!overflow) {
+            int32_t whole = -1;
+            if constexpr (HF) {
+              if (T.ignore_merges) {
+                if (lane == 0) whole = hf_vocab_lookup(T, nb + lws, lwe - lws);
+                whole = __shfl_sync(kFull, whole, 0);
+              }
+            }
+            if (whole >= 0) {
+              if (lane == 0) arena[lws] = whole;
+              total = 1;
+            } else {
+              n = coop_merge<SMALL>(T, sm, n, lane);
+              total = 0;
+              for (int sb = 0; sb < n; sb += 32) {
+                const int j = sb + lane;
+                int32_t tmp[4];
+                bool unk = false;
+                int c = 0;
+                if (j < n) c = sym_ids(T, sm.S[j], tmp, &unk);   // byte fallback: an unknown char is its byte ids
+                const int inc2 = warp_incl_scan(c, lane);
+                int o = lws + total + (inc2 - c);
+                for (int k = 0; k < c; ++k) arena[o++] = tmp[k];
+                total += __shfl_sync(kFull, inc2, 31);
+              }
+            }
+          }
+          if (lane == 0) lcnt[base + b] = total < 0 ? kNotPre : (uint16_t)total;
+          __syncwarp();
+        }
+        // ---- A1: short words that are not in the memo yet
+        if (rs.warm) {
+          bool miss = false;
+          U128 key;
+          if (have && !special && !is_long && memo_key(nb, ws, we, T.byte_mode, &key)) {
+            uint32_t slot = memo_slot(key, memo.mask);
+            miss = true;
+#pragma unroll 1
+            for (int way = 0; way < 2; ++way, slot ^= 1u) {
+              const U128 k = ld_b128(memo.table + (size_t)slot * 32);
+              if (k.lo == key.lo && k.hi == key.hi) { miss = false; break; }
+              if ((k.lo | k.hi) == 0) break;
+            }
+          }
+          const uint32_t mm = __ballot_sync(kFull, miss);
+          const int k = __popc(mm);
+          a1_misses += k;
+          if (np + k > 32) flush();
+          if (miss) sm.pend[np + __popc(mm & ((1u << lane) - 1))] = (uint16_t)w;
+          np += k;
+          if (np == 32) flush();
+        }
+      }
+      if (np) flush();
+      __syncwarp();
+    }
+  }
+
+  // 2. rounds of up to 32 consecutive words
+  int w0 = 0;
+  int n_slow = 0;
+  bool long_seen = false;
+  while (w0 < complete && !rs.deferred) {
+    const int w = w0 + lane;
+    const bool have = w < complete;
+    int ws = 0, we = 0, nsym = 0;
+    bool special = false;  // HF: the word is an added token
+    if (have) word_of(w, ws, we, nsym, special);
+    // a long word the pre-pass resolved: its ids wait in the arena, it takes part in the round like any other lane
+    bool pre = false;
+    if constexpr (MEMO && !UNI && !LONG) {
+      pre = arena != nullptr && have && !special && nsym > kMaxSym && lcnt[w] != kNotPre;
+    }
+    const uint32_t long_mask = __ballot_sync(kFull, have && (UNI || (nsym > kMaxSym && !pre)));  // Unigram: one word at a time
+    long_seen |= long_mask != 0 || __any_sync(kFull, pre);
     const int first_long = long_mask ? __ffs(long_mask) - 1 : 32;
     const bool active = have && lane < first_long;
 
@@ -1127,7 +1354,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     bool memo_hit = false;
     if constexpr (MEMO) {
       U128 key;
-      if (active && !special && memo_key(nb, ws, we, T.byte_mode, &key)) {
+      if (active && !special && !pre && memo_key(nb, ws, we, T.byte_mode, &key)) {
         uint32_t slot = memo_slot(key, memo.mask);
 #pragma unroll 1
         for (int way = 0; way < 2; ++way, slot ^= 1u) {
@@ -1161,83 +1388,12 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
       }
     }
 #endif
-    if (memo_hit) {
-    } else if (HF && active && special) {
-      int32_t id = 0;
-      hf_added_len(T, nb + ws, we - ws, &id);
-      sm.S[lane] = kResolvedFlag | (uint32_t)id;
-      alive = 1u;
-      cnt = 1;
-    } else if (active) {
-      bool direct = false;
-      if constexpr (HF) {
-        if (T.ignore_merges) {  // models/bpe/model.rs: a pre-token that is a vocabulary entry is that token
-          const int32_t id = hf_vocab_lookup(T, nb + ws, we - ws);
-          if (id >= 0) {
-            sm.S[lane] = kResolvedFlag | (uint32_t)id;
-            alive = 1u;
-            cnt = 1;
-            direct = true;
-          }
-        }
-      }
-      bool pu = false, first = true;
-      if (!direct) {
-        int n = 0;
-        for (int p = ws; p < we;) {
-          uint32_t adv;
-          sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
-          p += adv;
-          ++n;
-        }
-        bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
-        alive = lane_merge<SMALL>(T, sm, n, lane);
-      }
-      // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
-      // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
-      for (uint32_t m = direct ? 0u : alive; m;) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        int32_t tmp[4];
-        bool unk;
-        const uint32_t sym = sm.S[j * 32 + lane];
-        const int c = sym_ids(T, sym, tmp, &unk);
-        if (first) { first_unk = unk; first = false; }
-        if (!unk && c == 1) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
-        if (!(unk && pu && !T.byte_fallback)) cnt += c;
-        pu = unk;
-      }
-      last_unk = pu;
-      if constexpr (MEMO) {
-        // memoise: every surviving symbol resolved to exactly one id, at most four of them
-        const int k = __popc(alive);
-        U128 key;
-        if (k >= 1 && k <= MemoIds<SMALL>::kMax && k == cnt && !bare && memo_key(nb, ws, we, T.byte_mode, &key)) {
-          uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          bool ok = true;
-          int q = 0;
-          for (uint32_t m = alive; m; ++q) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t sym = sm.S[j * 32 + lane];
-            ok = ok && (sym & 0xC0000000u) == kResolvedFlag && (sym & 0x3FFFFFFFu) < (SMALL ? (1u << 16) : (1u << 28));
-            id[q] = sym & 0x0FFFFFFFu;
-          }
-          if (ok) {
-            const U128 val = MemoIds<SMALL>::pack(k, id);
-            uint32_t slot = memo_slot(key, memo.mask);
-            const U128 zero{0ull, 0ull};
-#pragma unroll 1
-            for (int way = 0; way < 2; ++way, slot ^= 1u) {
-              uint8_t* e = memo.table + (size_t)slot * 32;
-              const U128 old = cas_b128(e, zero, key);
-              if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
-              if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
-            }
-          }
-        }
-      }
+    if (pre && active) {
+      cnt = lcnt[w];   // ids parked in the arena by the pre-pass (byte fallback / byte level: no unknown merging)
+    } else if (!memo_hit && active) {
+      merge_word(ws, we, special, alive, cnt, first_unk, last_unk, bare);
     }
+    if (__any_sync(kFull, active && !pre && !memo_hit && !special)) ++n_slow;
     // cross-word unknown merging (byte_fallback off): drop the first id if the previous symbol was unknown too
     bool drop_first = false;
     if (!T.byte_fallback) {
@@ -1251,7 +1407,10 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     }
     const int incl = warp_incl_scan(cnt, lane);
     const int total = __shfl_sync(kFull, incl, 31);
-    if (active) {
+    if (active && pre) {
+      int64_t o = rs.n_out + (incl - cnt);
+      for (int q = 0; q < cnt; ++q) put_id(rs, o++, arena[ws + q]);
+    } else if (active) {
       int64_t o = rs.n_out + (incl - cnt);
       bool pu = false, first = true;
       for (uint32_t m = alive; m;) {
@@ -1441,6 +1600,12 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     rs.ascii = !T.byte_mode;
   }
   rs.rescan = false;
+  if constexpr (MEMO && !UNI && !LONG) {
+    // the next drain of this request (and, carried over, the next request of the batch) warms up when this one paid
+    // for misses, and resolves long words ahead when this one had any
+    rs.warm = n_slow >= 2 || a1_misses >= 8;
+    rs.had_long = long_seen;
+  }
   __syncwarp();
   return HF && hf_capped && !rs.deferred;
 }
@@ -1471,6 +1636,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int lane = threadIdx.x;
   const int drain_at = kNBuf - 3 * kFastWin - 8;  // room for one more fast-path step
+  bool warm_carry = false, long_carry = false;   // what the previous request's text looked like (same batch, same kind)
   unsigned long long warp_t0 = 0;
   if constexpr (!LONG) {
     if (T.warp_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(warp_t0));
@@ -1505,6 +1671,8 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     rs.bad_input = 0;
     rs.uni_score = 0.f;
     rs.deferred = false;
+    rs.warm = warm_carry;
+    rs.had_long = long_carry;
     rs.long_mode = false;
     rs.long_last_sp = false;
     rs.long_slot = -1;
@@ -1596,6 +1764,8 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     if constexpr (MODE == 2) {
       if (rs.deferred) { rs.deferred = false; rs.too_long = true; }  // no long-word pass for Unigram
     }
+    warm_carry = rs.warm;
+    long_carry = rs.had_long;
     if (lane == 0) {
       if (rs.deferred) {
         defer_list[atomicAdd(defer_count, 1u)] = (int32_t)r;
@@ -1797,6 +1967,8 @@ static int sp_warps_per_sm(const SpDev& dev) {
   return w;
 }
 
+size_t sp_warm_arena_bytes(const SpDev& dev, int n_req) { return (size_t)sp_encode_grid(dev, n_req) * kWarmSliceBytes; }
+
 int sp_encode_grid(const SpDev& dev, int n_req) {
   int n_sm = 0, d = 0;
   if (cudaGetDevice(&d) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d) != cudaSuccess)
@@ -1814,6 +1986,7 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
   dev.out_start = opts.out_start;
   dev.out_cap = opts.out_cap;
   dev.warp_ns = opts.warp_ns;
+  dev.warm_arena = nullptr;
   const bool small = dev.small_vocab != 0;
   const size_t smem = small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>);
   cudaError_t e0 = cudaSuccess;
@@ -1861,6 +2034,8 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
     e = cudaMemsetAsync(memo.table, 0, (size_t)memo.slots * 32, stream);  // the memo lives for this launch only
     if (e != cudaSuccess) return e;
   }
+  if (use_memo && memo.arena != nullptr && memo.arena_bytes >= (size_t)grid * kWarmSliceBytes)
+    dev.warm_arena = static_cast<uint8_t*>(memo.arena);
   uint8_t* const mt = use_memo ? static_cast<uint8_t*>(memo.table) : nullptr;
   const uint32_t mm = use_memo ? memo.slots - 1 : 0;
 #define XLLM_LAUNCH_PAIR(SMALL_, HF_, MEMO_)                                                                     \

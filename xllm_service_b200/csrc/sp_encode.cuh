@@ -65,6 +65,7 @@ struct SpDev {
   const int64_t* out_start;      // request r's ids go to ids + out_start[r] (at most out_cap[r]) instead of r * ids_stride
   const int32_t* out_cap;
   unsigned long long* warp_ns;   // [grid]: nanoseconds each warp of the throughput kernel spent from start to exit
+  uint8_t* warm_arena;           // [grid] slices of sp_warm_slice_bytes(): scratch of the warm-up pre-passes (sp_encode.cu 1b)
   uint8_t* long_pool;
   int* long_locks;
   uint32_t long_cap;   // symbols per slot
@@ -96,7 +97,12 @@ class SpDeviceModel {
 struct SpMemo {
   void* table = nullptr;
   uint32_t slots = 0;
+  // scratch of the warm-up pre-passes (natural text: memo misses merged in full rounds, long words resolved ahead of
+  // the in-order rounds); at least sp_warm_arena_bytes(dev, n_req) bytes, or null to leave the pre-passes off
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
 };
+size_t sp_warm_arena_bytes(const SpDev& dev, int n_req);
 uint32_t sp_memo_default_slots();  // XLLM_SP_MEMO_SLOTS (0 = off), default 2^18 = 8 MiB
 
 // text: all prompts back to back; offsets[n_req + 1] (bytes).  Request r's ids go to
