@@ -92,6 +92,7 @@ struct WarpSmemT {
   uint8_t nbuf[kNBuf];                       // normalized text (always starts at a word start)
   uint16_t wstart[kMaxWords];
   uint16_t pend[32];                         // warm-up pre-pass: words that missed the memo, waiting for a full round
+  uint16_t pendl[16];                        // ... and words of 17..32 symbols, waiting for a round of lane pairs
 };
 // Unigram kernels: plus the pieces found from each of 32 start positions (unigram_word)
 constexpr int kUniMaxMatch = 32;
@@ -565,7 +566,14 @@ __device__ __forceinline__ bool normalize_fast(const SpDev& T, SM& sm, ReqState&
 // ---------------------------------------------------------------------------- word merge
 // Fast path: this lane owns word [ws, we) with n <= 32 chars; symbols live in column `lane` of S / PM.
 // Returns the alive mask after all merges.
-template <bool SMALL, typename SM>
+// PAIR: the word has up to 2 * kMaxSym symbols and owns the columns of lanes `lane` (even) and `lane + 1`: symbol j
+// lives in row j mod kMaxSym of column lane + j / kMaxSym (warm-up pre-pass: 16 such words per round).
+template <bool PAIR>
+__device__ __forceinline__ int sym_col(int j) {
+  return PAIR ? ((j & (kMaxSym - 1)) * 32 + (j >> 4)) : j * 32;
+}
+static_assert(kMaxSym == 16, "sym_col<true> splits j into row j & 15 and column j >> 4");
+template <bool SMALL, bool PAIR = false, typename SM>
 __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, int lane) {
   using P = PMOps<SMALL>;
   uint32_t* S = sm.S + lane;
@@ -580,42 +588,42 @@ __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, in
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const bool have = j0 + u + 1 < n;
-        sy[u + 1] = have ? S[(j0 + u + 1) * 32] : kSymUnknownFlag;
+        sy[u + 1] = have ? S[sym_col<PAIR>(j0 + u + 1)] : kSymUnknownFlag;
         pr[u] = pair_probe_begin(T, sy[u], sy[u + 1]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (j0 + u + 1 < n) PM[(j0 + u) * 32] = P::pack(pair_probe_finish(T, sy[u], sy[u + 1], pr[u]));
+        if (j0 + u + 1 < n) PM[sym_col<PAIR>(j0 + u)] = P::pack(pair_probe_finish(T, sy[u], sy[u + 1], pr[u]));
       left = sy[4];
     }
   }
-  PM[(n - 1) * 32] = P::none();
-  uint32_t alive = (1u << n) - 1;
+  PM[sym_col<PAIR>(n - 1)] = P::none();
+  uint32_t alive = n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1;
   for (;;) {
     uint32_t best = P::kNone;
     int bj = 0;
     for (uint32_t m = alive; m;) {
       const int j = __ffs(m) - 1;
       m &= m - 1;
-      const uint32_t pr = P::prio_at(PM + j * 32);
+      const uint32_t pr = P::prio_at(PM + sym_col<PAIR>(j));
       if (pr < best) { best = pr; bj = j; }
     }
     if (best == P::kNone) break;
-    const uint32_t hi_mask = ~((2u << bj) - 1u);  // bits above bj
+    const uint32_t hi_mask = bj >= 31 ? 0u : ~((2u << bj) - 1u);  // bits above bj
     const int rj = __ffs(alive & hi_mask) - 1;
-    S[bj * 32] = P::merged(PM[bj * 32]);
+    S[sym_col<PAIR>(bj)] = P::merged(PM[sym_col<PAIR>(bj)]);
     alive &= ~(1u << rj);
     // the two pairs the merge created: both first probes in flight before either is consumed
     const uint32_t above = alive & hi_mask;
     const uint32_t below = alive & ((1u << bj) - 1u);
     const int pj = below ? 31 - __clz(below) : 0;
-    const uint32_t sm_ = S[bj * 32];
-    const uint32_t sr = above ? S[(__ffs(above) - 1) * 32] : kSymUnknownFlag;
-    const uint32_t sl = below ? S[pj * 32] : kSymUnknownFlag;
+    const uint32_t sm_ = S[sym_col<PAIR>(bj)];
+    const uint32_t sr = above ? S[sym_col<PAIR>(__ffs(above) - 1)] : kSymUnknownFlag;
+    const uint32_t sl = below ? S[sym_col<PAIR>(pj)] : kSymUnknownFlag;
     const PairProbe pa = pair_probe_begin(T, sm_, sr);
     const PairProbe pb = pair_probe_begin(T, sl, sm_);
-    PM[bj * 32] = P::pack(pair_probe_finish(T, sm_, sr, pa));
-    if (below) PM[pj * 32] = P::pack(pair_probe_finish(T, sl, sm_, pb));
+    PM[sym_col<PAIR>(bj)] = P::pack(pair_probe_finish(T, sm_, sr, pa));
+    if (below) PM[sym_col<PAIR>(pj)] = P::pack(pair_probe_finish(T, sl, sm_, pb));
   }
   return alive;
 }
@@ -1049,6 +1057,297 @@ __device__ int unigram_word_slow(const SpDev& T, SM& sm, const uint8_t* w, int l
   return n;
 }
 
+// byte range, symbol count and kind of word w of the current drain (w < complete)
+template <bool HF, typename SM>
+__device__ __forceinline__ void word_geom(const SpDev& T, const SM& sm, bool ascii, int w, int& ws, int& we, int& nsym,
+                                          bool& special) {
+  const uint8_t* nb = sm.nbuf;
+  ws = we = nsym = 0;
+  special = false;
+  if constexpr (HF) {
+    const uint16_t e = sm.wstart[w];
+    ws = e & kHfPosMask;
+    we = sm.wstart[w + 1] & kHfPosMask;
+    special = (e & kHfSpecialWord) != 0;  // the word is an added token
+    nsym = special ? 1 : we - ws;         // every byte is a symbol
+  } else {
+    ws = sm.wstart[w];
+    we = sm.wstart[w + 1];
+    if (ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
+    else
+      for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
+  }
+}
+
+// The merge path of one word per lane: symbols -> lane_merge -> resolve single-id symbols in place -> (MEMO) insert.
+// Used by the in-order rounds for memo misses and by the warm-up pre-pass.  Outputs: alive set in the lane's S column,
+// id count, unknown-symbol flags for the cross-word rule, bare-U+2581 flag.
+template <bool SMALL, bool HF, bool MEMO, typename SM>
+__device__ __forceinline__ void merge_word(const SpDev& T, SM& sm, MemoRef memo, int lane, int ws, int we, bool special,
+                                           uint32_t& alive, int& cnt, bool& first_unk, bool& last_unk, bool& bare) {
+  const uint8_t* nb = sm.nbuf;
+    alive = 0;
+    cnt = 0;
+    first_unk = last_unk = bare = false;
+    if (HF && special) {
+      int32_t id = 0;
+      hf_added_len(T, nb + ws, we - ws, &id);
+      sm.S[lane] = kResolvedFlag | (uint32_t)id;
+      alive = 1u;
+      cnt = 1;
+      return;
+    }
+    bool direct = false;
+    if constexpr (HF) {
+      if (T.ignore_merges) {  // models/bpe/model.rs: a pre-token that is a vocabulary entry is that token
+        const int32_t id = hf_vocab_lookup(T, nb + ws, we - ws);
+        if (id >= 0) {
+          sm.S[lane] = kResolvedFlag | (uint32_t)id;
+          alive = 1u;
+          cnt = 1;
+          direct = true;
+        }
+      }
+    }
+    bool pu = false, first = true;
+    if (!direct) {
+      int n = 0;
+      for (int p = ws; p < we;) {
+        uint32_t adv;
+        sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
+        p += adv;
+        ++n;
+      }
+      bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
+      alive = lane_merge<SMALL, false>(T, sm, n, lane);
+    }
+    // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
+    // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
+    for (uint32_t m = direct ? 0u : alive; m;) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      int32_t tmp[4];
+      bool unk;
+      const uint32_t sym = sm.S[j * 32 + lane];
+      const int c = sym_ids(T, sym, tmp, &unk);
+      if (first) { first_unk = unk; first = false; }
+      if (!unk && c == 1) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
+      if (!(unk && pu && !T.byte_fallback)) cnt += c;
+      pu = unk;
+    }
+    last_unk = pu;
+    if constexpr (MEMO) {
+      // memoise: every surviving symbol resolved to exactly one id, at most kMax of them
+      const int k = __popc(alive);
+      U128 key;
+      if (k >= 1 && k <= MemoIds<SMALL>::kMax && k == cnt && !bare && memo_key(nb, ws, we, T.byte_mode, &key)) {
+        uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool ok = true;
+        int q = 0;
+        for (uint32_t m = alive; m; ++q) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t sym = sm.S[j * 32 + lane];
+          ok = ok && (sym & 0xC0000000u) == kResolvedFlag && (sym & 0x3FFFFFFFu) < (SMALL ? (1u << 16) : (1u << 28));
+          id[q] = sym & 0x0FFFFFFFu;
+        }
+        if (ok) {
+          const U128 val = MemoIds<SMALL>::pack(k, id);
+          uint32_t slot = memo_slot(key, memo.mask);
+          const U128 zero{0ull, 0ull};
+#pragma unroll 1
+          for (int way = 0; way < 2; ++way, slot ^= 1u) {
+            uint8_t* e = memo.table + (size_t)slot * 32;
+            const U128 old = cas_b128(e, zero, key);
+            if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
+            if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
+          }
+        }
+      }
+    }
+}
+
+// Warm-up pre-passes (throughput kernel with a memo; natural text).  The rounds below go through the words in
+// order, 32 at a time, and a round runs at the speed of its slowest lane: ONE memo miss costs the whole round a merge,
+// and a word beyond the lane columns cuts the round short and is merged by the whole warp on its own.  On the
+// synthetic headline text both are rare; on real text 91 % of the rounds hold a miss and every tenth word is long.
+// So, when the previous drain looked like that:
+//   A1  probe the memo for every short word of the drain first, collect the misses and merge them 32 at a time in FULL
+//       rounds (results go to the memo only); the in-order rounds then find them there;
+//   A2  merge every long word (17..512 symbols) ahead of the rounds and park its ids in a per-warp global scratch
+//       (slot = the word's byte offset: ids never outnumber bytes); in the rounds such a word is an ordinary lane
+//       whose ids are read back from there, so the rounds are no longer cut.  Only for vocabularies without
+//       cross-word unknown merging (byte fallback, or byte-level), where a word's ids do not depend on its neighbours.
+template <bool SMALL, bool HF, typename SM>
+__device__ __noinline__ void warm_prepass(const SpDev& T, SM& sm, ReqState& rs, int complete, int lane, MemoRef memo,
+                                          int32_t*& arena, uint16_t*& lcnt, int& a1_misses) {
+  const uint8_t* nb = sm.nbuf;
+  if (T.warm_arena != nullptr && (rs.warm || rs.had_long)) {
+    uint8_t* slice = T.warm_arena + (size_t)blockIdx.x * kWarmSliceBytes;
+    const bool do_long = rs.had_long && (T.byte_fallback || T.byte_mode);
+    if (do_long) {
+      arena = reinterpret_cast<int32_t*>(slice);
+      lcnt = reinterpret_cast<uint16_t*>(slice + (size_t)kNBuf * 4);
+    }
+    int np = 0;  // words waiting in sm.pend[0 .. np)
+    auto flush = [&]() {
+      __syncwarp();
+      int ws = 0, we = 0, nsym = 0;
+      bool special = false;
+      if (lane < np) word_geom<HF>(T, sm, rs.ascii, sm.pend[lane], ws, we, nsym, special);
+      uint32_t alive;
+      int cnt;
+      bool fu, lu, bare;
+      if (lane < np) merge_word<SMALL, HF, true>(T, sm, memo, lane, ws, we, special, alive, cnt, fu, lu, bare);
+      np = 0;
+      __syncwarp();
+    };
+    // A2, words of 17..32 symbols: 16 at a time, one per lane PAIR (the even lane merges in the two lanes' columns)
+    int npl = 0;  // words waiting in sm.pendl[0 .. npl)
+    auto flush_pairs = [&]() {
+      __syncwarp();
+      const int k = lane >> 1;
+      const bool mine = (lane & 1) == 0 && k < npl;
+      if (mine) {
+        const int w = sm.pendl[k];
+        int ws, we, nsym;
+        bool special;
+        word_geom<HF>(T, sm, rs.ascii, w, ws, we, nsym, special);
+        int32_t whole = -1;
+        if constexpr (HF) {
+          if (T.ignore_merges) whole = hf_vocab_lookup(T, nb + ws, we - ws);
+        }
+        int o = ws;
+        if (whole >= 0) {
+          arena[o++] = whole;
+        } else {
+          int n = 0;
+          for (int p = ws; p < we;) {
+            uint32_t adv;
+            sm.S[sym_col<true>(n) + lane] = char_sym(T, nb + p, &adv);
+            p += adv;
+            ++n;
+          }
+          uint32_t alive = lane_merge<SMALL, true>(T, sm, n, lane);
+          for (; alive;) {
+            const int j = __ffs(alive) - 1;
+            alive &= alive - 1;
+            int32_t tmp[4];
+            bool unk;
+            const int c = sym_ids(T, sm.S[sym_col<true>(j) + lane], tmp, &unk);   // byte fallback: an unknown char is its byte ids
+            for (int q = 0; q < c; ++q) arena[o++] = tmp[q];
+          }
+        }
+        lcnt[w] = (uint16_t)(o - ws);
+      }
+      npl = 0;
+      __syncwarp();
+    };
+    for (int base = 0; base < complete; base += 32) {
+      const int w = base + lane;
+      const bool have = w < complete;
+      int ws = 0, we = 0, nsym = 0;
+      bool special = false;
+      if (have) word_geom<HF>(T, sm, rs.ascii, w, ws, we, nsym, special);
+      const bool is_long = have && !special && nsym > kMaxSym;
+      const bool is_mid = is_long && nsym <= 2 * kMaxSym;
+      if (do_long) {
+        const uint32_t mid = __ballot_sync(kFull, is_mid);
+        const int k = __popc(mid);
+        if (npl + k > 16) flush_pairs();
+        // more than 16 in one block of 32 words: the first 16 go now, the rest after a flush
+        const int rank = __popc(mid & ((1u << lane) - 1));
+        if (is_mid && rank < 16 - npl) sm.pendl[npl + rank] = (uint16_t)w;
+        const int took = k < 16 - npl ? k : 16 - npl;
+        npl += took;
+        if (npl == 16) flush_pairs();
+        if (took < k) {
+          if (is_mid && rank >= took) sm.pendl[rank - took] = (uint16_t)w;
+          npl = k - took;
+          if (npl == 16) flush_pairs();
+        }
+      }
+      // ---- A2: the words of more than 32 symbols of this block, one at a time, whole warp
+      uint32_t lm = __ballot_sync(kFull, do_long && is_long && !is_mid);
+      while (lm) {
+        const int b = __ffs(lm) - 1;
+        lm &= lm - 1;
+        const int lws = __shfl_sync(kFull, ws, b), lwe = __shfl_sync(kFull, we, b);
+        int n = 0;
+        bool overflow = false;
+        for (int pb = lws; pb < lwe; pb += 32) {
+          const int p = pb + lane;
+          const bool lead = p < lwe && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
+          const uint32_t m = __ballot_sync(kFull, lead);
+          const int idx = n + __popc(m & ((1u << lane) - 1));
+          if (lead) {
+            if (idx < kCoopMaxSym) { uint32_t adv; sm.S[idx] = char_sym(T, nb + p, &adv); }
+            else overflow = true;
+          }
+          n += __popc(m);
+        }
+        overflow = __any_sync(kFull, overflow);
+        __syncwarp();
+        int total = -1;   // ids written for this word, -1: left to the in-order cooperative path
+        if (!overflow) {
+          int32_t whole = -1;
+          if constexpr (HF) {
+            if (T.ignore_merges) {
+              if (lane == 0) whole = hf_vocab_lookup(T, nb + lws, lwe - lws);
+              whole = __shfl_sync(kFull, whole, 0);
+            }
+          }
+          if (whole >= 0) {
+            if (lane == 0) arena[lws] = whole;
+            total = 1;
+          } else {
+            n = coop_merge<SMALL>(T, sm, n, lane);
+            total = 0;
+            for (int sb = 0; sb < n; sb += 32) {
+              const int j = sb + lane;
+              int32_t tmp[4];
+              bool unk = false;
+              int c = 0;
+              if (j < n) c = sym_ids(T, sm.S[j], tmp, &unk);   // byte fallback: an unknown char is its byte ids
+              const int inc2 = warp_incl_scan(c, lane);
+              int o = lws + total + (inc2 - c);
+              for (int k = 0; k < c; ++k) arena[o++] = tmp[k];
+              total += __shfl_sync(kFull, inc2, 31);
+            }
+          }
+        }
+        if (lane == 0) lcnt[base + b] = total < 0 ? kNotPre : (uint16_t)total;
+        __syncwarp();
+      }
+      // ---- A1: short words that are not in the memo yet
+      if (rs.warm) {
+        bool miss = false;
+        U128 key;
+        if (have && !special && !is_long && memo_key(nb, ws, we, T.byte_mode, &key)) {
+          uint32_t slot = memo_slot(key, memo.mask);
+          miss = true;
+#pragma unroll 1
+          for (int way = 0; way < 2; ++way, slot ^= 1u) {
+            const U128 k = ld_b128(memo.table + (size_t)slot * 32);
+            if (k.lo == key.lo && k.hi == key.hi) { miss = false; break; }
+            if ((k.lo | k.hi) == 0) break;
+          }
+        }
+        const uint32_t mm = __ballot_sync(kFull, miss);
+        const int k = __popc(mm);
+        a1_misses += k;
+        if (np + k > 32) flush();
+        if (miss) sm.pend[np + __popc(mm & ((1u << lane) - 1))] = (uint16_t)w;
+        np += k;
+        if (np == 32) flush();
+      }
+    }
+    if (np) flush();
+    if (npl) flush_pairs();
+    __syncwarp();
+  }
+}
+
 // MODE: 0 SentencePiece BPE / tiktoken, 1 HF byte-level BPE (regex pre-tokenizer), 2 SentencePiece Unigram
 template <bool SMALL, bool LONG, int MODE, bool MEMO, typename SM>
 __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
@@ -1101,230 +1400,14 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
   }
   const int complete = HF ? nwords : (final ? nwords : nwords - 1);
 
-  // byte range, symbol count and kind of word w (w < complete)
-  auto word_of = [&](int w, int& ws, int& we, int& nsym, bool& special) {
-    ws = we = nsym = 0;
-    special = false;
-    if constexpr (HF) {
-      const uint16_t e = sm.wstart[w];
-      ws = e & kHfPosMask;
-      we = sm.wstart[w + 1] & kHfPosMask;
-      special = (e & kHfSpecialWord) != 0;  // the word is an added token
-      nsym = special ? 1 : we - ws;         // every byte is a symbol
-    } else {
-      ws = sm.wstart[w];
-      we = sm.wstart[w + 1];
-      if (rs.ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
-      else
-        for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
-    }
-  };
-  // The merge path of one word per lane: symbols -> lane_merge -> resolve single-id symbols in place -> (MEMO) insert.
-  // Used by the rounds below for memo misses and by the warm-up pre-pass.  Outputs: alive set in the lane's S column,
-  // id count, unknown-symbol flags for the cross-word rule, bare-U+2581 flag.
-  auto merge_word = [&](int ws, int we, bool special, uint32_t& alive, int& cnt, bool& first_unk, bool& last_unk,
-                        bool& bare) {
-    alive = 0;
-    cnt = 0;
-    first_unk = last_unk = bare = false;
-    if (HF && special) {
-      int32_t id = 0;
-      hf_added_len(T, nb + ws, we - ws, &id);
-      sm.S[lane] = kResolvedFlag | (uint32_t)id;
-      alive = 1u;
-      cnt = 1;
-      return;
-    }
-    bool direct = false;
-    if constexpr (HF) {
-      if (T.ignore_merges) {  // models/bpe/model.rs: a pre-token that is a vocabulary entry is that token
-        const int32_t id = hf_vocab_lookup(T, nb + ws, we - ws);
-        if (id >= 0) {
-          sm.S[lane] = kResolvedFlag | (uint32_t)id;
-          alive = 1u;
-          cnt = 1;
-          direct = true;
-        }
-      }
-    }
-    bool pu = false, first = true;
-    if (!direct) {
-      int n = 0;
-      for (int p = ws; p < we;) {
-        uint32_t adv;
-        sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
-        p += adv;
-        ++n;
-      }
-      bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
-      alive = lane_merge<SMALL>(T, sm, n, lane);
-    }
-    // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
-    // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
-    for (uint32_t m = direct ? 0u : alive; m;) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      int32_t tmp[4];
-      bool unk;
-      const uint32_t sym = sm.S[j * 32 + lane];
-      const int c = sym_ids(T, sym, tmp, &unk);
-      if (first) { first_unk = unk; first = false; }
-      if (!unk && c == 1) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
-      if (!(unk && pu && !T.byte_fallback)) cnt += c;
-      pu = unk;
-    }
-    last_unk = pu;
-    if constexpr (MEMO) {
-      // memoise: every surviving symbol resolved to exactly one id, at most kMax of them
-      const int k = __popc(alive);
-      U128 key;
-      if (k >= 1 && k <= MemoIds<SMALL>::kMax && k == cnt && !bare && memo_key(nb, ws, we, T.byte_mode, &key)) {
-        uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        bool ok = true;
-        int q = 0;
-        for (uint32_t m = alive; m; ++q) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const uint32_t sym = sm.S[j * 32 + lane];
-          ok = ok && (sym & 0xC0000000u) == kResolvedFlag && (sym & 0x3FFFFFFFu) < (SMALL ? (1u << 16) : (1u << 28));
-          id[q] = sym & 0x0FFFFFFFu;
-        }
-        if (ok) {
-          const U128 val = MemoIds<SMALL>::pack(k, id);
-          uint32_t slot = memo_slot(key, memo.mask);
-          const U128 zero{0ull, 0ull};
-#pragma unroll 1
-          for (int way = 0; way < 2; ++way, slot ^= 1u) {
-            uint8_t* e = memo.table + (size_t)slot * 32;
-            const U128 old = cas_b128(e, zero, key);
-            if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
-            if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
-          }
-        }
-      }
-    }
-  };
-
-  // 1b. warm-up pre-passes (throughput kernel with a memo; natural text).  The rounds below go through the words in
-  // order, 32 at a time, and a round runs at the speed of its slowest lane: ONE memo miss costs the whole round a merge,
-  // and a word beyond the lane columns cuts the round short and is merged by the whole warp on its own.  On the
-  // synthetic headline text both are rare; on real text 91 % of the rounds hold a miss and every tenth word is long.
-  // So, when the previous drain looked like that:
-  //   A1  probe the memo for every short word of the drain first, collect the misses and merge them 32 at a time in FULL
-  //       rounds (results go to the memo only); the in-order rounds then find them there;
-  //   A2  merge every long word (17..512 symbols) ahead of the rounds and park its ids in a per-warp global scratch
-  //       (slot = the word's byte offset: ids never outnumber bytes); in the rounds such a word is an ordinary lane
-  //       whose ids are read back from there, so the rounds are no longer cut.  Only for vocabularies without
-  //       cross-word unknown merging (byte fallback, or byte-level), where a word's ids do not depend on its neighbours.
+  // 1b. warm-up pre-passes for natural text (warm_prepass above): memo misses merged in full rounds, long words resolved
+  // into the per-warp scratch, both ahead of the in-order rounds; on when the previous drain looked like it needs them
   int32_t* arena = nullptr;
   uint16_t* lcnt = nullptr;
   int a1_misses = 0;
   if constexpr (MEMO && !UNI && !LONG) {
-    if (T.warm_arena != nullptr && (rs.warm || rs.had_long)) {
-      uint8_t* slice = T.warm_arena + (size_t)blockIdx.x * kWarmSliceBytes;
-      const bool do_long = rs.had_long && (T.byte_fallback || T.byte_mode);
-      if (do_long) {
-        arena = reinterpret_cast<int32_t*>(slice);
-        lcnt = reinterpret_cast<uint16_t*>(slice + (size_t)kNBuf * 4);
-      }
-      int np = 0;  // words waiting in sm.pend[0 .. np)
-      auto flush = [&]() {
-        __syncwarp();
-        int ws = 0, we = 0, nsym = 0;
-        bool special = false;
-        if (lane < np) word_of(sm.pend[lane], ws, we, nsym, special);
-        uint32_t alive;
-        int cnt;
-        bool fu, lu, bare;
-        if (lane < np) merge_word(ws, we, special, alive, cnt, fu, lu, bare);
-        np = 0;
-        __syncwarp();
-      };
-      for (int base = 0; base < complete; base += 32) {
-        const int w = base + lane;
-        const bool have = w < complete;
-        int ws = 0, we = 0, nsym = 0;
-        bool special = false;
-        if (have) word_of(w, ws, we, nsym, special);
-        const bool is_long = have && !special && nsym > kMaxSym;
-        // ---- A2: the long words of this block, one at a time, whole warp
-        uint32_t lm = __ballot_sync(kFull, do_long && is_long);
-        while (lm) {
-          const int b = __ffs(lm) - 1;
-          lm &= lm - 1;
-          const int lws = __shfl_sync(kFull, ws, b), lwe = __shfl_sync(kFull, we, b);
-          int n = 0;
-          bool overflow = false;
-          for (int pb = lws; pb < lwe; pb += 32) {
-            const int p = pb + lane;
-            const bool lead = p < lwe && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
-            const uint32_t m = __ballot_sync(kFull, lead);
-            const int idx = n + __popc(m & ((1u << lane) - 1));
-            if (lead) {
-              if (idx < kCoopMaxSym) { uint32_t adv; sm.S[idx] = char_sym(T, nb + p, &adv); }
-              else overflow = true;
-            }
-            n += __popc(m);
-          }
-          overflow = __any_sync(kFull, overflow);
-          __syncwarp();
-          int total = -1;   // ids written for this word, -1: left to the in-order cooperative path
-          if (!overflow) {
-            int32_t whole = -1;
-            if constexpr (HF) {
-              if (T.ignore_merges) {
-                if (lane == 0) whole = hf_vocab_lookup(T, nb + lws, lwe - lws);
-                whole = __shfl_sync(kFull, whole, 0);
-              }
-            }
-            if (whole >= 0) {
-              if (lane == 0) arena[lws] = whole;
-              total = 1;
-            } else {
-              n = coop_merge<SMALL>(T, sm, n, lane);
-              total = 0;
-              for (int sb = 0; sb < n; sb += 32) {
-                const int j = sb + lane;
-                int32_t tmp[4];
-                bool unk = false;
-                int c = 0;
-                if (j < n) c = sym_ids(T, sm.S[j], tmp, &unk);   // byte fallback: an unknown char is its byte ids
-                const int inc2 = warp_incl_scan(c, lane);
-                int o = lws + total + (inc2 - c);
-                for (int k = 0; k < c; ++k) arena[o++] = tmp[k];
-                total += __shfl_sync(kFull, inc2, 31);
-              }
-            }
-          }
-          if (lane == 0) lcnt[base + b] = total < 0 ? kNotPre : (uint16_t)total;
-          __syncwarp();
-        }
-        // ---- A1: short words that are not in the memo yet
-        if (rs.warm) {
-          bool miss = false;
-          U128 key;
-          if (have && !special && !is_long && memo_key(nb, ws, we, T.byte_mode, &key)) {
-            uint32_t slot = memo_slot(key, memo.mask);
-            miss = true;
-#pragma unroll 1
-            for (int way = 0; way < 2; ++way, slot ^= 1u) {
-              const U128 k = ld_b128(memo.table + (size_t)slot * 32);
-              if (k.lo == key.lo && k.hi == key.hi) { miss = false; break; }
-              if ((k.lo | k.hi) == 0) break;
-            }
-          }
-          const uint32_t mm = __ballot_sync(kFull, miss);
-          const int k = __popc(mm);
-          a1_misses += k;
-          if (np + k > 32) flush();
-          if (miss) sm.pend[np + __popc(mm & ((1u << lane) - 1))] = (uint16_t)w;
-          np += k;
-          if (np == 32) flush();
-        }
-      }
-      if (np) flush();
-      __syncwarp();
-    }
+    if (T.warm_arena != nullptr && (rs.warm || rs.had_long))
+      warm_prepass<SMALL, HF>(T, sm, rs, complete, lane, memo, arena, lcnt, a1_misses);
   }
 
   // 2. rounds of up to 32 consecutive words
@@ -1336,7 +1419,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     const bool have = w < complete;
     int ws = 0, we = 0, nsym = 0;
     bool special = false;  // HF: the word is an added token
-    if (have) word_of(w, ws, we, nsym, special);
+    if (have) word_geom<HF>(T, sm, rs.ascii, w, ws, we, nsym, special);
     // a long word the pre-pass resolved: its ids wait in the arena, it takes part in the round like any other lane
     bool pre = false;
     if constexpr (MEMO && !UNI && !LONG) {
@@ -1391,7 +1474,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     if (pre && active) {
       cnt = lcnt[w];   // ids parked in the arena by the pre-pass (byte fallback / byte level: no unknown merging)
     } else if (!memo_hit && active) {
-      merge_word(ws, we, special, alive, cnt, first_unk, last_unk, bare);
+      merge_word<SMALL, HF, MEMO>(T, sm, memo, lane, ws, we, special, alive, cnt, first_unk, last_unk, bare);
     }
     if (__any_sync(kFull, active && !pre && !memo_hit && !special)) ++n_slow;
     // cross-word unknown merging (byte_fallback off): drop the first id if the previous symbol was unknown too
