@@ -423,8 +423,22 @@ def honest_text(local, headline_batch, iters=3, corpus_bytes=256 << 20):
     out["natural_sp32k"] = timed(h1, pb.text, pb.offsets, 16384, lambda t: S.encode(t).tolist())
     out["natural_sp32k"]["tokenizer"] = "SentencePiece BPE 32000 (byte fallback, nmt_nfkc), memo on"
     h1.close()
-    h2 = x.Ingest(tokenizer_path=d_hf, device=local)
+    os.environ["XLLM_SP_WARM"] = "1"
+    try:
+        h1w = x.Ingest(tokenizer_path=d_sp, device=local)
+        h2w = x.Ingest(tokenizer_path=d_hf, device=local)
+    finally:
+        del os.environ["XLLM_SP_WARM"]
     H = o.HfBpeOracle(d_hf)
+    out["natural_sp32k_warm"] = timed(h1w, pb.text, pb.offsets, 16384, lambda t: S.encode(t).tolist())
+    out["natural_sp32k_warm"]["tokenizer"] = ("the same, through the opt-in warm-up kernels (XLLM_SP_WARM=1: memo misses "
+                                              "merged ahead in full rounds, long words resolved ahead of the rounds)")
+    h1w.close()
+    out["natural_hf128k_warm"] = timed(h2w, pb.text, pb.offsets, 16384,
+                                       lambda t: H.prefix_ids + H.encode(t).tolist() + H.suffix_ids)
+    out["natural_hf128k_warm"]["tokenizer"] = "HF byte-level BPE 128471 entries through the warm-up kernels"
+    h2w.close()
+    h2 = x.Ingest(tokenizer_path=d_hf, device=local)
     out["natural_hf128k"] = timed(h2, pb.text, pb.offsets, 16384,
                                   lambda t: H.prefix_ids + H.encode(t).tolist() + H.suffix_ids)
     out["natural_hf128k"]["tokenizer"] = ("HF byte-level BPE, GPT-2 regex, 128471 entries (non-SMALL kernels: ids "

@@ -20,6 +20,11 @@ VARIANTS = [
     ("off", {"XLLM_SP_MEMO_SLOTS": "0"}),
     ("wide", {"XLLM_SP_FORCE_WIDE": "1"}),
     ("wide_off", {"XLLM_SP_FORCE_WIDE": "1", "XLLM_SP_MEMO_SLOTS": "0"}),
+    # the warm-up kernels (drain_pass_warm: memo misses merged ahead in full rounds, long words resolved ahead into the
+    # per-warp scratch), narrow and wide, and with a memo so small that the warm-up's inserts mostly fail
+    ("warm", {"XLLM_SP_WARM": "1"}),
+    ("warm_wide", {"XLLM_SP_WARM": "1", "XLLM_SP_FORCE_WIDE": "1"}),
+    ("warm_tiny", {"XLLM_SP_WARM": "1", "XLLM_SP_MEMO_SLOTS": "4"}),
 ]
 
 

@@ -21,7 +21,7 @@ def _encode_all(h, texts, stride):
     return [ids[i, :n_ids[i]].tolist() for i in range(len(texts))]
 
 
-@pytest.mark.parametrize("memo", ["on", "off"])
+@pytest.mark.parametrize("memo", ["on", "off", "warm"])
 @pytest.mark.parametrize("model,key", [("sp_natural_32k", "sp"), ("hf_natural_128k", "hf")])
 def test_goldens(model, key, memo):
     import xllm_service_b200 as x
@@ -29,10 +29,13 @@ def test_goldens(model, key, memo):
         cases = json.load(f)["cases"]
     if memo == "off":
         os.environ["XLLM_SP_MEMO_SLOTS"] = "0"
+    if memo == "warm":
+        os.environ["XLLM_SP_WARM"] = "1"      # the warm-up kernels, which exist for exactly this kind of text
     try:
         h = x.Ingest(tokenizer_path=os.path.join(HERE, "golden", model))
     finally:
         os.environ.pop("XLLM_SP_MEMO_SLOTS", None)
+        os.environ.pop("XLLM_SP_WARM", None)
     texts = [bytes.fromhex(c["text"]) for c in cases]
     got = _encode_all(h, texts, 8192)
     bad = [i for i, (g, c) in enumerate(zip(got, cases)) if g != c[key]]
@@ -40,15 +43,22 @@ def test_goldens(model, key, memo):
     h.close()
 
 
+@pytest.mark.parametrize("warm", ["plain", "warm"])
 @pytest.mark.parametrize("model", ["sp_natural_32k", "hf_natural_128k"])
-def test_long_real_text_vs_oracle(oracle, model):
-    """~3 MB of this image's own source files cut into 16 KB prompts (what bench.py's natural-text line runs)."""
+def test_long_real_text_vs_oracle(oracle, model, warm):
+    """~3 MB of this image's own source files cut into 16 KB prompts (what bench.py's natural-text line runs), through
+    the plain kernels and through the warm-up kernels."""
     import xllm_service_b200 as x
     from xllm_service_b200 import workload
     corpus = workload.natural_corpus(3 << 20)
     pb = workload.cut_prompts(corpus, 16384)
     d = os.path.join(HERE, "golden", model)
-    h = x.Ingest(tokenizer_path=d)
+    if warm == "warm":
+        os.environ["XLLM_SP_WARM"] = "1"
+    try:
+        h = x.Ingest(tokenizer_path=d)
+    finally:
+        os.environ.pop("XLLM_SP_WARM", None)
     ids, n_ids, status = h.encode_batch(pb.text, pb.offsets, 16384)
     assert (status == 0).all()
     if model.startswith("sp"):

@@ -121,6 +121,7 @@ int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
       return rc;
     }
     h->memo_slots = sp_memo_default_slots();
+    if (const char* w = getenv("XLLM_SP_WARM")) h->sp_warm = atoi(w) != 0;
     if (const char* w = getenv("XLLM_PIPE_SLOTS")) {
       const int v = atoi(w);
       if (v >= 1 && v <= kPipeSlots) h->pipe_slots = v;
@@ -189,6 +190,7 @@ int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out) {
   (*out)->sp_tables = src->sp_tables;
   (*out)->sp_dev = src->sp_dev;
   (*out)->memo_slots = src->memo_slots;
+  (*out)->sp_warm = src->sp_warm;
   (*out)->pipe_slots = src->pipe_slots;
   (*out)->tokenizer_path = src->tokenizer_path;
   (*out)->shard = src->shard;
@@ -681,9 +683,11 @@ int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_te
     XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
     memo.table = h->d_memo.p;
     memo.slots = h->memo_slots;
-    memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
-    XLLM_TRY(h->d_arena.reserve(memo.arena_bytes));
-    memo.arena = h->d_arena.p;
+    if (h->sp_warm) {
+      memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
+      XLLM_TRY(h->d_arena.reserve(memo.arena_bytes));
+      memo.arena = h->d_arena.p;
+    }
   }
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), d_text, d_offsets, n_req, d_ids, ids_stride, d_n_ids, d_status,
                                  h->d_task_counter + 4, h->d_defer.as<int32_t>(), s, memo));
@@ -725,9 +729,11 @@ static int encode_batch_impl(xllm_ingest_t h, int32_t n_req, const uint8_t* text
     XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
     memo.table = h->d_memo.p;
     memo.slots = h->memo_slots;
-    memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
-    XLLM_TRY(h->d_arena.reserve(memo.arena_bytes));
-    memo.arena = h->d_arena.p;
+    if (h->sp_warm) {
+      memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
+      XLLM_TRY(h->d_arena.reserve(memo.arena_bytes));
+      memo.arena = h->d_arena.p;
+    }
   }
   // offsets are rebased on the device copy of the text: ship them relative to offsets[0]
   if (text_bytes)

@@ -381,7 +381,7 @@ static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_seg
     xllm::SpMemo memo;
     memo.table = h->memo_slots ? sl.d_memo.p : nullptr;
     memo.slots = h->memo_slots;
-    if (h->memo_slots) {   // kernels of all chunks run on one stream, one after the other: one scratch for the handle
+    if (h->memo_slots && h->sp_warm) {   // kernels of all chunks run on one stream, one after the other: one scratch for the handle
       memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
       if ((rc = h->d_arena.reserve(memo.arena_bytes)) != XLLM_OK) break;
       memo.arena = h->d_arena.p;

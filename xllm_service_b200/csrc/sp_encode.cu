@@ -91,8 +91,7 @@ struct WarpSmemT {
   typename PMOps<SMALL>::T PM[kCoopMaxSym];  // pair state at position j
   uint8_t nbuf[kNBuf];                       // normalized text (always starts at a word start)
   uint16_t wstart[kMaxWords];
-  uint16_t pend[32];                         // warm-up pre-pass: words that missed the memo, waiting for a full round
-  uint16_t pendl[16];                        // ... and words of 17..32 symbols, waiting for a round of lane pairs
+  uint16_t pend[32];                         // warm-up kernels: words that missed the memo, waiting for a full round
 };
 // Unigram kernels: plus the pieces found from each of 32 start positions (unigram_word)
 constexpr int kUniMaxMatch = 32;
@@ -322,8 +321,8 @@ struct ReqState {
   float uni_score;     // Unigram: best-path score at the start of the next word (running float, as upstream)
   int8_t bad_input;    // HF backend: 1 malformed UTF-8, 2 not provably NFC under a normalizer NFC
   bool deferred;       // needs the long-word kernel (this one was built without it)
-  bool warm;           // the last drain had several memo misses: warm the memo before the next drain's rounds
-  bool had_long;       // the last drain had words beyond the lane columns: resolve those ahead of the rounds
+  bool warm;           // warm-up kernels: the last drain had several memo misses
+  bool had_long;       // warm-up kernels: the last drain had words beyond the lane columns
   // long-word mode: the current pre-token is being streamed into a global scratch slot
   bool long_mode;
   bool long_last_sp;   // the last char appended to the slot is U+2581
@@ -566,14 +565,7 @@ __device__ __forceinline__ bool normalize_fast(const SpDev& T, SM& sm, ReqState&
 // ---------------------------------------------------------------------------- word merge
 // Fast path: this lane owns word [ws, we) with n <= 32 chars; symbols live in column `lane` of S / PM.
 // Returns the alive mask after all merges.
-// PAIR: the word has up to 2 * kMaxSym symbols and owns the columns of lanes `lane` (even) and `lane + 1`: symbol j
-// lives in row j mod kMaxSym of column lane + j / kMaxSym (warm-up pre-pass: 16 such words per round).
-template <bool PAIR>
-__device__ __forceinline__ int sym_col(int j) {
-  return PAIR ? ((j & (kMaxSym - 1)) * 32 + (j >> 4)) : j * 32;
-}
-static_assert(kMaxSym == 16, "sym_col<true> splits j into row j & 15 and column j >> 4");
-template <bool SMALL, bool PAIR = false, typename SM>
+template <bool SMALL, typename SM>
 __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, int lane) {
   using P = PMOps<SMALL>;
   uint32_t* S = sm.S + lane;
@@ -588,42 +580,42 @@ __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, in
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const bool have = j0 + u + 1 < n;
-        sy[u + 1] = have ? S[sym_col<PAIR>(j0 + u + 1)] : kSymUnknownFlag;
+        sy[u + 1] = have ? S[(j0 + u + 1) * 32] : kSymUnknownFlag;
         pr[u] = pair_probe_begin(T, sy[u], sy[u + 1]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (j0 + u + 1 < n) PM[sym_col<PAIR>(j0 + u)] = P::pack(pair_probe_finish(T, sy[u], sy[u + 1], pr[u]));
+        if (j0 + u + 1 < n) PM[(j0 + u) * 32] = P::pack(pair_probe_finish(T, sy[u], sy[u + 1], pr[u]));
       left = sy[4];
     }
   }
-  PM[sym_col<PAIR>(n - 1)] = P::none();
-  uint32_t alive = n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1;
+  PM[(n - 1) * 32] = P::none();
+  uint32_t alive = (1u << n) - 1;
   for (;;) {
     uint32_t best = P::kNone;
     int bj = 0;
     for (uint32_t m = alive; m;) {
       const int j = __ffs(m) - 1;
       m &= m - 1;
-      const uint32_t pr = P::prio_at(PM + sym_col<PAIR>(j));
+      const uint32_t pr = P::prio_at(PM + j * 32);
       if (pr < best) { best = pr; bj = j; }
     }
     if (best == P::kNone) break;
-    const uint32_t hi_mask = bj >= 31 ? 0u : ~((2u << bj) - 1u);  // bits above bj
+    const uint32_t hi_mask = ~((2u << bj) - 1u);  // bits above bj
     const int rj = __ffs(alive & hi_mask) - 1;
-    S[sym_col<PAIR>(bj)] = P::merged(PM[sym_col<PAIR>(bj)]);
+    S[bj * 32] = P::merged(PM[bj * 32]);
     alive &= ~(1u << rj);
     // the two pairs the merge created: both first probes in flight before either is consumed
     const uint32_t above = alive & hi_mask;
     const uint32_t below = alive & ((1u << bj) - 1u);
     const int pj = below ? 31 - __clz(below) : 0;
-    const uint32_t sm_ = S[sym_col<PAIR>(bj)];
-    const uint32_t sr = above ? S[sym_col<PAIR>(__ffs(above) - 1)] : kSymUnknownFlag;
-    const uint32_t sl = below ? S[sym_col<PAIR>(pj)] : kSymUnknownFlag;
+    const uint32_t sm_ = S[bj * 32];
+    const uint32_t sr = above ? S[(__ffs(above) - 1) * 32] : kSymUnknownFlag;
+    const uint32_t sl = below ? S[pj * 32] : kSymUnknownFlag;
     const PairProbe pa = pair_probe_begin(T, sm_, sr);
     const PairProbe pb = pair_probe_begin(T, sl, sm_);
-    PM[sym_col<PAIR>(bj)] = P::pack(pair_probe_finish(T, sm_, sr, pa));
-    if (below) PM[sym_col<PAIR>(pj)] = P::pack(pair_probe_finish(T, sl, sm_, pb));
+    PM[bj * 32] = P::pack(pair_probe_finish(T, sm_, sr, pa));
+    if (below) PM[pj * 32] = P::pack(pair_probe_finish(T, sl, sm_, pb));
   }
   return alive;
 }
@@ -1057,297 +1049,6 @@ __device__ int unigram_word_slow(const SpDev& T, SM& sm, const uint8_t* w, int l
   return n;
 }
 
-// byte range, symbol count and kind of word w of the current drain (w < complete)
-template <bool HF, typename SM>
-__device__ __forceinline__ void word_geom(const SpDev& T, const SM& sm, bool ascii, int w, int& ws, int& we, int& nsym,
-                                          bool& special) {
-  const uint8_t* nb = sm.nbuf;
-  ws = we = nsym = 0;
-  special = false;
-  if constexpr (HF) {
-    const uint16_t e = sm.wstart[w];
-    ws = e & kHfPosMask;
-    we = sm.wstart[w + 1] & kHfPosMask;
-    special = (e & kHfSpecialWord) != 0;  // the word is an added token
-    nsym = special ? 1 : we - ws;         // every byte is a symbol
-  } else {
-    ws = sm.wstart[w];
-    we = sm.wstart[w + 1];
-    if (ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
-    else
-      for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
-  }
-}
-
-// The merge path of one word per lane: symbols -> lane_merge -> resolve single-id symbols in place -> (MEMO) insert.
-// Used by the in-order rounds for memo misses and by the warm-up pre-pass.  Outputs: alive set in the lane's S column,
-// id count, unknown-symbol flags for the cross-word rule, bare-U+2581 flag.
-template <bool SMALL, bool HF, bool MEMO, typename SM>
-__device__ __forceinline__ void merge_word(const SpDev& T, SM& sm, MemoRef memo, int lane, int ws, int we, bool special,
-                                           uint32_t& alive, int& cnt, bool& first_unk, bool& last_unk, bool& bare) {
-  const uint8_t* nb = sm.nbuf;
-    alive = 0;
-    cnt = 0;
-    first_unk = last_unk = bare = false;
-    if (HF && special) {
-      int32_t id = 0;
-      hf_added_len(T, nb + ws, we - ws, &id);
-      sm.S[lane] = kResolvedFlag | (uint32_t)id;
-      alive = 1u;
-      cnt = 1;
-      return;
-    }
-    bool direct = false;
-    if constexpr (HF) {
-      if (T.ignore_merges) {  // models/bpe/model.rs: a pre-token that is a vocabulary entry is that token
-        const int32_t id = hf_vocab_lookup(T, nb + ws, we - ws);
-        if (id >= 0) {
-          sm.S[lane] = kResolvedFlag | (uint32_t)id;
-          alive = 1u;
-          cnt = 1;
-          direct = true;
-        }
-      }
-    }
-    bool pu = false, first = true;
-    if (!direct) {
-      int n = 0;
-      for (int p = ws; p < we;) {
-        uint32_t adv;
-        sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
-        p += adv;
-        ++n;
-      }
-      bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
-      alive = lane_merge<SMALL, false>(T, sm, n, lane);
-    }
-    // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
-    // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
-    for (uint32_t m = direct ? 0u : alive; m;) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      int32_t tmp[4];
-      bool unk;
-      const uint32_t sym = sm.S[j * 32 + lane];
-      const int c = sym_ids(T, sym, tmp, &unk);
-      if (first) { first_unk = unk; first = false; }
-      if (!unk && c == 1) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
-      if (!(unk && pu && !T.byte_fallback)) cnt += c;
-      pu = unk;
-    }
-    last_unk = pu;
-    if constexpr (MEMO) {
-      // memoise: every surviving symbol resolved to exactly one id, at most kMax of them
-      const int k = __popc(alive);
-      U128 key;
-      if (k >= 1 && k <= MemoIds<SMALL>::kMax && k == cnt && !bare && memo_key(nb, ws, we, T.byte_mode, &key)) {
-        uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        bool ok = true;
-        int q = 0;
-        for (uint32_t m = alive; m; ++q) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const uint32_t sym = sm.S[j * 32 + lane];
-          ok = ok && (sym & 0xC0000000u) == kResolvedFlag && (sym & 0x3FFFFFFFu) < (SMALL ? (1u << 16) : (1u << 28));
-          id[q] = sym & 0x0FFFFFFFu;
-        }
-        if (ok) {
-          const U128 val = MemoIds<SMALL>::pack(k, id);
-          uint32_t slot = memo_slot(key, memo.mask);
-          const U128 zero{0ull, 0ull};
-#pragma unroll 1
-          for (int way = 0; way < 2; ++way, slot ^= 1u) {
-            uint8_t* e = memo.table + (size_t)slot * 32;
-            const U128 old = cas_b128(e, zero, key);
-            if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
-            if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
-          }
-        }
-      }
-    }
-}
-
-// Warm-up pre-passes (throughput kernel with a memo; natural text).  The rounds below go through the words in
-// order, 32 at a time, and a round runs at the speed of its slowest lane: ONE memo miss costs the whole round a merge,
-// and a word beyond the lane columns cuts the round short and is merged by the whole warp on its own.  On the
-// synthetic headline text both are rare; on real text 91 % of the rounds hold a miss and every tenth word is long.
-// So, when the previous drain looked like that:
-//   A1  probe the memo for every short word of the drain first, collect the misses and merge them 32 at a time in FULL
-//       rounds (results go to the memo only); the in-order rounds then find them there;
-//   A2  merge every long word (17..512 symbols) ahead of the rounds and park its ids in a per-warp global scratch
-//       (slot = the word's byte offset: ids never outnumber bytes); in the rounds such a word is an ordinary lane
-//       whose ids are read back from there, so the rounds are no longer cut.  Only for vocabularies without
-//       cross-word unknown merging (byte fallback, or byte-level), where a word's ids do not depend on its neighbours.
-template <bool SMALL, bool HF, typename SM>
-__device__ __noinline__ void warm_prepass(const SpDev& T, SM& sm, ReqState& rs, int complete, int lane, MemoRef memo,
-                                          int32_t*& arena, uint16_t*& lcnt, int& a1_misses) {
-  const uint8_t* nb = sm.nbuf;
-  if (T.warm_arena != nullptr && (rs.warm || rs.had_long)) {
-    uint8_t* slice = T.warm_arena + (size_t)blockIdx.x * kWarmSliceBytes;
-    const bool do_long = rs.had_long && (T.byte_fallback || T.byte_mode);
-    if (do_long) {
-      arena = reinterpret_cast<int32_t*>(slice);
-      lcnt = reinterpret_cast<uint16_t*>(slice + (size_t)kNBuf * 4);
-    }
-    int np = 0;  // words waiting in sm.pend[0 .. np)
-    auto flush = [&]() {
-      __syncwarp();
-      int ws = 0, we = 0, nsym = 0;
-      bool special = false;
-      if (lane < np) word_geom<HF>(T, sm, rs.ascii, sm.pend[lane], ws, we, nsym, special);
-      uint32_t alive;
-      int cnt;
-      bool fu, lu, bare;
-      if (lane < np) merge_word<SMALL, HF, true>(T, sm, memo, lane, ws, we, special, alive, cnt, fu, lu, bare);
-      np = 0;
-      __syncwarp();
-    };
-    // A2, words of 17..32 symbols: 16 at a time, one per lane PAIR (the even lane merges in the two lanes' columns)
-    int npl = 0;  // words waiting in sm.pendl[0 .. npl)
-    auto flush_pairs = [&]() {
-      __syncwarp();
-      const int k = lane >> 1;
-      const bool mine = (lane & 1) == 0 && k < npl;
-      if (mine) {
-        const int w = sm.pendl[k];
-        int ws, we, nsym;
-        bool special;
-        word_geom<HF>(T, sm, rs.ascii, w, ws, we, nsym, special);
-        int32_t whole = -1;
-        if constexpr (HF) {
-          if (T.ignore_merges) whole = hf_vocab_lookup(T, nb + ws, we - ws);
-        }
-        int o = ws;
-        if (whole >= 0) {
-          arena[o++] = whole;
-        } else {
-          int n = 0;
-          for (int p = ws; p < we;) {
-            uint32_t adv;
-            sm.S[sym_col<true>(n) + lane] = char_sym(T, nb + p, &adv);
-            p += adv;
-            ++n;
-          }
-          uint32_t alive = lane_merge<SMALL, true>(T, sm, n, lane);
-          for (; alive;) {
-            const int j = __ffs(alive) - 1;
-            alive &= alive - 1;
-            int32_t tmp[4];
-            bool unk;
-            const int c = sym_ids(T, sm.S[sym_col<true>(j) + lane], tmp, &unk);   // byte fallback: an unknown char is its byte ids
-            for (int q = 0; q < c; ++q) arena[o++] = tmp[q];
-          }
-        }
-        lcnt[w] = (uint16_t)(o - ws);
-      }
-      npl = 0;
-      __syncwarp();
-    };
-    for (int base = 0; base < complete; base += 32) {
-      const int w = base + lane;
-      const bool have = w < complete;
-      int ws = 0, we = 0, nsym = 0;
-      bool special = false;
-      if (have) word_geom<HF>(T, sm, rs.ascii, w, ws, we, nsym, special);
-      const bool is_long = have && !special && nsym > kMaxSym;
-      const bool is_mid = is_long && nsym <= 2 * kMaxSym;
-      if (do_long) {
-        const uint32_t mid = __ballot_sync(kFull, is_mid);
-        const int k = __popc(mid);
-        if (npl + k > 16) flush_pairs();
-        // more than 16 in one block of 32 words: the first 16 go now, the rest after a flush
-        const int rank = __popc(mid & ((1u << lane) - 1));
-        if (is_mid && rank < 16 - npl) sm.pendl[npl + rank] = (uint16_t)w;
-        const int took = k < 16 - npl ? k : 16 - npl;
-        npl += took;
-        if (npl == 16) flush_pairs();
-        if (took < k) {
-          if (is_mid && rank >= took) sm.pendl[rank - took] = (uint16_t)w;
-          npl = k - took;
-          if (npl == 16) flush_pairs();
-        }
-      }
-      // ---- A2: the words of more than 32 symbols of this block, one at a time, whole warp
-      uint32_t lm = __ballot_sync(kFull, do_long && is_long && !is_mid);
-      while (lm) {
-        const int b = __ffs(lm) - 1;
-        lm &= lm - 1;
-        const int lws = __shfl_sync(kFull, ws, b), lwe = __shfl_sync(kFull, we, b);
-        int n = 0;
-        bool overflow = false;
-        for (int pb = lws; pb < lwe; pb += 32) {
-          const int p = pb + lane;
-          const bool lead = p < lwe && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
-          const uint32_t m = __ballot_sync(kFull, lead);
-          const int idx = n + __popc(m & ((1u << lane) - 1));
-          if (lead) {
-            if (idx < kCoopMaxSym) { uint32_t adv; sm.S[idx] = char_sym(T, nb + p, &adv); }
-            else overflow = true;
-          }
-          n += __popc(m);
-        }
-        overflow = __any_sync(kFull, overflow);
-        __syncwarp();
-        int total = -1;   // ids written for this word, -1: left to the in-order cooperative path
-        if (!overflow) {
-          int32_t whole = -1;
-          if constexpr (HF) {
-            if (T.ignore_merges) {
-              if (lane == 0) whole = hf_vocab_lookup(T, nb + lws, lwe - lws);
-              whole = __shfl_sync(kFull, whole, 0);
-            }
-          }
-          if (whole >= 0) {
-            if (lane == 0) arena[lws] = whole;
-            total = 1;
-          } else {
-            n = coop_merge<SMALL>(T, sm, n, lane);
-            total = 0;
-            for (int sb = 0; sb < n; sb += 32) {
-              const int j = sb + lane;
-              int32_t tmp[4];
-              bool unk = false;
-              int c = 0;
-              if (j < n) c = sym_ids(T, sm.S[j], tmp, &unk);   // byte fallback: an unknown char is its byte ids
-              const int inc2 = warp_incl_scan(c, lane);
-              int o = lws + total + (inc2 - c);
-              for (int k = 0; k < c; ++k) arena[o++] = tmp[k];
-              total += __shfl_sync(kFull, inc2, 31);
-            }
-          }
-        }
-        if (lane == 0) lcnt[base + b] = total < 0 ? kNotPre : (uint16_t)total;
-        __syncwarp();
-      }
-      // ---- A1: short words that are not in the memo yet
-      if (rs.warm) {
-        bool miss = false;
-        U128 key;
-        if (have && !special && !is_long && memo_key(nb, ws, we, T.byte_mode, &key)) {
-          uint32_t slot = memo_slot(key, memo.mask);
-          miss = true;
-#pragma unroll 1
-          for (int way = 0; way < 2; ++way, slot ^= 1u) {
-            const U128 k = ld_b128(memo.table + (size_t)slot * 32);
-            if (k.lo == key.lo && k.hi == key.hi) { miss = false; break; }
-            if ((k.lo | k.hi) == 0) break;
-          }
-        }
-        const uint32_t mm = __ballot_sync(kFull, miss);
-        const int k = __popc(mm);
-        a1_misses += k;
-        if (np + k > 32) flush();
-        if (miss) sm.pend[np + __popc(mm & ((1u << lane) - 1))] = (uint16_t)w;
-        np += k;
-        if (np == 32) flush();
-      }
-    }
-    if (np) flush();
-    if (npl) flush_pairs();
-    __syncwarp();
-  }
-}
-
 // MODE: 0 SentencePiece BPE / tiktoken, 1 HF byte-level BPE (regex pre-tokenizer), 2 SentencePiece Unigram
 template <bool SMALL, bool LONG, int MODE, bool MEMO, typename SM>
 __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
@@ -1400,14 +1101,635 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
   }
   const int complete = HF ? nwords : (final ? nwords : nwords - 1);
 
-  // 1b. warm-up pre-passes for natural text (warm_prepass above): memo misses merged in full rounds, long words resolved
-  // into the per-warp scratch, both ahead of the in-order rounds; on when the previous drain looked like it needs them
+  // 2. rounds of up to 32 consecutive words
+  int w0 = 0;
+  while (w0 < complete && !rs.deferred) {
+    const int w = w0 + lane;
+    const bool have = w < complete;
+    int ws = 0, we = 0, nsym = 0;
+    bool special = false;  // HF: the word is an added token
+    if constexpr (HF) {
+      if (have) {
+        const uint16_t e = sm.wstart[w];
+        ws = e & kHfPosMask;
+        we = sm.wstart[w + 1] & kHfPosMask;
+        special = (e & kHfSpecialWord) != 0;
+        nsym = special ? 1 : we - ws;  // every byte is a symbol
+      }
+    } else if (have) {
+      ws = sm.wstart[w];
+      we = sm.wstart[w + 1];
+      if (rs.ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
+      else
+        for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
+    }
+    const uint32_t long_mask = __ballot_sync(kFull, have && (UNI || nsym > kMaxSym));  // Unigram: one word at a time
+    const int first_long = long_mask ? __ffs(long_mask) - 1 : 32;
+    const bool active = have && lane < first_long;
+
+    // --- fast path: one word per lane
+    uint32_t alive = 0;
+    int cnt = 0;
+    bool first_unk = false, last_unk = false, bare = false;
+    bool memo_hit = false;
+    if constexpr (MEMO) {
+      U128 key;
+      if (active && !special && memo_key(nb, ws, we, T.byte_mode, &key)) {
+        uint32_t slot = memo_slot(key, memo.mask);
+#pragma unroll 1
+        for (int way = 0; way < 2; ++way, slot ^= 1u) {
+          const uint8_t* e = memo.table + (size_t)slot * 32;
+          const U128 k = ld_b128(e);
+          const U128 v = ld_b128(e + 16);
+          if (k.lo == key.lo && k.hi == key.hi) {
+            if (MemoIds<SMALL>::valid(v)) {
+              memo_hit = true;
+              cnt = MemoIds<SMALL>::count(v);
+              alive = (1u << cnt) - 1u;
+#pragma unroll
+              for (int q = 0; q < MemoIds<SMALL>::kMax; ++q)
+                if (q < cnt) sm.S[q * 32 + lane] = kResolvedFlag | MemoIds<SMALL>::id(v, q);
+            }
+            break;
+          }
+          if ((k.lo | k.hi) == 0) break;  // empty: the word was not seen yet
+        }
+      }
+    }
+#ifdef XLLM_MEMO_STATS
+    {
+      const uint32_t am = __ballot_sync(kFull, active), hm = __ballot_sync(kFull, memo_hit);
+      if (lane == 0) {
+        atomicAdd(&g_memo_stats[0], 1ull);                       // rounds
+        atomicAdd(&g_memo_stats[1], (unsigned long long)__popc(am));   // active words
+        atomicAdd(&g_memo_stats[2], (unsigned long long)__popc(hm));   // hits
+        if (am & ~hm) atomicAdd(&g_memo_stats[3], 1ull);         // rounds with a slow-path lane
+        if (first_long < 32) atomicAdd(&g_memo_stats[4], 1ull);  // rounds cut by a long word
+      }
+    }
+#endif
+    if (memo_hit) {
+    } else if (HF && active && special) {
+      int32_t id = 0;
+      hf_added_len(T, nb + ws, we - ws, &id);
+      sm.S[lane] = kResolvedFlag | (uint32_t)id;
+      alive = 1u;
+      cnt = 1;
+    } else if (active) {
+      bool direct = false;
+      if constexpr (HF) {
+        if (T.ignore_merges) {  // models/bpe/model.rs: a pre-token that is a vocabulary entry is that token
+          const int32_t id = hf_vocab_lookup(T, nb + ws, we - ws);
+          if (id >= 0) {
+            sm.S[lane] = kResolvedFlag | (uint32_t)id;
+            alive = 1u;
+            cnt = 1;
+            direct = true;
+          }
+        }
+      }
+      bool pu = false, first = true;
+      if (!direct) {
+        int n = 0;
+        for (int p = ws; p < we;) {
+          uint32_t adv;
+          sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
+          p += adv;
+          ++n;
+        }
+        bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
+        alive = lane_merge<SMALL>(T, sm, n, lane);
+      }
+      // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
+      // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
+      for (uint32_t m = direct ? 0u : alive; m;) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        int32_t tmp[4];
+        bool unk;
+        const uint32_t sym = sm.S[j * 32 + lane];
+        const int c = sym_ids(T, sym, tmp, &unk);
+        if (first) { first_unk = unk; first = false; }
+        if (!unk && c == 1) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
+        if (!(unk && pu && !T.byte_fallback)) cnt += c;
+        pu = unk;
+      }
+      last_unk = pu;
+      if constexpr (MEMO) {
+        // memoise: every surviving symbol resolved to exactly one id, at most four of them
+        const int k = __popc(alive);
+        U128 key;
+        if (k >= 1 && k <= MemoIds<SMALL>::kMax && k == cnt && !bare && memo_key(nb, ws, we, T.byte_mode, &key)) {
+          uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          bool ok = true;
+          int q = 0;
+          for (uint32_t m = alive; m; ++q) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t sym = sm.S[j * 32 + lane];
+            ok = ok && (sym & 0xC0000000u) == kResolvedFlag && (sym & 0x3FFFFFFFu) < (SMALL ? (1u << 16) : (1u << 28));
+            id[q] = sym & 0x0FFFFFFFu;
+          }
+          if (ok) {
+            const U128 val = MemoIds<SMALL>::pack(k, id);
+            uint32_t slot = memo_slot(key, memo.mask);
+            const U128 zero{0ull, 0ull};
+#pragma unroll 1
+            for (int way = 0; way < 2; ++way, slot ^= 1u) {
+              uint8_t* e = memo.table + (size_t)slot * 32;
+              const U128 old = cas_b128(e, zero, key);
+              if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
+              if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
+            }
+          }
+        }
+      }
+    }
+    // cross-word unknown merging (byte_fallback off): drop the first id if the previous symbol was unknown too
+    bool drop_first = false;
+    if (!T.byte_fallback) {
+      const uint32_t act_mask = __ballot_sync(kFull, active);
+      const uint32_t lu_mask = __ballot_sync(kFull, active && last_unk);
+      if (active && first_unk) {
+        const bool prev = lane == 0 ? rs.prev_unk : ((lu_mask >> (lane - 1)) & 1u);
+        if (prev) { drop_first = true; cnt -= 1; }
+      }
+      if (act_mask) rs.prev_unk = (lu_mask >> (31 - __clz(act_mask))) & 1u;
+    }
+    const int incl = warp_incl_scan(cnt, lane);
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (active) {
+      int64_t o = rs.n_out + (incl - cnt);
+      bool pu = false, first = true;
+      for (uint32_t m = alive; m;) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t sym = sm.S[j * 32 + lane];
+        if ((sym & 0xC0000000u) == kResolvedFlag) {  // known symbol: one id
+          put_id(rs, o++, (int32_t)(sym & 0x3FFFFFFFu));
+          pu = false;
+        } else {
+          int32_t tmp[4];
+          bool unk;
+          const int c = sym_ids(T, sym, tmp, &unk);
+          const bool skip = (unk && pu && !T.byte_fallback) || (first && drop_first);
+          if (!skip)
+            for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
+          pu = unk;
+        }
+        first = false;
+      }
+    }
+    rs.n_out += total;
+    // trailing bare-word bookkeeping: ids of the run of bare words at the end of what was emitted
+    {
+      const uint32_t act_mask = __ballot_sync(kFull, active);
+      const uint32_t nonbare = __ballot_sync(kFull, active && !bare);
+      if (act_mask) {
+        const int last_nb = nonbare ? 31 - __clz(nonbare) : -1;  // last non-bare lane
+        const int tail = __shfl_sync(kFull, incl, 31) - (last_nb >= 0 ? __shfl_sync(kFull, incl, last_nb) : 0);
+        rs.trailing_bare = (last_nb >= 0 ? 0 : rs.trailing_bare) + tail;
+      }
+    }
+    __syncwarp();
+    w0 += first_long < 32 ? first_long : 32;
+    if (w0 >= complete || first_long == 32) continue;
+
+    // --- cooperative path for the long word w0
+    {
+      const int lws = HF ? (sm.wstart[w0] & kHfPosMask) : sm.wstart[w0];
+      int lwe = HF ? (sm.wstart[w0 + 1] & kHfPosMask) : sm.wstart[w0 + 1];
+      int n = 0;
+      int words_taken = 1;
+      bool overflow = false;
+      bool uni_done = false;
+      if constexpr (UNI) {
+        auto is_bare = [&](int a, int b) { return b - a == 3 && nb[a] == 0xE2 && nb[a + 1] == 0x96 && nb[a + 2] == 0x81; };
+        const bool bare_word = is_bare(lws, lwe);
+        // No piece spans a word start, so consecutive words form one lattice: take as many complete words as the
+        // lattice scratch holds — the trie walks then fill all 32 lanes and the per-word overhead is paid once per run.
+        // A bare U+2581 word stays on its own (trailing-space bookkeeping).
+        if (!bare_word) {
+          while (w0 + words_taken < complete) {
+            const int a = sm.wstart[w0 + words_taken], b = sm.wstart[w0 + words_taken + 1];
+            if (b - lws > kUniMaxWord || is_bare(a, b)) break;
+            lwe = b;
+            ++words_taken;
+          }
+        }
+        const int len = lwe - lws;
+        if (len > kUniMaxWord) {
+          rs.too_long = true;  // the Viterbi lattice of one word lives in shared memory
+        } else {
+          n = unigram_word(T, sm, nb + lws, len, &rs.uni_score, lane);
+          const int64_t before = rs.n_out;
+          for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            int32_t tmp[4];
+            bool unk = false;
+            int c = 0;
+            if (j < n) {
+              const uint32_t sym = sm.S[j];
+              if ((sym & 0xC0000000u) == kResolvedFlag) { tmp[0] = (int32_t)(sym & 0x3FFFFFFFu); c = 1; }
+              else c = sym_ids(T, sym, tmp, &unk);
+            }
+            bool skip = false;
+            if (!T.byte_fallback) {
+              const uint32_t um = __ballot_sync(kFull, j < n && unk);
+              const bool prev = lane == 0 ? rs.prev_unk : ((um >> (lane - 1)) & 1u);
+              skip = unk && prev;
+              const int lastl = (n - base) >= 32 ? 31 : (n - base - 1);
+              rs.prev_unk = (um >> lastl) & 1u;
+            }
+            if (skip) c = 0;
+            const int inc2 = warp_incl_scan(c, lane);
+            int64_t o = rs.n_out + (inc2 - c);
+            for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
+            rs.n_out += __shfl_sync(kFull, inc2, 31);
+          }
+          rs.trailing_bare = bare_word ? rs.trailing_bare + (int32_t)(rs.n_out - before) : 0;
+        }
+        uni_done = true;
+      }
+      for (int base = lws; base < lwe && !uni_done; base += 32) {
+        const int p = base + lane;
+        const bool lead = p < lwe && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
+        const uint32_t m = __ballot_sync(kFull, lead);
+        const int idx = n + __popc(m & ((1u << lane) - 1));
+        if (lead) {
+          if (idx < kCoopMaxSym) { uint32_t adv; sm.S[idx] = char_sym(T, nb + p, &adv); }
+          else overflow = true;
+        }
+        n += __popc(m);
+      }
+      overflow = __any_sync(kFull, overflow);
+      __syncwarp();
+      int32_t whole = -1;
+      if constexpr (HF) {
+        if (T.ignore_merges && !overflow) {  // no vocabulary entry is longer than the cooperative path (host check)
+          if (lane == 0) whole = hf_vocab_lookup(T, nb + lws, lwe - lws);
+          whole = __shfl_sync(kFull, whole, 0);
+        }
+      }
+      if (uni_done) {
+      } else if (whole >= 0) {
+        if (lane == 0) put_id(rs, rs.n_out, whole);
+        rs.n_out += 1;
+        rs.trailing_bare = 0;
+      } else if (overflow) {
+        // more chars than the shared-memory scratch holds: merge it in a global scratch slot
+        if constexpr (!LONG) {
+          rs.deferred = true;
+        } else if (T.long_slots <= 0) {
+          rs.too_long = true;
+        } else {
+          rs.long_slot = long_slot_acquire(T.long_locks, T.long_slots, lane);
+          rs.long_n = 0;
+          if (long_append(T, sm, rs, lws, lwe, lane)) long_finish(T, rs, false, lane);
+          else rs.too_long = true;
+          long_slot_release(T.long_locks, rs.long_slot, lane);
+        }
+      } else {
+        n = coop_merge<SMALL>(T, sm, n, lane);
+        for (int base = 0; base < n; base += 32) {
+          const int j = base + lane;
+          int32_t tmp[4];
+          bool unk = false;
+          int c = 0;
+          if (j < n) c = sym_ids(T, sm.S[j], tmp, &unk);
+          bool skip = false;
+          if (!T.byte_fallback) {
+            const uint32_t um = __ballot_sync(kFull, j < n && unk);
+            const bool prev = lane == 0 ? rs.prev_unk : ((um >> (lane - 1)) & 1u);
+            skip = unk && prev;
+            const int lastl = (n - base) >= 32 ? 31 : (n - base - 1);
+            rs.prev_unk = (um >> lastl) & 1u;
+          }
+          if (skip) c = 0;
+          const int inc2 = warp_incl_scan(c, lane);
+          int64_t o = rs.n_out + (inc2 - c);
+          for (int k = 0; k < c; ++k) put_id(rs, o++, tmp[k]);
+          rs.n_out += __shfl_sync(kFull, inc2, 31);
+        }
+        rs.trailing_bare = 0;
+      }
+      __syncwarp();
+      w0 += words_taken;
+    }
+  }
+
+  // 3. keep the incomplete tail at the front of nbuf
+  if (!final || (HF && hf_tail < nlen)) {
+    const int ts = HF ? hf_tail : sm.wstart[nwords - 1];
+    const int tl = nlen - ts;
+    if (ts > 0) {
+      for (int base = 0; base < tl; base += 32) {
+        const int k = base + lane;
+        uint8_t c = 0;
+        if (k < tl) c = sm.nbuf[ts + k];
+        __syncwarp();
+        if (k < tl) sm.nbuf[k] = c;
+        __syncwarp();
+      }
+    }
+    rs.nlen = tl;
+    __syncwarp();  // every lane has read wstart[nwords - 1] (which is wstart[0] when one word is left)
+    if (lane == 0) sm.wstart[0] = 0;
+    rs.nw = 1;
+    if (!rs.ascii) {  // the kept tail decides whether the buffer is ASCII-only again
+      bool non_ascii = false;
+      const bool lead = tl >= 3 && sm.nbuf[0] == 0xE2 && sm.nbuf[1] == 0x96 && sm.nbuf[2] == 0x81;
+      for (int k = lane; k < tl; k += 32) non_ascii |= sm.nbuf[k] >= 0x80 && !(lead && k < 3);
+      rs.ascii = !T.byte_mode && !__any_sync(kFull, non_ascii);
+    }
+  } else {
+    rs.nlen = 0;
+    rs.nw = 0;
+    rs.ascii = !T.byte_mode;
+  }
+  rs.rescan = false;
+  __syncwarp();
+  return HF && hf_capped && !rs.deferred;
+}
+
+// drain_pass with the warm-up pre-passes (1b below) for natural text — a COPY of drain_pass with them worked in, kept
+// apart because carrying the extra state through the in-order rounds costs the plain kernel 25 % on the headline
+// workload (profiles/r02_experiment_warmup_*): the launcher picks the WARM kernels only when asked to (XLLM_SP_WARM=1).
+template <bool SMALL, bool LONG, int MODE, bool MEMO, typename SM>
+__device__ bool drain_pass_warm(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
+  constexpr bool HF = MODE == 1;
+  constexpr bool UNI = MODE == 2;
+  const uint8_t* nb = sm.nbuf;
+  int nlen = rs.nlen;
+  if (final && T.remove_extra_ws) {
+    // normalizer.cc: "Ignores trailing space" — strip trailing U+2581 from the stream
+    while (nlen >= 3 && nb[nlen - 3] == 0xE2 && nb[nlen - 2] == 0x96 && nb[nlen - 1] == 0x81) nlen -= 3;
+    if (nlen == 0) { rs.n_out -= rs.trailing_bare; rs.trailing_bare = 0; }
+  }
+  if (nlen == 0) { rs.nlen = 0; return false; }
+
+  // 1. word starts: recorded by the fast path, or re-derived after any general-path window
+  int nwords = 0;
+  int hf_tail = 0;
+  bool hf_capped = false;
+  if constexpr (HF) {
+    const HfScan sc = hf_scan(T, sm, nlen, final, lane);
+    if (sc.bad) { rs.bad_input = (int8_t)sc.bad; return false; }
+    nwords = sc.nwords;
+    hf_tail = sc.tail_start;
+    hf_capped = sc.capped;
+  } else if (!rs.rescan && !(final && nlen != rs.nlen)) {
+    nwords = rs.nw;
+  } else if (!rs.rescan) {
+    // trailing U+2581 were stripped: drop the starts that now lie at or past the end
+    nwords = rs.nw;
+    while (nwords > 1 && sm.wstart[nwords - 1] >= nlen) --nwords;
+  } else {
+    for (int base = 0; base < nlen; base += 32) {
+      const int p = base + lane;
+      bool st = false;
+      if (p < nlen) {
+        if (p == 0) st = true;
+        else if (T.split_mode != 0 && is_space_at(nb, p, nlen)) {
+          st = T.split_mode == 1 || !(p >= 3 && is_space_at(nb, p - 3, nlen));
+        }
+      }
+      const uint32_t m = __ballot_sync(kFull, st);
+      if (st) sm.wstart[nwords + __popc(m & ((1u << lane) - 1))] = (uint16_t)p;
+      nwords += __popc(m);
+    }
+  }
+  __syncwarp();
+  if constexpr (!HF) {
+    if (lane == 0) sm.wstart[nwords] = (uint16_t)nlen;
+    __syncwarp();
+  }
+  const int complete = HF ? nwords : (final ? nwords : nwords - 1);
+
+  // byte range, symbol count and kind of word w (w < complete)
+  auto word_of = [&](int w, int& ws, int& we, int& nsym, bool& special) {
+    ws = we = nsym = 0;
+    special = false;
+    if constexpr (HF) {
+      const uint16_t e = sm.wstart[w];
+      ws = e & kHfPosMask;
+      we = sm.wstart[w + 1] & kHfPosMask;
+      special = (e & kHfSpecialWord) != 0;  // the word is an added token
+      nsym = special ? 1 : we - ws;         // every byte is a symbol
+    } else {
+      ws = sm.wstart[w];
+      we = sm.wstart[w + 1];
+      if (rs.ascii) nsym = (we - ws) - (nb[ws] == 0xE2 ? 2 : 0);  // ASCII + one leading U+2581
+      else
+        for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
+    }
+  };
+  // The merge path of one word per lane: symbols -> lane_merge -> resolve single-id symbols in place -> (MEMO) insert.
+  // Used by the rounds below for memo misses and by the warm-up pre-pass.  Outputs: alive set in the lane's S column,
+  // id count, unknown-symbol flags for the cross-word rule, bare-U+2581 flag.
+  auto merge_word = [&](int ws, int we, bool special, uint32_t& alive, int& cnt, bool& first_unk, bool& last_unk,
+                        bool& bare) {
+    alive = 0;
+    cnt = 0;
+    first_unk = last_unk = bare = false;
+    if (HF && special) {
+      int32_t id = 0;
+      hf_added_len(T, nb + ws, we - ws, &id);
+      sm.S[lane] = kResolvedFlag | (uint32_t)id;
+      alive = 1u;
+      cnt = 1;
+      return;
+    }
+    bool direct = false;
+    if constexpr (HF) {
+      if (T.ignore_merges) {  // models/bpe/model.rs: a pre-token that is a vocabulary entry is that token
+        const int32_t id = hf_vocab_lookup(T, nb + ws, we - ws);
+        if (id >= 0) {
+          sm.S[lane] = kResolvedFlag | (uint32_t)id;
+          alive = 1u;
+          cnt = 1;
+          direct = true;
+        }
+      }
+    }
+    bool pu = false, first = true;
+    if (!direct) {
+      int n = 0;
+      for (int p = ws; p < we;) {
+        uint32_t adv;
+        sm.S[n * 32 + lane] = char_sym(T, nb + p, &adv);
+        p += adv;
+        ++n;
+      }
+      bare = (we - ws == 3) && n == 1 && sm.S[lane] == T.space_sym;
+      alive = lane_merge<SMALL>(T, sm, n, lane);
+    }
+    // pass 1: resolve every final symbol; single-id symbols are replaced in place by their token id
+    // (tagged), so pass 2 only re-derives the rare multi-id (byte fallback) ones
+    for (uint32_t m = direct ? 0u : alive; m;) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      int32_t tmp[4];
+      bool unk;
+      const uint32_t sym = sm.S[j * 32 + lane];
+      const int c = sym_ids(T, sym, tmp, &unk);
+      if (first) { first_unk = unk; first = false; }
+      if (!unk && c == 1) sm.S[j * 32 + lane] = kResolvedFlag | (uint32_t)tmp[0];
+      if (!(unk && pu && !T.byte_fallback)) cnt += c;
+      pu = unk;
+    }
+    last_unk = pu;
+    if constexpr (MEMO) {
+      // memoise: every surviving symbol resolved to exactly one id, at most kMax of them
+      const int k = __popc(alive);
+      U128 key;
+      if (k >= 1 && k <= MemoIds<SMALL>::kMax && k == cnt && !bare && memo_key(nb, ws, we, T.byte_mode, &key)) {
+        uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool ok = true;
+        int q = 0;
+        for (uint32_t m = alive; m; ++q) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t sym = sm.S[j * 32 + lane];
+          ok = ok && (sym & 0xC0000000u) == kResolvedFlag && (sym & 0x3FFFFFFFu) < (SMALL ? (1u << 16) : (1u << 28));
+          id[q] = sym & 0x0FFFFFFFu;
+        }
+        if (ok) {
+          const U128 val = MemoIds<SMALL>::pack(k, id);
+          uint32_t slot = memo_slot(key, memo.mask);
+          const U128 zero{0ull, 0ull};
+#pragma unroll 1
+          for (int way = 0; way < 2; ++way, slot ^= 1u) {
+            uint8_t* e = memo.table + (size_t)slot * 32;
+            const U128 old = cas_b128(e, zero, key);
+            if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
+            if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
+          }
+        }
+      }
+    }
+  };
+
+  // 1b. warm-up pre-passes (throughput kernel with a memo; natural text).  The rounds below go through the words in
+  // order, 32 at a time, and a round runs at the speed of its slowest lane: ONE memo miss costs the whole round a merge,
+  // and a word beyond the lane columns cuts the round short and is merged by the whole warp on its own.  On the
+  // synthetic headline text both are rare; on real text 91 % of the rounds hold a miss and every tenth word is long.
+  // So, when the previous drain looked like that:
+  //   A1  probe the memo for every short word of the drain first, collect the misses and merge them 32 at a time in FULL
+  //       rounds (results go to the memo only); the in-order rounds then find them there;
+  //   A2  merge every long word (17..512 symbols) ahead of the rounds and park its ids in a per-warp global scratch
+  //       (slot = the word's byte offset: ids never outnumber bytes); in the rounds such a word is an ordinary lane
+  //       whose ids are read back from there, so the rounds are no longer cut.  Only for vocabularies without
+  //       cross-word unknown merging (byte fallback, or byte-level), where a word's ids do not depend on its neighbours.
   int32_t* arena = nullptr;
   uint16_t* lcnt = nullptr;
   int a1_misses = 0;
   if constexpr (MEMO && !UNI && !LONG) {
-    if (T.warm_arena != nullptr && (rs.warm || rs.had_long))
-      warm_prepass<SMALL, HF>(T, sm, rs, complete, lane, memo, arena, lcnt, a1_misses);
+    if (T.warm_arena != nullptr && (rs.warm || rs.had_long)) {
+      uint8_t* slice = T.warm_arena + (size_t)blockIdx.x * kWarmSliceBytes;
+      const bool do_long = rs.had_long && (T.byte_fallback || T.byte_mode);
+      if (do_long) {
+        arena = reinterpret_cast<int32_t*>(slice);
+        lcnt = reinterpret_cast<uint16_t*>(slice + (size_t)kNBuf * 4);
+      }
+      int np = 0;  // words waiting in sm.pend[0 .. np)
+      auto flush = [&]() {
+        __syncwarp();
+        int ws = 0, we = 0, nsym = 0;
+        bool special = false;
+        if (lane < np) word_of(sm.pend[lane], ws, we, nsym, special);
+        uint32_t alive;
+        int cnt;
+        bool fu, lu, bare;
+        if (lane < np) merge_word(ws, we, special, alive, cnt, fu, lu, bare);
+        np = 0;
+        __syncwarp();
+      };
+      for (int base = 0; base < complete; base += 32) {
+        const int w = base + lane;
+        const bool have = w < complete;
+        int ws = 0, we = 0, nsym = 0;
+        bool special = false;
+        if (have) word_of(w, ws, we, nsym, special);
+        const bool is_long = have && !special && nsym > kMaxSym;
+        // ---- A2: the long words of this block, one at a time, whole warp
+        uint32_t lm = __ballot_sync(kFull, do_long && is_long);
+        while (lm) {
+          const int b = __ffs(lm) - 1;
+          lm &= lm - 1;
+          const int lws = __shfl_sync(kFull, ws, b), lwe = __shfl_sync(kFull, we, b);
+          int n = 0;
+          bool overflow = false;
+          for (int pb = lws; pb < lwe; pb += 32) {
+            const int p = pb + lane;
+            const bool lead = p < lwe && (T.byte_mode || (nb[p] & 0xC0) != 0x80);
+            const uint32_t m = __ballot_sync(kFull, lead);
+            const int idx = n + __popc(m & ((1u << lane) - 1));
+            if (lead) {
+              if (idx < kCoopMaxSym) { uint32_t adv; sm.S[idx] = char_sym(T, nb + p, &adv); }
+              else overflow = true;
+            }
+            n += __popc(m);
+          }
+          overflow = __any_sync(kFull, overflow);
+          __syncwarp();
+          int total = -1;   // ids written for this word, -1: left to the in-order cooperative path
+          if (!overflow) {
+            int32_t whole = -1;
+            if constexpr (HF) {
+              if (T.ignore_merges) {
+                if (lane == 0) whole = hf_vocab_lookup(T, nb + lws, lwe - lws);
+                whole = __shfl_sync(kFull, whole, 0);
+              }
+            }
+            if (whole >= 0) {
+              if (lane == 0) arena[lws] = whole;
+              total = 1;
+            } else {
+              n = coop_merge<SMALL>(T, sm, n, lane);
+              total = 0;
+              for (int sb = 0; sb < n; sb += 32) {
+                const int j = sb + lane;
+                int32_t tmp[4];
+                bool unk = false;
+                int c = 0;
+                if (j < n) c = sym_ids(T, sm.S[j], tmp, &unk);   // byte fallback: an unknown char is its byte ids
+                const int inc2 = warp_incl_scan(c, lane);
+                int o = lws + total + (inc2 - c);
+                for (int k = 0; k < c; ++k) arena[o++] = tmp[k];
+                total += __shfl_sync(kFull, inc2, 31);
+              }
+            }
+          }
+          if (lane == 0) lcnt[base + b] = total < 0 ? kNotPre : (uint16_t)total;
+          __syncwarp();
+        }
+        // ---- A1: short words that are not in the memo yet
+        if (rs.warm) {
+          bool miss = false;
+          U128 key;
+          if (have && !special && !is_long && memo_key(nb, ws, we, T.byte_mode, &key)) {
+            uint32_t slot = memo_slot(key, memo.mask);
+            miss = true;
+#pragma unroll 1
+            for (int way = 0; way < 2; ++way, slot ^= 1u) {
+              const U128 k = ld_b128(memo.table + (size_t)slot * 32);
+              if (k.lo == key.lo && k.hi == key.hi) { miss = false; break; }
+              if ((k.lo | k.hi) == 0) break;
+            }
+          }
+          const uint32_t mm = __ballot_sync(kFull, miss);
+          const int k = __popc(mm);
+          a1_misses += k;
+          if (np + k > 32) flush();
+          if (miss) sm.pend[np + __popc(mm & ((1u << lane) - 1))] = (uint16_t)w;
+          np += k;
+          if (np == 32) flush();
+        }
+      }
+      if (np) flush();
+      __syncwarp();
+    }
   }
 
   // 2. rounds of up to 32 consecutive words
@@ -1419,7 +1741,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     const bool have = w < complete;
     int ws = 0, we = 0, nsym = 0;
     bool special = false;  // HF: the word is an added token
-    if (have) word_geom<HF>(T, sm, rs.ascii, w, ws, we, nsym, special);
+    if (have) word_of(w, ws, we, nsym, special);
     // a long word the pre-pass resolved: its ids wait in the arena, it takes part in the round like any other lane
     bool pre = false;
     if constexpr (MEMO && !UNI && !LONG) {
@@ -1474,7 +1796,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
     if (pre && active) {
       cnt = lcnt[w];   // ids parked in the arena by the pre-pass (byte fallback / byte level: no unknown merging)
     } else if (!memo_hit && active) {
-      merge_word<SMALL, HF, MEMO>(T, sm, memo, lane, ws, we, special, alive, cnt, first_unk, last_unk, bare);
+      merge_word(ws, we, special, alive, cnt, first_unk, last_unk, bare);
     }
     if (__any_sync(kFull, active && !pre && !memo_hit && !special)) ++n_slow;
     // cross-word unknown merging (byte_fallback off): drop the first id if the previous symbol was unknown too
@@ -1693,9 +2015,15 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
   return HF && hf_capped && !rs.deferred;
 }
 
-template <bool SMALL, bool LONG, int MODE, bool MEMO, typename SM>
+template <bool SMALL, bool LONG, int MODE, bool MEMO, bool WARM = false, typename SM>
 __device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
-  if constexpr (MODE == 1) {
+  if constexpr (WARM) {
+    if constexpr (MODE == 1) {
+      while (drain_pass_warm<SMALL, LONG, 1, MEMO>(T, sm, rs, final, lane, memo)) {}
+    } else {
+      drain_pass_warm<SMALL, LONG, MODE, MEMO>(T, sm, rs, final, lane, memo);
+    }
+  } else if constexpr (MODE == 1) {
     while (drain_pass<SMALL, LONG, 1, MEMO>(T, sm, rs, final, lane, memo)) {}
   } else {
     drain_pass<SMALL, LONG, MODE, MEMO>(T, sm, rs, final, lane, memo);
@@ -1706,7 +2034,8 @@ __device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool
 // LONG == true : re-runs exactly the deferred requests (work list = defer_list[0 .. *defer_count)).
 // HF == true : byte-level BPE with the regex pre-tokenizer (split_mode 3).
 // MEMO == true: words are looked up in / added to the launch's word memo (never built together with LONG).
-template <bool SMALL, bool LONG, int MODE, bool MEMO>
+// WARM == true: drains go through drain_pass_warm (natural text; MEMO kernels only).
+template <bool SMALL, bool LONG, int MODE, bool MEMO, bool WARM = false>
 __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ offsets, int n_req, int32_t* __restrict__ ids,
     int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status, const __grid_constant__ SpDev T,
@@ -1719,7 +2048,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int lane = threadIdx.x;
   const int drain_at = kNBuf - 3 * kFastWin - 8;  // room for one more fast-path step
-  bool warm_carry = false, long_carry = false;   // what the previous request's text looked like (same batch, same kind)
+  bool warm_carry = false, long_carry = false;   // WARM: what the previous request's text looked like (same batch)
   unsigned long long warp_t0 = 0;
   if constexpr (!LONG) {
     if (T.warp_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(warp_t0));
@@ -1769,13 +2098,13 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       for (uint32_t pos = 0; pos < rs.len; pos += kFastWin) {
         normalize_fast(T, sm, rs, pos, lane);  // byte mode: a verbatim copy
         if (rs.nlen > drain_at) {
-          drain<SMALL, LONG, 1, MEMO>(T, sm, rs, false, lane, memo);
+          drain<SMALL, LONG, 1, MEMO, WARM>(T, sm, rs, false, lane, memo);
           // what is left is one unfinished pre-token (plus the look-ahead margin)
           if (rs.nlen > kLongEnterAt) rs.too_long = true;
           if (rs.too_long || rs.deferred || rs.bad_input) break;
         }
       }
-      if (!rs.too_long && !rs.deferred && !rs.bad_input) drain<SMALL, LONG, 1, MEMO>(T, sm, rs, true, lane, memo);
+      if (!rs.too_long && !rs.deferred && !rs.bad_input) drain<SMALL, LONG, 1, MEMO, WARM>(T, sm, rs, true, lane, memo);
       if (!rs.too_long && !rs.deferred && !rs.bad_input) {
         if (lane < T.n_suffix) put_id(rs, rs.n_out + lane, T.suffix_ids[lane]);
         rs.n_out += T.n_suffix;
@@ -1798,7 +2127,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
             if constexpr (LONG) {
               if (rs.long_mode) { long_consume(T, sm, rs, false, lane); consumed = true; }
             }
-            if (!consumed) drain<SMALL, LONG, MODE, MEMO>(T, sm, rs, false, lane, memo);
+            if (!consumed) drain<SMALL, LONG, MODE, MEMO, WARM>(T, sm, rs, false, lane, memo);
             if (!rs.too_long && !normalize_window(T, sm, rs, pos, carry_skip, lane)) {
               // still no room: the kept tail is one very long word -> stream it through a scratch slot
               bool entered = false;
@@ -1822,7 +2151,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
           }
         }
         if (!in_long && rs.nlen > drain_at) {
-          drain<SMALL, LONG, MODE, MEMO>(T, sm, rs, false, lane, memo);
+          drain<SMALL, LONG, MODE, MEMO, WARM>(T, sm, rs, false, lane, memo);
           if (rs.nlen > kLongEnterAt) {
             if constexpr (LONG) {
               if (!long_enter(T, sm, rs, lane)) rs.too_long = true;
@@ -1836,7 +2165,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       if constexpr (LONG) {
         if (!rs.too_long && rs.long_mode) long_consume(T, sm, rs, true, lane);
       }
-      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG, MODE, MEMO>(T, sm, rs, true, lane, memo);
+      if (!rs.too_long && !rs.deferred) drain<SMALL, LONG, MODE, MEMO, WARM>(T, sm, rs, true, lane, memo);
     }
     if constexpr (LONG) {
       if (rs.long_mode) {  // error exit while a slot is held
@@ -2091,6 +2420,10 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
         XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, true>), false)
         XLLM_SET_SMEM((sp_encode_kernel<true, false, 1, true>), true)
         XLLM_SET_SMEM((sp_encode_kernel<false, false, 1, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, true, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, true, true>), false)
+        XLLM_SET_SMEM((sp_encode_kernel<true, false, 1, true, true>), true)
+        XLLM_SET_SMEM((sp_encode_kernel<false, false, 1, true, true>), false)
         r = cudaFuncSetAttribute(sp_encode_kernel<true, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(WarpSmemUniT<true>));
         if (r != cudaSuccess) return r;
@@ -2117,13 +2450,18 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
     e = cudaMemsetAsync(memo.table, 0, (size_t)memo.slots * 32, stream);  // the memo lives for this launch only
     if (e != cudaSuccess) return e;
   }
-  if (use_memo && memo.arena != nullptr && memo.arena_bytes >= (size_t)grid * kWarmSliceBytes)
-    dev.warm_arena = static_cast<uint8_t*>(memo.arena);
+  // the warm-up kernels (drain_pass_warm) need their per-warp scratch; the caller passes it only when they are wanted
+  const bool warm = use_memo && !dev.unigram && memo.arena != nullptr && memo.arena_bytes >= (size_t)grid * kWarmSliceBytes;
+  if (warm) dev.warm_arena = static_cast<uint8_t*>(memo.arena);
   uint8_t* const mt = use_memo ? static_cast<uint8_t*>(memo.table) : nullptr;
   const uint32_t mm = use_memo ? memo.slots - 1 : 0;
 #define XLLM_LAUNCH_PAIR(SMALL_, HF_, MEMO_)                                                                     \
-  sp_encode_kernel<SMALL_, false, HF_, MEMO_><<<grid, 32, smem, stream>>>(                                       \
-      text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, mt, mm);    \
+  if (MEMO_ && warm)                                                                                             \
+    sp_encode_kernel<SMALL_, false, HF_, MEMO_, MEMO_><<<grid, 32, smem, stream>>>(                              \
+        text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, mt, mm);  \
+  else                                                                                                           \
+    sp_encode_kernel<SMALL_, false, HF_, MEMO_><<<grid, 32, smem, stream>>>(                                     \
+        text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, mt, mm);  \
   sp_encode_kernel<SMALL_, true, HF_, false><<<grid_long, 32, smem, stream>>>(                                   \
       text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters + 2, defer_list, counters + 1, nullptr, 0u);
   const bool hf = dev.split_mode == 3;
