@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libxllm_ingest.so")
+# XLLM_INGEST_LIB: a diagnostics build of the same library (e.g. -DXLLM_EXP_STATS counters), developer use only
+_LIB_PATH = os.environ.get("XLLM_INGEST_LIB") or os.path.join(_HERE, "libxllm_ingest.so")
 _lib = None
 
 

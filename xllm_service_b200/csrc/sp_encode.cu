@@ -1049,6 +1049,258 @@ __device__ int unigram_word_slow(const SpDev& T, SM& sm, const uint8_t* w, int l
   return n;
 }
 
+// ---------------------------------------------------------------------------- express path
+// One step tokenises one 128-byte source window straight from registers: no normalized-text buffer, no word list,
+// no symbol columns for words the memo knows.  It runs only in the BOUNDARY state — nbuf is empty, or holds exactly
+// the one U+2581 (dummy prefix / kept space) that leads the next word — and only for models with split_mode 1 and
+// remove_extra_whitespaces (every kept space starts a word, runs of spaces collapse), on windows that pass the
+// fast path's own test (every byte a simple or space-like ASCII byte followed by an ASCII byte), so the normalizer's
+// output is known without writing it:  word = maximal run of non-space bytes, led by U+2581 iff a kept space or the
+// dummy prefix precedes it.  Lane k takes the k-th COMPLETE word of the window (its end is in the window or at the
+// end of the text), pulls its <= 15 bytes out of the neighbouring lanes' registers, builds the memo key and probes;
+// a miss is merged in the lane's symbol column exactly as a drain round would and inserted.  Ids are written from
+// the memo payload.  The step consumes up to the start of the first word it did not take and leaves the state a
+// drain would have left.  Anything it cannot do exactly (a word over 15 bytes, an unknown symbol, a word of more
+// ids than a memo payload holds) returns 0 with nothing changed, and the window goes through the buffer path.
+#ifdef XLLM_EXP_STATS
+__device__ unsigned long long g_exp_stats[16];
+#define EXP_STAT(i) do { if (lane == 0) atomicAdd(&g_exp_stats[i], 1ull); } while (0)
+#else
+#define EXP_STAT(i) do { } while (0)
+#endif
+constexpr int kExpScratch = 8;  // wstart[kExpScratch ..]: 33 x {start, end} byte offsets of the window's words
+
+// Runs express steps from source offset pos for as long as they apply; returns the offset reached and sets *failed
+// when it stopped in front of a window it cannot do (the caller sends that window through the buffer path).
+// Windows are 4-byte ALIGNED: the step loads the 32 aligned words that start at or before pos, turns the bytes in
+// front of pos (and past the end of the text) into spaces, and never consumes byte 127 of a window unless the text
+// ends inside it — so every consumed byte has its successor inside the window, where it was checked to be ASCII.
+template <bool SMALL, bool MEMO, typename SM>
+__device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ReqState& rs, uint32_t pos, int lane,
+                                                MemoRef memo, bool* failed) {
+  const uint8_t* const src_end = rs.src + rs.len;
+  bool P = rs.nlen == 3;      // a U+2581 is pending in front of the next word
+  bool S = rs.prev_space;     // the normalizer's is_prev_space
+  uint8_t* const ex = reinterpret_cast<uint8_t*>(sm.wstart + kExpScratch);
+  const uint32_t lt = (1u << lane) - 1u;
+  auto load_window = [&](uint32_t at) {
+    const uint8_t* a = rs.src + at;
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(a - (reinterpret_cast<uintptr_t>(a) & 3u)) + lane;
+    return reinterpret_cast<const uint8_t*>(aw) < src_end ? __ldg(aw) : 0x20202020u;
+  };
+  uint32_t w = load_window(pos);
+  *failed = false;
+  for (;;) {
+    const uint8_t* const a = rs.src + pos;
+    const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3u);
+    const uint8_t* const wbase = a - skip;                         // the window's first (aligned) byte
+    const bool at_end = wbase + kFastWin >= src_end;               // the text ends inside this window
+    if (lane < kPrefetchWindows) {
+      const uint8_t* pf = wbase + (size_t)kFastWin * (kPrefetchFirst + lane);
+      if (pf < src_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    }
+    if (skip != 0u && lane == 0) {                                 // bytes in front of pos: spaces
+      const uint32_t m = (1u << (8u * skip)) - 1u;
+      w = (w & ~m) | (0x20202020u & m);
+    }
+    if (at_end) {                                                  // bytes past the end of the text: spaces
+      const long rem = src_end - (wbase + 4 * lane);
+      if (rem < 4) {
+        const uint32_t m = rem <= 0 ? 0u : (1u << (8u * (uint32_t)rem)) - 1u;
+        w = (w & m) | (0x20202020u & ~m);
+      }
+    }
+    {
+      // every byte a simple ASCII byte (then it is its own unit, given an ASCII successor) or a space-like one
+      bool ok = (w & 0x80808080u) == 0u;
+      bool fast_ok = false;
+      if (T.printable_simple)
+        fast_ok = ((((w | 0x80808080u) - 0x20202020u) & 0x80808080u) == 0x80808080u) &&  // every byte >= 0x20
+                  (((w + 0x01010101u) & 0x80808080u) == 0u);                               // every byte <= 0x7E
+      if (!__all_sync(kFull, ok && fast_ok)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t bk = (w >> (8 * k)) & 0xFFu;
+          const bool spl = (T.spacelike_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u;
+          ok = ok && (spl || ((T.simple_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u));
+          if (spl) w = (w & ~(0xFFu << (8 * k))) | (0x20u << (8 * k));
+        }
+        if (!__all_sync(kFull, ok)) { EXP_STAT(4); *failed = true; break; }
+      }
+    }
+    // non-space bytes of the lane's word; word starts / ends from the two neighbouring bytes
+    uint32_t ns4;
+    {
+      const uint32_t x = w ^ 0x20202020u;
+      const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);  // 0x80 in every zero byte of x
+      ns4 = ~(((z >> 7) * 0x01020408u) >> 24) & 0xFu;
+    }
+    uint32_t prev_ns = (__shfl_up_sync(kFull, ns4, 1) >> 3) & 1u;
+    uint32_t next_ns = __shfl_down_sync(kFull, ns4, 1) & 1u;
+    if (lane == 0) prev_ns = 0u;
+    if (lane == 31) next_ns = at_end ? 0u : 1u;                    // unknown successor: the word is not complete
+    if (!P && !S) {                                                // would continue a word that is not in the buffer
+      if ((__shfl_sync(kFull, ns4, 0) >> skip) & 1u) { EXP_STAT(5); *failed = true; break; }
+    }
+    const uint32_t st4 = ns4 & ~((ns4 << 1) | prev_ns) & 0xFu;
+    const uint32_t en4 = ns4 & ~((ns4 >> 1) | (next_ns << 3)) & 0xFu;
+    const uint32_t b1 = __ballot_sync(kFull, st4 != 0u), b2 = __ballot_sync(kFull, (st4 & (st4 - 1u)) != 0u);
+    const uint32_t inc = (!at_end && (__ballot_sync(kFull, (ns4 & 8u) != 0u) >> 31)) ? 1u : 0u;   // an unfinished word at the end
+    const int nstart = __popc(b1) + __popc(b2);
+    const int nend = nstart - (int)inc;
+    const int take = nend < 32 ? nend : 32;       // complete words this step resolves
+    if (nstart != 0 && take == 0) { EXP_STAT(6); *failed = true; break; }   // one unfinished word fills the window
+    const uint32_t nv = at_end ? (uint32_t)(src_end - wbase) : (uint32_t)kFastWin - 1u;
+    uint32_t cons = nv;                            // window bytes consumed (counted from wbase)
+    int total = 0;
+    bool S2 = true;
+    uint32_t w_next = 0;
+    if (take > 0) {
+      {
+        const uint32_t k0 = __popc(b1 & lt) + __popc(b2 & lt);
+        if (st4) {                                 // at most two starts / two ends in four bytes
+          if (k0 <= 32u) ex[2u * k0] = (uint8_t)(4 * lane + __ffs(st4) - 1);
+          if ((st4 & (st4 - 1u)) && k0 < 32u) ex[2u * k0 + 2u] = (uint8_t)(4 * lane + 31 - __clz(st4));
+        }
+        if (en4) {
+          const uint32_t e0 = k0 - (prev_ns & ns4 & 1u);   // words that ended before this lane = started - the one still open
+          if (e0 < 32u) ex[2u * e0 + 1u] = (uint8_t)(4 * lane + __ffs(en4) - 1);
+          if ((en4 & (en4 - 1u)) && e0 + 1u < 32u) ex[2u * e0 + 3u] = (uint8_t)(4 * lane + 31 - __clz(en4));
+        }
+      }
+      __syncwarp();
+      const bool active = lane < take;
+      const uint32_t se = reinterpret_cast<const uint16_t*>(ex)[active ? lane : 0];
+      if (take < nstart) cons = ex[2 * take];      // stop in front of the first word not taken
+      // the next window's bytes: in flight while this one's words are looked up
+      if (pos + (cons - skip) < rs.len) w_next = load_window(pos + (cons - skip));
+      const uint32_t s = se & 0xFFu;
+      const int n = (int)(se >> 8) - (int)s + 1;
+      if (__any_sync(kFull, active && n > kMemoMaxKeyBytes)) { EXP_STAT(7); *failed = true; break; }
+      // --- the word's bytes from the lanes that hold them
+      unsigned long long lo, hi;
+      {
+        const uint32_t j0 = s >> 2, bsh = (s & 3u) * 8u;
+        const bool wide = __any_sync(kFull, active && (s & 3u) + (uint32_t)n > 12u);
+        const uint32_t t0 = __shfl_sync(kFull, w, j0), t1 = __shfl_sync(kFull, w, j0 + 1), t2 = __shfl_sync(kFull, w, j0 + 2);
+        uint32_t t3 = 0, t4 = 0;
+        if (wide) { t3 = __shfl_sync(kFull, w, j0 + 3); t4 = __shfl_sync(kFull, w, j0 + 4); }
+        lo = (unsigned long long)__funnelshift_r(t0, t1, bsh) | ((unsigned long long)__funnelshift_r(t1, t2, bsh) << 32);
+        hi = (unsigned long long)__funnelshift_r(t2, t3, bsh) | ((unsigned long long)__funnelshift_r(t3, t4, bsh) << 32);
+        if (n < 8) { lo &= (1ull << (8 * n)) - 1ull; hi = 0ull; }
+        else hi &= (1ull << (8 * (n - 8))) - 1ull;
+      }
+      const bool lead = lane > 0 || P || (!S && s > skip);
+      U128 key;
+      key.lo = (lo << 8) | (unsigned long long)((lead ? 0x80u : 0u) | (uint32_t)n);
+      key.hi = (hi << 8) | (lo >> 56);
+      // --- memo
+      bool hit = false;
+      U128 v{0ull, 0ull};
+      if constexpr (MEMO) {
+        if (active) {
+          uint32_t slot = memo_slot(key, memo.mask);
+#pragma unroll 1
+          for (int way = 0; way < 2; ++way, slot ^= 1u) {
+            const uint8_t* e = memo.table + (size_t)slot * 32;
+            const U128 k = ld_b128(e);
+            const U128 val = ld_b128(e + 16);
+            if (k.lo == key.lo && k.hi == key.hi) {
+              if (MemoIds<SMALL>::valid(val)) { hit = true; v = val; }
+              break;
+            }
+            if ((k.lo | k.hi) == 0) break;
+          }
+        }
+      }
+      // --- misses: the merge of a drain round, from the bytes in registers
+      bool hard = false;
+      if (active && !hit) {
+        int m = 0;
+        if (lead) { sm.S[lane] = T.space_sym; m = 1; }
+        for (int i = 0; i < n; ++i) {
+          const uint32_t c = (uint32_t)((i < 8 ? lo >> (8 * i) : hi >> (8 * (i - 8))) & 0xFFull);
+          sm.S[(m++) * 32 + lane] = __ldg(T.ascii_sym + c);
+        }
+        const uint32_t alive = lane_merge<SMALL>(T, sm, m, lane);
+        const int k = __popc(alive);
+        uint32_t id[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        hard = k > MemoIds<SMALL>::kMax;
+        int q = 0;
+        for (uint32_t mm = alive; mm && !hard; ++q) {
+          const int j = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const uint32_t sym = sm.S[j * 32 + lane];
+          int32_t e = -1;
+          if (!(sym & kSymUnknownFlag)) e = __ldg(T.emit + sym);
+          if (e < 0 || (uint32_t)e >= (SMALL ? (1u << 16) : (1u << 28))) hard = true;   // unknown / byte fallback: buffer path
+          else id[q] = (uint32_t)e;
+        }
+        if (!hard) {
+          v = MemoIds<SMALL>::pack(k, id);
+          if constexpr (MEMO) {
+            uint32_t slot = memo_slot(key, memo.mask);
+            const U128 zero{0ull, 0ull};
+#pragma unroll 1
+            for (int way = 0; way < 2; ++way, slot ^= 1u) {
+              uint8_t* e = memo.table + (size_t)slot * 32;
+              const U128 old = cas_b128(e, zero, key);
+              if ((old.lo | old.hi) == 0) { st_b128(e + 16, v); break; }   // claimed: publish the ids
+              if (old.lo == key.lo && old.hi == key.hi) break;              // another warp owns this word
+            }
+          }
+        }
+      }
+      if (__any_sync(kFull, hard)) { EXP_STAT(8); *failed = true; break; }
+#ifdef XLLM_EXP_STATS
+      { const uint32_t am = __ballot_sync(kFull, active), hm = __ballot_sync(kFull, hit); if (lane == 0) { atomicAdd(&g_exp_stats[9], (unsigned long long)__popc(am)); atomicAdd(&g_exp_stats[10], (unsigned long long)__popc(hm)); if (am & ~hm) atomicAdd(&g_exp_stats[11], 1ull); } }
+#endif
+      // --- ids, in order
+      const int cnt = active ? MemoIds<SMALL>::count(v) : 0;
+      const int incl = warp_incl_scan(cnt, lane);
+      total = __shfl_sync(kFull, incl, 31);
+      const uint32_t c2 = __ballot_sync(kFull, cnt >= 2);
+      const int64_t o = rs.n_out + (incl - cnt);
+      if (cnt >= 1) put_id(rs, o, (int32_t)MemoIds<SMALL>::id(v, 0));
+      if (c2) {
+        const int maxcnt = (int)__reduce_max_sync(kFull, (uint32_t)cnt);
+#pragma unroll
+        for (int q = 1; q < MemoIds<SMALL>::kMax; ++q) {
+          if (q >= maxcnt) break;
+          if (q < cnt) put_id(rs, o + q, (int32_t)MemoIds<SMALL>::id(v, q));
+        }
+      }
+      rs.n_out += total;
+      rs.trailing_bare = 0;
+      rs.prev_unk = false;
+      if (take == nstart) S2 = !((__shfl_sync(kFull, ns4, (cons - 1u) >> 2) >> ((cons - 1u) & 3u)) & 1u);
+    } else {
+      if (pos + (cons - skip) < rs.len) w_next = load_window(pos + (cons - skip));
+    }
+    EXP_STAT(1);
+    // --- the state a drain would have left: is_prev_space, and the U+2581 a kept space puts in front of the next word
+    P = S2 && (take > 0 || P || !S);
+    S = S2;
+    pos += cons - skip;
+    if (pos >= rs.len) break;
+    w = w_next;
+    __syncwarp();
+  }
+  rs.prev_space = S;
+  if (P) {
+    if (rs.nlen != 3 && lane == 0) { sm.nbuf[0] = 0xE2; sm.nbuf[1] = 0x96; sm.nbuf[2] = 0x81; sm.wstart[0] = 0; }
+    rs.nlen = 3;
+    rs.nw = 1;
+  } else {
+    rs.nlen = 0;
+    rs.nw = 0;
+  }
+  rs.rescan = false;
+  rs.ascii = true;
+  __syncwarp();
+  return pos;
+}
+
 // MODE: 0 SentencePiece BPE / tiktoken, 1 HF byte-level BPE (regex pre-tokenizer), 2 SentencePiece Unigram
 template <bool SMALL, bool LONG, int MODE, bool MEMO, typename SM>
 __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int lane, MemoRef memo) {
@@ -2042,6 +2294,11 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     unsigned int* __restrict__ task_counter, int32_t* __restrict__ defer_list,
     unsigned int* __restrict__ defer_count, uint8_t* memo_table, uint32_t memo_mask) {
   constexpr bool HF = MODE == 1;
+  // the express path (express_step): SentencePiece BPE throughput kernels; per model: split before every U+2581,
+  // runs of spaces collapse, text normalised (not byte mode)
+  constexpr bool EXPRESS = MODE == 0 && !LONG && !WARM;
+  const bool express_model = EXPRESS && T.express && T.split_mode == 1 && T.remove_extra_ws && !T.byte_mode;
+  uint32_t exp_skip = 0, exp_fail = 0;   // windows to leave to the buffer path after a step that did not apply
   const MemoRef memo{memo_table, memo_mask};
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = typename std::conditional<MODE == 2, WarpSmemUniT<SMALL>, WarpSmemT<SMALL>>::type;
@@ -2118,6 +2375,39 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
       __syncwarp();
       uint32_t carry_skip = 0;
       for (uint32_t pos = 0; pos < rs.len;) {
+        // EXPRESS: force_drain 1 = drain now (the buffer ends in a kept space: what is left is the boundary state),
+        // 2 = drain everything (the next source byte is a space: every buffered word is complete)
+        int force_drain = 0;
+        if constexpr (EXPRESS) {
+          if (express_model && carry_skip == 0) {
+            if (exp_skip > 0) {
+              --exp_skip;
+            } else {
+              const int nl = rs.nlen;
+              const bool tail_sp = nl >= 3 && sm.nbuf[nl - 3] == 0xE2 && sm.nbuf[nl - 2] == 0x96 && sm.nbuf[nl - 1] == 0x81;
+              if (nl == 0 || (nl == 3 && tail_sp)) {
+                // boundary state: nbuf empty, or exactly the U+2581 that leads the next word
+                bool failed;
+                const uint32_t reached = express_run<SMALL, MEMO>(T, sm, rs, pos, lane, memo, &failed);
+                EXP_STAT(0);
+                const bool moved = reached != pos;
+                pos = reached;
+                if (!failed) break;                                   // the text is consumed
+                if (moved) exp_fail = 0;
+                exp_fail = exp_fail >= 31 ? 63 : 2 * exp_fail + 1;   // back off: 1, 3, 7 .. 63 windows on the buffer path
+                exp_skip = exp_fail;
+              } else if (tail_sp) {
+                force_drain = 1;
+              } else if (!rs.prev_space) {
+                const uint32_t c = __ldg(rs.src + pos);
+                if (c == 0x20u || (c < 0x80u && ((T.spacelike_ascii[(c >> 5) & 3] >> (c & 31)) & 1u))) force_drain = 2;
+              }
+            }
+          }
+        }
+        if (force_drain) {
+          EXP_STAT(2);
+        } else
         if (carry_skip == 0 && normalize_fast(T, sm, rs, pos, lane)) {
           pos += kFastWin;
         } else {
@@ -2150,8 +2440,9 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
             if (rs.nlen > kLongFlushAt) long_consume(T, sm, rs, false, lane);
           }
         }
-        if (!in_long && rs.nlen > drain_at) {
-          drain<SMALL, LONG, MODE, MEMO, WARM>(T, sm, rs, false, lane, memo);
+        if (!in_long && (rs.nlen > drain_at || force_drain)) {
+          drain<SMALL, LONG, MODE, MEMO, WARM>(T, sm, rs, force_drain == 2, lane, memo);
+          if (force_drain && !(rs.nlen == 0 || rs.nlen == 3)) exp_skip = 1;   // not a boundary after all: buffer path
           if (rs.nlen > kLongEnterAt) {
             if constexpr (LONG) {
               if (!long_enter(T, sm, rs, lane)) rs.too_long = true;
@@ -2206,6 +2497,13 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
 // ------------------------------------------------------------------------------ host side
 int g_warps_per_sm_override = 0;  // tuning knob (XLLM_SP_WARPS_PER_SM), 0 = fill shared memory
 
+#ifdef XLLM_EXP_STATS
+extern "C" void xllm_debug_exp_stats(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, g_exp_stats, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_exp_stats, z, sizeof(z));
+}
+#endif
 #ifdef XLLM_MEMO_STATS
 extern "C" void xllm_debug_memo_stats(unsigned long long* out) {
   cudaMemcpyFromSymbol(out, g_memo_stats, sizeof(unsigned long long) * 8);
@@ -2328,6 +2626,8 @@ int SpDeviceModel::upload(const SpTables& t) {
   if (const char* w = getenv("XLLM_SP_FORCE_WIDE"))  // tests: run a small vocabulary through the 32-bit-state kernels
     if (atoi(w) != 0) dev_.small_vocab = 0;
   if (const char* w = getenv("XLLM_SP_WARPS_PER_SM")) g_warps_per_sm_override = atoi(w);
+  dev_.express = 1;
+  if (const char* w = getenv("XLLM_SP_EXPRESS")) dev_.express = atoi(w) != 0 ? 1 : 0;   // 0: every window takes the buffer path
   // scratch pool for pre-tokens longer than the shared-memory paths hold
   uint32_t cap = 1u << 17;
   int slots = 64;

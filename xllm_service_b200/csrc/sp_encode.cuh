@@ -35,6 +35,7 @@ struct SpDev {
   uint8_t small_vocab;  // ranks and piece ids fit 16 bits: packed merge scratch
   uint8_t byte_mode;    // tiktoken tables: every byte is a symbol, text is copied verbatim
   uint8_t printable_simple;  // every byte 0x20..0x7E is "simple" (simple_ascii): word-at-a-time fast-path test
+  uint8_t express;           // express_step allowed (XLLM_SP_EXPRESS=0 turns it off)
   // global scratch pool for pre-tokens too long for shared memory (sp_long_word.cuh)
   // HF byte-level BPE (split_mode 3, hf_model.cc): Unicode classes for the GPT-2 regex, the added (special)
   // tokens matched verbatim in the text, and the template ids wrapped around every sequence
