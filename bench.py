@@ -877,8 +877,9 @@ def main():
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic_from_profiles(dom), "peak_source": peak_src,
                 "share_of_step": float(k_ms[list(kernels).index(dom)] / k_ms.sum()),
-                "note": "achieved = (text bytes + 4 B/token) / CUDA-event time of the kernel; the tokenizer is "
-                        "bound by instruction issue and shared-memory / L2 latency, not HBM (DESIGN.md 4.2)"}
+                "note": "achieved = (text bytes + 4 B/token) / CUDA-event time of the encode launches (memo clear + "
+                        "sp_express_kernel + the buffer-path and long-word kernels, empty grids on this workload); the "
+                        "tokenizer is bound by instruction issue and L2 latency, not HBM (DESIGN.md 4.2)"}
     line = {
         "metric": METRIC, "value": world * n * args.steps / (dev_ms / 1e3), "unit": "req/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -905,9 +906,9 @@ def main():
                         "d2h_bytes_per_step": d2h_bytes - 2 * n * T,
                         "note": "same call with xllm_ingest_io::ids_u16 (opt-in; vocabulary < 65536): token ids come "
                                 "back as uint16, checked equal to the int32 ids"},
-        # value region: encode (throughput + long-word pass) + hash + match/route (sharded: bucket, headers, owner
-        # probe, header gather, scan) per step; e2e region: the library's own count for one batch
-        "gpu_launches": args.steps * ((9 if sharded_mode else 4) + h.last_batch_stats()[1]),
+        # value region: encode (express kernel + buffer-path kernel + long-word pass) + hash + match/route (sharded:
+        # bucket, headers, owner probe, header gather, scan) per step; e2e region: the library's own count for one batch
+        "gpu_launches": args.steps * ((10 if sharded_mode else 5) + h.last_batch_stats()[1]),
         "roofline": roofline,
         "kernels": kernels,
     }

@@ -82,7 +82,7 @@ def test_default_pipeline_any_batch_size(oracle, n_req):
     try:
         out = h.ingest_batch(b.text, b.offsets, 128, want_match=False)
         chunks, launches = h.last_batch_stats()
-        assert chunks >= 1 and launches == 4 * chunks          # encode x2 + row prep + hash per chunk
+        assert chunks >= 1 and launches == 5 * chunks          # encode x3 (express, buffer path, long words) + row prep + hash per chunk
         assert (out["status"] == 0).all()
         ref_ids, ref_n = sp.encode_batch(b.text, b.offsets, 128)
         assert (out["n_ids"] == ref_n).all()
@@ -118,7 +118,7 @@ def test_short_rows_still_get_a_routing_decision(oracle):
     h.ingest_batch_ptrs(n, b.text.ctypes.data, b.offsets.ctypes.data, ids.ctypes.data, 64, n_ids.ctypes.data,
                         status.ctypes.data, 0, 0, match.ctypes.data, routing.ctypes.data)
     chunks, launches = h.last_batch_stats()
-    assert launches == 4 * chunks      # encode x2 + row prep + match/route, no hash
+    assert launches == 5 * chunks      # encode x3 + row prep + match/route, no hash
     want = P.route(np.zeros(0, np.int32))
     assert want["ok"]
     for r in range(n):

@@ -677,7 +677,7 @@ int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_te
   std::lock_guard<std::mutex> lock(h->mu);
   XLLM_CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
-  XLLM_TRY(h->d_defer.reserve((size_t)n_req * 4));
+  XLLM_TRY(h->d_defer.reserve(xllm::sp_encode_scratch_bytes(n_req)));
   SpMemo memo;
   if (h->memo_slots) {
     XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
@@ -690,7 +690,7 @@ int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_te
     }
   }
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), d_text, d_offsets, n_req, d_ids, ids_stride, d_n_ids, d_status,
-                                 h->d_task_counter + 4, h->d_defer.as<int32_t>(), s, memo));
+                                 h->d_task_counter + 4, h->d_defer.p, s, memo));
   return XLLM_OK;
 }
 
@@ -722,7 +722,7 @@ static int encode_batch_impl(xllm_ingest_t h, int32_t n_req, const uint8_t* text
   XLLM_TRY(h->d_ids.reserve((size_t)n_req * (size_t)ids_stride * 4 + 16));
   XLLM_TRY(h->d_n_ids.reserve((size_t)n_req * 4));
   XLLM_TRY(h->d_status.reserve((size_t)n_req * 4));
-  XLLM_TRY(h->d_defer.reserve((size_t)n_req * 4));
+  XLLM_TRY(h->d_defer.reserve(xllm::sp_encode_scratch_bytes(n_req)));
   cudaStream_t s = h->stream;
   SpMemo memo;
   if (h->memo_slots) {
@@ -749,7 +749,7 @@ static int encode_batch_impl(xllm_ingest_t h, int32_t n_req, const uint8_t* text
   }
   XLLM_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), h->d_text.as<uint8_t>() - offsets[0], h->d_offsets.as<int64_t>(),
                                  n_req, h->d_ids.as<int32_t>(), ids_stride, h->d_n_ids.as<int32_t>(),
-                                 h->d_status.as<int32_t>(), h->d_task_counter + 4, h->d_defer.as<int32_t>(), s, memo,
+                                 h->d_status.as<int32_t>(), h->d_task_counter + 4, h->d_defer.p, s, memo,
                                  opts));
   if (warp_ns) {
     const int take = grid < warp_cap ? grid : warp_cap;

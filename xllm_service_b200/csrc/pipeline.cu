@@ -123,7 +123,7 @@ int PipeSlot::ensure(size_t text_bytes, int n, int64_t ids_stride, int64_t keys_
   if ((rc = d_ids.reserve((size_t)n_req * (size_t)ids_stride * 4 + 64)) != XLLM_OK) return rc;
   if ((rc = d_n_ids.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_status.reserve((size_t)n * 4)) != XLLM_OK) return rc;
-  if ((rc = d_defer.reserve((size_t)n * 4)) != XLLM_OK) return rc;
+  if ((rc = d_defer.reserve(xllm::sp_encode_scratch_bytes(n))) != XLLM_OK) return rc;
   if ((rc = d_tok_start.reserve((size_t)n * 8)) != XLLM_OK) return rc;
   if ((rc = d_n_tok.reserve((size_t)n * 4)) != XLLM_OK) return rc;
   if ((rc = d_key_start.reserve((size_t)n * 8)) != XLLM_OK) return rc;
@@ -424,7 +424,7 @@ static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_seg
       if ((rc = sl.d_seg_src.reserve((size_t)(s1 - s0) * 8 + 8)) != XLLM_OK) break;
       if ((rc = sl.d_req_seg.reserve((size_t)(m + 1) * 4)) != XLLM_OK) break;
       if ((rc = sl.d_span.reserve((size_t)(sp1 - sp0) * 4 + 4)) != XLLM_OK) break;
-      if ((rc = sl.d_defer.reserve((size_t)mp * 4 + 4)) != XLLM_OK) break;
+      if ((rc = sl.d_defer.reserve(xllm::sp_encode_scratch_bytes(mp))) != XLLM_OK) break;
       if (mp) {
         PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_piece_out_start.p, ostart.data(), (size_t)mp * 8, cudaMemcpyHostToDevice, s_in));
         PIPE_CUDA_TRY(cudaMemcpyAsync(sl.d_piece_out_cap.p, ocap.data(), (size_t)mp * 4, cudaMemcpyHostToDevice, s_in));
@@ -444,14 +444,14 @@ static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_seg
     if (!seg) {
       PIPE_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), m,
                                      sl.d_ids.as<int32_t>(), io->ids_stride, sl.d_n_ids.as<int32_t>(),
-                                     sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s_k, memo));
+                                     sl.d_status.as<int32_t>(), sl.counters, sl.d_defer.p, s_k, memo));
     } else {
       xllm::SpLaunchOpts opts;
       opts.out_start = sl.d_piece_out_start.as<int64_t>();
       opts.out_cap = sl.d_piece_out_cap.as<int32_t>();
       PIPE_CUDA_TRY(sp_encode_launch(h->sp_dev->dev(), sl.d_text.as<uint8_t>() - t0, sl.d_offsets.as<int64_t>(), mp,
                                      sl.d_piece_ids.as<int32_t>(), 0, sl.d_piece_n.as<int32_t>(),
-                                     sl.d_piece_status.as<int32_t>(), sl.counters, sl.d_defer.as<int32_t>(), s_k, memo,
+                                     sl.d_piece_status.as<int32_t>(), sl.counters, sl.d_defer.p, s_k, memo,
                                      opts));
       assemble_segments_kernel<<<(m + 3) / 4, 128, 0, s_k>>>(
           sl.d_req_seg.as<int32_t>(), sl.d_seg_len.as<int32_t>(), sl.d_seg_src.as<int64_t>(),
@@ -527,7 +527,7 @@ static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_seg
     mark(4, s_out);
     sl.busy = true;
     h->last_chunks += 1;
-    h->last_launches += 2 + (keys_stride > 0 || want_match ? 1 : 0) + (keys_stride > 0 ? 1 : 0) + (want_match ? 1 : 0);  // encode x2, prep, hash, match+route
+    h->last_launches += sp_encode_kernel_launches(h->sp_dev->dev(), h->memo_slots != 0, h->sp_warm) + (keys_stride > 0 || want_match ? 1 : 0) + (keys_stride > 0 ? 1 : 0) + (want_match ? 1 : 0);  // encode x2 or x3, prep, hash, match+route
     slot = (slot + 1) % n_slots;
     c0 = c1;
   }

@@ -1068,20 +1068,43 @@ __device__ unsigned long long g_exp_stats[16];
 #else
 #define EXP_STAT(i) do { } while (0)
 #endif
-constexpr int kExpScratch = 8;  // wstart[kExpScratch ..]: 33 x {start, end} byte offsets of the window's words
 
 // Runs express steps from source offset pos for as long as they apply; returns the offset reached and sets *failed
 // when it stopped in front of a window it cannot do (the caller sends that window through the buffer path).
 // Windows are 4-byte ALIGNED: the step loads the 32 aligned words that start at or before pos, turns the bytes in
 // front of pos (and past the end of the text) into spaces, and never consumes byte 127 of a window unless the text
 // ends inside it — so every consumed byte has its successor inside the window, where it was checked to be ASCII.
+struct ExpReq {
+  const uint8_t* src;
+  uint32_t len;
+  int32_t* out;
+  int64_t cap;     // ids that fit the row
+  int64_t n_out;   // ids produced so far (may exceed cap)
+  bool P;          // a U+2581 is pending in front of the next word (dummy prefix / kept space)
+  bool S;          // the normalizer's is_prev_space
+};
+// per warp: symbol columns for the words the memo does not know yet + the window's {start, end} pairs
+template <bool SMALL>
+struct ExpSmemT {
+  uint32_t S[kMaxSym * 32];
+  typename PMOps<SMALL>::T PM[kMaxSym * 32];
+  uint8_t ex[80];
+};
+// what the buffer-path kernel needs to take a request over where the express kernel stopped
+struct ExpResume {
+  uint32_t pos;      // source bytes consumed
+  uint32_t flags;    // bit 0: P, bit 1: S
+  long long n_out;
+};
+
 template <bool SMALL, bool MEMO, typename SM>
-__device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ReqState& rs, uint32_t pos, int lane,
+__device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& rs, uint32_t pos, int lane,
                                                 MemoRef memo, bool* failed) {
   const uint8_t* const src_end = rs.src + rs.len;
-  bool P = rs.nlen == 3;      // a U+2581 is pending in front of the next word
-  bool S = rs.prev_space;     // the normalizer's is_prev_space
-  uint8_t* const ex = reinterpret_cast<uint8_t*>(sm.wstart + kExpScratch);
+  bool P = rs.P;
+  bool S = rs.S;
+  uint8_t* const ex = sm.ex;
+  auto put = [&](int64_t at, int32_t id) { if (at < rs.cap) rs.out[at] = id; };
   const uint32_t lt = (1u << lane) - 1u;
   auto load_window = [&](uint32_t at) {
     const uint8_t* a = rs.src + at;
@@ -1261,18 +1284,16 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ReqState
       total = __shfl_sync(kFull, incl, 31);
       const uint32_t c2 = __ballot_sync(kFull, cnt >= 2);
       const int64_t o = rs.n_out + (incl - cnt);
-      if (cnt >= 1) put_id(rs, o, (int32_t)MemoIds<SMALL>::id(v, 0));
+      if (cnt >= 1) put(o, (int32_t)MemoIds<SMALL>::id(v, 0));
       if (c2) {
         const int maxcnt = (int)__reduce_max_sync(kFull, (uint32_t)cnt);
 #pragma unroll
         for (int q = 1; q < MemoIds<SMALL>::kMax; ++q) {
           if (q >= maxcnt) break;
-          if (q < cnt) put_id(rs, o + q, (int32_t)MemoIds<SMALL>::id(v, q));
+          if (q < cnt) put(o + q, (int32_t)MemoIds<SMALL>::id(v, q));
         }
       }
       rs.n_out += total;
-      rs.trailing_bare = 0;
-      rs.prev_unk = false;
       if (take == nstart) S2 = !((__shfl_sync(kFull, ns4, (cons - 1u) >> 2) >> ((cons - 1u) & 3u)) & 1u);
     } else {
       if (pos + (cons - skip) < rs.len) w_next = load_window(pos + (cons - skip));
@@ -1286,19 +1307,70 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ReqState
     w = w_next;
     __syncwarp();
   }
-  rs.prev_space = S;
-  if (P) {
-    if (rs.nlen != 3 && lane == 0) { sm.nbuf[0] = 0xE2; sm.nbuf[1] = 0x96; sm.nbuf[2] = 0x81; sm.wstart[0] = 0; }
-    rs.nlen = 3;
-    rs.nw = 1;
-  } else {
-    rs.nlen = 0;
-    rs.nw = 0;
-  }
-  rs.rescan = false;
-  rs.ascii = true;
+  rs.P = P;
+  rs.S = S;
   __syncwarp();
   return pos;
+}
+
+// The express kernel: every request starts here when the model allows it (split_mode 1, remove_extra_whitespaces,
+// normalised text).  A request it carries to the end is finished (a pending U+2581 is the trailing space the
+// normalizer strips); one it cannot is handed to the buffer-path kernel with its position, id count and
+// whitespace state, through legacy_list / resume.  kExpWarps independent warps per block.
+constexpr int kExpWarps = 4;
+#ifndef XLLM_EXP_MIN_BLOCKS
+#define XLLM_EXP_MIN_BLOCKS 10
+#endif
+template <bool SMALL>
+__global__ void __launch_bounds__(kExpWarps * 32, XLLM_EXP_MIN_BLOCKS) sp_express_kernel(
+    const uint8_t* __restrict__ text, const int64_t* __restrict__ offsets, int n_req, int32_t* __restrict__ ids,
+    int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status, const __grid_constant__ SpDev T,
+    unsigned int* __restrict__ task_counter, int32_t* __restrict__ legacy_list, unsigned int* __restrict__ legacy_count,
+    ExpResume* __restrict__ resume, uint8_t* memo_table, uint32_t memo_mask) {
+  const MemoRef memo{memo_table, memo_mask};
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using SM = ExpSmemT<SMALL>;
+  SM& sm = reinterpret_cast<SM*>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  unsigned long long warp_t0 = 0;
+  if (T.warp_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(warp_t0));
+  for (;;) {
+    unsigned int r = 0;
+    if (lane == 0) r = atomicAdd(task_counter, 1u);
+    r = __shfl_sync(kFull, r, 0);
+    if (r >= (unsigned)n_req) break;
+    ExpReq rq;
+    const int64_t beg = offsets[r];
+    rq.src = text + beg;
+    rq.len = (uint32_t)(offsets[r + 1] - beg);
+    rq.out = T.out_start ? ids + T.out_start[r] : ids + (int64_t)r * ids_stride;
+    rq.cap = T.out_cap ? (int64_t)T.out_cap[r] : ids_stride;
+    rq.n_out = 0;
+    rq.P = T.add_dummy_prefix != 0;
+    rq.S = true;   // is_prev_space starts true under remove_extra_whitespaces
+    bool failed = false;
+    uint32_t pos = 0;
+    if (rq.len > 0) pos = express_run<SMALL, true>(T, sm, rq, 0u, lane, memo, &failed);
+    if (lane == 0) {
+      if (!failed) {
+        n_ids[r] = (int32_t)rq.n_out;
+        status[r] = rq.n_out > rq.cap ? kEncTruncated : kEncOk;
+      } else {
+        ExpResume rr;
+        rr.pos = pos;
+        rr.flags = (rq.P ? 1u : 0u) | (rq.S ? 2u : 0u);
+        rr.n_out = rq.n_out;
+        resume[r] = rr;
+        legacy_list[atomicAdd(legacy_count, 1u)] = (int32_t)r;
+      }
+    }
+    __syncwarp();
+  }
+  if (T.warp_ns && lane == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    T.warp_ns[blockIdx.x * kExpWarps + (threadIdx.x >> 5)] = t1 - warp_t0;
+  }
 }
 
 // MODE: 0 SentencePiece BPE / tiktoken, 1 HF byte-level BPE (regex pre-tokenizer), 2 SentencePiece Unigram
@@ -2294,11 +2366,6 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     unsigned int* __restrict__ task_counter, int32_t* __restrict__ defer_list,
     unsigned int* __restrict__ defer_count, uint8_t* memo_table, uint32_t memo_mask) {
   constexpr bool HF = MODE == 1;
-  // the express path (express_step): SentencePiece BPE throughput kernels; per model: split before every U+2581,
-  // runs of spaces collapse, text normalised (not byte mode)
-  constexpr bool EXPRESS = MODE == 0 && !LONG && !WARM;
-  const bool express_model = EXPRESS && T.express && T.split_mode == 1 && T.remove_extra_ws && !T.byte_mode;
-  uint32_t exp_skip = 0, exp_fail = 0;   // windows to leave to the buffer path after a step that did not apply
   const MemoRef memo{memo_table, memo_mask};
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = typename std::conditional<MODE == 2, WarpSmemUniT<SMALL>, WarpSmemT<SMALL>>::type;
@@ -2318,6 +2385,9 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     if constexpr (LONG) {
       if (r >= *defer_count) break;
       r = (unsigned)defer_list[r];
+    } else if (T.work_list) {   // the requests the express kernel handed over
+      if (r >= *T.work_count) break;
+      r = (unsigned)T.work_list[r];
     } else {
       if (r >= (unsigned)n_req) break;
     }
@@ -2367,47 +2437,25 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
         rs.n_out += T.n_suffix;
       }
     } else if (rs.len > 0) {
-      if (T.add_dummy_prefix) {
+      bool lead_space = T.add_dummy_prefix;
+      uint32_t pos0 = 0;
+      if constexpr (MODE == 0) {
+        if (T.resume) {   // taken over from the express kernel: its ids are in the row, a pending U+2581 leads the next word
+          const ExpResume rr = reinterpret_cast<const ExpResume*>(T.resume)[r];
+          pos0 = rr.pos;
+          rs.n_out = rr.n_out;
+          lead_space = (rr.flags & 1u) != 0;
+          rs.prev_space = (rr.flags & 2u) != 0;
+        }
+      }
+      if (lead_space) {
         if (lane == 0) { sm.nbuf[0] = 0xE2; sm.nbuf[1] = 0x96; sm.nbuf[2] = 0x81; sm.wstart[0] = 0; }
         rs.nlen = 3;
         rs.nw = 1;
       }
       __syncwarp();
       uint32_t carry_skip = 0;
-      for (uint32_t pos = 0; pos < rs.len;) {
-        // EXPRESS: force_drain 1 = drain now (the buffer ends in a kept space: what is left is the boundary state),
-        // 2 = drain everything (the next source byte is a space: every buffered word is complete)
-        int force_drain = 0;
-        if constexpr (EXPRESS) {
-          if (express_model && carry_skip == 0) {
-            if (exp_skip > 0) {
-              --exp_skip;
-            } else {
-              const int nl = rs.nlen;
-              const bool tail_sp = nl >= 3 && sm.nbuf[nl - 3] == 0xE2 && sm.nbuf[nl - 2] == 0x96 && sm.nbuf[nl - 1] == 0x81;
-              if (nl == 0 || (nl == 3 && tail_sp)) {
-                // boundary state: nbuf empty, or exactly the U+2581 that leads the next word
-                bool failed;
-                const uint32_t reached = express_run<SMALL, MEMO>(T, sm, rs, pos, lane, memo, &failed);
-                EXP_STAT(0);
-                const bool moved = reached != pos;
-                pos = reached;
-                if (!failed) break;                                   // the text is consumed
-                if (moved) exp_fail = 0;
-                exp_fail = exp_fail >= 31 ? 63 : 2 * exp_fail + 1;   // back off: 1, 3, 7 .. 63 windows on the buffer path
-                exp_skip = exp_fail;
-              } else if (tail_sp) {
-                force_drain = 1;
-              } else if (!rs.prev_space) {
-                const uint32_t c = __ldg(rs.src + pos);
-                if (c == 0x20u || (c < 0x80u && ((T.spacelike_ascii[(c >> 5) & 3] >> (c & 31)) & 1u))) force_drain = 2;
-              }
-            }
-          }
-        }
-        if (force_drain) {
-          EXP_STAT(2);
-        } else
+      for (uint32_t pos = pos0; pos < rs.len;) {
         if (carry_skip == 0 && normalize_fast(T, sm, rs, pos, lane)) {
           pos += kFastWin;
         } else {
@@ -2440,9 +2488,8 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
             if (rs.nlen > kLongFlushAt) long_consume(T, sm, rs, false, lane);
           }
         }
-        if (!in_long && (rs.nlen > drain_at || force_drain)) {
-          drain<SMALL, LONG, MODE, MEMO, WARM>(T, sm, rs, force_drain == 2, lane, memo);
-          if (force_drain && !(rs.nlen == 0 || rs.nlen == 3)) exp_skip = 1;   // not a boundary after all: buffer path
+        if (!in_long && rs.nlen > drain_at) {
+          drain<SMALL, LONG, MODE, MEMO, WARM>(T, sm, rs, false, lane, memo);
           if (rs.nlen > kLongEnterAt) {
             if constexpr (LONG) {
               if (!long_enter(T, sm, rs, lane)) rs.too_long = true;
@@ -2487,7 +2534,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
     if (T.warp_ns && lane == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      T.warp_ns[blockIdx.x] = t1 - warp_t0;
+      T.warp_ns[blockIdx.x] += t1 - warp_t0;   // on top of the express kernel's share, if it ran (the caller zeroes the array)
     }
   }
 }
@@ -2679,19 +2726,62 @@ static int sp_warps_per_sm(const SpDev& dev) {
   return w;
 }
 
-size_t sp_warm_arena_bytes(const SpDev& dev, int n_req) { return (size_t)sp_encode_grid(dev, n_req) * kWarmSliceBytes; }
-
-int sp_encode_grid(const SpDev& dev, int n_req) {
+static int sp_legacy_grid(const SpDev& dev, int n_req) {
   int n_sm = 0, d = 0;
   if (cudaGetDevice(&d) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d) != cudaSuccess)
     return 0;
   const int grid = n_sm * sp_warps_per_sm(dev);
   return grid > n_req ? n_req : grid;
 }
+size_t sp_warm_arena_bytes(const SpDev& dev, int n_req) { return (size_t)sp_legacy_grid(dev, n_req) * kWarmSliceBytes; }
+
+// the express kernel runs in front of the buffer-path kernel for these models (and only with the word memo on)
+static bool sp_express_model(const SpDev& dev) {
+  return dev.express && !dev.unigram && !dev.byte_mode && dev.split_mode == 1 && dev.remove_extra_ws;
+}
+// blocks of kExpWarps warps the express kernel launches for n_req requests (resident blocks x SMs at most)
+static int sp_express_blocks(const SpDev& dev, int n_req) {
+  static int per_sm[2] = {0, 0};
+  const bool small = dev.small_vocab != 0;
+  int n_sm = 0, d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d) != cudaSuccess)
+    return 0;
+  if (per_sm[small] == 0) {
+    int b = 0;
+    const cudaError_t e =
+        small ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sp_express_kernel<true>, kExpWarps * 32,
+                                                              kExpWarps * sizeof(ExpSmemT<true>))
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sp_express_kernel<false>, kExpWarps * 32,
+                                                              kExpWarps * sizeof(ExpSmemT<false>));
+    per_sm[small] = (e == cudaSuccess && b > 0) ? b : 1;
+  }
+  int blocks = n_sm * per_sm[small];
+  if (const char* w = getenv("XLLM_SP_EXPRESS_BLOCKS_PER_SM")) {
+    const int v = atoi(w);
+    if (v > 0 && v < per_sm[small]) blocks = n_sm * v;
+  }
+  const int need = (n_req + kExpWarps - 1) / kExpWarps;
+  return blocks > need ? need : blocks;
+}
+
+int sp_encode_grid(const SpDev& dev, int n_req) {
+  const int legacy = sp_legacy_grid(dev, n_req);
+  const int express = sp_express_model(dev) ? sp_express_blocks(dev, n_req) * kExpWarps : 0;
+  return legacy > express ? legacy : express;
+}
+
+int sp_encode_kernel_launches(const SpDev& dev, bool memo_on, bool warm) {
+  return 2 + ((memo_on && !warm && sp_express_model(dev)) ? 1 : 0);
+}
+
+size_t sp_encode_scratch_bytes(int n_req) {
+  const size_t n = (size_t)(n_req > 0 ? n_req : 0);
+  return ((n * 8 + 15) & ~(size_t)15) + n * sizeof(ExpResume) + 16;
+}
 
 cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
                              int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
-                             int32_t* defer_list, cudaStream_t stream, SpMemo memo, SpLaunchOpts opts) {
+                             void* scratch, cudaStream_t stream, SpMemo memo, SpLaunchOpts opts) {
   if (n_req <= 0) return cudaSuccess;
   DeviceOnce& once = g_sp_once;
   SpDev dev = dev_in;   // the kernel takes the table descriptor by value: the per-launch options ride along
@@ -2699,6 +2789,13 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
   dev.out_cap = opts.out_cap;
   dev.warp_ns = opts.warp_ns;
   dev.warm_arena = nullptr;
+  dev.work_list = nullptr;
+  dev.work_count = nullptr;
+  dev.resume = nullptr;
+  // scratch (sp_encode_scratch_bytes): [deferred requests n][handed-over requests n][resume records n]
+  int32_t* const defer_list = static_cast<int32_t*>(scratch);
+  int32_t* const legacy_list = defer_list + n_req;
+  ExpResume* const resume = reinterpret_cast<ExpResume*>(static_cast<uint8_t*>(scratch) + (((size_t)n_req * 8 + 15) & ~(size_t)15));
   const bool small = dev.small_vocab != 0;
   const size_t smem = small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>);
   cudaError_t e0 = cudaSuccess;
@@ -2735,8 +2832,9 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
       },
       &e0);
   if (e0 != cudaSuccess) return e0;
-  // counters[0]: task counter, [1]: deferred count, [2]: task counter of the long-word pass
-  cudaError_t e = cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), stream);
+  // counters[0]: task counter, [1]: deferred count, [2]: task counter of the long-word pass,
+  // [3]: task counter of the express kernel, [4]: requests it handed over
+  cudaError_t e = cudaMemsetAsync(counters, 0, 5 * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
   int warps_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (warps_per_sm > 27) warps_per_sm = 27;
@@ -2755,6 +2853,21 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
   if (warm) dev.warm_arena = static_cast<uint8_t*>(memo.arena);
   uint8_t* const mt = use_memo ? static_cast<uint8_t*>(memo.table) : nullptr;
   const uint32_t mm = use_memo ? memo.slots - 1 : 0;
+  // the express kernel first; what it cannot finish continues in the buffer-path kernel below (work list + resume records)
+  if (use_memo && !warm && sp_express_model(dev)) {
+    const int blocks = sp_express_blocks(dev, n_req);
+    if (small)
+      sp_express_kernel<true><<<blocks, kExpWarps * 32, kExpWarps * sizeof(ExpSmemT<true>), stream>>>(
+          text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters + 3, legacy_list, counters + 4, resume, mt, mm);
+    else
+      sp_express_kernel<false><<<blocks, kExpWarps * 32, kExpWarps * sizeof(ExpSmemT<false>), stream>>>(
+          text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters + 3, legacy_list, counters + 4, resume, mt, mm);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dev.work_list = legacy_list;
+    dev.work_count = counters + 4;
+    dev.resume = resume;
+  }
 #define XLLM_LAUNCH_PAIR(SMALL_, HF_, MEMO_)                                                                     \
   if (MEMO_ && warm)                                                                                             \
     sp_encode_kernel<SMALL_, false, HF_, MEMO_, MEMO_><<<grid, 32, smem, stream>>>(                              \

@@ -67,6 +67,9 @@ struct SpDev {
   const int32_t* out_cap;
   unsigned long long* warp_ns;   // [grid]: nanoseconds each warp of the throughput kernel spent from start to exit
   uint8_t* warm_arena;           // [grid] slices of sp_warm_slice_bytes(): scratch of the warm-up pre-passes (sp_encode.cu 1b)
+  const int32_t* work_list;      // buffer-path kernel after the express kernel: the requests handed over, their count,
+  const unsigned int* work_count;  // and where each one resumes (ExpResume records, sp_encode.cu)
+  const void* resume;
   uint8_t* long_pool;
   int* long_locks;
   uint32_t long_cap;   // symbols per slot
@@ -108,9 +111,10 @@ uint32_t sp_memo_default_slots();  // XLLM_SP_MEMO_SLOTS (0 = off), default 2^18
 
 // text: all prompts back to back; offsets[n_req + 1] (bytes).  Request r's ids go to
 // ids + r * ids_stride (at most ids_stride of them), n_ids[r] = full count, status[r] = kEnc*.
-// counters: 4 zero-initialisable uint32 in device memory; defer_list: n_req int32 of device scratch (requests
-// that need the long-word pass).  Two launches: the throughput kernel, then the long-word kernel over the
-// deferred requests (a no-op grid when there are none).
+// counters: 8 uint32 in device memory; scratch: sp_encode_scratch_bytes(n_req) of device memory (work lists of the
+// follow-up kernels + resume records).  Launches: the express kernel (models it applies to, memo on), the
+// buffer-path throughput kernel over what is left, the long-word kernel over the deferred requests (no-op grids
+// when there is nothing to do).
 struct SpLaunchOpts {
   // ragged output rows (text pieces of segmented requests, pipeline.cu): ids + out_start[r], capacity out_cap[r]
   const int64_t* out_start = nullptr;
@@ -120,9 +124,11 @@ struct SpLaunchOpts {
   unsigned long long* warp_ns = nullptr;
 };
 int sp_encode_grid(const SpDev& dev, int n_req);   // warps (= blocks) the throughput kernel launches for n_req requests
+int sp_encode_kernel_launches(const SpDev& dev, bool memo_on, bool warm);   // kernels one sp_encode_launch enqueues (2 or 3)
+size_t sp_encode_scratch_bytes(int n_req);          // device scratch one launch over n_req requests needs
 cudaError_t sp_encode_launch(const SpDev& dev, const uint8_t* text, const int64_t* offsets, int n_req, int32_t* ids,
                              int64_t ids_stride, int32_t* n_ids, int32_t* status, unsigned int* counters,
-                             int32_t* defer_list, cudaStream_t stream, SpMemo memo = SpMemo(),
+                             void* scratch, cudaStream_t stream, SpMemo memo = SpMemo(),
                              SpLaunchOpts opts = SpLaunchOpts());
 
 }  // namespace xllm
