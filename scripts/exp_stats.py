@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Express-path counters of the encode kernel on the headline text (needs the diagnostics build:
-scripts/build_stats_lib.sh, XLLM_INGEST_LIB=build/stats/libxllm_ingest_stats.so)."""
+scripts/build_variant.sh stats -DXLLM_EXP_STATS, XLLM_INGEST_LIB=build/stats/libxllm_ingest_stats.so)."""
 import ctypes, json, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1088,7 +1088,7 @@ template <bool SMALL>
 struct ExpSmemT {
   uint32_t S[kMaxSym * 32];
   typename PMOps<SMALL>::T PM[kMaxSym * 32];
-  uint8_t ex[80];
+  uint8_t ex[144];   // {start, end} per word, <= 64 words in 128 bytes (+ the entry a second start / end may spill to)
 };
 // what the buffer-path kernel needs to take a request over where the express kernel stopped
 struct ExpResume {
@@ -1100,34 +1100,35 @@ struct ExpResume {
 template <bool SMALL, bool MEMO, typename SM>
 __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& rs, uint32_t pos, int lane,
                                                 MemoRef memo, bool* failed) {
-  const uint8_t* const src_end = rs.src + rs.len;
+  // 32-bit coordinates: v = byte offset from the aligned word that holds the request's first byte
+  const uint32_t A = (uint32_t)(reinterpret_cast<uintptr_t>(rs.src) & 3u);
+  const uint32_t* const base = reinterpret_cast<const uint32_t*>(rs.src - A);
+  const uint32_t vlen = rs.len + A;                 // end of the text
+  const uint32_t nwords = (vlen + 3u) >> 2;         // aligned words that hold text
   bool P = rs.P;
   bool S = rs.S;
   uint8_t* const ex = sm.ex;
-  auto put = [&](int64_t at, int32_t id) { if (at < rs.cap) rs.out[at] = id; };
+  int32_t* const out = rs.out;
+  const int32_t cap = rs.cap > 0x7fffffffll ? 0x7fffffff : (int32_t)rs.cap;
+  int32_t n_out = (int32_t)rs.n_out;
   const uint32_t lt = (1u << lane) - 1u;
-  auto load_window = [&](uint32_t at) {
-    const uint8_t* a = rs.src + at;
-    const uint32_t* aw = reinterpret_cast<const uint32_t*>(a - (reinterpret_cast<uintptr_t>(a) & 3u)) + lane;
-    return reinterpret_cast<const uint8_t*>(aw) < src_end ? __ldg(aw) : 0x20202020u;
+  auto load_window = [&](uint32_t at) {             // the 32 aligned words from the one that holds byte `at`
+    const uint32_t i = (at >> 2) + (uint32_t)lane;
+    return i < nwords ? __ldg(base + i) : 0x20202020u;
   };
-  uint32_t w = load_window(pos);
+  uint32_t v = pos + A;
+  uint32_t w = load_window(v);
   *failed = false;
   for (;;) {
-    const uint8_t* const a = rs.src + pos;
-    const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3u);
-    const uint8_t* const wbase = a - skip;                         // the window's first (aligned) byte
-    const bool at_end = wbase + kFastWin >= src_end;               // the text ends inside this window
-    if (lane < kPrefetchWindows) {
-      const uint8_t* pf = wbase + (size_t)kFastWin * (kPrefetchFirst + lane);
-      if (pf < src_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-    }
-    if (skip != 0u && lane == 0) {                                 // bytes in front of pos: spaces
+    const uint32_t skip = v & 3u;
+    const uint32_t wb = v - skip;                                  // the window's first (aligned) byte
+    const bool at_end = wb + (uint32_t)kFastWin >= vlen;           // the text ends inside this window
+    if (skip != 0u && lane == 0) {                                 // bytes in front of the position: spaces
       const uint32_t m = (1u << (8u * skip)) - 1u;
       w = (w & ~m) | (0x20202020u & m);
     }
     if (at_end) {                                                  // bytes past the end of the text: spaces
-      const long rem = src_end - (wbase + 4 * lane);
+      const int rem = (int)(vlen - wb) - 4 * lane;
       if (rem < 4) {
         const uint32_t m = rem <= 0 ? 0u : (1u << (8u * (uint32_t)rem)) - 1u;
         w = (w & m) | (0x20202020u & ~m);
@@ -1167,28 +1168,27 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
     }
     const uint32_t st4 = ns4 & ~((ns4 << 1) | prev_ns) & 0xFu;
     const uint32_t en4 = ns4 & ~((ns4 >> 1) | (next_ns << 3)) & 0xFu;
-    const uint32_t b1 = __ballot_sync(kFull, st4 != 0u), b2 = __ballot_sync(kFull, (st4 & (st4 - 1u)) != 0u);
-    const uint32_t inc = (!at_end && (__ballot_sync(kFull, (ns4 & 8u) != 0u) >> 31)) ? 1u : 0u;   // an unfinished word at the end
+    const uint32_t st_two = st4 & (st4 - 1u), en_two = en4 & (en4 - 1u);   // the second start / end of the lane, if any
+    const uint32_t b1 = __ballot_sync(kFull, st4 != 0u), b2 = __ballot_sync(kFull, st_two != 0u);
+    const uint32_t last_ns = __ballot_sync(kFull, (ns4 & 8u) != 0u) >> 31;
     const int nstart = __popc(b1) + __popc(b2);
-    const int nend = nstart - (int)inc;
-    const int take = nend < 32 ? nend : 32;       // complete words this step resolves
+    const int nend = nstart - (int)(at_end ? 0u : last_ns);       // an unfinished word at the end of the window
+    const int take = nend < 32 ? nend : 32;                        // complete words this step resolves
     if (nstart != 0 && take == 0) { EXP_STAT(6); *failed = true; break; }   // one unfinished word fills the window
-    const uint32_t nv = at_end ? (uint32_t)(src_end - wbase) : (uint32_t)kFastWin - 1u;
-    uint32_t cons = nv;                            // window bytes consumed (counted from wbase)
-    int total = 0;
+    uint32_t cons = at_end ? vlen - wb : (uint32_t)kFastWin - 1u;  // window bytes consumed (counted from wb)
     bool S2 = true;
     uint32_t w_next = 0;
     if (take > 0) {
       {
         const uint32_t k0 = __popc(b1 & lt) + __popc(b2 & lt);
-        if (st4) {                                 // at most two starts / two ends in four bytes
-          if (k0 <= 32u) ex[2u * k0] = (uint8_t)(4 * lane + __ffs(st4) - 1);
-          if ((st4 & (st4 - 1u)) && k0 < 32u) ex[2u * k0 + 2u] = (uint8_t)(4 * lane + 31 - __clz(st4));
+        if (st4) {                                 // at most two starts / two ends in four bytes (<= 64 words a window)
+          ex[2u * k0] = (uint8_t)(4 * lane + __ffs(st4) - 1);
+          if (st_two) ex[2u * k0 + 2u] = (uint8_t)(4 * lane + 31 - __clz(st4));
         }
         if (en4) {
           const uint32_t e0 = k0 - (prev_ns & ns4 & 1u);   // words that ended before this lane = started - the one still open
-          if (e0 < 32u) ex[2u * e0 + 1u] = (uint8_t)(4 * lane + __ffs(en4) - 1);
-          if ((en4 & (en4 - 1u)) && e0 + 1u < 32u) ex[2u * e0 + 3u] = (uint8_t)(4 * lane + 31 - __clz(en4));
+          ex[2u * e0 + 1u] = (uint8_t)(4 * lane + __ffs(en4) - 1);
+          if (en_two) ex[2u * e0 + 3u] = (uint8_t)(4 * lane + 31 - __clz(en4));
         }
       }
       __syncwarp();
@@ -1196,7 +1196,7 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
       const uint32_t se = reinterpret_cast<const uint16_t*>(ex)[active ? lane : 0];
       if (take < nstart) cons = ex[2 * take];      // stop in front of the first word not taken
       // the next window's bytes: in flight while this one's words are looked up
-      if (pos + (cons - skip) < rs.len) w_next = load_window(pos + (cons - skip));
+      w_next = load_window(wb + cons);
       const uint32_t s = se & 0xFFu;
       const int n = (int)(se >> 8) - (int)s + 1;
       if (__any_sync(kFull, active && n > kMemoMaxKeyBytes)) { EXP_STAT(7); *failed = true; break; }
@@ -1219,7 +1219,7 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
       key.hi = (hi << 8) | (lo >> 56);
       // --- memo
       bool hit = false;
-      U128 v{0ull, 0ull};
+      U128 val{0ull, 0ull};
       if constexpr (MEMO) {
         if (active) {
           uint32_t slot = memo_slot(key, memo.mask);
@@ -1227,9 +1227,9 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
           for (int way = 0; way < 2; ++way, slot ^= 1u) {
             const uint8_t* e = memo.table + (size_t)slot * 32;
             const U128 k = ld_b128(e);
-            const U128 val = ld_b128(e + 16);
+            val = ld_b128(e + 16);
             if (k.lo == key.lo && k.hi == key.hi) {
-              if (MemoIds<SMALL>::valid(val)) { hit = true; v = val; }
+              hit = MemoIds<SMALL>::valid(val);
               break;
             }
             if ((k.lo | k.hi) == 0) break;
@@ -1260,7 +1260,7 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
           else id[q] = (uint32_t)e;
         }
         if (!hard) {
-          v = MemoIds<SMALL>::pack(k, id);
+          val = MemoIds<SMALL>::pack(k, id);
           if constexpr (MEMO) {
             uint32_t slot = memo_slot(key, memo.mask);
             const U128 zero{0ull, 0ull};
@@ -1268,8 +1268,8 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
             for (int way = 0; way < 2; ++way, slot ^= 1u) {
               uint8_t* e = memo.table + (size_t)slot * 32;
               const U128 old = cas_b128(e, zero, key);
-              if ((old.lo | old.hi) == 0) { st_b128(e + 16, v); break; }   // claimed: publish the ids
-              if (old.lo == key.lo && old.hi == key.hi) break;              // another warp owns this word
+              if ((old.lo | old.hi) == 0) { st_b128(e + 16, val); break; }   // claimed: publish the ids
+              if (old.lo == key.lo && old.hi == key.hi) break;                // another warp owns this word
             }
           }
         }
@@ -1278,39 +1278,46 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
 #ifdef XLLM_EXP_STATS
       { const uint32_t am = __ballot_sync(kFull, active), hm = __ballot_sync(kFull, hit); if (lane == 0) { atomicAdd(&g_exp_stats[9], (unsigned long long)__popc(am)); atomicAdd(&g_exp_stats[10], (unsigned long long)__popc(hm)); if (am & ~hm) atomicAdd(&g_exp_stats[11], 1ull); } }
 #endif
-      // --- ids, in order
-      const int cnt = active ? MemoIds<SMALL>::count(v) : 0;
-      const int incl = warp_incl_scan(cnt, lane);
-      total = __shfl_sync(kFull, incl, 31);
-      const uint32_t c2 = __ballot_sync(kFull, cnt >= 2);
-      const int64_t o = rs.n_out + (incl - cnt);
-      if (cnt >= 1) put(o, (int32_t)MemoIds<SMALL>::id(v, 0));
-      if (c2) {
-        const int maxcnt = (int)__reduce_max_sync(kFull, (uint32_t)cnt);
+      // --- ids, in order: the counts are 3-bit, so three ballots give every lane its offset
+      const int cnt = active ? MemoIds<SMALL>::count(val) : 0;
+      const uint32_t cb0 = __ballot_sync(kFull, cnt & 1), cb1 = __ballot_sync(kFull, cnt & 2), cb2 = __ballot_sync(kFull, cnt & 4);
+      const int total = __popc(cb0) + 2 * __popc(cb1) + 4 * __popc(cb2);
+      const int o = n_out + __popc(cb0 & lt) + 2 * __popc(cb1 & lt) + 4 * __popc(cb2 & lt);
+      if (n_out + total <= cap) {      // the whole step fits the row (always, but for a truncating ids_stride)
+        if (cnt >= 1) out[o] = (int32_t)MemoIds<SMALL>::id(val, 0);
+        if (cb1 | cb2) {
+          if (cnt >= 2) out[o + 1] = (int32_t)MemoIds<SMALL>::id(val, 1);
+          if (cnt >= 3) out[o + 2] = (int32_t)MemoIds<SMALL>::id(val, 2);
+          if (cb2) {
 #pragma unroll
-        for (int q = 1; q < MemoIds<SMALL>::kMax; ++q) {
-          if (q >= maxcnt) break;
-          if (q < cnt) put(o + q, (int32_t)MemoIds<SMALL>::id(v, q));
+            for (int q = 3; q < MemoIds<SMALL>::kMax; ++q)
+              if (q < cnt) out[o + q] = (int32_t)MemoIds<SMALL>::id(val, q);
+          }
         }
+      } else {
+#pragma unroll
+        for (int q = 0; q < MemoIds<SMALL>::kMax; ++q)
+          if (q < cnt && o + q < cap) out[o + q] = (int32_t)MemoIds<SMALL>::id(val, q);
       }
-      rs.n_out += total;
+      n_out += total;
       if (take == nstart) S2 = !((__shfl_sync(kFull, ns4, (cons - 1u) >> 2) >> ((cons - 1u) & 3u)) & 1u);
     } else {
-      if (pos + (cons - skip) < rs.len) w_next = load_window(pos + (cons - skip));
+      w_next = load_window(wb + cons);
     }
     EXP_STAT(1);
     // --- the state a drain would have left: is_prev_space, and the U+2581 a kept space puts in front of the next word
     P = S2 && (take > 0 || P || !S);
     S = S2;
-    pos += cons - skip;
-    if (pos >= rs.len) break;
+    v = wb + cons;
+    if (v >= vlen) break;
     w = w_next;
     __syncwarp();
   }
   rs.P = P;
   rs.S = S;
+  rs.n_out = n_out;
   __syncwarp();
-  return pos;
+  return v - A;
 }
 
 // The express kernel: every request starts here when the model allows it (split_mode 1, remove_extra_whitespaces,
@@ -1319,7 +1326,7 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
 // whitespace state, through legacy_list / resume.  kExpWarps independent warps per block.
 constexpr int kExpWarps = 4;
 #ifndef XLLM_EXP_MIN_BLOCKS
-#define XLLM_EXP_MIN_BLOCKS 10
+#define XLLM_EXP_MIN_BLOCKS 8
 #endif
 template <bool SMALL>
 __global__ void __launch_bounds__(kExpWarps * 32, XLLM_EXP_MIN_BLOCKS) sp_express_kernel(
