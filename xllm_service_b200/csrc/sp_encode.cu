@@ -1082,6 +1082,7 @@ struct ExpReq {
   int64_t n_out;   // ids produced so far (may exceed cap)
   bool P;          // a U+2581 is pending in front of the next word (dummy prefix / kept space)
   bool S;          // the normalizer's is_prev_space
+  bool U;          // the last emitted symbol was unknown (matters with byte_fallback off only)
 };
 // per warp: symbol columns for the words the memo does not know yet + the window's {start, end} pairs
 template <bool SMALL>
@@ -1093,9 +1094,89 @@ struct ExpSmemT {
 // what the buffer-path kernel needs to take a request over where the express kernel stopped
 struct ExpResume {
   uint32_t pos;      // source bytes consumed
-  uint32_t flags;    // bit 0: P, bit 1: S
+  uint32_t flags;    // bit 0: P, bit 1: S, bit 2: U (ExpReq)
   long long n_out;
 };
+
+// A word the lane path does not take — more than 15 bytes, or one whose ids do not fit a memo payload (an unknown
+// symbol, byte fallback, more than 7 / 4 ids) — merged by the whole warp in the flat symbol scratch, as the buffer
+// path's cooperative branch does.  v0 = offset of its first byte.  Finds the word's end (a space / space-like byte or
+// the end of the text), checking that every byte is a simple ASCII byte; false (nothing emitted) when it is not, or
+// when the word has more chars than the scratch holds.  On success *v_end = the offset of the byte after the word.
+template <bool SMALL, typename SM>
+__device__ __noinline__ bool express_long_word(const SpDev& T, SM& sm, const uint32_t* base, uint32_t nwords,
+                                               uint32_t vlen, uint32_t v0, bool lead, int32_t* out, int32_t cap,
+                                               int32_t* n_out_io, bool* prev_unk_io, uint32_t* v_end, int lane) {
+  // --- the end of the word
+  uint32_t end = 0;
+  bool found = false;
+  for (uint32_t wb = v0 & ~3u; !found; wb += (uint32_t)kFastWin) {
+    if (wb - (v0 & ~3u) > (uint32_t)kCoopMaxSym) return false;   // longer than the scratch
+    const uint32_t i = (wb >> 2) + (uint32_t)lane;
+    uint32_t w = i < nwords ? __ldg(base + i) : 0x20202020u;
+    const uint32_t b0 = wb + 4u * lane;                            // offset of the lane's first byte
+    uint32_t sp4 = 0, bad4 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t bk = (w >> (8 * k)) & 0xFFu;
+      const uint32_t at = b0 + k;
+      if (at < v0) continue;                                       // in front of the word
+      if (at >= vlen) { sp4 |= 1u << k; continue; }                // past the end of the text: ends the word
+      if (bk >= 0x80u) { bad4 |= 1u << k; continue; }
+      const bool spl = bk == 0x20u || ((T.spacelike_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u);
+      const bool simple = (T.simple_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u;
+      if (spl && (bk != 0x20u || simple)) sp4 |= 1u << k;
+      else if (!simple) bad4 |= 1u << k;
+    }
+    const uint32_t spm = __ballot_sync(kFull, sp4 != 0u), badm = __ballot_sync(kFull, bad4 != 0u);
+    if (spm) {
+      const int L = __ffs(spm) - 1;
+      const uint32_t sL = __shfl_sync(kFull, sp4, L), bL = __shfl_sync(kFull, bad4, L);
+      const int k = __ffs(sL) - 1;
+      if ((badm & ((1u << L) - 1u)) || (bL & ((1u << k) - 1u))) return false;   // a byte the fast rules do not cover
+      end = wb + 4u * L + k;
+      found = true;
+    } else if (badm) {
+      return false;
+    }
+  }
+  const int nbytes = (int)(end - v0);
+  const int nsym = nbytes + (lead ? 1 : 0);
+  if (nbytes < 1 || nsym > kCoopMaxSym) return false;
+  // --- symbols, merge, ids
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(base) + v0;
+  if (lead && lane == 0) sm.S[0] = T.space_sym;
+  for (int i = lane; i < nbytes; i += 32) sm.S[i + (lead ? 1 : 0)] = __ldg(T.ascii_sym + __ldg(bytes + i));
+  __syncwarp();
+  const int n = coop_merge<SMALL>(T, sm, nsym, lane);
+  int32_t n_out = *n_out_io;
+  bool prev_unk = *prev_unk_io;
+  for (int b = 0; b < n; b += 32) {
+    const int j = b + lane;
+    int32_t tmp[4];
+    bool unk = false;
+    int c = 0;
+    if (j < n) c = sym_ids(T, sm.S[j], tmp, &unk);
+    if (!T.byte_fallback) {   // consecutive unknown symbols give one <unk>
+      const uint32_t um = __ballot_sync(kFull, j < n && unk);
+      const bool prev = lane == 0 ? prev_unk : ((um >> (lane - 1)) & 1u);
+      if (unk && prev) c = 0;
+      const int lastl = (n - b) >= 32 ? 31 : (n - b - 1);
+      prev_unk = (um >> lastl) & 1u;
+    }
+    const int inc = warp_incl_scan(c, lane);
+    int32_t o = n_out + (inc - c);
+    for (int k = 0; k < c; ++k, ++o)
+      if (o < cap) out[o] = tmp[k];
+    n_out += __shfl_sync(kFull, inc, 31);
+  }
+  if (T.byte_fallback) prev_unk = false;
+  *n_out_io = n_out;
+  *prev_unk_io = prev_unk;
+  *v_end = end;
+  __syncwarp();
+  return true;
+}
 
 template <bool SMALL, bool MEMO, typename SM>
 __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& rs, uint32_t pos, int lane,
@@ -1107,6 +1188,7 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
   const uint32_t nwords = (vlen + 3u) >> 2;         // aligned words that hold text
   bool P = rs.P;
   bool S = rs.S;
+  bool U = rs.U;
   uint8_t* const ex = sm.ex;
   int32_t* const out = rs.out;
   const int32_t cap = rs.cap > 0x7fffffffll ? 0x7fffffff : (int32_t)rs.cap;
@@ -1173,12 +1255,11 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
     const uint32_t last_ns = __ballot_sync(kFull, (ns4 & 8u) != 0u) >> 31;
     const int nstart = __popc(b1) + __popc(b2);
     const int nend = nstart - (int)(at_end ? 0u : last_ns);       // an unfinished word at the end of the window
-    const int take = nend < 32 ? nend : 32;                        // complete words this step resolves
-    if (nstart != 0 && take == 0) { EXP_STAT(6); *failed = true; break; }   // one unfinished word fills the window
+    int take = nend < 32 ? nend : 32;                              // complete words this step resolves
     uint32_t cons = at_end ? vlen - wb : (uint32_t)kFastWin - 1u;  // window bytes consumed (counted from wb)
     bool S2 = true;
     uint32_t w_next = 0;
-    if (take > 0) {
+    if (nstart > 0) {
       {
         const uint32_t k0 = __popc(b1 & lt) + __popc(b2 & lt);
         if (st4) {                                 // at most two starts / two ends in four bytes (<= 64 words a window)
@@ -1192,14 +1273,49 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
         }
       }
       __syncwarp();
+      const uint32_t se = reinterpret_cast<const uint16_t*>(ex)[lane < take ? lane : 0];
+      const uint32_t s = se & 0xFFu;
+      const int n = (int)(se >> 8) - (int)s + 1;
+      // the lane path takes words of up to 15 bytes: stop in front of the first longer one
+      const uint32_t long_mask = __ballot_sync(kFull, lane < take && n > kMemoMaxKeyBytes);
+      if (long_mask) take = __ffs(long_mask) - 1;
+      if (take == 0) {
+        // the first word is long, or not finished inside this window
+        const uint32_t s0 = ex[0];
+        if (!long_mask && s0 > skip) {
+          cons = s0;                               // only spaces in front of it: take those, the word starts the next window
+          w_next = load_window(wb + cons);
+        } else {
+          uint32_t v_end = 0;
+          int32_t io_n = n_out;                    // only these copies have their address taken
+          bool io_u = U;
+          const bool done = express_long_word<SMALL>(T, sm, base, nwords, vlen, wb + s0, P || (!S && s0 > skip), out, cap,
+                                                     &io_n, &io_u, &v_end, lane);
+          n_out = io_n;
+          U = io_u;
+          if (!done) {
+            EXP_STAT(7);
+            if (s0 > skip) {                       // hand over at the word, with the spaces in front of it consumed
+              P = P || !S;
+              S = true;
+              v = wb + s0;
+            }
+            *failed = true;
+            break;
+          }
+          EXP_STAT(6);
+          P = false;                               // the byte before v_end is the word's last: nothing pending
+          S = false;
+          v = v_end;
+          if (v >= vlen) break;
+          w = load_window(v);
+          continue;
+        }
+      } else {
       const bool active = lane < take;
-      const uint32_t se = reinterpret_cast<const uint16_t*>(ex)[active ? lane : 0];
       if (take < nstart) cons = ex[2 * take];      // stop in front of the first word not taken
       // the next window's bytes: in flight while this one's words are looked up
       w_next = load_window(wb + cons);
-      const uint32_t s = se & 0xFFu;
-      const int n = (int)(se >> 8) - (int)s + 1;
-      if (__any_sync(kFull, active && n > kMemoMaxKeyBytes)) { EXP_STAT(7); *failed = true; break; }
       // --- the word's bytes from the lanes that hold them
       unsigned long long lo, hi;
       {
@@ -1274,12 +1390,48 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
           }
         }
       }
-      if (__any_sync(kFull, hard)) { EXP_STAT(8); *failed = true; break; }
+      {
+        // a word whose ids do not fit a memo payload: the words in front of it go out now, the word itself through
+        // the cooperative path
+        const uint32_t hard_mask = __ballot_sync(kFull, hard);
+        if (hard_mask) {
+          const int fh = __ffs(hard_mask) - 1;
+          EXP_STAT(8);
+          if (fh == 0) {
+            const uint32_t s0 = ex[0];
+            uint32_t v_end = 0;
+            int32_t io_n = n_out;
+            bool io_u = U;
+            const bool done = express_long_word<SMALL>(T, sm, base, nwords, vlen, wb + s0, P || (!S && s0 > skip), out,
+                                                       cap, &io_n, &io_u, &v_end, lane);
+            n_out = io_n;
+            U = io_u;
+            if (!done) {
+              if (s0 > skip) {
+                P = P || !S;
+                S = true;
+                v = wb + s0;
+              }
+              *failed = true;
+              break;
+            }
+            P = false;
+            S = false;
+            v = v_end;
+            if (v >= vlen) break;
+            w = load_window(v);
+            continue;
+          }
+          take = fh;
+          cons = ex[2 * take];
+          w_next = load_window(wb + cons);
+        }
+      }
 #ifdef XLLM_EXP_STATS
       { const uint32_t am = __ballot_sync(kFull, active), hm = __ballot_sync(kFull, hit); if (lane == 0) { atomicAdd(&g_exp_stats[9], (unsigned long long)__popc(am)); atomicAdd(&g_exp_stats[10], (unsigned long long)__popc(hm)); if (am & ~hm) atomicAdd(&g_exp_stats[11], 1ull); } }
 #endif
       // --- ids, in order: the counts are 3-bit, so three ballots give every lane its offset
-      const int cnt = active ? MemoIds<SMALL>::count(val) : 0;
+      const int cnt = lane < take ? MemoIds<SMALL>::count(val) : 0;
       const uint32_t cb0 = __ballot_sync(kFull, cnt & 1), cb1 = __ballot_sync(kFull, cnt & 2), cb2 = __ballot_sync(kFull, cnt & 4);
       const int total = __popc(cb0) + 2 * __popc(cb1) + 4 * __popc(cb2);
       const int o = n_out + __popc(cb0 & lt) + 2 * __popc(cb1 & lt) + 4 * __popc(cb2 & lt);
@@ -1300,7 +1452,9 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
           if (q < cnt && o + q < cap) out[o + q] = (int32_t)MemoIds<SMALL>::id(val, q);
       }
       n_out += total;
+      U = false;
       if (take == nstart) S2 = !((__shfl_sync(kFull, ns4, (cons - 1u) >> 2) >> ((cons - 1u) & 3u)) & 1u);
+      }
     } else {
       w_next = load_window(wb + cons);
     }
@@ -1315,6 +1469,7 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
   }
   rs.P = P;
   rs.S = S;
+  rs.U = U;
   rs.n_out = n_out;
   __syncwarp();
   return v - A;
@@ -1355,9 +1510,13 @@ __global__ void __launch_bounds__(kExpWarps * 32, XLLM_EXP_MIN_BLOCKS) sp_expres
     rq.n_out = 0;
     rq.P = T.add_dummy_prefix != 0;
     rq.S = true;   // is_prev_space starts true under remove_extra_whitespaces
+    rq.U = false;
     bool failed = false;
     uint32_t pos = 0;
     if (rq.len > 0) pos = express_run<SMALL, true>(T, sm, rq, 0u, lane, memo, &failed);
+#ifdef XLLM_EXP_STATS
+    if (lane == 0) { atomicAdd(&g_exp_stats[12], (unsigned long long)pos); atomicAdd(&g_exp_stats[13], (unsigned long long)rq.len); atomicAdd(&g_exp_stats[14], failed ? 1ull : 0ull); }
+#endif
     if (lane == 0) {
       if (!failed) {
         n_ids[r] = (int32_t)rq.n_out;
@@ -1365,7 +1524,7 @@ __global__ void __launch_bounds__(kExpWarps * 32, XLLM_EXP_MIN_BLOCKS) sp_expres
       } else {
         ExpResume rr;
         rr.pos = pos;
-        rr.flags = (rq.P ? 1u : 0u) | (rq.S ? 2u : 0u);
+        rr.flags = (rq.P ? 1u : 0u) | (rq.S ? 2u : 0u) | (rq.U ? 4u : 0u);
         rr.n_out = rq.n_out;
         resume[r] = rr;
         legacy_list[atomicAdd(legacy_count, 1u)] = (int32_t)r;
@@ -2453,6 +2612,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
           rs.n_out = rr.n_out;
           lead_space = (rr.flags & 1u) != 0;
           rs.prev_space = (rr.flags & 2u) != 0;
+          rs.prev_unk = (rr.flags & 4u) != 0;
         }
       }
       if (lead_space) {
