@@ -620,11 +620,63 @@ __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, in
   return alive;
 }
 
+// Cooperative merge of a word of n <= 64 symbols held flat in S[0..n), entirely in registers: lane l owns positions
+// l and l + 32 (symbol + the state of the pair that starts there), the alive set is a 64-bit mask every lane holds.
+// Per merge: two warp reductions find the best pair (priority, then leftmost), three shuffles bring the merged
+// symbol and the two neighbours, and the two new pairs are looked up by their owner lanes at the same time.
+// Nothing moves; the survivors are compacted into S[0..ret) at the end.  Same order as coop_merge / lane_merge.
+template <bool SMALL>
+__device__ __noinline__ int coop_merge64(const SpDev& T, uint32_t* S, int n, int lane) {
+  const int p0 = lane, p1 = lane + 32;
+  uint32_t sym0 = p0 < n ? S[p0] : kSymUnknownFlag, sym1 = p1 < n ? S[p1] : kSymUnknownFlag;
+  const uint32_t nx0 = p0 + 1 < n ? S[p0 + 1] : kSymUnknownFlag, nx1 = p1 + 1 < n ? S[p1 + 1] : kSymUnknownFlag;
+  uint2 pm0 = make_uint2(kNoPrio, 0), pm1 = make_uint2(kNoPrio, 0);
+  {
+    const PairProbe a = pair_probe_begin(T, sym0, nx0), b = pair_probe_begin(T, sym1, nx1);   // both in flight
+    if (p0 + 1 < n) pm0 = pair_probe_finish(T, sym0, nx0, a);
+    if (p1 + 1 < n) pm1 = pair_probe_finish(T, sym1, nx1, b);
+  }
+  unsigned long long alive = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+  for (;;) {
+    const uint32_t best_prio = __reduce_min_sync(kFull, pm0.x < pm1.x ? pm0.x : pm1.x);
+    if (best_prio == kNoPrio) break;
+    const uint32_t mine = pm0.x == best_prio ? (uint32_t)p0 : (pm1.x == best_prio ? (uint32_t)p1 : 64u);
+    const int bj = (int)__reduce_min_sync(kFull, mine);                 // leftmost pair of the best priority
+    const unsigned long long above = alive & ~((2ull << bj) - 1ull);   // bj < 63 here: a pair has a right half
+    const int rj = __ffsll((long long)above) - 1;                        // its right half: removed
+    alive &= ~(1ull << rj);
+    const unsigned long long above2 = above & ~(1ull << rj);
+    const unsigned long long below = alive & ((1ull << bj) - 1ull);
+    const int nr = above2 ? __ffsll((long long)above2) - 1 : -1;       // next survivor to the right
+    const int pj = below ? 63 - __clzll((long long)below) : -1;         // previous survivor
+    const uint32_t merged = __shfl_sync(kFull, bj < 32 ? pm0.y : pm1.y, bj & 31);
+    const uint32_t sym_nr = __shfl_sync(kFull, (nr & 32) ? sym1 : sym0, nr & 31);
+    const uint32_t sym_pj = __shfl_sync(kFull, (pj & 32) ? sym1 : sym0, pj & 31);
+    if (lane == (bj & 31)) {
+      const uint2 v = nr >= 0 ? pair_lookup(T, merged, sym_nr) : make_uint2(kNoPrio, 0);
+      if (bj < 32) { sym0 = merged; pm0 = v; } else { sym1 = merged; pm1 = v; }
+    }
+    if (lane == (rj & 31)) {                                             // the removed position offers no pair any more
+      if (rj < 32) pm0 = make_uint2(kNoPrio, 0); else pm1 = make_uint2(kNoPrio, 0);
+    }
+    if (pj >= 0 && lane == (pj & 31)) {
+      const uint2 v = pair_lookup(T, sym_pj, merged);
+      if (pj < 32) pm0 = v; else pm1 = v;
+    }
+  }
+  __syncwarp();
+  if ((alive >> p0) & 1ull) S[__popcll(alive & ((1ull << p0) - 1ull))] = sym0;
+  if (p1 < 64 && ((alive >> p1) & 1ull)) S[__popcll(alive & ((1ull << p1) - 1ull))] = sym1;
+  __syncwarp();
+  return __popcll(alive);
+}
+
 // Cooperative path: the whole warp merges one word of n (33..1024) chars held flat in S[0..n).
 // Returns the final symbol count; S[0..ret) are the final symbols in order.
 template <bool SMALL, typename SM>
 __device__ int coop_merge(const SpDev& T, SM& sm, int n, int lane) {
   using P = PMOps<SMALL>;
+  if (n <= 64) return coop_merge64<SMALL>(T, sm.S, n, lane);
   for (int j = lane; j < n; j += 32)
     sm.PM[j] = j + 1 < n ? P::pack(pair_lookup(T, sm.S[j], sm.S[j + 1])) : P::none();
   __syncwarp();
@@ -655,12 +707,13 @@ __device__ int coop_merge(const SpDev& T, SM& sm, int n, int lane) {
       __syncwarp();
     }
     --n;
+    // the two pairs the merge created, looked up by two lanes at the same time
     if (lane == 0) {
       sm.S[bj] = merged;
       sm.PM[bj] = bj + 1 < n ? P::pack(pair_lookup(T, merged, sm.S[bj + 1])) : P::none();
+    } else if (lane == 1 && bj > 0) {
+      sm.PM[bj - 1] = P::pack(pair_lookup(T, sm.S[bj - 1], merged));
     }
-    __syncwarp();
-    if (lane == 1 && bj > 0) sm.PM[bj - 1] = P::pack(pair_lookup(T, sm.S[bj - 1], sm.S[bj]));
     __syncwarp();
   }
   return n;
