@@ -43,6 +43,7 @@ namespace {
 
 constexpr int kNBuf = 2048;        // normalized-text staging buffer per warp (bytes)
 constexpr int kFastWin = 128;      // source bytes per fast-path step (4 per lane)
+constexpr int kExpWin = 256;       // source bytes per express step (8 per lane)
 constexpr int kPrefetchFirst = 2;  // fast path: prefetch windows pos + 2 .. pos + 2 + kPrefetchWindows - 1 into L2
 constexpr int kPrefetchWindows = 2;
 constexpr int kLongEnterAt = 1024;   // a kept tail (one incomplete word) longer than this switches to long mode
@@ -1142,7 +1143,7 @@ template <bool SMALL>
 struct ExpSmemT {
   uint32_t S[kMaxSym * 32];
   typename PMOps<SMALL>::T PM[kMaxSym * 32];
-  uint8_t ex[144];   // {start, end} per word, <= 64 words in 128 bytes (+ the entry a second start / end may spill to)
+  uint8_t ex[272];   // {start, end} per word, <= 128 words in 256 bytes
 };
 // what the buffer-path kernel needs to take a request over where the express kernel stopped
 struct ExpResume {
@@ -1234,11 +1235,13 @@ __device__ __noinline__ bool express_long_word(const SpDev& T, SM& sm, const uin
 template <bool SMALL, bool MEMO, typename SM>
 __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& rs, uint32_t pos, int lane,
                                                 MemoRef memo, bool* failed) {
-  // 32-bit coordinates: v = byte offset from the aligned word that holds the request's first byte
-  const uint32_t A = (uint32_t)(reinterpret_cast<uintptr_t>(rs.src) & 3u);
+  // 32-bit coordinates: v = byte offset from the 8-byte-aligned address at or below the request's first byte
+  const uint32_t A = (uint32_t)(reinterpret_cast<uintptr_t>(rs.src) & 7u);
   const uint32_t* const base = reinterpret_cast<const uint32_t*>(rs.src - A);
+  const uint2* const base8 = reinterpret_cast<const uint2*>(rs.src - A);
   const uint32_t vlen = rs.len + A;                 // end of the text
-  const uint32_t nwords = (vlen + 3u) >> 2;         // aligned words that hold text
+  const uint32_t nwords = (vlen + 3u) >> 2;         // aligned 4-byte words that hold text (express_long_word)
+  const uint32_t nquads = (vlen + 7u) >> 3;         // aligned 8-byte units that hold text
   bool P = rs.P;
   bool S = rs.S;
   bool U = rs.U;
@@ -1247,83 +1250,86 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
   const int32_t cap = rs.cap > 0x7fffffffll ? 0x7fffffff : (int32_t)rs.cap;
   int32_t n_out = (int32_t)rs.n_out;
   const uint32_t lt = (1u << lane) - 1u;
-  auto load_window = [&](uint32_t at) {             // the 32 aligned words from the one that holds byte `at`
-    const uint32_t i = (at >> 2) + (uint32_t)lane;
-    return i < nwords ? __ldg(base + i) : 0x20202020u;
+  auto load_window = [&](uint32_t at) {             // the 32 aligned 8-byte units from the one that holds byte `at`
+    const uint32_t i = (at >> 3) + (uint32_t)lane;
+    return i < nquads ? __ldg(base8 + i) : make_uint2(0x20202020u, 0x20202020u);
   };
   uint32_t v = pos + A;
-  uint32_t w = load_window(v);
+  uint2 w = load_window(v);
   *failed = false;
   for (;;) {
-    const uint32_t skip = v & 3u;
+    const uint32_t skip = v & 7u;
     const uint32_t wb = v - skip;                                  // the window's first (aligned) byte
-    const bool at_end = wb + (uint32_t)kFastWin >= vlen;           // the text ends inside this window
+    const bool at_end = wb + (uint32_t)kExpWin >= vlen;            // the text ends inside this window
     if (skip != 0u && lane == 0) {                                 // bytes in front of the position: spaces
-      const uint32_t m = (1u << (8u * skip)) - 1u;
-      w = (w & ~m) | (0x20202020u & m);
+      const unsigned long long m = (1ull << (8u * skip)) - 1ull;
+      const unsigned long long q = (((unsigned long long)w.y << 32) | w.x);
+      const unsigned long long r = (q & ~m) | (0x2020202020202020ull & m);
+      w = make_uint2((uint32_t)r, (uint32_t)(r >> 32));
     }
     if (at_end) {                                                  // bytes past the end of the text: spaces
-      const int rem = (int)(vlen - wb) - 4 * lane;
-      if (rem < 4) {
-        const uint32_t m = rem <= 0 ? 0u : (1u << (8u * (uint32_t)rem)) - 1u;
-        w = (w & m) | (0x20202020u & ~m);
+      const int rem = (int)(vlen - wb) - 8 * lane;
+      if (rem < 8) {
+        const unsigned long long m = rem <= 0 ? 0ull : (1ull << (8u * (uint32_t)rem)) - 1ull;
+        const unsigned long long q = (((unsigned long long)w.y << 32) | w.x);
+        const unsigned long long r = (q & m) | (0x2020202020202020ull & ~m);
+        w = make_uint2((uint32_t)r, (uint32_t)(r >> 32));
       }
     }
     {
       // every byte a simple ASCII byte (then it is its own unit, given an ASCII successor) or a space-like one
-      bool ok = (w & 0x80808080u) == 0u;
+      bool ok = ((w.x | w.y) & 0x80808080u) == 0u;
       bool fast_ok = false;
       if (T.printable_simple)
-        fast_ok = ((((w | 0x80808080u) - 0x20202020u) & 0x80808080u) == 0x80808080u) &&  // every byte >= 0x20
-                  (((w + 0x01010101u) & 0x80808080u) == 0u);                               // every byte <= 0x7E
+        fast_ok = (((((w.x | 0x80808080u) - 0x20202020u) & ((w.y | 0x80808080u) - 0x20202020u)) & 0x80808080u) ==
+                   0x80808080u) &&                                                              // every byte >= 0x20
+                  ((((w.x + 0x01010101u) | (w.y + 0x01010101u)) & 0x80808080u) == 0u);          // every byte <= 0x7E
       if (!__all_sync(kFull, ok && fast_ok)) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t bk = (w >> (8 * k)) & 0xFFu;
+        for (int k = 0; k < 8; ++k) {
+          uint32_t& half = k < 4 ? w.x : w.y;
+          const uint32_t bk = (half >> (8 * (k & 3))) & 0xFFu;
           const bool spl = (T.spacelike_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u;
           ok = ok && (spl || ((T.simple_ascii[(bk >> 5) & 3] >> (bk & 31)) & 1u));
-          if (spl) w = (w & ~(0xFFu << (8 * k))) | (0x20u << (8 * k));
+          if (spl) half = (half & ~(0xFFu << (8 * (k & 3)))) | (0x20u << (8 * (k & 3)));
         }
         if (!__all_sync(kFull, ok)) { EXP_STAT(4); *failed = true; break; }
       }
     }
-    // non-space bytes of the lane's word; word starts / ends from the two neighbouring bytes
-    uint32_t ns4;
+    // non-space bytes of the lane's 8 bytes; word starts / ends from the two neighbouring bytes
+    uint32_t ns8;
     {
-      const uint32_t x = w ^ 0x20202020u;
-      const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);  // 0x80 in every zero byte of x
-      ns4 = ~(((z >> 7) * 0x01020408u) >> 24) & 0xFu;
+      const uint32_t x0 = w.x ^ 0x20202020u, x1 = w.y ^ 0x20202020u;
+      const uint32_t z0 = ~(((x0 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x0 | 0x7F7F7F7Fu);  // 0x80 in every zero byte
+      const uint32_t z1 = ~(((x1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x1 | 0x7F7F7F7Fu);
+      const uint32_t sp8 = ((((z0 >> 7) * 0x01020408u) >> 24) & 0xFu) | ((((z1 >> 7) * 0x01020408u) >> 20) & 0xF0u);
+      ns8 = ~sp8 & 0xFFu;
     }
-    uint32_t prev_ns = (__shfl_up_sync(kFull, ns4, 1) >> 3) & 1u;
-    uint32_t next_ns = __shfl_down_sync(kFull, ns4, 1) & 1u;
+    uint32_t prev_ns = (__shfl_up_sync(kFull, ns8, 1) >> 7) & 1u;
+    uint32_t next_ns = __shfl_down_sync(kFull, ns8, 1) & 1u;
     if (lane == 0) prev_ns = 0u;
     if (lane == 31) next_ns = at_end ? 0u : 1u;                    // unknown successor: the word is not complete
     if (!P && !S) {                                                // would continue a word that is not in the buffer
-      if ((__shfl_sync(kFull, ns4, 0) >> skip) & 1u) { EXP_STAT(5); *failed = true; break; }
+      if ((__shfl_sync(kFull, ns8, 0) >> skip) & 1u) { EXP_STAT(5); *failed = true; break; }
     }
-    const uint32_t st4 = ns4 & ~((ns4 << 1) | prev_ns) & 0xFu;
-    const uint32_t en4 = ns4 & ~((ns4 >> 1) | (next_ns << 3)) & 0xFu;
-    const uint32_t st_two = st4 & (st4 - 1u), en_two = en4 & (en4 - 1u);   // the second start / end of the lane, if any
-    const uint32_t b1 = __ballot_sync(kFull, st4 != 0u), b2 = __ballot_sync(kFull, st_two != 0u);
-    const uint32_t last_ns = __ballot_sync(kFull, (ns4 & 8u) != 0u) >> 31;
-    const int nstart = __popc(b1) + __popc(b2);
+    const uint32_t st8 = ns8 & ~((ns8 << 1) | prev_ns) & 0xFFu;
+    const uint32_t en8 = ns8 & ~((ns8 >> 1) | (next_ns << 7)) & 0xFFu;
+    // starts per lane: 0..4 (three bits) -> three ballots give every lane the index of its first start
+    const uint32_t cs = __popc(st8);
+    const uint32_t b0 = __ballot_sync(kFull, cs & 1u), b1 = __ballot_sync(kFull, cs & 2u), b2 = __ballot_sync(kFull, cs & 4u);
+    const uint32_t last_ns = __ballot_sync(kFull, (ns8 & 0x80u) != 0u) >> 31;
+    const int nstart = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     const int nend = nstart - (int)(at_end ? 0u : last_ns);       // an unfinished word at the end of the window
     int take = nend < 32 ? nend : 32;                              // complete words this step resolves
-    uint32_t cons = at_end ? vlen - wb : (uint32_t)kFastWin - 1u;  // window bytes consumed (counted from wb)
+    uint32_t cons = at_end ? vlen - wb : (uint32_t)kExpWin - 1u;   // window bytes consumed (counted from wb)
     bool S2 = true;
-    uint32_t w_next = 0;
+    uint2 w_next = make_uint2(0u, 0u);
     if (nstart > 0) {
       {
-        const uint32_t k0 = __popc(b1 & lt) + __popc(b2 & lt);
-        if (st4) {                                 // at most two starts / two ends in four bytes (<= 64 words a window)
-          ex[2u * k0] = (uint8_t)(4 * lane + __ffs(st4) - 1);
-          if (st_two) ex[2u * k0 + 2u] = (uint8_t)(4 * lane + 31 - __clz(st4));
-        }
-        if (en4) {
-          const uint32_t e0 = k0 - (prev_ns & ns4 & 1u);   // words that ended before this lane = started - the one still open
-          ex[2u * e0 + 1u] = (uint8_t)(4 * lane + __ffs(en4) - 1);
-          if (en_two) ex[2u * e0 + 3u] = (uint8_t)(4 * lane + 31 - __clz(en4));
-        }
+        uint32_t k = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+        uint32_t e = k - (prev_ns & ns8 & 1u);     // words that ended before this lane = started - the one still open
+        for (uint32_t m = st8; m; m &= m - 1u, ++k) ex[2u * k] = (uint8_t)(8 * lane + __ffs(m) - 1);
+        for (uint32_t m = en8; m; m &= m - 1u, ++e) ex[2u * e + 1u] = (uint8_t)(8 * lane + __ffs(m) - 1);
       }
       __syncwarp();
       const uint32_t se = reinterpret_cast<const uint16_t*>(ex)[lane < take ? lane : 0];
@@ -1369,14 +1375,17 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
       if (take < nstart) cons = ex[2 * take];      // stop in front of the first word not taken
       // the next window's bytes: in flight while this one's words are looked up
       w_next = load_window(wb + cons);
-      // --- the word's bytes from the lanes that hold them
+      // --- the word's bytes from the lanes that hold them: 4-byte pieces j .. j + 4 of the window, two per lane
       unsigned long long lo, hi;
       {
-        const uint32_t j0 = s >> 2, bsh = (s & 3u) * 8u;
+        const uint32_t j = s >> 2, L0 = j >> 1, bsh = (s & 3u) * 8u;
+        const bool odd = (j & 1u) != 0u;
         const bool wide = __any_sync(kFull, active && (s & 3u) + (uint32_t)n > 12u);
-        const uint32_t t0 = __shfl_sync(kFull, w, j0), t1 = __shfl_sync(kFull, w, j0 + 1), t2 = __shfl_sync(kFull, w, j0 + 2);
-        uint32_t t3 = 0, t4 = 0;
-        if (wide) { t3 = __shfl_sync(kFull, w, j0 + 3); t4 = __shfl_sync(kFull, w, j0 + 4); }
+        const uint32_t p0 = __shfl_sync(kFull, w.x, L0), p1 = __shfl_sync(kFull, w.y, L0);
+        const uint32_t p2 = __shfl_sync(kFull, w.x, L0 + 1), p3 = __shfl_sync(kFull, w.y, L0 + 1);
+        uint32_t p4 = 0, p5 = 0;
+        if (wide) { p4 = __shfl_sync(kFull, w.x, L0 + 2); p5 = __shfl_sync(kFull, w.y, L0 + 2); }
+        const uint32_t t0 = odd ? p1 : p0, t1 = odd ? p2 : p1, t2 = odd ? p3 : p2, t3 = odd ? p4 : p3, t4 = odd ? p5 : p4;
         lo = (unsigned long long)__funnelshift_r(t0, t1, bsh) | ((unsigned long long)__funnelshift_r(t1, t2, bsh) << 32);
         hi = (unsigned long long)__funnelshift_r(t2, t3, bsh) | ((unsigned long long)__funnelshift_r(t3, t4, bsh) << 32);
         if (n < 8) { lo &= (1ull << (8 * n)) - 1ull; hi = 0ull; }
@@ -1506,7 +1515,7 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
       }
       n_out += total;
       U = false;
-      if (take == nstart) S2 = !((__shfl_sync(kFull, ns4, (cons - 1u) >> 2) >> ((cons - 1u) & 3u)) & 1u);
+      if (take == nstart) S2 = !((__shfl_sync(kFull, ns8, (cons - 1u) >> 3) >> ((cons - 1u) & 7u)) & 1u);
       }
     } else {
       w_next = load_window(wb + cons);
