@@ -105,7 +105,33 @@ struct FastSmem {
   uint4 keys[kRowsPerWarp * kKeyRowU4];         // 4.5 KB
   uint8_t* row_key[kRowsPerWarp];               // key base pointer of each row
   int32_t row_nb[kRowsPerWarp];                 // blocks in each row
+  unsigned long long bar[STAGES];               // BULK: one mbarrier per stage (32 arrivals + the copies' bytes)
 };
+
+// ---- bulk-copy staging (XLLM_XXH3_BULK=1): every lane moves its own row's 128-byte quarter with one
+// cp.async.bulk (the async proxy's copy engine instead of eight 16-byte LDGSTS issued by the warp); completion is
+// counted in bytes on the stage's mbarrier
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared.b64 st, [%0]; }" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect(unsigned long long* b, unsigned bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared.b64 st, [%0], %1; }" ::"r"(smem_u32(b)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile(
+      "{ .reg .pred p;\n"
+      "XLLM_MBAR_WAIT_%=: mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
+      "@!p bra XLLM_MBAR_WAIT_%=; }"
+      ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
 
 __device__ __forceinline__ uint4 lds128(const uint4* p) {
   uint4 v;
@@ -167,7 +193,7 @@ __device__ __forceinline__ void finish_block(uint64_t (&acc)[8], const Xxh3Const
   hi = xxh3_avalanche(rh);
 }
 
-template <int STAGES>
+template <int STAGES, bool BULK = false>
 __global__ void __launch_bounds__(32) xxh3_chain128_kernel(const int32_t* __restrict__ tokens,
                                                            const int64_t* __restrict__ tok_start,
                                                            const int32_t* __restrict__ n_tok,
@@ -181,6 +207,16 @@ __global__ void __launch_bounds__(32) xxh3_chain128_kernel(const int32_t* __rest
   const int n_tasks = (n_req + kRowsPerWarp - 1) / kRowsPerWarp;
   const int piece = lane & 7;   // which 16 B of a row's 128-byte quarter this lane copies
   const int rsub = lane >> 3;   // copies cover 4 rows per instruction: row = 4 * it + rsub
+  // BULK: stage / phase of the next unit to issue and to consume (issued == consumed at every task boundary)
+  int b_islot = 0, b_cslot = 0;
+  unsigned b_ipar = 0, b_cpar = 0;
+  if constexpr (BULK) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) mbar_init(&sm.bar[i], 32);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
 
   for (;;) {
     unsigned int task = 0;
@@ -215,6 +251,26 @@ __global__ void __launch_bounds__(32) xxh3_chain128_kernel(const int32_t* __rest
     // Issue the copies of pipeline unit u = 4 * b + qtr into slot u % STAGES.
     auto issue = [&](int u, int slot) {
       const int b = u >> 2;
+      if constexpr (BULK) {
+        if (b < max_nb) {
+          // lane == row: one 128-byte bulk copy when the row is 16-byte aligned, else the lane copies its quarter itself
+          const int32_t* src = my_tok + b * kBlockTokens + (u & 3) * 32;
+          uint4* dst = sm.stage[b_islot] + lane * kQRowU4;
+          if (b >= my_nb) {
+            mbar_arrive(&sm.bar[b_islot]);
+          } else if ((reinterpret_cast<uintptr_t>(my_tok) & 15u) == 0) {
+            mbar_arrive_expect(&sm.bar[b_islot], 128u);
+            bulk_g2s(dst, src, 128u, &sm.bar[b_islot]);
+          } else {
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) d32[i] = (uint32_t)__ldg(src + i);
+            mbar_arrive(&sm.bar[b_islot]);
+          }
+          if (++b_islot == STAGES) { b_islot = 0; b_ipar ^= 1u; }
+        }
+        return;
+      }
       if (b < max_nb) {
         uint4* st = sm.stage[slot] + rsub * kQRowU4 + piece;
         const int tok_off = b * kBlockTokens + (u & 3) * 32;
@@ -253,7 +309,13 @@ __global__ void __launch_bounds__(32) xxh3_chain128_kernel(const int32_t* __rest
   do {                                                                        \
     issue(4 * b + (QTR) + STAGES - 1, issue_slot);                            \
     issue_slot = (issue_slot + 1 == STAGES) ? 0 : issue_slot + 1;             \
-    cp_async_wait<STAGES - 1>();                                              \
+    if constexpr (BULK) {                                                     \
+      mbar_wait(&sm.bar[b_cslot], b_cpar);                                    \
+      slot = b_cslot;                                                         \
+      if (++b_cslot == STAGES) { b_cslot = 0; b_cpar ^= 1u; }                 \
+    } else {                                                                  \
+      cp_async_wait<STAGES - 1>();                                            \
+    }                                                                         \
     __syncwarp();                                                             \
     if (active) {                                                             \
       const uint4* row = sm.stage[slot] + lane * kQRowU4;                     \
@@ -537,6 +599,9 @@ cudaError_t xxh3_chain_launch(const int32_t* tokens, const int64_t* tok_start, c
     cudaError_t e0 = cudaSuccess;
     const int n_sm = once.get(
         [&] {
+          cudaError_t r = cudaFuncSetAttribute(xxh3_chain128_kernel<kFastStages, true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (r != cudaSuccess) return r;
           return cudaFuncSetAttribute(xxh3_chain128_kernel<kFastStages>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         },
@@ -551,8 +616,13 @@ cudaError_t xxh3_chain_launch(const int32_t* tokens, const int64_t* tok_start, c
     const int max_warps = n_sm * warps_per_sm;
     const int rounds = (n_tasks + max_warps - 1) / max_warps;
     int grid = (n_tasks + rounds - 1) / rounds;
-    xxh3_chain128_kernel<kFastStages><<<grid, 32, smem, stream>>>(tokens, tok_start, n_tok, keys, key_start, n_req,
-                                                                  consts, task_counter);
+    static const bool bulk = [] { const char* w = getenv("XLLM_XXH3_BULK"); return w && atoi(w) != 0; }();
+    if (bulk)
+      xxh3_chain128_kernel<kFastStages, true><<<grid, 32, smem, stream>>>(tokens, tok_start, n_tok, keys, key_start,
+                                                                          n_req, consts, task_counter);
+    else
+      xxh3_chain128_kernel<kFastStages><<<grid, 32, smem, stream>>>(tokens, tok_start, n_tok, keys, key_start, n_req,
+                                                                    consts, task_counter);
     return cudaGetLastError();
   }
   const int threads = 128;
