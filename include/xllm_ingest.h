@@ -284,6 +284,12 @@ int xllm_ingest_batch_segments(xllm_ingest_t h, const xllm_ingest_io* io, const 
  * per chunk (defaults 4096 / 96 MiB; chunk sizes ramp up from chunk_requests/16 and taper off at the end;
  * 4 chunks in flight over one upload, one kernel and one download stream). */
 int xllm_set_pipeline(xllm_ingest_t h, int32_t chunk_requests, int64_t chunk_bytes);
+/* Word memo of the tokenizer kernels (word bytes -> token ids, immutable entries, one table per launch site).
+ * persist_requests == 0 (default): every encode launch starts from an empty table, nothing is carried from one batch
+ * to the next.  persist_requests == N > 0: a table is kept across launches and cleared once it has seen N requests —
+ * the service setting (host/ingest_batcher.h): small batches no longer pay for the cold table, results are identical
+ * either way (a stale table is only ever less complete).  Env XLLM_SP_MEMO_PERSIST=N sets it at create. */
+int xllm_set_memo_policy(xllm_ingest_t h, int64_t persist_requests);
 /* Chunks and kernel launches of the most recent xllm_ingest_batch on this handle (for launch accounting). */
 int xllm_last_batch_stats(xllm_ingest_t h, int32_t* n_chunks, int32_t* n_kernel_launches);
 /* Page-locked host memory for the batch buffers. */

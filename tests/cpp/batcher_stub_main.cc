@@ -17,6 +17,7 @@
 static std::atomic<int> g_inside{0}, g_overlap{0}, g_calls{0}, g_max_batch{0};
 
 extern "C" {
+int xllm_set_memo_policy(xllm_ingest_t, int64_t) { return XLLM_OK; }
 int xllm_host_alloc(void** out, size_t bytes) { *out = malloc(bytes ? bytes : 1); return *out ? XLLM_OK : XLLM_ERR_NOMEM; }
 void xllm_host_free(void* p) { free(p); }
 static int g_vocab = 8000;   // < 65536: the batcher takes the narrow (uint16) id download; 0x20000: the int32 one

@@ -131,3 +131,36 @@ def test_pipeline_chunks_each_have_their_own_memo(oracle):
             assert ids[i, :n_ids[i]].tolist() == sp.encode(t).tolist(), i
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("model,kind", [(SP_DIR, "sp"), (HF_DIR, "hf")])
+def test_memo_kept_across_launches(oracle, model, kind):
+    """xllm_set_memo_policy(N): the table survives between launches (the service setting) and is cleared after N requests;
+    different batches one after the other, through the single-launch entry point and through the chunk pipeline, all
+    equal the oracle — a stale table is only ever less complete, never wrong."""
+    import xllm_service_b200 as x
+    from xllm_service_b200 import workload
+    orc = oracle.SentencePieceOracle(model) if kind == "sp" else oracle.HfBpeOracle(model)
+    h = x.Ingest(tokenizer_path=model)
+    try:
+        h.set_memo_policy(500)                  # three batches of 164 prompts stay on one table, the fourth clears it
+        for seed in (11, 12, 11, 13, 14, 12):
+            texts = _texts(seed)
+            got, status = _encode_all(h, texts)
+            assert (status == 0).all()
+            bad = [t[:40] for t, g in zip(texts, got) if g != orc.encode(t).tolist()]
+            assert not bad, (seed, len(bad), bad[:3])
+        h.set_pipeline(23, 1 << 16)
+        for seed in (21, 22, 21):
+            texts = _texts(seed)
+            b = workload.pack_prompts(texts)
+            stride = 3 * max(len(t) for t in texts) + 8
+            res = h.ingest_batch(b.text, b.offsets, stride, want_keys=False, want_match=False)
+            assert (res["status"] == 0).all()
+            for i, t in enumerate(texts):
+                assert res["ids"][i, :res["n_ids"][i]].tolist() == orc.encode(t).tolist(), (seed, i)
+        h.set_memo_policy(0)                    # back to a fresh table per launch
+        got, status = _encode_all(h, _texts(31))
+        assert (status == 0).all() and got == [orc.encode(t).tolist() for t in _texts(31)]
+    finally:
+        h.close()

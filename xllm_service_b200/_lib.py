@@ -123,6 +123,7 @@ def _declare(L):
     L.xllm_index_put_bulk.argtypes = [_VP, ctypes.c_int64, _VP, _VP, _VP, _VP]
     L.xllm_index_export.argtypes = [_VP, ctypes.c_int64, _VP, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_int64)]
     L.xllm_set_pipeline.argtypes = [_VP, ctypes.c_int32, ctypes.c_int64]
+    L.xllm_set_memo_policy.argtypes = [_VP, ctypes.c_int64]
     L.xllm_last_batch_stats.argtypes = [_VP, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
     L.xllm_host_alloc.argtypes = [ctypes.POINTER(_VP), ctypes.c_size_t]
     L.xllm_host_free.argtypes = [_VP]

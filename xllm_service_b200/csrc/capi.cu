@@ -121,6 +121,7 @@ int xllm_ingest_create(const xllm_ingest_config* cfg, xllm_ingest_t* out) {
       return rc;
     }
     h->memo_slots = sp_memo_default_slots();
+    if (const char* w = getenv("XLLM_SP_MEMO_PERSIST")) h->memo_persist_requests = atoll(w) > 0 ? atoll(w) : 0;
     if (const char* w = getenv("XLLM_SP_WARM")) h->sp_warm = atoi(w) != 0;
     if (const char* w = getenv("XLLM_PIPE_SLOTS")) {
       const int v = atoi(w);
@@ -190,6 +191,7 @@ int xllm_ingest_clone(xllm_ingest_t src, xllm_ingest_t* out) {
   (*out)->sp_tables = src->sp_tables;
   (*out)->sp_dev = src->sp_dev;
   (*out)->memo_slots = src->memo_slots;
+  (*out)->memo_persist_requests = src->memo_persist_requests;
   (*out)->sp_warm = src->sp_warm;
   (*out)->pipe_slots = src->pipe_slots;
   (*out)->tokenizer_path = src->tokenizer_path;
@@ -683,6 +685,7 @@ int xllm_encode_batch_device(xllm_ingest_t h, int32_t n_req, const uint8_t* d_te
     XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
     memo.table = h->d_memo.p;
     memo.slots = h->memo_slots;
+    memo.clear = xllm::memo_needs_clear(h->memo_persist_requests, &h->memo_age, n_req);
     if (h->sp_warm) {
       memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
       XLLM_TRY(h->d_arena.reserve(memo.arena_bytes));
@@ -729,6 +732,7 @@ static int encode_batch_impl(xllm_ingest_t h, int32_t n_req, const uint8_t* text
     XLLM_TRY(h->d_memo.reserve((size_t)h->memo_slots * 32));
     memo.table = h->d_memo.p;
     memo.slots = h->memo_slots;
+    memo.clear = xllm::memo_needs_clear(h->memo_persist_requests, &h->memo_age, n_req);
     if (h->sp_warm) {
       memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
       XLLM_TRY(h->d_arena.reserve(memo.arena_bytes));

@@ -35,13 +35,23 @@ struct PinBuf {
   T* as() { return static_cast<T*>(p); }
 };
 
+// Memo policy (xllm_set_memo_policy): should the launch about to encode n_req requests clear the table whose age
+// (requests since its last clear, -1 = never cleared) is *age?  Updates *age for that launch.
+inline bool memo_needs_clear(int64_t persist_requests, int64_t* age, int64_t n_req) {
+  const bool clear = persist_requests <= 0 || *age < 0 || *age >= persist_requests;
+  *age = (clear ? 0 : *age) + n_req;
+  return clear;
+}
+
 // One in-flight chunk of xllm_ingest_batch: its own stream + device buffers.
 constexpr int kPipeSlots = 32;  // upper bound; xllm_ingest::pipe_slots are used
 struct PipeSlot {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // uploaded / kernels done / downloaded
   bool busy = false;                                // ev[2] of an earlier chunk of this batch is pending
   unsigned int* counters = nullptr;
-  DevBuf d_memo;  // this slot's word memo (sp_encode.cuh): cleared by every encode launch on the slot's stream
+  DevBuf d_memo;  // this slot's word memo (sp_encode.cuh): cleared by every encode launch on the slot's stream,
+                  // or kept for memo_persist_requests requests (xllm_set_memo_policy)
+  int64_t memo_age = -1;  // requests encoded since the table was last cleared; -1 = never cleared (must be)
   DevBuf d_defer, d_text, d_offsets, d_ids, d_n_ids, d_status, d_tok_start, d_n_tok, d_key_start, d_n_blocks, d_keys, d_masks,
       d_match, d_routing;
   // segmented requests (xllm_ingest_batch_segments): text pieces encode into ragged temporary rows, then the
@@ -91,6 +101,8 @@ struct xllm_ingest {
   // scratch for the host-pointer entry points
   xllm::DevBuf d_text, d_offsets, d_ids, d_n_ids, d_status, d_defer;
   xllm::DevBuf d_memo;      // word memo of the single-launch encode entry points
+  int64_t memo_age = -1;    // requests encoded since d_memo was last cleared; -1 = never
+  int64_t memo_persist_requests = 0;  // 0: every launch clears its memo; N > 0: a memo is kept until it has seen N requests
   xllm::DevBuf d_arena;     // warm-up scratch of the encode kernel (per handle: launches on one handle are serialised)
   uint32_t memo_slots = 0;  // 0 = memo off
   bool sp_warm = false;     // XLLM_SP_WARM=1: launch the warm-up tokenizer kernels (natural text; sp_encode.cu drain_pass_warm)

@@ -381,6 +381,7 @@ static int ingest_core(xllm_ingest_t h, const xllm_ingest_io* io, const xllm_seg
     xllm::SpMemo memo;
     memo.table = h->memo_slots ? sl.d_memo.p : nullptr;
     memo.slots = h->memo_slots;
+    if (h->memo_slots) memo.clear = xllm::memo_needs_clear(h->memo_persist_requests, &sl.memo_age, seg ? (int64_t)(p1 - p0) : (int64_t)m);
     if (h->memo_slots && h->sp_warm) {   // kernels of all chunks run on one stream, one after the other: one scratch for the handle
       memo.arena_bytes = sp_warm_arena_bytes(h->sp_dev->dev(), 1 << 30);   // the full grid's worth: never regrown
       if ((rc = h->d_arena.reserve(memo.arena_bytes)) != XLLM_OK) break;
@@ -576,6 +577,13 @@ int xllm_last_batch_stats(xllm_ingest_t h, int32_t* n_chunks, int32_t* n_kernel_
   std::lock_guard<std::mutex> lock(h->mu);
   if (n_chunks) *n_chunks = h->last_chunks;
   if (n_kernel_launches) *n_kernel_launches = h->last_launches;
+  return XLLM_OK;
+}
+
+int xllm_set_memo_policy(xllm_ingest_t h, int64_t persist_requests) {
+  if (!h || persist_requests < 0) return XLLM_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->memo_persist_requests = persist_requests;
   return XLLM_OK;
 }
 

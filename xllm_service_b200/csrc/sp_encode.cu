@@ -3073,8 +3073,8 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
   int grid_long = n_sm * 2;
   if (grid_long > n_req) grid_long = n_req;
   const bool use_memo = memo.table != nullptr && memo.slots >= 2 && (memo.slots & (memo.slots - 1)) == 0;
-  if (use_memo) {
-    e = cudaMemsetAsync(memo.table, 0, (size_t)memo.slots * 32, stream);  // the memo lives for this launch only
+  if (use_memo && memo.clear) {
+    e = cudaMemsetAsync(memo.table, 0, (size_t)memo.slots * 32, stream);  // default policy: the memo lives for this launch only
     if (e != cudaSuccess) return e;
   }
   // the warm-up kernels (drain_pass_warm) need their per-warp scratch; the caller passes it only when they are wanted

@@ -101,6 +101,9 @@ class SpDeviceModel {
 struct SpMemo {
   void* table = nullptr;
   uint32_t slots = 0;
+  // false: the launch reuses what earlier launches left in the table (same tokenizer model; entries are immutable, so a
+  // stale table is only ever less complete) — the caller's policy decides when to clear (xllm_set_memo_policy)
+  bool clear = true;
   // scratch of the warm-up pre-passes (natural text: memo misses merged in full rounds, long words resolved ahead of
   // the in-order rounds); at least sp_warm_arena_bytes(dev, n_req) bytes, or null to leave the pre-passes off
   void* arena = nullptr;

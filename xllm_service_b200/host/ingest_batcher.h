@@ -48,11 +48,14 @@ class IngestBatcher {
  public:
   // `h` must outlive the batcher.  max_tokens bounds the ids returned per request.
   IngestBatcher(xllm_ingest_t h, int max_batch, size_t max_bytes, int max_tokens, int block_size, int max_wait_us,
-                bool want_routing, int offline_defer_us = 20000)
+                bool want_routing, int offline_defer_us = 20000, int64_t memo_persist_requests = 1 << 20)
       : h_(h), max_batch_(max_batch), max_bytes_(max_bytes), max_tokens_(max_tokens),
         keys_stride_(max_tokens / block_size), max_wait_us_(max_wait_us), want_routing_(want_routing),
         offline_defer_us_(offline_defer_us) {
     ok_ = true;
+    // a service's batches are small and come one after the other: keep the tokenizer's word memo across launches
+    // (cleared every memo_persist_requests requests) instead of starting every batch from an empty table
+    xllm_set_memo_policy(h, memo_persist_requests);
     // vocabularies below 65 536 pieces: take the ids as uint16 (half the bytes over PCIe) and widen them in hand_out,
     // during the copy into the caller's std::vector<int32_t> that happens anyway
     int32_t vocab = 0;

@@ -272,6 +272,10 @@ class Ingest:
     def set_pipeline(self, chunk_requests, chunk_bytes):
         check(self._L.xllm_set_pipeline(self._h, chunk_requests, chunk_bytes))
 
+    def set_memo_policy(self, persist_requests):
+        """0: every encode launch clears its word memo (default); N > 0: a memo is kept until it has seen N requests."""
+        check(self._L.xllm_set_memo_policy(self._h, persist_requests))
+
     def last_batch_stats(self):
         """(chunks, kernel launches) of the most recent ingest_batch on this handle."""
         c, k = ctypes.c_int32(), ctypes.c_int32()
