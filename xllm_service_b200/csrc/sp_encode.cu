@@ -86,10 +86,17 @@ struct PMOps<true> {
   }
 };
 
-template <bool SMALL>
+// ROWS = chars per word on the lane-per-word path (the lane's column height).  16 for the SentencePiece kernels; the HF
+// byte-level kernels take 32 (kHfRows): natural text through a byte-level BPE has 10 % of its pre-tokens between 17 and 32
+// bytes, and a 32-row column keeps them on the lane path (32 words merged at once) instead of the one-word-at-a-time
+// cooperative path — at the price of 8 KB more shared memory per warp (17 / 13 resident warps instead of 27 / 18).
+constexpr int kHfRows = 32;
+template <bool SMALL, int ROWS = kMaxSym>
 struct WarpSmemT {
-  uint32_t S[kCoopMaxSym];                   // symbols: lane columns S[j * 32 + lane] (lane path) or flat (cooperative)
-  typename PMOps<SMALL>::T PM[kCoopMaxSym];  // pair state at position j
+  static constexpr int kRows = ROWS;
+  static constexpr int kSyms = ROWS * 32 > kCoopMaxSym ? ROWS * 32 : kCoopMaxSym;
+  uint32_t S[kSyms];                   // symbols: lane columns S[j * 32 + lane] (lane path) or flat (cooperative)
+  typename PMOps<SMALL>::T PM[kSyms];  // pair state at position j
   uint8_t nbuf[kNBuf];                       // normalized text (always starts at a word start)
   uint16_t wstart[kMaxWords];
   uint16_t pend[32];                         // warm-up kernels: words that missed the memo, waiting for a full round
@@ -591,7 +598,7 @@ __device__ __forceinline__ uint32_t lane_merge(const SpDev& T, SM& sm, int n, in
     }
   }
   PM[(n - 1) * 32] = P::none();
-  uint32_t alive = (1u << n) - 1;
+  uint32_t alive = n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1;
   for (;;) {
     uint32_t best = P::kNone;
     int bj = 0;
@@ -1675,7 +1682,7 @@ __device__ bool drain_pass(const SpDev& T, SM& sm, ReqState& rs, bool final, int
       else
         for (int p = ws; p < we; ++p) nsym += T.byte_mode || (nb[p] & 0xC0) != 0x80;
     }
-    const uint32_t long_mask = __ballot_sync(kFull, have && (UNI || nsym > kMaxSym));  // Unigram: one word at a time
+    const uint32_t long_mask = __ballot_sync(kFull, have && (UNI || nsym > SM::kRows));  // Unigram: one word at a time
     const int first_long = long_mask ? __ffs(long_mask) - 1 : 32;
     const bool active = have && lane < first_long;
 
@@ -2588,7 +2595,7 @@ __device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool
 // MEMO == true: words are looked up in / added to the launch's word memo (never built together with LONG).
 // WARM == true: drains go through drain_pass_warm (natural text; MEMO kernels only).
 template <bool SMALL, bool LONG, int MODE, bool MEMO, bool WARM = false>
-__global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
+__global__ void __launch_bounds__(32, LONG ? 8 : ((MODE == 1 && !WARM) ? 16 : 27)) sp_encode_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ offsets, int n_req, int32_t* __restrict__ ids,
     int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status, const __grid_constant__ SpDev T,
     unsigned int* __restrict__ task_counter, int32_t* __restrict__ defer_list,
@@ -2596,7 +2603,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : 27) sp_encode_kernel(
   constexpr bool HF = MODE == 1;
   const MemoRef memo{memo_table, memo_mask};
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using SM = typename std::conditional<MODE == 2, WarpSmemUniT<SMALL>, WarpSmemT<SMALL>>::type;
+  using SM = typename std::conditional<MODE == 2, WarpSmemUniT<SMALL>, WarpSmemT<SMALL, (MODE == 1 && !WARM) ? kHfRows : kMaxSym>>::type;
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int lane = threadIdx.x;
   const int drain_at = kNBuf - 3 * kFastWin - 8;  // room for one more fast-path step
@@ -2945,9 +2952,11 @@ int SpDeviceModel::upload(const SpTables& t) {
 
 static DeviceOnce g_sp_once;
 
-static int sp_warps_per_sm(const SpDev& dev) {
+static int sp_warps_per_sm(const SpDev& dev, bool warm = false) {
   const bool small = dev.small_vocab != 0;
+  const bool hf = dev.split_mode == 3 && !warm;   // the warm-up kernels keep 16-row columns
   const size_t smem = dev.unigram ? (small ? sizeof(WarpSmemUniT<true>) : sizeof(WarpSmemUniT<false>))
+                      : hf        ? (small ? sizeof(WarpSmemT<true, kHfRows>) : sizeof(WarpSmemT<false, kHfRows>))
                                   : (small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>));
   int w = (int)((227 * 1024) / (smem + 1024));
   if (w > 27) w = 27;
@@ -2955,14 +2964,14 @@ static int sp_warps_per_sm(const SpDev& dev) {
   return w;
 }
 
-static int sp_legacy_grid(const SpDev& dev, int n_req) {
+static int sp_legacy_grid(const SpDev& dev, int n_req, bool warm = false) {
   int n_sm = 0, d = 0;
   if (cudaGetDevice(&d) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d) != cudaSuccess)
     return 0;
-  const int grid = n_sm * sp_warps_per_sm(dev);
+  const int grid = n_sm * sp_warps_per_sm(dev, warm);
   return grid > n_req ? n_req : grid;
 }
-size_t sp_warm_arena_bytes(const SpDev& dev, int n_req) { return (size_t)sp_legacy_grid(dev, n_req) * kWarmSliceBytes; }
+size_t sp_warm_arena_bytes(const SpDev& dev, int n_req) { return (size_t)sp_legacy_grid(dev, n_req, true) * kWarmSliceBytes; }
 
 // the express kernel runs in front of the buffer-path kernel for these models (and only with the word memo on)
 static bool sp_express_model(const SpDev& dev) {
@@ -3026,7 +3035,10 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
   int32_t* const legacy_list = defer_list + n_req;
   ExpResume* const resume = reinterpret_cast<ExpResume*>(static_cast<uint8_t*>(scratch) + (((size_t)n_req * 8 + 15) & ~(size_t)15));
   const bool small = dev.small_vocab != 0;
-  const size_t smem = small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>);
+  const bool hf = dev.split_mode == 3;
+  // the HF kernels (not their warm-up variants) use 32-row lane columns
+  const size_t smem16 = small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>);
+  const size_t smem_long = hf ? (small ? sizeof(WarpSmemT<true, kHfRows>) : sizeof(WarpSmemT<false, kHfRows>)) : smem16;
   cudaError_t e0 = cudaSuccess;
   const int n_sm = once.get(
       [&] {
@@ -3034,18 +3046,21 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
 #define XLLM_SET_SMEM(K, B)                                                                          \
         r = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B>)); \
         if (r != cudaSuccess) return r;
+#define XLLM_SET_SMEM_HF(K, B)                                                                                \
+        r = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B, kHfRows>)); \
+        if (r != cudaSuccess) return r;
         XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, false>), true)
         XLLM_SET_SMEM((sp_encode_kernel<true, true, 0, false>), true)
         XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, false>), false)
         XLLM_SET_SMEM((sp_encode_kernel<false, true, 0, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, 1, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<true, true, 1, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, 1, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<false, true, 1, false>), false)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<true, false, 1, false>), true)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<true, true, 1, false>), true)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<false, false, 1, false>), false)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<false, true, 1, false>), false)
         XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, true>), true)
         XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, true>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, 1, true>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, 1, true>), false)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<true, false, 1, true>), true)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<false, false, 1, true>), false)
         XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, true, true>), true)
         XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, true, true>), false)
         XLLM_SET_SMEM((sp_encode_kernel<true, false, 1, true, true>), true)
@@ -3057,6 +3072,7 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
                                  (int)sizeof(WarpSmemUniT<false>));
         if (r != cudaSuccess) return r;
 #undef XLLM_SET_SMEM
+#undef XLLM_SET_SMEM_HF
         return cudaSuccess;
       },
       &e0);
@@ -3065,11 +3081,13 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
   // [3]: task counter of the express kernel, [4]: requests it handed over
   cudaError_t e = cudaMemsetAsync(counters, 0, 5 * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
-  int warps_per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (warps_per_sm > 27) warps_per_sm = 27;
-  if (g_warps_per_sm_override > 0 && g_warps_per_sm_override < warps_per_sm) warps_per_sm = g_warps_per_sm_override;
-  int grid = n_sm * warps_per_sm;
-  if (grid > n_req) grid = n_req;
+  auto grid_for = [&](size_t smem_bytes) {
+    int warps_per_sm = (int)((227 * 1024) / (smem_bytes + 1024));
+    if (warps_per_sm > 27) warps_per_sm = 27;
+    if (g_warps_per_sm_override > 0 && g_warps_per_sm_override < warps_per_sm) warps_per_sm = g_warps_per_sm_override;
+    const int g = n_sm * warps_per_sm;
+    return g > n_req ? n_req : g;
+  };
   int grid_long = n_sm * 2;
   if (grid_long > n_req) grid_long = n_req;
   const bool use_memo = memo.table != nullptr && memo.slots >= 2 && (memo.slots & (memo.slots - 1)) == 0;
@@ -3078,7 +3096,10 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
     if (e != cudaSuccess) return e;
   }
   // the warm-up kernels (drain_pass_warm) need their per-warp scratch; the caller passes it only when they are wanted
-  const bool warm = use_memo && !dev.unigram && memo.arena != nullptr && memo.arena_bytes >= (size_t)grid * kWarmSliceBytes;
+  const bool warm = use_memo && !dev.unigram && memo.arena != nullptr &&
+                    memo.arena_bytes >= (size_t)grid_for(smem16) * kWarmSliceBytes;
+  const size_t smem = warm ? smem16 : smem_long;   // the throughput kernel's shared memory: 16-row columns when warm
+  const int grid = grid_for(smem);
   if (warm) dev.warm_arena = static_cast<uint8_t*>(memo.arena);
   uint8_t* const mt = use_memo ? static_cast<uint8_t*>(memo.table) : nullptr;
   const uint32_t mm = use_memo ? memo.slots - 1 : 0;
@@ -3104,9 +3125,8 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
   else                                                                                                           \
     sp_encode_kernel<SMALL_, false, HF_, MEMO_><<<grid, 32, smem, stream>>>(                                     \
         text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters, defer_list, counters + 1, mt, mm);  \
-  sp_encode_kernel<SMALL_, true, HF_, false><<<grid_long, 32, smem, stream>>>(                                   \
+  sp_encode_kernel<SMALL_, true, HF_, false><<<grid_long, 32, smem_long, stream>>>(                              \
       text, offsets, n_req, ids, ids_stride, n_ids, status, dev, counters + 2, defer_list, counters + 1, nullptr, 0u);
-  const bool hf = dev.split_mode == 3;
   if (dev.unigram) {
     // Viterbi per word from a running score: no word memo (the result depends on the prefix), no long-word pass
     const size_t usmem = small ? sizeof(WarpSmemUniT<true>) : sizeof(WarpSmemUniT<false>);
