@@ -11,6 +11,12 @@
 //   tiktoken in the service's regex-less mode (tiktoken_tokenizer.cpp:115-294): byte symbols, merges by rank
 //   HF `tokenizer.json` byte-level BPE (fast_tokenizer.cpp:20-30): hf_pretok.cuh in front of the same merges
 //
+// Two throughput kernels.  sp_express_kernel (SentencePiece BPE models with split_mode 1 + remove_extra_whitespaces,
+// memo on) tokenises 256-byte windows of plain ASCII text straight from registers — no normalized-text buffer, no word
+// list: lane k takes the window's k-th word, probes the word memo with a key built from the neighbouring lanes'
+// registers and stores the ids from the memo payload (express_run below).  What its rules do not cover is handed to
+// sp_encode_kernel, the general kernel described next, which is also the only kernel of every other backend.
+//
 // Why the BPE merge is exact AND parallel: no NORMAL piece of the loaded model holds U+2581 anywhere but
 // at its first char (checked by the host loader: SpTables::split_mode), so no merge can ever
 // span the boundary in front of a U+2581.  The priority-ordered global merge therefore factors
