@@ -1212,6 +1212,7 @@ __device__ __noinline__ bool express_long_word(const SpDev& T, SM& sm, const uin
   if (nbytes < 1 || nsym > kCoopMaxSym) return false;
   // --- symbols, merge, ids
   const uint8_t* bytes = reinterpret_cast<const uint8_t*>(base) + v0;
+  __syncwarp();   // the lanes' own merges of this step (their columns of S / PM) are done before S is rewritten flat
   if (lead && lane == 0) sm.S[0] = T.space_sym;
   for (int i = lane; i < nbytes; i += 32) sm.S[i + (lead ? 1 : 0)] = __ldg(T.ascii_sym + __ldg(bytes + i));
   __syncwarp();
