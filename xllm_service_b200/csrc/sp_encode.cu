@@ -92,8 +92,8 @@ struct PMOps<true> {
   }
 };
 
-// ROWS = chars per word on the lane-per-word path (the lane's column height).  16 for the SentencePiece kernels; the HF
-// byte-level kernels take 32 (kHfRows): natural text through a byte-level BPE has 10 % of its pre-tokens between 17 and 32
+// ROWS = chars per word on the lane-per-word path (the lane's column height).  16 for the warm-up and Unigram kernels;
+// the buffer-path BPE kernels take 32 (kHfRows, first measured on the HF byte-level kernels): natural text through a byte-level BPE has 10 % of its pre-tokens between 17 and 32
 // bytes, and a 32-row column keeps them on the lane path (32 words merged at once) instead of the one-word-at-a-time
 // cooperative path — at the price of 8 KB more shared memory per warp (17 / 13 resident warps instead of 27 / 18).
 constexpr int kHfRows = 32;
@@ -1158,6 +1158,8 @@ struct ExpSmemT {
   typename PMOps<SMALL>::T PM[kMaxSym * 32];
   uint8_t ex[272];   // {start, end} per word, <= 128 words in 256 bytes
 };
+constexpr int kExpLongWords = 4;     // express_run: long words a request may put through the cooperative path ...
+constexpr int kExpLongEvery = 512;   // ... at a density above one per this many bytes before it is handed over
 // what the buffer-path kernel needs to take a request over where the express kernel stopped
 struct ExpResume {
   uint32_t pos;      // source bytes consumed
@@ -1259,6 +1261,7 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
   bool P = rs.P;
   bool S = rs.S;
   bool U = rs.U;
+  int n_long = 0;             // long words this request sent through the cooperative path
   uint8_t* const ex = sm.ex;
   int32_t* const out = rs.out;
   const int32_t cap = rs.cap > 0x7fffffffll ? 0x7fffffff : (int32_t)rs.cap;
@@ -1362,8 +1365,13 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
           uint32_t v_end = 0;
           int32_t io_n = n_out;                    // only these copies have their address taken
           bool io_u = U;
-          const bool done = express_long_word<SMALL>(T, sm, base, nwords, vlen, wb + s0, P || (!S && s0 > skip), out, cap,
-                                                     &io_n, &io_u, &v_end, lane);
+          // a text dense in long words (natural text: one in ~100 bytes) is better off in the buffer-path kernel, which
+          // merges words of up to 32 symbols 32 at a time in lane columns: after kExpLongWords of them at more than one
+          // per kExpLongEvery bytes the rest of the request is handed over
+          ++n_long;
+          const bool dense = n_long > kExpLongWords && (uint32_t)n_long * (uint32_t)kExpLongEvery > wb + s0 - A;
+          const bool done = !dense && express_long_word<SMALL>(T, sm, base, nwords, vlen, wb + s0, P || (!S && s0 > skip),
+                                                               out, cap, &io_n, &io_u, &v_end, lane);
           n_out = io_n;
           U = io_u;
           if (!done) {
@@ -1478,8 +1486,10 @@ __device__ __forceinline__ uint32_t express_run(const SpDev& T, SM& sm, ExpReq& 
             uint32_t v_end = 0;
             int32_t io_n = n_out;
             bool io_u = U;
-            const bool done = express_long_word<SMALL>(T, sm, base, nwords, vlen, wb + s0, P || (!S && s0 > skip), out,
-                                                       cap, &io_n, &io_u, &v_end, lane);
+            ++n_long;                              // counts like a long word (see above)
+            const bool dense = n_long > kExpLongWords && (uint32_t)n_long * (uint32_t)kExpLongEvery > wb + s0 - A;
+            const bool done = !dense && express_long_word<SMALL>(T, sm, base, nwords, vlen, wb + s0,
+                                                                 P || (!S && s0 > skip), out, cap, &io_n, &io_u, &v_end, lane);
             n_out = io_n;
             U = io_u;
             if (!done) {
@@ -2602,7 +2612,7 @@ __device__ __forceinline__ void drain(const SpDev& T, SM& sm, ReqState& rs, bool
 // MEMO == true: words are looked up in / added to the launch's word memo (never built together with LONG).
 // WARM == true: drains go through drain_pass_warm (natural text; MEMO kernels only).
 template <bool SMALL, bool LONG, int MODE, bool MEMO, bool WARM = false>
-__global__ void __launch_bounds__(32, LONG ? 8 : ((MODE == 1 && !WARM) ? 16 : 27)) sp_encode_kernel(
+__global__ void __launch_bounds__(32, LONG ? 8 : ((MODE != 2 && !WARM) ? 16 : 27)) sp_encode_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ offsets, int n_req, int32_t* __restrict__ ids,
     int64_t ids_stride, int32_t* __restrict__ n_ids, int32_t* __restrict__ status, const __grid_constant__ SpDev T,
     unsigned int* __restrict__ task_counter, int32_t* __restrict__ defer_list,
@@ -2610,7 +2620,7 @@ __global__ void __launch_bounds__(32, LONG ? 8 : ((MODE == 1 && !WARM) ? 16 : 27
   constexpr bool HF = MODE == 1;
   const MemoRef memo{memo_table, memo_mask};
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using SM = typename std::conditional<MODE == 2, WarpSmemUniT<SMALL>, WarpSmemT<SMALL, (MODE == 1 && !WARM) ? kHfRows : kMaxSym>>::type;
+  using SM = typename std::conditional<MODE == 2, WarpSmemUniT<SMALL>, WarpSmemT<SMALL, (MODE != 2 && !WARM) ? kHfRows : kMaxSym>>::type;
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int lane = threadIdx.x;
   const int drain_at = kNBuf - 3 * kFastWin - 8;  // room for one more fast-path step
@@ -2961,7 +2971,7 @@ static DeviceOnce g_sp_once;
 
 static int sp_warps_per_sm(const SpDev& dev, bool warm = false) {
   const bool small = dev.small_vocab != 0;
-  const bool hf = dev.split_mode == 3 && !warm;   // the warm-up kernels keep 16-row columns
+  const bool hf = !warm;   // every buffer-path BPE kernel has 32-row columns; the warm-up kernels keep 16
   const size_t smem = dev.unigram ? (small ? sizeof(WarpSmemUniT<true>) : sizeof(WarpSmemUniT<false>))
                       : hf        ? (small ? sizeof(WarpSmemT<true, kHfRows>) : sizeof(WarpSmemT<false, kHfRows>))
                                   : (small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>));
@@ -3045,7 +3055,7 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
   const bool hf = dev.split_mode == 3;
   // the HF kernels (not their warm-up variants) use 32-row lane columns
   const size_t smem16 = small ? sizeof(WarpSmemT<true>) : sizeof(WarpSmemT<false>);
-  const size_t smem_long = hf ? (small ? sizeof(WarpSmemT<true, kHfRows>) : sizeof(WarpSmemT<false, kHfRows>)) : smem16;
+  const size_t smem_long = small ? sizeof(WarpSmemT<true, kHfRows>) : sizeof(WarpSmemT<false, kHfRows>);
   cudaError_t e0 = cudaSuccess;
   const int n_sm = once.get(
       [&] {
@@ -3056,16 +3066,16 @@ cudaError_t sp_encode_launch(const SpDev& dev_in, const uint8_t* text, const int
 #define XLLM_SET_SMEM_HF(K, B)                                                                                \
         r = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmemT<B, kHfRows>)); \
         if (r != cudaSuccess) return r;
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<true, true, 0, false>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<false, true, 0, false>), false)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<true, false, 0, false>), true)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<true, true, 0, false>), true)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<false, false, 0, false>), false)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<false, true, 0, false>), false)
         XLLM_SET_SMEM_HF((sp_encode_kernel<true, false, 1, false>), true)
         XLLM_SET_SMEM_HF((sp_encode_kernel<true, true, 1, false>), true)
         XLLM_SET_SMEM_HF((sp_encode_kernel<false, false, 1, false>), false)
         XLLM_SET_SMEM_HF((sp_encode_kernel<false, true, 1, false>), false)
-        XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, true>), true)
-        XLLM_SET_SMEM((sp_encode_kernel<false, false, 0, true>), false)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<true, false, 0, true>), true)
+        XLLM_SET_SMEM_HF((sp_encode_kernel<false, false, 0, true>), false)
         XLLM_SET_SMEM_HF((sp_encode_kernel<true, false, 1, true>), true)
         XLLM_SET_SMEM_HF((sp_encode_kernel<false, false, 1, true>), false)
         XLLM_SET_SMEM((sp_encode_kernel<true, false, 0, true, true>), true)
