@@ -324,7 +324,7 @@ def run_c5(h, wcnt, n_req, steps, rank_seed=0):
         "mean_matched_blocks_online": float(mt["max_matched_block_num"].mean()),
         "persistent_grid_tail": {"warps": int(warp_ms.size), "max_ms": float(warp_ms.max()),
                                  "mean_ms": float(warp_ms.mean()), "max_over_mean": float(warp_ms.max() / warp_ms.mean()),
-                                 "note": "busy time per warp of sp_encode_kernel over all text pieces of the batch "
+                                 "note": "busy time per warp slot of the tokenizer kernels (sp_express_kernel + what it hands to sp_encode_kernel) over all text pieces of the batch "
                                          "(one warp takes one piece at a time from a shared counter)"},
     }
 
