@@ -1,4 +1,5 @@
 // CPU unit test of csrc/pipeline_schedule.h: every schedule covers the batch exactly with chunks in [1, chunk_req].
+#include <cstdint>
 #include <cstdio>
 #include <vector>
 
@@ -36,6 +37,17 @@ int main() {
     const long want_head[] = {512, 1024, 2048, 4096};
     for (int i = 0; i < 4; ++i) if (sizes[(size_t)i] != want_head[i]) { ++fails; printf("head %d = %ld\n", i, sizes[(size_t)i]); }
     if (sizes.back() != 1024) { ++fails; printf("tail = %ld\n", sizes.back()); }
+  }
+  // memo policy (xllm_set_memo_policy): age-based clearing of a word memo that outlives its launch
+  {
+    int64_t age = -1;
+    if (!xllm::memo_needs_clear(0, &age, 10) || age != 10) { ++fails; printf("policy 0 must clear every launch\n"); }
+    if (!xllm::memo_needs_clear(0, &age, 5) || age != 5) { ++fails; printf("policy 0, second launch\n"); }
+    age = -1;
+    if (!xllm::memo_needs_clear(100, &age, 40) || age != 40) { ++fails; printf("a never-cleared table must be cleared\n"); }
+    if (xllm::memo_needs_clear(100, &age, 40) || age != 80) { ++fails; printf("kept below the limit\n"); }
+    if (xllm::memo_needs_clear(100, &age, 40) || age != 120) { ++fails; printf("the launch that crosses the limit still keeps it\n"); }
+    if (!xllm::memo_needs_clear(100, &age, 7) || age != 7) { ++fails; printf("cleared once it has seen the limit\n"); }
   }
   printf(fails ? "FAILED %d\n" : "OK\n", fails);
   return fails ? 1 : 0;

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <memory>
+
+#include "pipeline_schedule.h"
 #include <mutex>
 #include <string>
 #include <vector>
@@ -34,14 +36,6 @@ struct PinBuf {
   template <typename T>
   T* as() { return static_cast<T*>(p); }
 };
-
-// Memo policy (xllm_set_memo_policy): should the launch about to encode n_req requests clear the table whose age
-// (requests since its last clear, -1 = never cleared) is *age?  Updates *age for that launch.
-inline bool memo_needs_clear(int64_t persist_requests, int64_t* age, int64_t n_req) {
-  const bool clear = persist_requests <= 0 || *age < 0 || *age >= persist_requests;
-  *age = (clear ? 0 : *age) + n_req;
-  return clear;
-}
 
 // One in-flight chunk of xllm_ingest_batch: its own stream + device buffers.
 constexpr int kPipeSlots = 32;  // upper bound; xllm_ingest::pipe_slots are used

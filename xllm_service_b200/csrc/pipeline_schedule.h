@@ -27,4 +27,12 @@ struct ChunkSchedule {
   }
 };
 
+// Memo policy (xllm_set_memo_policy): should the launch about to encode n_req requests clear the table whose age
+// (requests since its last clear, -1 = never cleared) is *age?  Updates *age for that launch.
+inline bool memo_needs_clear(int64_t persist_requests, int64_t* age, int64_t n_req) {
+  const bool clear = persist_requests <= 0 || *age < 0 || *age >= persist_requests;
+  *age = (clear ? 0 : *age) + n_req;
+  return clear;
+}
+
 }  // namespace xllm
